@@ -1,0 +1,227 @@
+#!/usr/bin/env python
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference envs.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+Inputs are seeded exactly as SURVEY.md section 8d prescribes:
+  * initial targets of env e: ``np.random.seed(10_000 + e)`` then the reference's own
+    ``reset()`` (MT19937 normals, env/flight_env_easy.py:107-108);
+  * actions: ``np.random.default_rng(1234).integers(0, 3, size=(T, E, n))``;
+  * detection uniforms: keyed Philox draw, seed 42, key (env_id, episode, t, i, j)
+    (oracle/refharness.py: KeyedDraws).
+The fixtures are what the oracle (tests/test_oracle_golden.py) and the CUDA path
+(tests/test_gpu_*.py) are pinned against.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle import refharness as rh  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+SEED = 42
+TARGETS_TXT = os.path.join(rh.REFERENCE_ROOT, "flight_targets.txt")
+
+
+def found_mask(env):
+    return sum(1 << j for j, t in enumerate(env.target_list) if t.find)
+
+
+def run_flight(cls_name, n_agents, agent_mode, E, T, env_id_base, target_mode=0, second_episode=0,
+               map_steps=(), **over):
+    ref = rh.import_reference()
+    cls = ref[cls_name]
+    envname = "flight_easy" if cls_name == "FlightSearchEnvEasy" else "flight"
+    circle = rh.load_targets_reference_semantics(TARGETS_TXT)
+    args = rh.make_args(envname, n_agents=n_agents, agent_mode=agent_mode, target_mode=target_mode, **over)
+    m = args.target_num
+    S = 4 * n_agents + 3 * m
+    actions = np.random.default_rng(1234).integers(0, 3, size=(T, E, n_agents), dtype=np.uint8)
+    has_map = cls_name == "FlightSearchEnv"
+    g = dict(
+        tgt_xy=np.zeros((E, m, 2)), init_xy=np.zeros((E, n_agents, 2)), init_yaw=np.zeros((E, n_agents)),
+        init_found=np.zeros(E, np.uint32), init_win=np.zeros(E, np.uint8),
+        init_obs=np.zeros((E, n_agents, 4)), init_state=np.zeros((E, S)),
+        actions=actions,
+        xy=np.zeros((T, E, n_agents, 2)), yaw=np.zeros((T, E, n_agents)), out=np.zeros((T, E, n_agents), np.uint8),
+        found=np.zeros((T, E), np.uint32), reward=np.zeros((T, E)), terminated=np.zeros((T, E), np.uint8),
+        win=np.zeros((T, E), np.uint8), target_find=np.zeros((T, E), np.int32), time_step=np.zeros((T, E), np.int32),
+        obs=np.zeros((T, E, n_agents, 4)), state=np.zeros((T, E, S)),
+        n_steps=np.zeros(E, np.int32), n_draws=np.zeros(E, np.int64),
+    )
+    if has_map:
+        g["map_steps"] = np.array(map_steps, np.int32)
+        g["init_map"] = np.zeros((E, args.map_size, args.map_size))
+        g["maps"] = np.zeros((len(map_steps), E, args.map_size, args.map_size))
+        g["final_map"] = np.zeros((E, args.map_size, args.map_size))
+        if second_episode:
+            g["ep2_tgt_xy"] = np.zeros((E, m, 2))
+            g["ep2_actions"] = np.random.default_rng(4321).integers(0, 3, size=(second_episode, E, n_agents), dtype=np.uint8)
+            g["ep2_map"] = np.zeros((E, args.map_size, args.map_size))
+            g["ep2_found"] = np.zeros((second_episode, E), np.uint32)
+            g["ep2_reward"] = np.zeros((second_episode, E))
+    for e in range(E):
+        env_id = env_id_base + e
+        draws = rh.KeyedDraws(SEED, env_id, episode=0)
+        np.random.seed(10_000 + env_id)
+        with draws:
+            draws.t = 0
+            env = rh.quiet(cls, args, circle)           # ctor calls reset(init=True)
+        g["tgt_xy"][e] = np.array(env.target_pos, dtype=np.float64)
+        g["init_xy"][e] = np.array(env.agent_pos, dtype=np.float64)
+        g["init_yaw"][e] = np.array(env.agent_yaw, dtype=np.float64)
+        g["init_found"][e] = found_mask(env)
+        g["init_win"][e] = int(env.win_flag)
+        if has_map:
+            g["init_map"][e] = env.prob_map
+            g["init_obs"][e] = env.get_obs()[:, -4:]
+        else:
+            g["init_obs"][e] = env.get_obs()
+        g["init_state"][e] = env.get_state()
+        done = False
+        for t in range(T):
+            if not done:
+                with draws:
+                    draws.t = t + 1
+                    r, term, win = env.step([int(a) for a in actions[t, e]])
+                g["n_steps"][e] = t + 1
+                done = bool(term)
+            else:
+                r, term = 0.0, True            # masked no-op after termination (batched API contract)
+            g["xy"][t, e] = np.array(env.agent_pos, dtype=np.float64)
+            g["yaw"][t, e] = np.array(env.agent_yaw, dtype=np.float64)
+            g["out"][t, e] = np.array(env.out_flag)
+            g["found"][t, e] = found_mask(env)
+            g["reward"][t, e] = r
+            g["terminated"][t, e] = int(term)
+            g["win"][t, e] = int(env.win_flag)
+            g["target_find"][t, e] = env.target_find
+            g["time_step"][t, e] = env.time_step
+            g["obs"][t, e] = env.get_obs()[:, -4:]
+            g["state"][t, e] = env.get_state()
+            if has_map and (t + 1) in map_steps:
+                g["maps"][list(map_steps).index(t + 1), e] = env.prob_map
+        if has_map:
+            g["final_map"][e] = env.prob_map
+            if second_episode:
+                # reset() WITHOUT init: the map must survive (flight_env.py:84-86)
+                draws2 = rh.KeyedDraws(SEED, env_id, episode=1)
+                np.random.seed(20_000 + env_id)
+                with draws2:
+                    draws2.t = 0
+                    env.reset()
+                g["ep2_tgt_xy"][e] = np.array(env.target_pos, dtype=np.float64)
+                for t in range(second_episode):
+                    with draws2:
+                        draws2.t = t + 1
+                        r, term, win = env.step([int(a) for a in g["ep2_actions"][t, e]])
+                    g["ep2_found"][t, e] = found_mask(env)
+                    g["ep2_reward"][t, e] = r
+                g["ep2_map"][e] = env.prob_map
+        g["n_draws"][e] = draws.n_draws
+    g["meta"] = np.array([n_agents, m, args.map_size, args.view_range, args.time_limit, agent_mode, target_mode,
+                          env_id_base, SEED], np.int64)
+    g["fmeta"] = np.array([args.agent_velocity, args.detect_prob, args.safe_dist, args.force_dist], np.float64)
+    return g
+
+
+def run_search(n_agents, target_num, map_size, view_range, agent_mode, target_mode, E, T, env_id_base):
+    ref = rh.import_reference()
+    cls = ref["SearchEnv"]
+    args = rh.make_args("search", n_agents=n_agents, target_num=target_num, map_size=map_size,
+                        view_range=view_range, agent_mode=agent_mode, target_mode=target_mode)
+    S = 2 * view_range - 1
+    rng = np.random.default_rng(1234)
+    g = dict(
+        cells=np.zeros((E, target_num, 2), np.int32), init_pos=np.zeros((E, n_agents, 2), np.int32),
+        init_obs=np.zeros((E, n_agents, S * S + 2)), init_state=np.zeros((E, 2 * map_size ** 2), np.uint8),
+        init_freq=np.zeros((E, map_size, map_size), np.int32),
+        actions=np.zeros((T, E, n_agents), np.uint8), avail=np.zeros((T, E, n_agents, 4), np.uint8),
+        pos=np.zeros((T, E, n_agents, 2), np.int32), reward=np.zeros((T, E)), terminated=np.zeros((T, E), np.uint8),
+        target_find=np.zeros((T, E), np.int32), obs=np.zeros((T, E, n_agents, S * S + 2), np.float32),
+        state=np.zeros((T, E, 2 * map_size ** 2), np.uint8), freq=np.zeros((E, map_size, map_size), np.int32),
+        found=np.zeros((T, E, target_num), np.uint8), n_steps=np.zeros(E, np.int32),
+    )
+    for e in range(E):
+        np.random.seed(10_000 + env_id_base + e)
+        env = rh.quiet(cls, args)
+        g["cells"][e] = np.array([t.pos for t in env.target_list])
+        g["init_pos"][e] = np.array(env.agent_pos)
+        g["init_obs"][e] = rh.quiet(env.get_obs)
+        g["init_state"][e] = env.get_state().astype(np.uint8)
+        g["init_freq"][e] = env.freq_map.astype(np.int32)
+        done = False
+        for t in range(T):
+            av = np.array([env.get_avail_agent_actions(i) for i in range(n_agents)])
+            g["avail"][t, e] = av.astype(np.uint8)
+            act = np.array([rng.choice(np.nonzero(av[i])[0]) for i in range(n_agents)], np.uint8)
+            g["actions"][t, e] = act
+            if not done:
+                r, term, _ = env.step([int(a) for a in act])
+                g["n_steps"][e] = t + 1
+                done = bool(term)
+            else:
+                r, term = 0.0, True
+            g["pos"][t, e] = np.array(env.agent_pos)
+            g["reward"][t, e] = r
+            g["terminated"][t, e] = int(term)
+            g["target_find"][t, e] = env.target_find
+            g["obs"][t, e] = rh.quiet(env.get_obs)
+            g["state"][t, e] = env.get_state().astype(np.uint8)
+            g["found"][t, e] = np.array([int(x.find) for x in env.target_list], np.uint8)
+        g["freq"][e] = env.freq_map.astype(np.int32)
+    g["meta"] = np.array([n_agents, target_num, map_size, view_range, agent_mode, target_mode, env_id_base], np.int64)
+    return g
+
+
+def thin(g, keep_every, keys=("obs", "state")):
+    """obs/state are derivable from xy/yaw/found; keep every k-th step to bound fixture size."""
+    for k in keys:
+        g[k] = g[k][keep_every - 1::keep_every].copy()
+    g["thin"] = np.array([keep_every], np.int32)
+    return g
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    jobs = {
+        # name: (generator, kwargs)
+        "easy_1a_am0": lambda: thin(run_flight("FlightSearchEnvEasy", 1, 0, E=6, T=200, env_id_base=0), 10),
+        "easy_3a_am0": lambda: thin(run_flight("FlightSearchEnvEasy", 3, 0, E=8, T=200, env_id_base=100), 10),
+        "easy_3a_am1": lambda: thin(run_flight("FlightSearchEnvEasy", 3, 1, E=4, T=200, env_id_base=150), 10),
+        "easy_5a_am2": lambda: thin(run_flight("FlightSearchEnvEasy", 5, 2, E=6, T=200, env_id_base=200), 10),
+        "easy_5a_am3": lambda: thin(run_flight("FlightSearchEnvEasy", 5, 3, E=6, T=200, env_id_base=300), 10),
+        # close-quarters: 5 agents on a 12x12 map so the repulsion/wall paths fire constantly
+        "easy_5a_crowded": lambda: thin(run_flight("FlightSearchEnvEasy", 5, 1, E=4, T=200, env_id_base=400,
+                                                     target_mode=1, map_size=12, view_range=3), 10),
+        "easy_3a_tm1": lambda: thin(run_flight("FlightSearchEnvEasy", 3, 0, E=4, T=200, env_id_base=500,
+                                                 target_mode=1), 10),
+        "flight_3a_am0": lambda: thin(run_flight("FlightSearchEnv", 3, 0, E=3, T=200, env_id_base=600,
+                                                   second_episode=25,
+                                                   map_steps=(1, 2, 3, 5, 10, 20, 50, 100, 150, 200)), 20),
+        "flight_2a_small": lambda: thin(run_flight("FlightSearchEnv", 2, 1, E=2, T=80, env_id_base=700,
+                                                     target_mode=1, map_size=20, view_range=4, time_limit=80,
+                                                     second_episode=10, map_steps=(1, 2, 5, 10, 40, 80)), 20),
+        "search_3a_default": lambda: thin(run_search(3, 15, 50, 7, 0, 0, E=3, T=120, env_id_base=800), 10),
+        "search_4a_am1_tm1": lambda: thin(run_search(4, 10, 20, 4, 1, 1, E=3, T=80, env_id_base=850), 10),
+        "search_5a_am2": lambda: thin(run_search(5, 12, 24, 3, 2, 0, E=2, T=80, env_id_base=870), 10),
+        "search_64a_1000t": lambda: thin(run_search(64, 1000, 64, 7, 0, 0, E=1, T=30, env_id_base=900), 10),
+    }
+    only = sys.argv[1:]
+    for name, job in jobs.items():
+        if only and name not in only:
+            continue
+        g = job()
+        path = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(path, **g)
+        print("%-22s %8.1f KB" % (name, os.path.getsize(path) / 1024))
+
+
+if __name__ == "__main__":
+    main()
