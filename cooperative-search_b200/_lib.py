@@ -1,0 +1,134 @@
+"""ctypes binding of libcoopsearch.so (the C ABI declared in include/coopsearch.h).
+
+There is no CPU fallback: if the library is missing and cannot be built, importing an env raises.
+"""
+import ctypes as C
+import os
+
+from . import build as _build
+
+CS_OK = 0
+CS_RESET_INIT = 1
+CS_RESET_KEEP_TARGETS = 2
+CS_RESET_KEEP_EPISODE = 4
+CS_NUM_STATS = 8
+CS_META_WORDS = 8
+META_FOUND, META_NEWFOUND, META_OUT, META_TIME, META_EPISODE, META_FLAGS, META_EPREWARD = range(7)
+FLAG_WIN, FLAG_DONE = 1, 2
+STAT_NAMES = ("episodes", "episode_reward_sum", "targets_found_sum", "wins", "episode_len_sum",
+              "env_steps", "illegal_moves", "map_cells_touched")
+
+
+class CoopSearchError(Exception):
+    """Raised where the reference raises a bare Exception(msg) (e.g. flight_env_easy.py:136,180,186,257)."""
+
+
+class FlightCfg(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("num_envs", C.c_int32), ("n_agents", C.c_int32), ("target_num", C.c_int32),
+        ("map_size", C.c_int32), ("view_range", C.c_int32), ("time_limit", C.c_int32), ("agent_mode", C.c_int32),
+        ("target_mode", C.c_int32), ("variant", C.c_int32), ("auto_reset", C.c_int32), ("count_touched", C.c_int32),
+        ("lanes_per_env", C.c_int32), ("device", C.c_int32),
+        ("velocity", C.c_double), ("detect_prob", C.c_double), ("safe_dist", C.c_double), ("force_dist", C.c_double),
+        ("seed", C.c_uint32), ("env_id_base", C.c_uint32),
+    ]
+
+
+class FlightBuffers(C.Structure):
+    _fields_ = [
+        ("dyn", C.c_void_p), ("dyn_doubles", C.c_int32), ("yaw_off", C.c_int32), ("meta_off", C.c_int32),
+        ("state_len", C.c_int32), ("tgt", C.c_void_p), ("obs", C.c_void_p), ("state", C.c_void_p),
+        ("reward", C.c_void_p), ("terminated", C.c_void_p), ("win", C.c_void_p), ("target_find", C.c_void_p),
+        ("prob_map", C.c_void_p), ("stats", C.c_void_p),
+    ]
+
+
+class FlightHostIO(C.Structure):
+    _fields_ = [("actions", C.c_void_p), ("reward", C.c_void_p), ("terminated", C.c_void_p), ("win", C.c_void_p),
+                ("obs", C.c_void_p), ("state", C.c_void_p)]
+
+
+class SearchCfg(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("num_envs", C.c_int32), ("n_agents", C.c_int32), ("target_num", C.c_int32),
+        ("map_size", C.c_int32), ("view_range", C.c_int32), ("agent_mode", C.c_int32), ("target_mode", C.c_int32),
+        ("auto_reset", C.c_int32), ("device", C.c_int32), ("seed", C.c_uint32), ("env_id_base", C.c_uint32),
+    ]
+
+
+class SearchBuffers(C.Structure):
+    _fields_ = [
+        ("pos", C.c_void_p), ("target_bits", C.c_void_p), ("unfound_bits", C.c_void_p), ("freq", C.c_void_p),
+        ("counters", C.c_void_p), ("words_per_row", C.c_int32), ("obs", C.c_void_p), ("state", C.c_void_p),
+        ("avail", C.c_void_p), ("reward", C.c_void_p), ("terminated", C.c_void_p), ("target_find", C.c_void_p),
+        ("stats", C.c_void_p),
+    ]
+
+
+class SearchHostIO(C.Structure):
+    _fields_ = [("actions", C.c_void_p), ("reward", C.c_void_p), ("terminated", C.c_void_p), ("obs", C.c_void_p),
+                ("state", C.c_void_p), ("avail", C.c_void_p)]
+
+
+# name -> (restype, argtypes); every symbol include/coopsearch.h declares
+SIGNATURES = {
+    "cs_version": (C.c_int, []),
+    "cs_last_error": (C.c_char_p, []),
+    "cs_launch_count": (C.c_uint64, []),
+    "cs_flight_lanes_per_env": (C.c_int, [C.c_void_p]),
+    "cs_debug_philox": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "cs_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint64]),
+    "cs_host_free": (C.c_int, [C.c_void_p]),
+    "cs_flight_create": (C.c_int, [C.POINTER(FlightCfg), C.POINTER(C.c_void_p)]),
+    "cs_flight_destroy": (None, [C.c_void_p]),
+    "cs_flight_buffers_get": (C.c_int, [C.c_void_p, C.POINTER(FlightBuffers)]),
+    "cs_flight_env_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
+    "cs_flight_set_target_template": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_int32]),
+    "cs_flight_reset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "cs_flight_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cs_flight_step_random": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "cs_flight_obs_full": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cs_flight_step_host": (C.c_int, [C.c_void_p, C.POINTER(FlightHostIO), C.c_void_p]),
+    "cs_flight_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_void_p]),
+    "cs_search_create": (C.c_int, [C.POINTER(SearchCfg), C.POINTER(C.c_void_p)]),
+    "cs_search_destroy": (None, [C.c_void_p]),
+    "cs_search_buffers_get": (C.c_int, [C.c_void_p, C.POINTER(SearchBuffers)]),
+    "cs_search_env_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
+    "cs_search_set_targets": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cs_search_reset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "cs_search_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cs_search_step_random": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "cs_search_step_host": (C.c_int, [C.c_void_p, C.POINTER(SearchHostIO), C.c_void_p]),
+    "cs_search_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_void_p]),
+}
+
+_lib = None
+
+
+def load(build_if_missing=True):
+    """Loads (building first when stale and nvcc is available) the CUDA library.  Never falls back."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if build_if_missing and _build.is_stale():
+        try:
+            _build.build_library()
+        except Exception as exc:  # stale-but-present libraries are still usable on a box without nvcc
+            if not os.path.exists(path):
+                raise CoopSearchError("libcoopsearch.so is missing and could not be built: %s" % exc)
+    if not os.path.exists(path):
+        raise CoopSearchError("libcoopsearch.so not found at %s -- run __graft_entry__.build()" % path)
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)       # AttributeError here = header/library mismatch: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(code, what=""):
+    if code != CS_OK:
+        msg = load().cs_last_error().decode("utf-8", "replace")
+        raise CoopSearchError("%s failed (%d): %s" % (what or "libcoopsearch call", code, msg))

@@ -1,0 +1,49 @@
+"""Builds csrc/libcoopsearch.so in-tree with nvcc for sm_100a (no JIT cache, no torch extension)."""
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libcoopsearch.so")
+SOURCES = ["runtime.cu", "flight.cu", "search.cu"]
+HEADERS = ["cs_common.cuh", "cs_philox.cuh", os.path.join("..", "..", "include", "coopsearch.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-fmad=false",          # keep the reference's separate mul/add roundings
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+def _nvcc():
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(exe):
+        raise RuntimeError("nvcc not found; libcoopsearch.so must be prebuilt (python -c 'import __graft_entry__ as g; g.build()')")
+    return exe
+
+
+def sources():
+    return [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+
+
+def is_stale():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = sources() + [os.path.normpath(os.path.join(CSRC, h)) for h in HEADERS]
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build_library(force=False, verbose=False):
+    """Compile every CUDA source into one shared library.  Returns the library path."""
+    if not force and not is_stale():
+        return LIB_PATH
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + sources()
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), proc.stderr[-4000:]))
+    if verbose:
+        print(proc.stderr)
+    return LIB_PATH

@@ -1,0 +1,897 @@
+// flight_easy / flight env-step hot path for B200 (sm_100a).
+//
+// What is restated here (reference: WZN1ng/Cooperative-Search, pure Python):
+//   _agent_step + _potential_energy_force   env/flight_env_easy.py:255-301, env/flight_env.py:305-355
+//   _update_obs (detection, reward, win)    env/flight_env_easy.py:223-253, env/flight_env.py:232-266
+//   _update_prob_map / _percent_in_...      env/flight_env.py:275-303
+//   step / reset / get_obs / get_state      env/flight_env_easy.py:79-221,303-314
+//
+// Design (DESIGN.md has the full account):
+//   * one GROUP of LPE lanes (1..32, template) per env instance; a CTA of 128 threads stages the
+//     fp64 state records of its 128/LPE envs in shared memory with coalesced 16-byte loads, the
+//     groups work on the staged records, and the CTA writes state + fp32 outputs back coalesced.
+//   * positions / headings / targets are fp64 so that the in-range test and the wall test take the
+//     same branch as the reference's Python floats; compiled with -fmad=false so a*b+c keeps the
+//     reference's two roundings.
+//   * detection draws are keyed Philox words (cs_philox.cuh), order independent.
+//   * the belief-map update (variant 1) runs warp-per-env inside the same kernel, half-warp per
+//     map row so that every load/store instruction covers one contiguous 64-byte run of a row.
+#include <math.h>
+#include <new>
+#include "cs_common.cuh"
+#include "cs_philox.cuh"
+
+namespace {
+
+constexpr int kThreads = 128;
+
+enum : uint32_t { SLOT_EMIT = 1u, SLOT_TGT_DIRTY = 2u };
+
+struct FlightParams {
+    int E, n, m, M, T;
+    int variant, auto_reset, agent_mode, target_mode, count_touched;
+    // per-env record geometry (doubles)
+    int rec, yaw_off, meta_off, state_len;
+    // shared-memory slot geometry (doubles)
+    int s_tgt, s_cs, s_out, s_res, s_am, s_box, s_hit, s_stride;
+    double Md, half_M, inv_half, R, R2, v, fk, fd2, near2, q_miss;
+    double turn, pi, two_pi, three_pi, half_pi;
+    long long thr;
+    uint32_t seed, env_id_base;
+    double* dyn;
+    double* tgt;
+    float* obs;
+    float* state;
+    float* reward;
+    uint8_t* terminated;
+    uint8_t* win;
+    int32_t* target_find;
+    float* prob_map;
+    double* stats;
+    const double* tmpl;   // [m][5]: x, y, sx, sy, random   (already scaled by a = M/10)
+};
+
+struct SlotRes {
+    float reward;
+    uint8_t terminated;
+    uint8_t win;
+    uint8_t flags;   // SLOT_*
+    uint8_t pad;
+};
+
+__device__ __forceinline__ uint32_t* slot_meta(const FlightParams& p, double* S) {
+    return reinterpret_cast<uint32_t*>(S + p.meta_off);
+}
+
+// ------------------------------------------------------------------------------------------------
+// wall handling of one agent: env/flight_env_easy.py:278-290 ('>' test), env/flight_env.py:328 ('>=')
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t fl_wall(const FlightParams& p, double* S, int a, double x, double y) {
+    const double Md = p.Md;
+    const bool outside = p.variant ? (x < 0.0 || x >= Md || y < 0.0 || y >= Md)
+                                   : (x < 0.0 || x > Md || y < 0.0 || y > Md);
+    if (outside) {
+        x = fmin(fmax(x, 0.0), Md);
+        y = fmin(fmax(y, 0.0), Md);
+        double* yaw = S + p.yaw_off;
+        double* cs = S + p.s_cs;
+        const double h = yaw[a];
+        yaw[a] = (h <= p.pi) ? (p.pi - h) : (p.three_pi - h);
+        cs[a] = -cs[a];   // cos(pi - h) = cos(3pi - h) = -cos(h); sin unchanged (fp32 outputs only)
+    }
+    S[2 * a] = x;
+    S[2 * a + 1] = y;
+    return outside ? 1u : 0u;
+}
+
+// ------------------------------------------------------------------------------------------------
+// _agent_step: heading update, advance, repulsion (Gauss-Seidel), wall.  Returns the out-of-map mask.
+// ------------------------------------------------------------------------------------------------
+template <int LPE>
+__device__ __forceinline__ uint32_t fl_move(const FlightParams& p, double* S, int lane, const uint8_t* act) {
+    using G = Group<LPE>;
+    const int n = p.n;
+    double* yaw = S + p.yaw_off;
+    double* cs = S + p.s_cs;
+    for (int a = lane; a < n; a += LPE) {
+        const int u = act[a];
+        double h = yaw[a];
+        h += (u == 1) ? p.turn : ((u == 2) ? -p.turn : 0.0);      // dyaw = [0, pi/18, -pi/18]  (:259-262)
+        if (h > p.two_pi) h -= p.two_pi;                          // strict tests (:263-266)
+        else if (h < 0.0) h += p.two_pi;
+        double sn, c;
+        sincos(h, &sn, &c);
+        yaw[a] = h;
+        cs[a] = c;
+        cs[n + a] = sn;
+    }
+    G::sync();
+    // Can any repulsion term be non-zero this step?  If every pair of OLD positions is farther apart
+    // than force_dist + |v| (with slack), no agent receives a force, every displacement is <= |v|, and
+    // by induction over the sequential update order no later agent does either.
+    bool close = false;
+    for (int a = lane; a < n; a += LPE) {
+        const double xa = S[2 * a], ya = S[2 * a + 1];
+        for (int q = a + 1; q < n; ++q) {
+            const double dx = S[2 * q] - xa, dy = S[2 * q + 1] - ya;
+            close |= (dx * dx + dy * dy < p.near2);
+        }
+    }
+    close = G::any(close);
+    uint32_t outbits = 0;
+    if (!close) {
+        for (int a = lane; a < n; a += LPE) {
+            const double x = S[2 * a] + p.v * cs[a];              // x += v*cos(yaw)   (:267-268)
+            const double y = S[2 * a + 1] + p.v * cs[n + a];
+            outbits |= fl_wall(p, S, a, x, y) << a;
+        }
+    } else if (lane == 0) {
+        // sequential, in place: agent k sees its own OLD position and the already-moved j<k (:271,:293-301)
+        for (int k = 0; k < n; ++k) {
+            const double x0 = S[2 * k], y0 = S[2 * k + 1];
+            double x = x0 + p.v * cs[k];
+            double y = y0 + p.v * cs[n + k];
+            double fx = 0.0, fy = 0.0;
+            for (int q = 0; q < n; ++q) {
+                if (q == k) continue;
+                const double xa = S[2 * q], ya = S[2 * q + 1];
+                const double ax = xa - x0, ay = ya - y0;
+                if (ax * ax + ay * ay < p.fd2 && (xa != x0 || ya != y0)) {
+                    const double ex = x0 - xa, ey = y0 - ya;
+                    const double r2 = ex * ex + ey * ey;
+                    fx += p.fk * ex / r2;
+                    fy += p.fk * ey / r2;
+                }
+            }
+            x += fx;
+            y += fy;
+            outbits |= fl_wall(p, S, k, x, y) << k;
+        }
+    }
+    outbits = G::reduce_or(outbits);
+    return outbits;
+}
+
+// ------------------------------------------------------------------------------------------------
+// belief map: _update_prob_map + _percent_in_agent_viewrange (env/flight_env.py:275-303), warp per env
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned fl_probmap(const FlightParams& p, double* S, int lane, float* map, uint32_t newf) {
+    const int n = p.n, M = p.M;
+    int* box = reinterpret_cast<int*>(S + p.s_box);   // [n][4]: i0, i1, j0, j1  (cells that can have a corner inside)
+    int* hit = reinterpret_cast<int*>(S + p.s_hit);   // cells of the targets found by this sensing call
+    const double* T = S + p.s_tgt;
+    for (int a = lane; a < n; a += 32) {
+        const double ax = S[2 * a], ay = S[2 * a + 1];
+        box[4 * a + 0] = max(0, (int)floor(ax - p.R));
+        box[4 * a + 1] = min(M - 1, (int)ceil(ax + p.R) - 1);
+        box[4 * a + 2] = max(0, (int)floor(ay - p.R));
+        box[4 * a + 3] = min(M - 1, (int)ceil(ay + p.R) - 1);
+    }
+    const int nh = __popc(newf);
+    if (lane < p.m && ((newf >> lane) & 1u)) {
+        const int k = __popc(newf & ((1u << lane) - 1u));
+        // idx = min(int(x), M-1): Python int() truncates toward zero (flight_env.py:279)
+        const int ci = min((int)fmin(T[2 * lane], p.Md), M - 1);
+        const int cj = min((int)fmin(T[2 * lane + 1], p.Md), M - 1);
+        hit[k] = (ci < 0 || cj < 0) ? -1 : ci * M + cj;
+    }
+    __syncwarp();
+    unsigned touched = 0;
+    const int col = lane & 15, half = lane >> 4;
+    for (int a = 0; a < n; ++a) {
+        const int i0 = box[4 * a], i1 = box[4 * a + 1], j0 = box[4 * a + 2], j1 = box[4 * a + 3];
+        for (int jc = j0; jc <= j1; jc += 16) {
+            const int j = jc + col;
+            if (j > j1) continue;
+            const double y0 = (double)j, y1 = (double)(j + 1);
+            for (int i = i0 + half; i <= i1; i += 2) {
+                bool mine = true;     // a cell inside several boxes belongs to the first of them
+                for (int b = 0; b < a; ++b)
+                    mine &= !(i >= box[4 * b] && i <= box[4 * b + 1] && j >= box[4 * b + 2] && j <= box[4 * b + 3]);
+                if (!mine) continue;
+                const double x0 = (double)i, x1 = (double)(i + 1);
+                uint32_t bits = 0;
+                for (int q = 0; q < n; ++q) {
+                    const double ax = S[2 * q], ay = S[2 * q + 1];
+                    const double dx0 = x0 - ax, dx1 = x1 - ax, dy0 = y0 - ay, dy1 = y1 - ay;
+                    const double sx0 = dx0 * dx0, sx1 = dx1 * dx1, sy0 = dy0 * dy0, sy1 = dy1 * dy1;
+                    bits |= (sx0 + sy0 < p.R2) ? 1u : 0u;     // strict '<' (:300)
+                    bits |= (sx1 + sy0 < p.R2) ? 2u : 0u;
+                    bits |= (sx0 + sy1 < p.R2) ? 4u : 0u;
+                    bits |= (sx1 + sy1 < p.R2) ? 8u : 0u;
+                }
+                if (!bits) continue;                          // percent == 0 -> untouched (:285-286)
+                ++touched;
+                const int cell = i * M + j;
+                bool is_hit = false;
+                for (int k = 0; k < nh; ++k) is_hit |= (hit[k] == cell);
+                if (is_hit) {
+                    map[cell] = 1.0f;                         // (:288-289)
+                } else {
+                    const double pv = (double)map[cell];
+                    const double frac = 0.25 * (double)__popc(bits);
+                    const double num = frac * p.q_miss * pv;  // percent*(1-d)*p  (:292)
+                    const double den = p.q_miss * pv + (1.0 - pv);
+                    map[cell] = (float)(num / den);
+                }
+            }
+        }
+    }
+    return touched;
+}
+
+// ------------------------------------------------------------------------------------------------
+// _update_obs: detection + reward + win.  Returns the reward (all lanes), updates meta (lane 0).
+// ------------------------------------------------------------------------------------------------
+template <int LPE>
+__device__ __forceinline__ int fl_sense(const FlightParams& p, double* S, int lane, uint32_t env_id, uint32_t t,
+                                        uint32_t outbits, float* map, unsigned* touched) {
+    using G = Group<LPE>;
+    const int n = p.n, m = p.m;
+    uint32_t* meta = slot_meta(p, S);
+    const double* T = S + p.s_tgt;
+    uint32_t* am = reinterpret_cast<uint32_t*>(S + p.s_am);
+    const uint32_t found = meta[CS_META_FOUND];
+    const uint32_t episode = meta[CS_META_EPISODE];
+    const uint32_t flags = meta[CS_META_FLAGS];
+    uint32_t cand = 0;
+    for (int j = lane; j < m; j += LPE) {
+        if ((found >> j) & 1u) continue;                 // draw is irrelevant once found (:239)
+        const double tx = T[2 * j], ty = T[2 * j + 1];
+        uint32_t amask = 0;
+        for (int i = 0; i < n; ++i) {
+            const double dx = tx - S[2 * i], dy = ty - S[2 * i + 1];
+            if (dx * dx + dy * dy <= p.R2) amask |= 1u << i;    // '<=' (:237)
+        }
+        if (amask) {
+            am[j] = amask;
+            cand |= 1u << j;
+        }
+    }
+    uint32_t newf = 0;
+    while (cand) {
+        const int j = __ffs(cand) - 1;
+        cand &= cand - 1;
+        const uint32_t amask = am[j];
+        for (int blk = 0; 4 * blk < n; ++blk) {
+            const uint32_t bits = (amask >> (4 * blk)) & 0xFu;
+            if (!bits) continue;
+            const cs_u4 w = cs_detect_words(p.seed, env_id, episode, t, (uint32_t)blk, (uint32_t)j);
+            const bool got = ((bits & 1u) && (long long)w.x <= p.thr) || ((bits & 2u) && (long long)w.y <= p.thr) ||
+                             ((bits & 4u) && (long long)w.z <= p.thr) || ((bits & 8u) && (long long)w.w <= p.thr);
+            if (got) {
+                newf |= 1u << j;
+                break;
+            }
+        }
+    }
+    newf = G::reduce_or(newf);      // also orders every lane's reads of meta before lane 0's writes below
+    const uint32_t all = found | newf;
+    const int c = __popc(newf);
+    int rew = -1 + 10 * c;          // MOVE_COST + FIND_ONE_TGT per new target (:228,:241)
+    uint32_t nflags = flags;
+    if (c > 0 && __popc(all) == m && !(flags & CS_FLAG_WIN)) {
+        rew += 100;                 // FIND_ALL_TGT (:244-246)
+        nflags |= CS_FLAG_WIN;
+    }
+    rew -= __popc(outbits);         // OUT_PUNISH per agent outside (:249-250)
+    if (lane == 0) {
+        meta[CS_META_FOUND] = all;
+        meta[CS_META_NEWFOUND] = newf;
+        meta[CS_META_OUT] = outbits;
+        meta[CS_META_FLAGS] = nflags;
+    }
+    if (LPE == 32 && p.variant) {
+        __syncwarp();
+        const unsigned tc = fl_probmap(p, S, lane, map, newf);
+        if (p.count_touched) *touched += tc;
+    }
+    G::sync();
+    return rew;
+}
+
+// ------------------------------------------------------------------------------------------------
+// reset: env/flight_env_easy.py:79-180 (without the trailing _update_obs, which the caller runs)
+// ------------------------------------------------------------------------------------------------
+template <int LPE>
+__device__ __forceinline__ void fl_reset(const FlightParams& p, double* S, int lane, uint32_t env_id, uint32_t rflags,
+                                         float* map, SlotRes* res) {
+    using G = Group<LPE>;
+    const int n = p.n, m = p.m;
+    uint32_t* meta = slot_meta(p, S);
+    const uint32_t episode = meta[CS_META_EPISODE] + ((rflags & CS_RESET_KEEP_EPISODE) ? 0u : 1u);
+    G::sync();
+    if (lane == 0) {
+        meta[CS_META_FOUND] = 0;
+        meta[CS_META_NEWFOUND] = 0;
+        meta[CS_META_OUT] = 0;
+        meta[CS_META_TIME] = 0;
+        meta[CS_META_EPISODE] = episode;
+        meta[CS_META_FLAGS] = 0;
+        meta[CS_META_EPREWARD] = 0;
+        meta[CS_META_RESERVED] = 0;
+        res->flags |= SLOT_EMIT | ((rflags & CS_RESET_KEEP_TARGETS) ? 0u : SLOT_TGT_DIRTY);
+    }
+    if (!(rflags & CS_RESET_KEEP_TARGETS)) {
+        double* T = S + p.s_tgt;
+        for (int j = lane; j < m; j += LPE) {
+            const cs_u4 w = cs_philox4x32_10(env_id, (episode & 0xFFFFu) << 16, (uint32_t)j, 0u, p.seed, CS_STREAM_TARGET);
+            const double u1 = cs_u53(w.x, w.y), u2 = cs_u53(w.z, w.w);
+            double x, y;
+            if (p.target_mode == 0) {
+                const double* row = p.tmpl + 5 * j;
+                x = row[0];
+                y = row[1];
+                if (row[4] != 0.0) {                      // deter == 'f' (:106-110)
+                    const double rad = sqrt(-2.0 * log(u1));
+                    double sn, c;
+                    sincos(2.0 * p.pi * u2, &sn, &c);
+                    x += row[2] * 2.0 * (rad * c - 0.5);
+                    y += row[3] * 2.0 * (rad * sn - 0.5);
+                }
+            } else {                                      // target_mode 1 (:122-127)
+                x = p.Md * u1;
+                y = p.Md * u2;
+            }
+            T[2 * j] = x;
+            T[2 * j + 1] = y;
+        }
+    }
+    double* yaw = S + p.yaw_off;
+    double* cs = S + p.s_cs;
+    for (int a = lane; a < n; a += LPE) {
+        const double lin = (n != 1) ? (double)(a * p.M) / (double)(n - 1) : p.Md / 2.0;   // (:140-143)
+        double x, y, h;
+        switch (p.agent_mode) {
+            case 0: x = lin; y = 0.0; h = p.half_pi; break;
+            case 1: x = lin; y = p.Md / 2.0; h = p.half_pi; break;
+            case 2: x = 0.0; y = lin; h = 0.0; break;
+            default: x = p.Md; y = lin; h = p.pi; break;
+        }
+        S[2 * a] = x;
+        S[2 * a + 1] = y;
+        yaw[a] = h;
+        double sn, c;
+        sincos(h, &sn, &c);
+        cs[a] = c;
+        cs[n + a] = sn;
+    }
+    if (p.variant && (rflags & CS_RESET_INIT)) {
+        for (int c = lane; c < p.M * p.M; c += LPE) map[c] = 0.5f;       // flight_env.py:84-86
+    }
+    G::sync();
+}
+
+// get_obs / get_state rows of one env into the slot's fp32 staging area (flight_env_easy.py:190-221)
+template <int LPE>
+__device__ __forceinline__ void fl_emit(const FlightParams& p, double* S, int lane) {
+    const int n = p.n, m = p.m;
+    float* out = reinterpret_cast<float*>(S + p.s_out);
+    const double* cs = S + p.s_cs;
+    const double* T = S + p.s_tgt;
+    const uint32_t found = slot_meta(p, S)[CS_META_FOUND];
+    for (int a = lane; a < n; a += LPE) {
+        out[4 * a + 0] = (float)((S[2 * a] - p.half_M) * p.inv_half);
+        out[4 * a + 1] = (float)((S[2 * a + 1] - p.half_M) * p.inv_half);
+        out[4 * a + 2] = (float)cs[a];
+        out[4 * a + 3] = (float)cs[n + a];
+    }
+    float* to = out + 4 * n;
+    for (int j = lane; j < m; j += LPE) {
+        to[3 * j + 0] = (float)((T[2 * j] - p.half_M) * p.inv_half);
+        to[3 * j + 1] = (float)((T[2 * j + 1] - p.half_M) * p.inv_half);
+        to[3 * j + 2] = ((found >> j) & 1u) ? 1.0f : 0.0f;
+    }
+}
+
+enum { MODE_STEP = 0, MODE_RESET = 1 };
+
+// actions == nullptr in MODE_STEP: uniform-random policy drawn in-kernel (alg=random, agent/agent.py:34-36)
+template <int LPE, int MODE>
+__global__ void __launch_bounds__(kThreads) flight_kernel(const FlightParams p, const uint8_t* __restrict__ actions,
+                                                          const uint8_t* __restrict__ mask, uint32_t rflags) {
+    using G = Group<LPE>;
+    constexpr int EPC = kThreads / LPE;
+    extern __shared__ double smem[];
+    __shared__ double s_stats[CS_NUM_STATS];
+
+    const int tid = threadIdx.x;
+    const int e0 = blockIdx.x * EPC;
+    const int cnt = min(EPC, p.E - e0);
+    if (tid < CS_NUM_STATS) s_stats[tid] = 0.0;
+
+    // ---- stage records: global -> shared, 16-byte coalesced -------------------------------------
+    {
+        const double2* gd = reinterpret_cast<const double2*>(p.dyn + (size_t)e0 * p.rec);
+        const int rec2 = p.rec >> 1;
+        for (int idx = tid; idx < cnt * rec2; idx += kThreads) {
+            const int e = idx / rec2, k = idx - e * rec2;
+            const double2 v = gd[idx];
+            double* S = smem + e * p.s_stride;
+            S[2 * k] = v.x;
+            S[2 * k + 1] = v.y;
+        }
+        const double2* gt = reinterpret_cast<const double2*>(p.tgt + (size_t)e0 * 2 * p.m);
+        const int m2 = p.m;   // 2m doubles = m double2
+        for (int idx = tid; idx < cnt * m2; idx += kThreads) {
+            const int e = idx / m2, k = idx - e * m2;
+            const double2 v = gt[idx];
+            double* S = smem + e * p.s_stride + p.s_tgt;
+            S[2 * k] = v.x;
+            S[2 * k + 1] = v.y;
+        }
+    }
+    __syncthreads();
+
+    const int g = tid / LPE;
+    const int lane = tid % LPE;
+    const int e = e0 + g;
+    if (g < cnt) {
+        double* S = smem + g * p.s_stride;
+        uint32_t* meta = slot_meta(p, S);
+        SlotRes* res = reinterpret_cast<SlotRes*>(S + p.s_res);
+        const uint32_t env_id = p.env_id_base + (uint32_t)e;
+        float* map = p.variant ? p.prob_map + (size_t)e * p.M * p.M : nullptr;
+        unsigned touched = 0;
+        if (lane == 0) {
+            res->reward = 0.f;
+            res->terminated = 0;
+            res->win = 0;
+            res->flags = 0;
+        }
+        G::sync();
+        if (MODE == MODE_STEP) {
+            const uint32_t flags0 = meta[CS_META_FLAGS];
+            const uint32_t time0 = meta[CS_META_TIME];
+            const uint32_t episode0 = meta[CS_META_EPISODE];
+            bool done = (flags0 & CS_FLAG_DONE) != 0;
+            G::sync();
+            if (!done) {
+                const uint8_t* act;
+                if (actions != nullptr) {
+                    act = actions + (size_t)e * p.n;
+                } else {
+                    // one Philox block serves 4 agents; action = word % 3 (np.random.randint(0, 3), agent.py:36).
+                    // Staged in the slot's `am` scratch, which fl_sense only touches after fl_move consumed it.
+                    uint8_t* ra = reinterpret_cast<uint8_t*>(S + p.s_am);
+                    for (int a = lane; a < p.n; a += LPE) {
+                        const cs_u4 w = cs_philox4x32_10(env_id, ((episode0 & 0xFFFFu) << 16) | ((time0 + 1u) & 0xFFFFu),
+                                                         (uint32_t)(a >> 2), 0u, p.seed, CS_STREAM_POLICY);
+                        ra[a] = (uint8_t)(cs_word(w, a & 3) % 3u);
+                    }
+                    G::sync();
+                    act = ra;
+                }
+                const uint32_t outbits = fl_move<LPE>(p, S, lane, act);
+                G::sync();
+                const int rew = fl_sense<LPE>(p, S, lane, env_id, time0 + 1u, outbits, map, &touched);
+                const uint32_t time1 = time0 + 1u;
+                const uint32_t fl1 = meta[CS_META_FLAGS];
+                const int nfound = __popc(meta[CS_META_FOUND]);
+                const bool term = (nfound >= p.m) || ((int)time1 >= p.T);       // (:311-312)
+                G::sync();
+                if (lane == 0) {
+                    const float epr = __uint_as_float(meta[CS_META_EPREWARD]) + (float)rew;
+                    meta[CS_META_TIME] = time1;
+                    meta[CS_META_EPREWARD] = __float_as_uint(epr);
+                    meta[CS_META_FLAGS] = fl1 | (term ? CS_FLAG_DONE : 0u);
+                    res->reward = (float)rew;
+                    res->terminated = term ? 1 : 0;
+                    res->win = (fl1 & CS_FLAG_WIN) ? 1 : 0;
+                    res->flags |= SLOT_EMIT;
+                    atomicAdd(&s_stats[CS_STAT_ENV_STEPS], 1.0);
+                    if (term) {
+                        atomicAdd(&s_stats[CS_STAT_EPISODES], 1.0);
+                        atomicAdd(&s_stats[CS_STAT_EP_REWARD], (double)epr);
+                        atomicAdd(&s_stats[CS_STAT_TARGETS_FOUND], (double)nfound);
+                        atomicAdd(&s_stats[CS_STAT_WINS], (fl1 & CS_FLAG_WIN) ? 1.0 : 0.0);
+                        atomicAdd(&s_stats[CS_STAT_EP_LEN], (double)time1);
+                    }
+                }
+                done = term;
+                G::sync();
+            } else if (lane == 0) {
+                res->reward = 0.f;                     // masked no-op on a finished env
+                res->terminated = 1;
+                res->win = (flags0 & CS_FLAG_WIN) ? 1 : 0;
+            }
+            if (p.auto_reset && done) {
+                G::sync();
+                fl_reset<LPE>(p, S, lane, env_id, 0u, map, res);
+                (void)fl_sense<LPE>(p, S, lane, env_id, 0u, 0u, map, &touched);   // reward discarded (:182)
+            }
+        } else {
+            const bool sel = (mask == nullptr) || (mask[e] != 0);
+            if (sel) {
+                fl_reset<LPE>(p, S, lane, env_id, rflags, map, res);
+                (void)fl_sense<LPE>(p, S, lane, env_id, 0u, 0u, map, &touched);
+                if (lane == 0) {
+                    res->reward = 0.f;
+                    res->terminated = 0;
+                    res->win = (meta[CS_META_FLAGS] & CS_FLAG_WIN) ? 1 : 0;
+                }
+            }
+        }
+        G::sync();
+        if (res->flags & SLOT_EMIT) fl_emit<LPE>(p, S, lane);
+        if (LPE == 32 && p.variant && p.count_touched) {
+            const unsigned tot = __reduce_add_sync(0xffffffffu, touched);
+            if (lane == 0 && tot) atomicAdd(&s_stats[CS_STAT_TOUCHED], (double)tot);
+        }
+    }
+    __syncthreads();
+
+    // ---- write back: shared -> global, coalesced ------------------------------------------------
+    {
+        double2* gd = reinterpret_cast<double2*>(p.dyn + (size_t)e0 * p.rec);
+        const int rec2 = p.rec >> 1;
+        for (int idx = tid; idx < cnt * rec2; idx += kThreads) {
+            const int le = idx / rec2, k = idx - le * rec2;
+            double* S = smem + le * p.s_stride;
+            const SlotRes* res = reinterpret_cast<const SlotRes*>(S + p.s_res);
+            if (res->flags & SLOT_EMIT) gd[idx] = make_double2(S[2 * k], S[2 * k + 1]);
+        }
+        double2* gt = reinterpret_cast<double2*>(p.tgt + (size_t)e0 * 2 * p.m);
+        const int m2 = p.m;
+        for (int idx = tid; idx < cnt * m2; idx += kThreads) {
+            const int le = idx / m2, k = idx - le * m2;
+            double* S = smem + le * p.s_stride;
+            const SlotRes* res = reinterpret_cast<const SlotRes*>(S + p.s_res);
+            if (res->flags & SLOT_TGT_DIRTY) gt[idx] = make_double2(S[p.s_tgt + 2 * k], S[p.s_tgt + 2 * k + 1]);
+        }
+        float* gs = p.state + (size_t)e0 * p.state_len;
+        for (int idx = tid; idx < cnt * p.state_len; idx += kThreads) {
+            const int le = idx / p.state_len, k = idx - le * p.state_len;
+            double* S = smem + le * p.s_stride;
+            const SlotRes* res = reinterpret_cast<const SlotRes*>(S + p.s_res);
+            if (res->flags & SLOT_EMIT) gs[idx] = reinterpret_cast<const float*>(S + p.s_out)[k];
+        }
+        float* go = p.obs + (size_t)e0 * 4 * p.n;
+        const int on = 4 * p.n;
+        for (int idx = tid; idx < cnt * on; idx += kThreads) {
+            const int le = idx / on, k = idx - le * on;
+            double* S = smem + le * p.s_stride;
+            const SlotRes* res = reinterpret_cast<const SlotRes*>(S + p.s_res);
+            if (res->flags & SLOT_EMIT) go[idx] = reinterpret_cast<const float*>(S + p.s_out)[k];
+        }
+        for (int le = tid; le < cnt; le += kThreads) {
+            double* S = smem + le * p.s_stride;
+            const SlotRes* res = reinterpret_cast<const SlotRes*>(S + p.s_res);
+            if (MODE == MODE_STEP || (res->flags & SLOT_EMIT)) {
+                p.reward[e0 + le] = res->reward;
+                p.terminated[e0 + le] = res->terminated;
+                p.win[e0 + le] = res->win;
+                p.target_find[e0 + le] = __popc(slot_meta(p, S)[CS_META_FOUND]);
+            }
+        }
+        if (tid < CS_NUM_STATS && s_stats[tid] != 0.0) atomicAdd(p.stats + tid, s_stats[tid]);
+    }
+}
+
+// Reference-shaped observation of the flight variant: [E][n][M*M+4] (flight_env.py:223-230)
+__global__ void __launch_bounds__(256) flight_obs_full_kernel(const float* __restrict__ map, const float* __restrict__ obs,
+                                                              float* __restrict__ out, int E, int n, int cells4) {
+    // one row = cells4 float4 of the map + 1 float4 of agent features; rows = E*n
+    const long long rows = (long long)E * n;
+    const int row4 = cells4 + 1;
+    const long long total = rows * row4;
+    const float4* m4 = reinterpret_cast<const float4*>(map);
+    const float4* o4 = reinterpret_cast<const float4*>(obs);
+    float4* out4 = reinterpret_cast<float4*>(out);
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long r = idx / row4;
+        const int k = (int)(idx - r * row4);
+        const long long e = r / n;
+        out4[idx] = (k < cells4) ? m4[e * cells4 + k] : o4[r];
+    }
+}
+
+__global__ void flight_obs_full_scalar_kernel(const float* __restrict__ map, const float* __restrict__ obs,
+                                              float* __restrict__ out, int E, int n, int cells) {
+    const long long rows = (long long)E * n;
+    const int rowlen = cells + 4;
+    const long long total = rows * rowlen;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long r = idx / rowlen;
+        const int k = (int)(idx - r * rowlen);
+        const long long e = r / n;
+        out[idx] = (k < cells) ? map[e * cells + k] : obs[r * 4 + (k - cells)];
+    }
+}
+
+}  // namespace
+
+// =================================================================================================
+// host side
+// =================================================================================================
+struct cs_flight {
+    cs_flight_cfg cfg;
+    FlightParams p;
+    int lpe;
+    size_t smem_bytes;
+    int grid;
+    double* d_tmpl;
+    uint8_t* d_actions;   // device staging of the *_host entry point's actions
+    bool have_tmpl;
+};
+
+namespace {
+
+int pick_lpe(const cs_flight_cfg& c) {
+    if (c.variant == 1) return 32;
+    if (c.lanes_per_env) return c.lanes_per_env;
+    // enough warps to occupy 148 SMs x 16 warps before trading lanes for instruction efficiency
+    const long long want = 148LL * 16 * 32;
+    int lpe = 32;
+    while (lpe > 1 && (long long)c.num_envs * lpe > want) lpe >>= 1;
+    return lpe;
+}
+
+template <int LPE>
+cudaError_t launch_flight(const cs_flight* h, int mode, const uint8_t* actions, const uint8_t* mask, uint32_t rflags,
+                          cudaStream_t st) {
+    if (mode == MODE_STEP)
+        flight_kernel<LPE, MODE_STEP><<<h->grid, kThreads, h->smem_bytes, st>>>(h->p, actions, mask, rflags);
+    else
+        flight_kernel<LPE, MODE_RESET><<<h->grid, kThreads, h->smem_bytes, st>>>(h->p, actions, mask, rflags);
+    cs_count_launch(1);
+    return cudaGetLastError();
+}
+
+template <int LPE>
+cudaError_t set_smem_attr(size_t bytes) {
+    cudaError_t e = cudaFuncSetAttribute(flight_kernel<LPE, MODE_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(flight_kernel<LPE, MODE_RESET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+cudaError_t dispatch(const cs_flight* h, int mode, const uint8_t* actions, const uint8_t* mask, uint32_t rflags,
+                     cudaStream_t st) {
+    switch (h->lpe) {
+        case 1: return launch_flight<1>(h, mode, actions, mask, rflags, st);
+        case 2: return launch_flight<2>(h, mode, actions, mask, rflags, st);
+        case 4: return launch_flight<4>(h, mode, actions, mask, rflags, st);
+        case 8: return launch_flight<8>(h, mode, actions, mask, rflags, st);
+        case 16: return launch_flight<16>(h, mode, actions, mask, rflags, st);
+        default: return launch_flight<32>(h, mode, actions, mask, rflags, st);
+    }
+}
+
+cudaError_t dispatch_attr(int lpe, size_t bytes) {
+    switch (lpe) {
+        case 1: return set_smem_attr<1>(bytes);
+        case 2: return set_smem_attr<2>(bytes);
+        case 4: return set_smem_attr<4>(bytes);
+        case 8: return set_smem_attr<8>(bytes);
+        case 16: return set_smem_attr<16>(bytes);
+        default: return set_smem_attr<32>(bytes);
+    }
+}
+
+inline int up2(int v) { return (v + 1) & ~1; }
+
+}  // namespace
+
+extern "C" {
+
+int cs_flight_create(const cs_flight_cfg* cfg, cs_flight** out) {
+    CS_REQUIRE(cfg && out, "cs_flight_create: null argument");
+    CS_REQUIRE(cfg->struct_size == sizeof(cs_flight_cfg), "cs_flight_create: cfg.struct_size %u != %zu (ABI mismatch)",
+               cfg->struct_size, sizeof(cs_flight_cfg));
+    CS_REQUIRE(cfg->num_envs > 0, "num_envs must be > 0");
+    CS_REQUIRE(cfg->n_agents >= 1 && cfg->n_agents <= CS_MAX_AGENTS, "n_agents must be in 1..%d", CS_MAX_AGENTS);
+    CS_REQUIRE(cfg->target_num >= 1 && cfg->target_num <= CS_MAX_TARGETS, "target_num must be in 1..%d", CS_MAX_TARGETS);
+    CS_REQUIRE(cfg->map_size >= 2 && cfg->map_size <= 4096, "map_size out of range");
+    CS_REQUIRE(cfg->view_range >= 1, "view_range must be >= 1");
+    CS_REQUIRE(cfg->time_limit >= 1 && cfg->time_limit <= 65535, "time_limit must be in 1..65535");
+    CS_REQUIRE(cfg->agent_mode >= 0 && cfg->agent_mode <= 3, "No such agent mode");      // flight_env_easy.py:180
+    CS_REQUIRE(cfg->target_mode == 0 || cfg->target_mode == 1, "No such target mode");   // flight_env_easy.py:136
+    CS_REQUIRE(cfg->variant == 0 || cfg->variant == 1, "variant must be 0 (flight_easy) or 1 (flight)");
+    const int l = cfg->lanes_per_env;
+    CS_REQUIRE(l == 0 || l == 1 || l == 2 || l == 4 || l == 8 || l == 16 || l == 32, "lanes_per_env must be 0 or a power of two <= 32");
+
+    cs_flight* h = new (std::nothrow) cs_flight();
+    if (!h) { cs_set_error("out of host memory"); return CS_ERR_NOMEM; }
+    memset(h, 0, sizeof(*h));
+    h->cfg = *cfg;
+    CS_CUDA(cudaSetDevice(cfg->device));
+
+    FlightParams& p = h->p;
+    const int n = cfg->n_agents, m = cfg->target_num, M = cfg->map_size;
+    p.E = cfg->num_envs; p.n = n; p.m = m; p.M = M; p.T = cfg->time_limit;
+    p.variant = cfg->variant; p.auto_reset = cfg->auto_reset; p.agent_mode = cfg->agent_mode;
+    p.target_mode = cfg->target_mode; p.count_touched = cfg->count_touched;
+    p.yaw_off = 2 * n;
+    p.meta_off = up2(3 * n);
+    p.rec = p.meta_off + CS_META_WORDS / 2;
+    p.state_len = 4 * n + 3 * m;
+    // shared slot: record | targets | cos,sin | fp32 outputs | result | amask scratch | boxes | hit cells
+    int off = p.rec;
+    p.s_tgt = off; off += 2 * m;
+    p.s_cs = off; off += 2 * n;
+    p.s_out = off; off += up2(p.state_len) / 2;
+    p.s_res = off; off += 1;
+    p.s_am = off; off += up2(m > (n + 3) / 4 ? m : (n + 3) / 4) / 2;
+    p.s_box = off; off += cfg->variant ? 2 * n : 0;
+    p.s_hit = off; off += cfg->variant ? up2(m) / 2 : 0;
+    p.s_stride = off | 1;      // odd stride in doubles: conflict-free slot-strided 64-bit accesses
+    // constants, computed exactly as the reference's Python floats are
+    p.Md = (double)M;
+    p.half_M = 0.5 * (double)M;
+    p.inv_half = 1.0 / ((double)M / 2.0);
+    p.R = (double)cfg->view_range;
+    p.R2 = (double)cfg->view_range * (double)cfg->view_range;
+    p.v = cfg->velocity;
+    p.fk = cfg->safe_dist * 0.8 * cfg->velocity;                 // safe_dist*POTENTIAL_FORCE_FACTOR*velocity (:299)
+    p.fd2 = cfg->force_dist * cfg->force_dist;
+    const double reach = cfg->force_dist + 1.01 * fabs(cfg->velocity) + 1e-9;
+    p.near2 = reach * reach;
+    p.q_miss = 1.0 - cfg->detect_prob;                           // (1 - detect_prob) (flight_env.py:292)
+    p.pi = M_PI; p.two_pi = 2 * M_PI; p.three_pi = 3 * M_PI; p.half_pi = M_PI / 2; p.turn = M_PI / 18;
+    if (cfg->detect_prob >= 1.0) p.thr = 0xFFFFFFFFLL;
+    else if (cfg->detect_prob < 0.0) p.thr = -1;
+    else p.thr = (long long)floor(cfg->detect_prob * 4294967296.0);
+    p.seed = cfg->seed; p.env_id_base = cfg->env_id_base;
+
+    h->lpe = pick_lpe(*cfg);
+    const int epc = kThreads / h->lpe;
+    h->smem_bytes = (size_t)epc * p.s_stride * sizeof(double);
+    if (h->smem_bytes > 200 * 1024) {
+        // fall back to more lanes per env until the CTA's slots fit
+        while (h->lpe < 32 && (size_t)(kThreads / h->lpe) * p.s_stride * sizeof(double) > 200 * 1024) h->lpe <<= 1;
+        h->smem_bytes = (size_t)(kThreads / h->lpe) * p.s_stride * sizeof(double);
+    }
+    h->grid = (p.E + (kThreads / h->lpe) - 1) / (kThreads / h->lpe);
+    CS_CUDA(dispatch_attr(h->lpe, h->smem_bytes));
+
+    const size_t E = (size_t)p.E;
+    CS_CUDA(cudaMalloc(&p.dyn, E * p.rec * sizeof(double)));
+    CS_CUDA(cudaMemset(p.dyn, 0, E * p.rec * sizeof(double)));
+    // episode counter starts at -1 so that the first reset opens episode 0
+    CS_CUDA(cudaMemset2D(reinterpret_cast<uint32_t*>(p.dyn + p.meta_off) + CS_META_EPISODE, p.rec * sizeof(double), 0xFF,
+                         sizeof(uint32_t), E));
+    CS_CUDA(cudaMalloc(&p.tgt, E * 2 * m * sizeof(double)));
+    CS_CUDA(cudaMemset(p.tgt, 0, E * 2 * m * sizeof(double)));
+    CS_CUDA(cudaMalloc(&p.obs, E * 4 * n * sizeof(float)));
+    CS_CUDA(cudaMemset(p.obs, 0, E * 4 * n * sizeof(float)));
+    CS_CUDA(cudaMalloc(&p.state, E * p.state_len * sizeof(float)));
+    CS_CUDA(cudaMemset(p.state, 0, E * p.state_len * sizeof(float)));
+    CS_CUDA(cudaMalloc(&p.reward, E * sizeof(float)));
+    CS_CUDA(cudaMemset(p.reward, 0, E * sizeof(float)));
+    CS_CUDA(cudaMalloc(&p.terminated, E));
+    CS_CUDA(cudaMemset(p.terminated, 0, E));
+    CS_CUDA(cudaMalloc(&p.win, E));
+    CS_CUDA(cudaMemset(p.win, 0, E));
+    CS_CUDA(cudaMalloc(&p.target_find, E * sizeof(int32_t)));
+    CS_CUDA(cudaMemset(p.target_find, 0, E * sizeof(int32_t)));
+    CS_CUDA(cudaMalloc(&p.stats, CS_NUM_STATS * sizeof(double)));
+    CS_CUDA(cudaMemset(p.stats, 0, CS_NUM_STATS * sizeof(double)));
+    CS_CUDA(cudaMalloc(&h->d_tmpl, (size_t)m * 5 * sizeof(double)));
+    CS_CUDA(cudaMemset(h->d_tmpl, 0, (size_t)m * 5 * sizeof(double)));
+    p.tmpl = h->d_tmpl;
+    if (cfg->variant) {
+        CS_CUDA(cudaMalloc(&p.prob_map, E * M * M * sizeof(float)));
+        CS_CUDA(cudaMemset(p.prob_map, 0, E * M * M * sizeof(float)));
+    }
+    CS_CUDA(cudaMalloc(&h->d_actions, E * n));
+    *out = h;
+    return CS_OK;
+}
+
+void cs_flight_destroy(cs_flight* h) {
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    cudaFree(h->p.dyn); cudaFree(h->p.tgt); cudaFree(h->p.obs); cudaFree(h->p.state); cudaFree(h->p.reward);
+    cudaFree(h->p.terminated); cudaFree(h->p.win); cudaFree(h->p.target_find); cudaFree(h->p.stats);
+    cudaFree(h->d_tmpl); cudaFree(h->p.prob_map); cudaFree(h->d_actions);
+    delete h;
+}
+
+int cs_flight_buffers_get(cs_flight* h, cs_flight_buffers* b) {
+    CS_REQUIRE(h && b, "cs_flight_buffers_get: null argument");
+    const FlightParams& p = h->p;
+    b->dyn = p.dyn; b->dyn_doubles = p.rec; b->yaw_off = p.yaw_off; b->meta_off = p.meta_off; b->state_len = p.state_len;
+    b->tgt = p.tgt; b->obs = p.obs; b->state = p.state; b->reward = p.reward; b->terminated = p.terminated;
+    b->win = p.win; b->target_find = p.target_find; b->prob_map = p.prob_map; b->stats = p.stats;
+    return CS_OK;
+}
+
+int cs_flight_env_info(const cs_flight* h, int32_t* out4) {
+    CS_REQUIRE(h && out4, "cs_flight_env_info: null argument");
+    out4[0] = 3;                       // n_actions       (flight_env_easy.py:32)
+    out4[1] = h->p.state_len;          // state_shape     (:33)
+    out4[2] = 4;                       // obs_shape       (:35)
+    out4[3] = h->p.T;                  // episode_limit   (:76)
+    return CS_OK;
+}
+
+int cs_flight_lanes_per_env(const cs_flight* h) { return h ? h->lpe : CS_ERR_INVALID; }
+
+int cs_flight_set_target_template(cs_flight* h, const double* rows, int32_t nrows) {
+    CS_REQUIRE(h && rows, "cs_flight_set_target_template: null argument");
+    CS_REQUIRE(nrows >= h->p.m, "target template has %d rows, target_num is %d", nrows, h->p.m);
+    const int m = h->p.m;
+    double* tmp = new (std::nothrow) double[(size_t)m * 5];
+    if (!tmp) { cs_set_error("out of host memory"); return CS_ERR_NOMEM; }
+    const double a = (double)h->p.M / 10.0;                  // a = map_size/10  (flight_env_easy.py:97)
+    for (int j = 0; j < m; ++j) {
+        tmp[5 * j + 0] = a * rows[5 * j + 0];
+        tmp[5 * j + 1] = a * rows[5 * j + 1];
+        tmp[5 * j + 2] = a * rows[5 * j + 2];
+        tmp[5 * j + 3] = a * rows[5 * j + 3];
+        tmp[5 * j + 4] = rows[5 * j + 4];
+    }
+    cudaError_t e = cudaSetDevice(h->cfg.device);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_tmpl, tmp, (size_t)m * 5 * sizeof(double), cudaMemcpyHostToDevice);
+    delete[] tmp;
+    CS_CUDA(e);
+    h->have_tmpl = true;
+    return CS_OK;
+}
+
+int cs_flight_reset(cs_flight* h, const uint8_t* d_mask, uint32_t flags, void* stream) {
+    CS_REQUIRE(h, "cs_flight_reset: null handle");
+    CS_REQUIRE((flags & CS_RESET_KEEP_TARGETS) || h->p.target_mode == 1 || h->have_tmpl,
+               "target_mode 0 needs cs_flight_set_target_template before reset");
+    CS_CUDA(dispatch(h, MODE_RESET, nullptr, d_mask, flags, (cudaStream_t)stream));
+    return CS_OK;
+}
+
+int cs_flight_step(cs_flight* h, const uint8_t* d_actions, void* stream) {
+    CS_REQUIRE(h && d_actions, "cs_flight_step: null argument");
+    CS_CUDA(dispatch(h, MODE_STEP, d_actions, nullptr, 0u, (cudaStream_t)stream));
+    return CS_OK;
+}
+
+int cs_flight_step_random(cs_flight* h, int32_t k, void* stream) {
+    CS_REQUIRE(h && k >= 0, "cs_flight_step_random: bad argument");
+    for (int i = 0; i < k; ++i) CS_CUDA(dispatch(h, MODE_STEP, nullptr, nullptr, 0u, (cudaStream_t)stream));
+    return CS_OK;
+}
+
+int cs_flight_obs_full(cs_flight* h, float* d_out, void* stream) {
+    CS_REQUIRE(h && d_out, "cs_flight_obs_full: null argument");
+    CS_REQUIRE(h->p.variant == 1, "cs_flight_obs_full: only the flight (prob map) variant has a map observation");
+    const FlightParams& p = h->p;
+    const int cells = p.M * p.M;
+    const long long total = (long long)p.E * p.n * (cells + 4);
+    if (cells % 4 == 0) {
+        const long long t4 = total / 4;
+        const int grid = (int)((t4 + 255) / 256 < (long long)CS_NUM_SMS_B200 * 16 ? (t4 + 255) / 256 : CS_NUM_SMS_B200 * 16);
+        flight_obs_full_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p.prob_map, p.obs, d_out, p.E, p.n, cells / 4);
+    } else {
+        const int grid = (int)((total + 255) / 256 < (long long)CS_NUM_SMS_B200 * 16 ? (total + 255) / 256 : CS_NUM_SMS_B200 * 16);
+        flight_obs_full_scalar_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p.prob_map, p.obs, d_out, p.E, p.n, cells);
+    }
+    cs_count_launch(1);
+    CS_CUDA(cudaGetLastError());
+    return CS_OK;
+}
+
+int cs_flight_step_host(cs_flight* h, const cs_flight_host_io* io, void* stream) {
+    CS_REQUIRE(h && io && io->actions, "cs_flight_step_host: null argument");
+    const FlightParams& p = h->p;
+    const size_t E = (size_t)p.E;
+    cudaStream_t st = (cudaStream_t)stream;
+    CS_CUDA(cudaSetDevice(h->cfg.device));
+    CS_CUDA(cudaMemcpyAsync(h->d_actions, io->actions, E * p.n, cudaMemcpyHostToDevice, st));
+    CS_CUDA(dispatch(h, MODE_STEP, h->d_actions, nullptr, 0u, st));
+    if (io->reward) CS_CUDA(cudaMemcpyAsync(io->reward, p.reward, E * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (io->terminated) CS_CUDA(cudaMemcpyAsync(io->terminated, p.terminated, E, cudaMemcpyDeviceToHost, st));
+    if (io->win) CS_CUDA(cudaMemcpyAsync(io->win, p.win, E, cudaMemcpyDeviceToHost, st));
+    if (io->obs) CS_CUDA(cudaMemcpyAsync(io->obs, p.obs, E * 4 * p.n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (io->state) CS_CUDA(cudaMemcpyAsync(io->state, p.state, E * p.state_len * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CS_CUDA(cudaStreamSynchronize(st));
+    return CS_OK;
+}
+
+int cs_flight_stats(cs_flight* h, double* h_out, void* stream) {
+    CS_REQUIRE(h && h_out, "cs_flight_stats: null argument");
+    CS_CUDA(cudaMemcpyAsync(h_out, h->p.stats, CS_NUM_STATS * sizeof(double), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return CS_OK;
+}
+
+}  // extern "C"

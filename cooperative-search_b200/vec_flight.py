@@ -1,0 +1,339 @@
+"""Batched flight_easy / flight environments behind the reference's SMAC-style env protocol.
+
+Mirrors the interface that common/rollout.py:24-201 and main.py:114,134 of the reference call on
+``FlightSearchEnvEasy`` (env/flight_env_easy.py) and ``FlightSearchEnv`` (env/flight_env.py):
+``get_env_info, reset, step, get_obs, get_state, get_avail_agent_actions, target_find, close,
+render`` -- same names, same argument meaning, same error behaviour -- with a leading ``num_envs``
+axis on everything and torch CUDA tensors instead of numpy arrays.  All arithmetic happens in
+hand-written sm_100a kernels behind the C ABI of include/coopsearch.h; torch is used for device
+memory views and streams only.  There is no CPU path.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import CoopSearchError
+
+
+class _DevView:
+    """Exposes a library-owned device buffer through __cuda_array_interface__ (zero-copy)."""
+
+    def __init__(self, ptr, shape, typestr, owner):
+        self.__cuda_array_interface__ = {"shape": tuple(int(s) for s in shape), "typestr": typestr,
+                                         "data": (int(ptr), False), "version": 2, "strides": None}
+        self._owner = owner
+
+
+def _wrap(ptr, shape, typestr, device, owner):
+    t = torch.as_tensor(_DevView(ptr, shape, typestr, owner), device=device)
+    t._cs_owner = owner           # keep the handle alive as long as any view is
+    return t
+
+
+def load_targets(filename):
+    """circle_dict of main.py:19-32: skip the header line, whitespace-split rows of
+    ``x y deter priority dx dy`` (blank lines ignored)."""
+    cols = {"x": [], "y": [], "deter": [], "priority": [], "dx": [], "dy": []}
+    with open(filename, "r") as fh:
+        rows = fh.readlines()[1:]
+    for row in rows:
+        tok = row.split()
+        if not tok:
+            continue
+        cols["x"].append(float(tok[0])); cols["y"].append(float(tok[1])); cols["deter"].append(tok[2])
+        cols["priority"].append(int(tok[3])); cols["dx"].append(float(tok[4])); cols["dy"].append(float(tok[5]))
+    return cols
+
+
+class _Handle:
+    def __init__(self, ptr):
+        self.ptr = ptr
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                _lib.load().cs_flight_destroy(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+class _VecFlightBase:
+    VARIANT = 0
+    ENV_NAME = "flight_easy"
+
+    def __init__(self, args, circle_dict=None, num_envs=1, device=None, seed=0, env_id_base=0,
+                 auto_reset=False, lanes_per_env=0, count_touched=False, reset=True):
+        if not torch.cuda.is_available():
+            raise CoopSearchError("coopsearch_b200 needs a CUDA device (B200); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.args = args
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.num_envs = int(num_envs)
+        self.map_size = int(args.map_size)
+        self.target_num = int(args.target_num)
+        self.target_mode = int(args.target_mode)
+        self.agent_mode = int(args.agent_mode)
+        self.n_agents = int(args.n_agents)
+        self.view_range = int(args.view_range)
+        self.time_limit = int(args.time_limit)
+        self.detect_prob = float(args.detect_prob)
+        self.safe_dist = float(args.safe_dist)
+        self.velocity = float(args.agent_velocity)
+        self.force_dist = float(args.force_dist)
+        # stored-but-unused by the dynamics, as in the reference (flight_env_easy.py:26,28)
+        self.turn_limit = getattr(args, "turn_limit", None)
+        self.wrong_alarm_prob = getattr(args, "wrong_alarm_prob", None)
+        self.circle_dict = circle_dict
+        self.n_actions = 3
+        self.state_shape = self.n_agents * 4 + self.target_num * 3
+        self.obs_shape = 4
+        self.seed = int(seed)
+        self.env_id_base = int(env_id_base)
+        self.auto_reset = bool(auto_reset)
+
+        cfg = _lib.FlightCfg(
+            struct_size=C.sizeof(_lib.FlightCfg), num_envs=self.num_envs, n_agents=self.n_agents,
+            target_num=self.target_num, map_size=self.map_size, view_range=self.view_range,
+            time_limit=self.time_limit, agent_mode=self.agent_mode, target_mode=self.target_mode,
+            variant=self.VARIANT, auto_reset=int(self.auto_reset), count_touched=int(count_touched),
+            lanes_per_env=int(lanes_per_env), device=self.device.index,
+            velocity=self.velocity, detect_prob=self.detect_prob, safe_dist=self.safe_dist,
+            force_dist=self.force_dist, seed=self.seed & 0xFFFFFFFF, env_id_base=self.env_id_base & 0xFFFFFFFF)
+        hp = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.cs_flight_create(C.byref(cfg), C.byref(hp)), "cs_flight_create")
+        self._h = _Handle(hp.value)
+        if self.target_mode == 0 and circle_dict is not None:
+            self._set_template(circle_dict)
+        b = _lib.FlightBuffers()
+        _lib.check(self.lib.cs_flight_buffers_get(self._h.ptr, C.byref(b)), "cs_flight_buffers_get")
+        self._b = b
+        E, n, m, M = self.num_envs, self.n_agents, self.target_num, self.map_size
+        dev, own = self.device, self._h
+        self._dyn = _wrap(b.dyn, (E, b.dyn_doubles), "<f8", dev, own)
+        self.agent_xy = self._dyn[:, :2 * n].unflatten(1, (n, 2))            # [E,n,2] f64 view
+        self.agent_yaw = self._dyn[:, b.yaw_off:b.yaw_off + n]               # [E,n]   f64 view
+        self.meta = _wrap(b.dyn, (E, 2 * b.dyn_doubles), "<i4", dev, own)[:, 2 * b.meta_off:2 * b.meta_off + _lib.CS_META_WORDS]
+        self.tgt_xy = _wrap(b.tgt, (E, m, 2), "<f8", dev, own)
+        self._obs = _wrap(b.obs, (E, n, 4), "<f4", dev, own)
+        self._state = _wrap(b.state, (E, b.state_len), "<f4", dev, own)
+        self._reward = _wrap(b.reward, (E,), "<f4", dev, own)
+        self._terminated = _wrap(b.terminated, (E,), "|u1", dev, own)
+        self._win = _wrap(b.win, (E,), "|u1", dev, own)
+        self._target_find = _wrap(b.target_find, (E,), "<i4", dev, own)
+        self._stats = _wrap(b.stats, (_lib.CS_NUM_STATS,), "<f8", dev, own)
+        self.prob_map = _wrap(b.prob_map, (E, M, M), "<f4", dev, own) if b.prob_map else None
+        self._avail = torch.ones((E, n, self.n_actions), dtype=torch.float32, device=dev)
+        self._host = None
+        print('Init Env ' + getattr(args, "env", self.ENV_NAME) + ' {}a{}t(agent mode:{}, target mode:{}) x{} envs on {}'.format(
+            self.n_agents, self.target_num, self.agent_mode, self.target_mode, self.num_envs, self.device))
+        if reset:
+            self.reset(init=True)     # the reference ctor ends with reset(init=True) (flight_env_easy.py:68)
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _set_template(self, cd):
+        m = self.target_num
+        if len(cd["x"]) < m:
+            raise CoopSearchError("target file has %d rows, target_num is %d" % (len(cd["x"]), m))
+        rows = (C.c_double * (5 * m))()
+        for j in range(m):
+            rows[5 * j + 0] = cd["x"][j]; rows[5 * j + 1] = cd["y"][j]
+            rows[5 * j + 2] = cd["dx"][j]; rows[5 * j + 3] = cd["dy"][j]
+            rows[5 * j + 4] = 1.0 if cd["deter"][j] == "f" else 0.0
+        _lib.check(self.lib.cs_flight_set_target_template(self._h.ptr, rows, m), "cs_flight_set_target_template")
+
+    @property
+    def lanes_per_env(self):
+        return int(self.lib.cs_flight_lanes_per_env(self._h.ptr))
+
+    # ------------------------------------------------------------ reference API
+    def get_env_info(self):
+        """flight_env_easy.py:71-77 (+ n_envs)."""
+        out = (C.c_int32 * 4)()
+        _lib.check(self.lib.cs_flight_env_info(self._h.ptr, out), "cs_flight_env_info")
+        return {"n_actions": out[0], "state_shape": out[1], "obs_shape": out[2], "episode_limit": out[3],
+                "n_envs": self.num_envs}
+
+    def reset(self, init=False, mask=None, targets=None, keep_episode=False):
+        """reset(init) (flight_env_easy.py:79-182) of every env, or of those with mask[e] != 0.
+
+        targets: optional [E,m,2] float64 tensor/array of target coordinates to inject (parity tests:
+        the reference's own MT19937-drawn layout); otherwise targets are redrawn on the device."""
+        flags = _lib.CS_RESET_INIT if init else 0
+        if keep_episode:
+            flags |= _lib.CS_RESET_KEEP_EPISODE
+        if targets is not None:
+            t = torch.as_tensor(np.asarray(targets) if not torch.is_tensor(targets) else targets,
+                                dtype=torch.float64, device=self.device)
+            if tuple(t.shape) != (self.num_envs, self.target_num, 2):
+                raise CoopSearchError("targets must have shape (num_envs, target_num, 2)")
+            self.tgt_xy.copy_(t)
+            flags |= _lib.CS_RESET_KEEP_TARGETS
+        mptr = None
+        if mask is not None:
+            mask = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+            if mask.numel() != self.num_envs:
+                raise CoopSearchError("mask must have num_envs elements")
+            mptr = C.c_void_p(mask.data_ptr())
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.cs_flight_reset(self._h.ptr, mptr, flags, self._stream()), "cs_flight_reset")
+
+    def _as_actions(self, actions):
+        if torch.is_tensor(actions):
+            a = actions.to(device=self.device, dtype=torch.uint8)
+        else:
+            a = torch.as_tensor(np.asarray(actions, dtype=np.uint8), device=self.device)
+        if a.dim() == 1 and self.num_envs == 1:
+            a = a.unsqueeze(0)
+        if a.dim() != 2 or a.shape[0] != self.num_envs or a.shape[1] != self.n_agents:
+            raise CoopSearchError('Act num mismatch agent')          # flight_env_easy.py:256-257
+        return a.contiguous()
+
+    def step(self, actions):
+        """step(act_list) (flight_env_easy.py:303-314) -> (reward [E] f32, terminated [E] u8, win [E] u8).
+        Returned tensors are views of library-owned buffers, overwritten by the next step."""
+        a = self._as_actions(actions)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.cs_flight_step(self._h.ptr, C.c_void_p(a.data_ptr()), self._stream()), "cs_flight_step")
+        return self._reward, self._terminated, self._win
+
+    def step_random(self, k=1):
+        """k steps under the uniform-random policy drawn inside the kernel (alg=random, agent/agent.py:34-36)."""
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.cs_flight_step_random(self._h.ptr, int(k), self._stream()), "cs_flight_step_random")
+        return self._reward, self._terminated, self._win
+
+    def get_obs(self):
+        """[E,n,4] (flight_env_easy.py:218-221)."""
+        return self._obs
+
+    def get_state(self):
+        """[E,4n+3m] (flight_env_easy.py:190-216)."""
+        return self._state
+
+    def get_avail_agent_actions(self, agent_id):
+        if agent_id >= self.n_agents:
+            raise CoopSearchError('Agent id out of range')            # flight_env_easy.py:185-186
+        return self._avail[:, agent_id]
+
+    def get_avail_actions(self):
+        return self._avail
+
+    @property
+    def target_find(self):
+        return self._target_find
+
+    @property
+    def win_flag(self):
+        return self._win
+
+    @property
+    def time_step(self):
+        return self.meta[:, _lib.META_TIME]
+
+    @property
+    def found_mask(self):
+        return self.meta[:, _lib.META_FOUND]
+
+    @property
+    def out_mask(self):
+        return self.meta[:, _lib.META_OUT]
+
+    def close(self):
+        pass
+
+    def render(self):
+        raise CoopSearchError("render() is not part of the batched hot path")
+
+    # ------------------------------------------------------------------ extras
+    def stats(self):
+        """Running sums over finished episodes on this GPU (the vector all-reduced by dist.allreduce_stats)."""
+        out = (C.c_double * _lib.CS_NUM_STATS)()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.cs_flight_stats(self._h.ptr, out, self._stream()), "cs_flight_stats")
+        return dict(zip(_lib.STAT_NAMES, list(out)))
+
+    @property
+    def stats_tensor(self):
+        return self._stats
+
+    def get_state_dict(self):
+        """Checkpoint of the full env state (the reference never checkpoints env state)."""
+        d = {"dyn": self._dyn.clone(), "tgt": self.tgt_xy.clone()}
+        if self.prob_map is not None:
+            d["prob_map"] = self.prob_map.clone()
+        return d
+
+    def set_state_dict(self, d):
+        self._dyn.copy_(d["dyn"])
+        self.tgt_xy.copy_(d["tgt"])
+        if self.prob_map is not None and "prob_map" in d:
+            self.prob_map.copy_(d["prob_map"])
+
+    def host_buffers(self):
+        """Pinned host staging used by step_host (allocated once)."""
+        if self._host is None:
+            E, n = self.num_envs, self.n_agents
+            pin = lambda *shape, dtype: torch.empty(shape, dtype=dtype).pin_memory()
+            self._host = {
+                "actions": pin(E, n, dtype=torch.uint8), "reward": pin(E, dtype=torch.float32),
+                "terminated": pin(E, dtype=torch.uint8), "win": pin(E, dtype=torch.uint8),
+                "obs": pin(E, n, 4, dtype=torch.float32), "state": pin(E, self.state_shape, dtype=torch.float32),
+            }
+        return self._host
+
+    def step_host(self, actions, want_obs=True, want_state=True):
+        """The call a CPU-side rollout makes: HOST actions in, HOST results out (numpy views of pinned
+        buffers).  H2D + kernel + D2H happen inside cs_flight_step_host."""
+        hb = self.host_buffers()
+        a = np.asarray(actions, dtype=np.uint8)
+        if a.shape != (self.num_envs, self.n_agents):
+            raise CoopSearchError('Act num mismatch agent')
+        hb["actions"].numpy()[...] = a
+        io = _lib.FlightHostIO(
+            actions=hb["actions"].data_ptr(), reward=hb["reward"].data_ptr(), terminated=hb["terminated"].data_ptr(),
+            win=hb["win"].data_ptr(), obs=hb["obs"].data_ptr() if want_obs else None,
+            state=hb["state"].data_ptr() if want_state else None)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.cs_flight_step_host(self._h.ptr, C.byref(io), self._stream()), "cs_flight_step_host")
+        return (hb["reward"].numpy(), hb["terminated"].numpy(), hb["win"].numpy(),
+                hb["obs"].numpy() if want_obs else None, hb["state"].numpy() if want_state else None)
+
+
+class VecFlightEasyEnv(_VecFlightBase):
+    """num_envs x FlightSearchEnvEasy (env/flight_env_easy.py)."""
+    VARIANT = 0
+    ENV_NAME = "flight_easy"
+
+
+class VecFlightEnv(_VecFlightBase):
+    """num_envs x FlightSearchEnv (env/flight_env.py): flight_easy dynamics with the '>=' wall test
+    (:328) plus the per-env probability map updated by every sensing call (:275-303)."""
+    VARIANT = 1
+    ENV_NAME = "flight"
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self._obs_full = None
+
+    def get_obs(self, full=True):
+        """Reference-shaped [E,n,M*M+4] = prob_map.ravel() || 4 features (flight_env.py:223-230),
+        materialised by a streaming kernel.  full=False returns the [E,n,4] features only; the map
+        itself is available zero-copy as ``self.prob_map`` ([E,M,M])."""
+        if not full:
+            return self._obs
+        if self._obs_full is None:
+            self._obs_full = torch.empty((self.num_envs, self.n_agents, self.map_size ** 2 + 4),
+                                         dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.cs_flight_obs_full(self._h.ptr, C.c_void_p(self._obs_full.data_ptr()), self._stream()),
+                       "cs_flight_obs_full")
+        return self._obs_full

@@ -1,0 +1,225 @@
+/*
+ * coopsearch.h -- C ABI of libcoopsearch.so (B200 / sm_100a batched env-step hot path).
+ *
+ * The reference (WZN1ng/Cooperative-Search) is pure Python and has no FFI; its "plugin
+ * interface" for this path is the duck-typed SMAC-style env protocol that
+ * common/rollout.py:24-201 and main.py:114,134 call.  Every entry point below names the
+ * reference method it replaces.  Python binds these with ctypes
+ * (cooperative-search_b200/_lib.py); INTEGRATION.md shows the stub a reference
+ * maintainer would add.
+ *
+ * Conventions
+ *   - plain C types only; every function returns CS_OK (0) or a negative cs_status;
+ *     cs_last_error() gives a thread-local message.  Nothing throws across the ABI.
+ *   - a handle owns its device memory (state + output buffers).  cs_*_buffers() exposes
+ *     the device pointers so the host language can wrap them zero-copy.
+ *   - all calls taking a `stream` (a cudaStream_t passed as void*) are asynchronous on
+ *     that stream and never synchronise; *_host calls take HOST pointers, do their own
+ *     H2D/D2H copies on the given stream and return after the results are in host memory.
+ *   - a handle is not thread-safe; use one handle per host thread / stream.
+ *   - global env ids are env_id_base + local index; every random draw is keyed by the
+ *     GLOBAL id, so results do not depend on how envs are sharded over GPUs.
+ */
+#ifndef COOPSEARCH_H_
+#define COOPSEARCH_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CS_ABI_VERSION 1
+#define CS_MAX_AGENTS 32   /* flight envs: out-of-map flags live in one 32-bit word   */
+#define CS_MAX_TARGETS 32  /* flight envs: found flags live in one 32-bit word        */
+#define CS_NUM_STATS 8
+
+typedef enum cs_status {
+    CS_OK = 0,
+    CS_ERR_INVALID = -1,      /* bad argument / config (reference: raise Exception(...))   */
+    CS_ERR_CUDA = -2,         /* a CUDA runtime call failed                                */
+    CS_ERR_NOMEM = -3,
+    CS_ERR_UNSUPPORTED = -4
+} cs_status;
+
+/* cs_*_reset flags */
+#define CS_RESET_INIT 1u          /* reset(init=True): flight variant refills prob_map=0.5
+                                     (env/flight_env.py:84-86)                              */
+#define CS_RESET_KEEP_TARGETS 2u  /* keep the target coordinates/cells currently in the
+                                     state buffers (parity tests inject the reference's)   */
+#define CS_RESET_KEEP_EPISODE 4u  /* do not advance the per-env episode counter            */
+
+/* meta words of a flight env (uint32 each), see cs_flight_buffers.dyn */
+enum { CS_META_FOUND = 0, CS_META_NEWFOUND = 1, CS_META_OUT = 2, CS_META_TIME = 3,
+       CS_META_EPISODE = 4, CS_META_FLAGS = 5, CS_META_EPREWARD = 6, CS_META_RESERVED = 7,
+       CS_META_WORDS = 8 };
+#define CS_FLAG_WIN 1u
+#define CS_FLAG_DONE 2u
+
+/* indices into the stats vector (doubles); the vector all-reduced over NCCL */
+enum { CS_STAT_EPISODES = 0, CS_STAT_EP_REWARD = 1, CS_STAT_TARGETS_FOUND = 2, CS_STAT_WINS = 3,
+       CS_STAT_EP_LEN = 4, CS_STAT_ENV_STEPS = 5, CS_STAT_ILLEGAL = 6, CS_STAT_TOUCHED = 7 };
+
+int cs_version(void);
+const char* cs_last_error(void);
+/* number of kernels this library has launched in the calling process (bench "gpu_launches") */
+uint64_t cs_launch_count(void);
+
+/* lanes per env the handle's step kernel was instantiated with (tuning visibility) */
+struct cs_flight;
+int cs_flight_lanes_per_env(const struct cs_flight* env);
+/* test hook: d_in6 [count][6] = Philox counter(4) + key(2) -> d_out4 [count][4] words */
+int cs_debug_philox(const uint32_t* d_in6, uint32_t* d_out4, int32_t count, void* stream);
+
+/* Pinned host memory for the *_host entry points. */
+int cs_host_alloc(void** out, uint64_t bytes);
+int cs_host_free(void* p);
+
+/* ===================================================================================
+ * flight_easy / flight  (env/flight_env_easy.py, env/flight_env.py)
+ * =================================================================================== */
+typedef struct cs_flight_cfg {
+    uint32_t struct_size;   /* sizeof(cs_flight_cfg), ABI check                            */
+    int32_t num_envs;       /* E: env instances owned by this handle (this GPU's shard)    */
+    int32_t n_agents;       /* args.n_agents      (flight_env_easy.py:22)                  */
+    int32_t target_num;     /* args.target_num    (:19)                                    */
+    int32_t map_size;       /* args.map_size      (:18)                                    */
+    int32_t view_range;     /* args.view_range    (:23)                                    */
+    int32_t time_limit;     /* args.time_limit    (:25), <= 65535                          */
+    int32_t agent_mode;     /* 0..3               (:139-180)                               */
+    int32_t target_mode;    /* 0 file template, 1 uniform (:95-136)                        */
+    int32_t variant;        /* 0 = flight_easy (wall test '>'), 1 = flight (prob map, '>=')*/
+    int32_t auto_reset;     /* 1: a terminated env is reset inside the same step call      */
+    int32_t count_touched;  /* 1: accumulate #prob-map cells updated into CS_STAT_TOUCHED  */
+    int32_t lanes_per_env;  /* 0 = choose from E; else 1,2,4,8,16,32 (variant 1 forces 32) */
+    int32_t device;         /* CUDA device ordinal                                         */
+    double velocity;        /* args.agent_velocity                                         */
+    double detect_prob;     /* args.detect_prob                                            */
+    double safe_dist;       /* args.safe_dist                                              */
+    double force_dist;      /* args.force_dist                                             */
+    uint32_t seed;          /* Philox key word 0                                           */
+    uint32_t env_id_base;   /* global id of local env 0                                    */
+} cs_flight_cfg;
+
+typedef struct cs_flight cs_flight;
+
+/* Device pointers of a flight handle.  fp64 internal state, fp32/u8 outputs.
+ *   dyn : [E][dyn_doubles] doubles; per env  x0,y0,..,x(n-1),y(n-1) | yaw0..yaw(n-1) |
+ *         pad to meta_off | CS_META_WORDS uint32 meta words (see enum above)
+ *   tgt : [E][m][2] doubles, target coordinates (target_pos, flight_env_easy.py:113)      */
+typedef struct cs_flight_buffers {
+    double* dyn;
+    int32_t dyn_doubles;
+    int32_t yaw_off;        /* = 2n   (doubles)                                            */
+    int32_t meta_off;       /* doubles; meta words start at (uint32*)(rec + meta_off)      */
+    int32_t state_len;      /* 4n + 3m                                                     */
+    double* tgt;
+    float* obs;             /* [E][n][4]     get_obs   (flight_env_easy.py:218-221)        */
+    float* state;           /* [E][4n+3m]    get_state (:190-216)                          */
+    float* reward;          /* [E]           step()[0] (:314)                              */
+    uint8_t* terminated;    /* [E]           step()[1]                                     */
+    uint8_t* win;           /* [E]           step()[2] (win_flag)                          */
+    int32_t* target_find;   /* [E]           attribute target_find (rollout.py:79)         */
+    float* prob_map;        /* [E][M][M] (variant 1) else NULL; prob_map[i][j], i<->x      */
+    double* stats;          /* [CS_NUM_STATS] running sums over finished episodes          */
+} cs_flight_buffers;
+
+/* FlightSearchEnvEasy.__init__ / FlightSearchEnv.__init__ (flight_env_easy.py:15-69).
+ * Allocates state; envs are NOT reset until cs_flight_reset is called. */
+int cs_flight_create(const cs_flight_cfg* cfg, cs_flight** out);
+void cs_flight_destroy(cs_flight* env);
+int cs_flight_buffers_get(cs_flight* env, cs_flight_buffers* out);
+/* get_env_info (flight_env_easy.py:71-77): out4 = n_actions, state_shape, obs_shape, episode_limit */
+int cs_flight_env_info(const cs_flight* env, int32_t* out4);
+/* circle_dict of main.py:19-32 for target_mode 0: host array [m][5] doubles
+ * (x, y, dx, dy, deter=='f' ? 1 : 0) in FILE units (the a = map_size/10 scale is applied inside,
+ * flight_env_easy.py:97-103). */
+int cs_flight_set_target_template(cs_flight* env, const double* host_rows, int32_t rows);
+/* reset(init) (flight_env_easy.py:79-182) for envs with mask[e] != 0 (device u8 [E]; NULL = all). */
+int cs_flight_reset(cs_flight* env, const uint8_t* d_mask, uint32_t flags, void* stream);
+/* step(act_list) (flight_env_easy.py:303-314).  d_actions: device u8 [E][n], values 0..2.
+ * Envs whose DONE flag is set are a masked no-op (reward 0, terminated 1) unless auto_reset. */
+int cs_flight_step(cs_flight* env, const uint8_t* d_actions, void* stream);
+/* k steps under the uniform-random policy drawn in-kernel (alg=random, agent/agent.py:34-36). */
+int cs_flight_step_random(cs_flight* env, int32_t k, void* stream);
+/* Reference-shaped observation of the flight variant (flight_env.py:223-230):
+ * d_out [E][n][M*M+4] = prob_map.ravel() || (x^,y^,cos,sin). */
+int cs_flight_obs_full(cs_flight* env, float* d_out, void* stream);
+/* Host-buffer step: the call a CPU-side rollout makes.  h_actions [E][n] u8.  Any output pointer
+ * may be NULL (not copied).  Blocks until outputs are in host memory. */
+typedef struct cs_flight_host_io {
+    const uint8_t* actions;
+    float* reward;
+    uint8_t* terminated;
+    uint8_t* win;
+    float* obs;
+    float* state;
+} cs_flight_host_io;
+int cs_flight_step_host(cs_flight* env, const cs_flight_host_io* io, void* stream);
+/* Copies the stats vector to host (synchronises the stream). */
+int cs_flight_stats(cs_flight* env, double* h_out, void* stream);
+
+/* ===================================================================================
+ * search_env  (env/search_env.py)
+ * =================================================================================== */
+typedef struct cs_search_cfg {
+    uint32_t struct_size;
+    int32_t num_envs;
+    int32_t n_agents;       /* search_env.py:25 */
+    int32_t target_num;     /* :21 */
+    int32_t map_size;       /* :20 */
+    int32_t view_range;     /* :26 */
+    int32_t agent_mode;     /* 0 centre square, 1 bottom-left, 2 bottom row (:146-180) */
+    int32_t target_mode;    /* 0 uniform cells, 1 edge band (:86-104) */
+    int32_t auto_reset;
+    int32_t device;
+    uint32_t seed;
+    uint32_t env_id_base;
+} cs_search_cfg;
+
+typedef struct cs_search cs_search;
+
+typedef struct cs_search_buffers {
+    int32_t* pos;           /* [E][n][2]  agent_pos                                        */
+    uint32_t* target_bits;  /* [E][M][W]  bit y of row x: target_map[x][y] (sticky)        */
+    uint32_t* unfound_bits; /* [E][M][W]  targets not yet found                            */
+    int32_t* freq;          /* [E][M][M]  freq_map, never cleared (search_env.py:39)       */
+    int32_t* counters;      /* [E][4]     target_find, time_step, flags(done|illegal), episode */
+    int32_t words_per_row;  /* W = ceil(M/32)                                              */
+    float* obs;             /* [E][n][(2R-1)^2+2]  get_obs   (:203-227)                    */
+    float* state;           /* [E][M][M][2]        get_state (:186-200)                    */
+    uint8_t* avail;         /* [E][n][4]           get_avail_agent_actions (:230-243)      */
+    float* reward;          /* [E] */
+    uint8_t* terminated;    /* [E] */
+    int32_t* target_find;   /* [E] */
+    double* stats;          /* [CS_NUM_STATS] */
+} cs_search_buffers;
+
+int cs_search_create(const cs_search_cfg* cfg, cs_search** out);
+void cs_search_destroy(cs_search* env);
+int cs_search_buffers_get(cs_search* env, cs_search_buffers* out);
+/* get_env_info (search_env.py:60-66): n_actions, state_shape, obs_shape, episode_limit */
+int cs_search_env_info(const cs_search* env, int32_t* out4);
+/* Inject target cells for CS_RESET_KEEP_TARGETS: d_cells device int32 [E][m][2]. */
+int cs_search_set_targets(cs_search* env, const int32_t* d_cells, void* stream);
+/* reset (search_env.py:69-183); init=False semantics, freq_map is never cleared. */
+int cs_search_reset(cs_search* env, const uint8_t* d_mask, uint32_t flags, void* stream);
+/* step(act_list) (search_env.py:246-296); d_actions u8 [E][n] in 0..3.  An illegal move
+ * (reference raises, :293) sets the env's illegal flag and leaves that agent in place. */
+int cs_search_step(cs_search* env, const uint8_t* d_actions, void* stream);
+int cs_search_step_random(cs_search* env, int32_t k, void* stream);
+typedef struct cs_search_host_io {
+    const uint8_t* actions;
+    float* reward;
+    uint8_t* terminated;
+    float* obs;
+    float* state;
+    uint8_t* avail;
+} cs_search_host_io;
+int cs_search_step_host(cs_search* env, const cs_search_host_io* io, void* stream);
+int cs_search_stats(cs_search* env, double* h_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COOPSEARCH_H_ */

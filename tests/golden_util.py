@@ -23,3 +23,16 @@ def flight_spec_kwargs(g, variant):
     return dict(n_agents=n, target_num=m, map_size=M, view_range=R, time_limit=T, agent_mode=am,
                 target_mode=tm, velocity=as_num(vel), detect_prob=d, safe_dist=as_num(safe),
                 force_dist=as_num(fd), variant=variant), base, seed
+
+
+TEMPLATE = {
+    # flight_targets.txt of the reference (main.py:19-32 parsing), embedded so the GPU box needs no reference tree
+    "x": [5, 2, 7.5, 2.8, 6.9, 5.5, 5.3, 1.8, 3, 4.5, 6.3, 8, 0.9, 9.4, 4.2],
+    "y": [9.1, 7.5, 7, 8, 8.5, 8, 6.6, 6.8, 5.7, 5, 5.7, 6.7, 8.7, 9, 9.3],
+    "deter": ["f", "t", "f", "f", "t", "f", "t", "t", "f", "f", "t", "f", "f", "t", "f"],
+    "priority": [3, 3, 3, 2, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1, 1],
+    "dx": [0.2, 0.3, 0.3, 0.27, 0.25, 0.25, 0.1, 0.28, 0.18, 0.23, 0.31, 0.29, 0.15, 0.21, 0.34],
+    "dy": [0.2, 0.3, 0.26, 0.27, 0.25, 0.25, 0.12, 0.28, 0.18, 0.25, 0.30, 0.28, 0.16, 0.21, 0.33],
+}
+
+

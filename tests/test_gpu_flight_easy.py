@@ -1,0 +1,238 @@
+"""GPU parity of the flight_easy CUDA path (through the C ABI) against
+  (1) golden trajectories of the unmodified reference (tests/golden/easy_*.npz), and
+  (2) the Python oracle on fresh seeded inputs,
+plus the batched-API contracts (masking, auto-reset, shard invariance, host-buffer step).
+
+Bars: found masks / rewards / terminated / win / target_find / time_step / out flags bit-exact;
+fp64 positions and headings to 1e-9 (CUDA sincos vs libm differ in the last ulp); fp32 obs/state to
+rtol 1e-5 + atol 1e-6 (north_star tolerance; SURVEY.md section 7 hard part 2 for the atol)."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import golden_util as gu
+from oracle.py_envs import FlightOracle, FlightSpec
+
+pytestmark = pytest.mark.gpu
+
+
+def make_args(kw):
+    return types.SimpleNamespace(
+        env="flight_easy" if kw["variant"] == "easy" else "flight",
+        map_size=kw["map_size"], target_num=kw["target_num"], target_mode=kw["target_mode"],
+        agent_mode=kw["agent_mode"], n_agents=kw["n_agents"], view_range=kw["view_range"],
+        time_limit=kw["time_limit"], detect_prob=kw["detect_prob"], safe_dist=kw["safe_dist"],
+        agent_velocity=kw["velocity"], force_dist=kw["force_dist"], turn_limit=np.pi / 4, wrong_alarm_prob=0.1)
+
+
+TEMPLATE = gu.TEMPLATE
+
+
+def cpu(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize("lpe", [0, 1, 4, 32])
+@pytest.mark.parametrize("name", gu.EASY_FIXTURES)
+def test_matches_reference_golden(name, lpe):
+    import coopsearch_b200 as cs
+    g = gu.load(name)
+    kw, base, seed = gu.flight_spec_kwargs(g, "easy")
+    T, E = g["reward"].shape
+    n = kw["n_agents"]
+    env = cs.VecFlightEasyEnv(make_args(kw), None, num_envs=E, seed=seed, env_id_base=base, lanes_per_env=lpe, reset=False)
+    env.reset(init=True, targets=g["tgt_xy"])
+    torch.cuda.synchronize()
+    assert np.array_equal(cpu(env.found_mask).astype(np.uint32), g["init_found"])
+    assert np.array_equal(cpu(env.win_flag), g["init_win"])
+    np.testing.assert_allclose(cpu(env.agent_xy), g["init_xy"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(cpu(env.agent_yaw), g["init_yaw"], rtol=0, atol=1e-15)
+    np.testing.assert_allclose(cpu(env.get_state()), g["init_state"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(cpu(env.get_obs()), g["init_obs"], rtol=1e-5, atol=1e-6)
+    thin = int(g["thin"][0])
+    for t in range(T):
+        r, term, win = env.step(g["actions"][t])
+        where = "%s lpe=%d step %d" % (name, lpe, t)
+        assert np.array_equal(cpu(env.found_mask).astype(np.uint32), g["found"][t]), where
+        assert np.array_equal(cpu(r), g["reward"][t].astype(np.float32)), where
+        assert np.array_equal(cpu(term), g["terminated"][t]), where
+        assert np.array_equal(cpu(win), g["win"][t]), where
+        assert np.array_equal(cpu(env.target_find), g["target_find"][t]), where
+        assert np.array_equal(cpu(env.time_step), g["time_step"][t]), where
+        out = (cpu(env.out_mask)[:, None] >> np.arange(n)[None, :]) & 1
+        assert np.array_equal(out.astype(np.uint8), g["out"][t]), where
+        np.testing.assert_allclose(cpu(env.agent_xy), g["xy"][t], rtol=0, atol=1e-9, err_msg=where)
+        np.testing.assert_allclose(cpu(env.agent_yaw), g["yaw"][t], rtol=0, atol=1e-12, err_msg=where)
+        if (t + 1) % thin == 0:
+            k = (t + 1) // thin - 1
+            np.testing.assert_allclose(cpu(env.get_state()), g["state"][k], rtol=1e-5, atol=1e-6, err_msg=where)
+            np.testing.assert_allclose(cpu(env.get_obs()), g["obs"][k], rtol=1e-5, atol=1e-6, err_msg=where)
+
+
+def run_oracle(spec, template, seed, ids, actions, targets=None):
+    """Python-oracle trajectories for env ids `ids`; actions [T, len(ids), n]."""
+    T = actions.shape[0]
+    n = spec.n_agents
+    res = dict(found=np.zeros((T, len(ids)), np.uint32), reward=np.zeros((T, len(ids)), np.float32),
+               term=np.zeros((T, len(ids)), np.uint8), win=np.zeros((T, len(ids)), np.uint8),
+               xy=np.zeros((T, len(ids), n, 2)), tgt=np.zeros((len(ids), spec.target_num, 2)),
+               state=np.zeros((T, len(ids), spec.state_shape)))
+    for k, eid in enumerate(ids):
+        o = FlightOracle(spec, template, seed, int(eid))
+        o.reset(targets=None if targets is None else targets[k], init=True)
+        res["tgt"][k] = np.array(o.tgt)
+        done = False
+        for t in range(T):
+            r = 0.0
+            if not done:
+                r, done, _ = o.step(actions[t, k])
+            res["found"][t, k] = o.found_mask()
+            res["reward"][t, k] = r
+            res["term"][t, k] = int(done)
+            res["win"][t, k] = int(o.win)
+            res["xy"][t, k] = np.array(o.pos, float)
+            res["state"][t, k] = o.get_state()
+    return res
+
+
+@pytest.mark.parametrize("n_agents,agent_mode,target_mode,lpe", [(3, 0, 0, 0), (5, 2, 0, 8), (5, 3, 1, 1), (1, 1, 0, 2), (8, 0, 1, 16)])
+def test_device_reset_and_steps_match_oracle(n_agents, agent_mode, target_mode, lpe):
+    """Targets drawn on the device (keyed Box-Muller / uniform) + full episodes vs the oracle."""
+    import coopsearch_b200 as cs
+    E, T, seed, base = 96, 200, 7, 5000
+    spec = FlightSpec(n_agents=n_agents, agent_mode=agent_mode, target_mode=target_mode)
+    kw = dict(spec.__dict__)
+    env = cs.VecFlightEasyEnv(make_args(kw), TEMPLATE, num_envs=E, seed=seed, env_id_base=base, lanes_per_env=lpe)
+    actions = np.random.default_rng(99).integers(0, 3, size=(T, E, n_agents), dtype=np.uint8)
+    want = run_oracle(spec, TEMPLATE, seed, base + np.arange(E), actions)
+    np.testing.assert_allclose(cpu(env.tgt_xy), want["tgt"], rtol=0, atol=1e-9)
+    for t in range(T):
+        r, term, win = env.step(actions[t])
+        where = "step %d" % t
+        assert np.array_equal(cpu(env.found_mask).astype(np.uint32), want["found"][t]), where
+        assert np.array_equal(cpu(r), want["reward"][t]), where
+        assert np.array_equal(cpu(term), want["term"][t]), where
+        assert np.array_equal(cpu(win), want["win"][t]), where
+        np.testing.assert_allclose(cpu(env.agent_xy), want["xy"][t], rtol=0, atol=1e-8, err_msg=where)
+        if t % 25 == 0:
+            np.testing.assert_allclose(cpu(env.get_state()), want["state"][t], rtol=1e-5, atol=1e-6, err_msg=where)
+
+
+def test_shard_invariance_and_lane_invariance():
+    """Results depend on the GLOBAL env id only: one 64-env handle == two 32-env handles with
+    env_id_base offsets (what 1 vs 2 GPUs do), bit for bit, and every lanes-per-env instantiation agrees."""
+    import coopsearch_b200 as cs
+    spec = FlightSpec(n_agents=5, agent_mode=2)
+    args = make_args(dict(spec.__dict__))
+    E, T = 64, 120
+    actions = torch.from_numpy(np.random.default_rng(5).integers(0, 3, size=(T, E, 5), dtype=np.uint8)).cuda()
+    whole = cs.VecFlightEasyEnv(args, TEMPLATE, num_envs=E, seed=3, env_id_base=1000, lanes_per_env=8)
+    lo = cs.VecFlightEasyEnv(args, TEMPLATE, num_envs=32, seed=3, env_id_base=1000, lanes_per_env=1)
+    hi = cs.VecFlightEasyEnv(args, TEMPLATE, num_envs=32, seed=3, env_id_base=1032, lanes_per_env=32)
+    for t in range(T):
+        rw, tw, ww = whole.step(actions[t])
+        rl, tl, wl = lo.step(actions[t, :32])
+        rh, th, wh = hi.step(actions[t, 32:])
+        assert torch.equal(rw, torch.cat([rl, rh]))
+        assert torch.equal(tw, torch.cat([tl, th]))
+        assert torch.equal(whole._dyn, torch.cat([lo._dyn, hi._dyn]))
+        assert torch.equal(whole.get_state(), torch.cat([lo.get_state(), hi.get_state()]))
+
+
+def test_auto_reset_and_stats():
+    import coopsearch_b200 as cs
+    spec = FlightSpec(n_agents=3, time_limit=40)
+    args = make_args(dict(spec.__dict__))
+    E = 200
+    env = cs.VecFlightEasyEnv(args, TEMPLATE, num_envs=E, seed=11, auto_reset=True)
+    total_r = np.zeros(E)
+    ep_sum, eps, steps = 0.0, 0, 0
+    for t in range(100):
+        r, term, win = env.step_random(1)
+        total_r += cpu(r)
+        term = cpu(term).astype(bool)
+        ep_sum += total_r[term].sum()
+        eps += int(term.sum())
+        total_r[term] = 0
+        steps += E
+        ts = cpu(env.time_step)
+        assert np.all(ts[term] == 0)                 # terminated envs were reset in the same call
+        assert np.all(ts <= 40)
+    st = env.stats()
+    assert st["env_steps"] == steps
+    assert st["episodes"] == eps and eps >= 2 * E
+    assert abs(st["episode_reward_sum"] - ep_sum) < 1e-6 * max(1.0, abs(ep_sum))
+    assert st["episode_len_sum"] <= 40 * eps
+
+
+def test_masked_noop_after_termination_and_partial_reset():
+    import coopsearch_b200 as cs
+    spec = FlightSpec(n_agents=3, time_limit=5)
+    args = make_args(dict(spec.__dict__))
+    env = cs.VecFlightEasyEnv(args, TEMPLATE, num_envs=8, seed=1)
+    for _ in range(5):
+        r, term, _ = env.step_random(1)
+    assert cpu(term).all()
+    snap = env._dyn.clone()
+    state = env.get_state().clone()
+    r, term, _ = env.step_random(1)
+    assert cpu(term).all() and not cpu(r).any()
+    assert torch.equal(env._dyn, snap) and torch.equal(env.get_state(), state)
+    mask = torch.tensor([1, 0, 0, 1, 0, 0, 0, 0], dtype=torch.uint8, device="cuda")
+    env.reset(mask=mask)
+    ts = cpu(env.time_step)
+    assert list(ts) == [0, 5, 5, 0, 5, 5, 5, 5]
+    r, term, _ = env.step_random(1)
+    assert list(cpu(term)) == [0, 1, 1, 0, 1, 1, 1, 1]
+    assert list(cpu(env.meta[:, 4])) == [1, 0, 0, 1, 0, 0, 0, 0]      # episode counters
+
+
+def test_host_buffer_step_equals_device_step():
+    import coopsearch_b200 as cs
+    spec = FlightSpec(n_agents=3)
+    args = make_args(dict(spec.__dict__))
+    a = cs.VecFlightEasyEnv(args, TEMPLATE, num_envs=50, seed=2)
+    b = cs.VecFlightEasyEnv(args, TEMPLATE, num_envs=50, seed=2)
+    rng = np.random.default_rng(0)
+    for t in range(30):
+        act = rng.integers(0, 3, size=(50, 3), dtype=np.uint8)
+        r, term, win = a.step(act)
+        hr, hterm, hwin, hobs, hstate = b.step_host(act)
+        assert np.array_equal(cpu(r), hr) and np.array_equal(cpu(term), hterm) and np.array_equal(cpu(win), hwin)
+        assert np.array_equal(cpu(a.get_obs()), hobs) and np.array_equal(cpu(a.get_state()), hstate)
+
+
+def test_reference_error_behaviour():
+    import coopsearch_b200 as cs
+    spec = FlightSpec(n_agents=3)
+    args = make_args(dict(spec.__dict__))
+    env = cs.VecFlightEasyEnv(args, TEMPLATE, num_envs=4)
+    with pytest.raises(Exception, match="Act num mismatch agent"):
+        env.step(np.zeros((4, 2), np.uint8))
+    with pytest.raises(Exception, match="Agent id out of range"):
+        env.get_avail_agent_actions(3)
+    assert env.get_avail_agent_actions(2).shape == (4, 3) and bool((env.get_avail_actions() == 1).all())
+    bad = make_args(dict(spec.__dict__)); bad.agent_mode = 7
+    with pytest.raises(Exception, match="No such agent mode"):
+        cs.VecFlightEasyEnv(bad, TEMPLATE, num_envs=4)
+    bad = make_args(dict(spec.__dict__)); bad.target_mode = 5
+    with pytest.raises(Exception, match="No such target mode"):
+        cs.VecFlightEasyEnv(bad, TEMPLATE, num_envs=4)
+    info = env.get_env_info()
+    assert (info["n_actions"], info["state_shape"], info["obs_shape"], info["episode_limit"]) == (3, 57, 4, 200)
+
+
+def test_single_env_adapter_types():
+    import coopsearch_b200 as cs
+    spec = FlightSpec(n_agents=3)
+    args = make_args(dict(spec.__dict__))
+    env = cs.SingleEnvAdapter(cs.VecFlightEasyEnv(args, TEMPLATE, num_envs=1, seed=4))
+    env.reset()
+    o, s = env.get_obs(), env.get_state()
+    assert o.shape == (3, 4) and o.dtype == np.float64 and s.shape == (57,) and s.dtype == np.float64
+    r, term, info = env.step([np.int64(1), torch.tensor(2), 0])
+    assert isinstance(r, float) and isinstance(term, bool) and isinstance(info, bool)
+    assert isinstance(env.target_find, int)
+    assert np.array_equal(env.get_avail_agent_actions(0), np.ones(3))
