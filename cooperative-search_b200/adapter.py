@@ -38,7 +38,7 @@ class SingleEnvAdapter:
         out = self.vec.step(acts)
         reward = float(out[0][0].item())
         terminated = bool(out[1][0].item())
-        info = bool(out[2][0].item()) if len(out) > 2 and out[2] is not None else ''
+        info = out[2] if isinstance(out[2], str) else bool(out[2][0].item())     # win flag (flight) / '' (search)
         return reward, terminated, info
 
     @property

@@ -18,6 +18,7 @@
 //     map row so that every load/store instruction covers one contiguous 64-byte run of a row.
 #include <math.h>
 #include <new>
+#include <vector>
 #include "cs_common.cuh"
 #include "cs_philox.cuh"
 
@@ -49,6 +50,11 @@ struct FlightParams {
     float* prob_map;
     double* stats;
     const double* tmpl;   // [m][5]: x, y, sx, sy, random   (already scaled by a = M/10)
+    // heading-lattice trig table (see HeadingLut below)
+    const longlong2* lut_meta;   // [37]: x = bit pattern of the cluster centre, y = base | (half << 32)
+    const double2* lut;          // (sin, cos) of every bit pattern in every cluster window, from the HOST libm
+    double inv_turn;             // 18/pi
+    double cos0, sin0;           // cos/sin of the start heading of agent_mode, from the host libm
 };
 
 struct SlotRes {
@@ -61,6 +67,40 @@ struct SlotRes {
 
 __device__ __forceinline__ uint32_t* slot_meta(const FlightParams& p, double* S) {
     return reinterpret_cast<uint32_t*>(S + p.meta_off);
+}
+
+// ------------------------------------------------------------------------------------------------
+// cos/sin of a heading.
+//
+// Headings only ever take the values reachable from {0, pi/2, pi} under +-pi/18 turns, the 2*pi wrap and
+// the wall reflection (flight_env_easy.py:259-266,281-284): 37 clusters of fp64 values, each a few hundred
+// ulps wide after 200 steps (rounding drift ~1.7e-16 per step).  Whether an agent that comes back to a
+// wall ends at y = 0.0 or y = -5e-17 -- and therefore its out-of-map flag, its reward and its reflected
+// heading -- depends on the LAST BIT of sin/cos, and the reference's bits are those of the host libm
+// (numpy -> glibc), which is not correctly rounded (measured: 2 of 652 evaluations).  So the handle tabulates
+// the host libm's sin/cos for every bit pattern in every cluster window at create time and the kernel looks
+// the pair up (one 16-byte load) -- bit-identical to the reference and cheaper than evaluating sincos().
+// Off-lattice headings (user-injected state) fall back to CUDA's sincos (<= 2 ulp).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void heading_sincos(const FlightParams& p, double h, double* sn, double* c) {
+    const int k = __double2int_rn(h * p.inv_turn);
+    if (k == 0 && fabs(h) < 7.450580596923828e-09) {   // |h| < 2^-27: libm returns sin = h, cos = 1
+        *sn = h;
+        *c = 1.0;
+        return;
+    }
+    if (k >= 1 && k <= 36) {
+        const longlong2 mt = __ldg(p.lut_meta + k);
+        const long long off = __double_as_longlong(h) - mt.x;
+        const long long half = mt.y >> 32;
+        if (off >= -half && off <= half) {
+            const double2 v = __ldg(p.lut + ((mt.y & 0xffffffffLL) + half + off));
+            *sn = v.x;
+            *c = v.y;
+            return;
+        }
+    }
+    sincos(h, sn, c);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -100,7 +140,7 @@ __device__ __forceinline__ uint32_t fl_move(const FlightParams& p, double* S, in
         if (h > p.two_pi) h -= p.two_pi;                          // strict tests (:263-266)
         else if (h < 0.0) h += p.two_pi;
         double sn, c;
-        sincos(h, &sn, &c);
+        heading_sincos(p, h, &sn, &c);
         yaw[a] = h;
         cs[a] = c;
         cs[n + a] = sn;
@@ -351,10 +391,8 @@ __device__ __forceinline__ void fl_reset(const FlightParams& p, double* S, int l
         S[2 * a] = x;
         S[2 * a + 1] = y;
         yaw[a] = h;
-        double sn, c;
-        sincos(h, &sn, &c);
-        cs[a] = c;
-        cs[n + a] = sn;
+        cs[a] = p.cos0;
+        cs[n + a] = p.sin0;
     }
     if (p.variant && (rflags & CS_RESET_INIT)) {
         for (int c = lane; c < p.M * p.M; c += LPE) map[c] = 0.5f;       // flight_env.py:84-86
@@ -614,6 +652,8 @@ struct cs_flight {
     int grid;
     double* d_tmpl;
     uint8_t* d_actions;   // device staging of the *_host entry point's actions
+    longlong2* d_lut_meta;
+    double2* d_lut;
     bool have_tmpl;
 };
 
@@ -671,6 +711,62 @@ cudaError_t dispatch_attr(int lpe, size_t bytes) {
 }
 
 inline int up2(int v) { return (v + 1) & ~1; }
+
+// Host-side heading table (see heading_sincos): clusters k = 1..36 around k*pi/18, window = rounding drift after
+// `time_limit` steps with a 1.5x margin (measured drift: +-3.4e-14 after 200 steps ~ 1.7e-16 per step).
+struct HeadingLut {
+    std::vector<longlong2> meta;
+    std::vector<double2> tab;
+};
+
+inline double ulp_of(double v) {
+    long long b;
+    memcpy(&b, &v, 8);
+    ++b;
+    double w;
+    memcpy(&w, &b, 8);
+    return w - v;
+}
+
+void build_heading_lut(int time_limit, HeadingLut* out) {
+    const double drift = ((double)time_limit + 16.0) * 2.6e-16;
+    out->meta.assign(37, make_longlong2(0, 0));
+    out->tab.clear();
+    for (int k = 1; k <= 36; ++k) {
+        const double centre = (double)k * M_PI / 18.0;
+        long long cb;
+        memcpy(&cb, &centre, 8);
+        long long half = (long long)ceil(drift / ulp_of(centre * 0.999)) + 4;
+        if (half > 16384) half = 16384;             // very long episodes: the tail falls back to sincos()
+        const long long base = (long long)out->tab.size();
+        for (long long off = -half; off <= half; ++off) {
+            const long long bits = cb + off;
+            double h;
+            memcpy(&h, &bits, 8);
+            out->tab.push_back(make_double2(sin(h), cos(h)));     // HOST libm: the reference's own bits
+        }
+        out->meta[k] = make_longlong2(cb, base | (half << 32));
+    }
+}
+
+// host mirror of the device lookup (tests call it through cs_debug_heading_lut)
+void host_heading_sincos(const HeadingLut& lut, double h, double* sn, double* c, int* from_table) {
+    const int k = (int)nearbyint(h * (18.0 / M_PI));
+    *from_table = 1;
+    if (k == 0 && fabs(h) < 7.450580596923828e-09) { *sn = h; *c = 1.0; return; }
+    if (k >= 1 && k <= 36) {
+        long long hb;
+        memcpy(&hb, &h, 8);
+        const long long off = hb - lut.meta[k].x, half = lut.meta[k].y >> 32;
+        if (off >= -half && off <= half) {
+            const double2 v = lut.tab[(size_t)((lut.meta[k].y & 0xffffffffLL) + half + off)];
+            *sn = v.x; *c = v.y;
+            return;
+        }
+    }
+    *from_table = 0;
+    *sn = sin(h); *c = cos(h);
+}
 
 }  // namespace
 
@@ -734,6 +830,12 @@ int cs_flight_create(const cs_flight_cfg* cfg, cs_flight** out) {
     else if (cfg->detect_prob < 0.0) p.thr = -1;
     else p.thr = (long long)floor(cfg->detect_prob * 4294967296.0);
     p.seed = cfg->seed; p.env_id_base = cfg->env_id_base;
+    p.inv_turn = 18.0 / M_PI;
+    {
+        const double h0 = (cfg->agent_mode <= 1) ? M_PI / 2 : (cfg->agent_mode == 2 ? 0.0 : M_PI);
+        p.cos0 = cos(h0);
+        p.sin0 = sin(h0);
+    }
 
     h->lpe = pick_lpe(*cfg);
     const int epc = kThreads / h->lpe;
@@ -776,6 +878,16 @@ int cs_flight_create(const cs_flight_cfg* cfg, cs_flight** out) {
         CS_CUDA(cudaMemset(p.prob_map, 0, E * M * M * sizeof(float)));
     }
     CS_CUDA(cudaMalloc(&h->d_actions, E * n));
+    {
+        HeadingLut lut;
+        build_heading_lut(cfg->time_limit, &lut);
+        CS_CUDA(cudaMalloc(&h->d_lut_meta, lut.meta.size() * sizeof(longlong2)));
+        CS_CUDA(cudaMemcpy(h->d_lut_meta, lut.meta.data(), lut.meta.size() * sizeof(longlong2), cudaMemcpyHostToDevice));
+        CS_CUDA(cudaMalloc(&h->d_lut, lut.tab.size() * sizeof(double2)));
+        CS_CUDA(cudaMemcpy(h->d_lut, lut.tab.data(), lut.tab.size() * sizeof(double2), cudaMemcpyHostToDevice));
+        p.lut_meta = h->d_lut_meta;
+        p.lut = h->d_lut;
+    }
     *out = h;
     return CS_OK;
 }
@@ -785,7 +897,7 @@ void cs_flight_destroy(cs_flight* h) {
     cudaSetDevice(h->cfg.device);
     cudaFree(h->p.dyn); cudaFree(h->p.tgt); cudaFree(h->p.obs); cudaFree(h->p.state); cudaFree(h->p.reward);
     cudaFree(h->p.terminated); cudaFree(h->p.win); cudaFree(h->p.target_find); cudaFree(h->p.stats);
-    cudaFree(h->d_tmpl); cudaFree(h->p.prob_map); cudaFree(h->d_actions);
+    cudaFree(h->d_tmpl); cudaFree(h->p.prob_map); cudaFree(h->d_actions); cudaFree(h->d_lut_meta); cudaFree(h->d_lut);
     delete h;
 }
 
@@ -808,6 +920,20 @@ int cs_flight_env_info(const cs_flight* h, int32_t* out4) {
 }
 
 int cs_flight_lanes_per_env(const cs_flight* h) { return h ? h->lpe : CS_ERR_INVALID; }
+
+// test hook (host only, no GPU needed): the heading table's sin/cos for `count` headings
+int cs_debug_heading_lut(int32_t time_limit, const double* h_in, int32_t count, double* sin_out, double* cos_out,
+                         int32_t* from_table) {
+    CS_REQUIRE(h_in && sin_out && cos_out && time_limit >= 1, "cs_debug_heading_lut: bad argument");
+    HeadingLut lut;
+    build_heading_lut(time_limit, &lut);
+    for (int i = 0; i < count; ++i) {
+        int ft = 0;
+        host_heading_sincos(lut, h_in[i], &sin_out[i], &cos_out[i], &ft);
+        if (from_table) from_table[i] = ft;
+    }
+    return (int)lut.tab.size();
+}
 
 int cs_flight_set_target_template(cs_flight* h, const double* rows, int32_t nrows) {
     CS_REQUIRE(h && rows, "cs_flight_set_target_template: null argument");

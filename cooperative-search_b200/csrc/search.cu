@@ -1,14 +1,490 @@
-// placeholder until the search_env kernels land
+// search_env discrete-grid env-step hot path for B200 (sm_100a).
+//
+// Restates (reference: WZN1ng/Cooperative-Search, env/search_env.py):
+//   reset                      :69-183   (agent layouts :146-180; target modes 0/1 :86-104)
+//   _agent_step + step         :246-296  (move, freq_map, 1/freq reward, disc detection)
+//   _update_obs / get_obs      :203-227  ((2R-1)^2 window + raw position)
+//   _update_state / get_state  :186-200  (plane 0 targets (sticky), plane 1 agents)
+//   get_avail_agent_actions    :230-243
+//
+// Design: one CTA (128 threads) per env instance.  Target presence and "not yet found" live as bit
+// rows (one bit per cell) staged in shared memory; detection is an atomicAnd of each agent's disc row
+// masks against the unfound rows (the returned old word says which targets THIS agent found, so
+// simultaneous sightings are counted once); observation windows and the two state planes are emitted
+// with fully coalesced stores straight from the bit rows.  The path is write-bandwidth bound:
+// ~4n((2R-1)^2+2) + 8M^2 bytes per env-step.
+#include <math.h>
+#include <new>
 #include "cs_common.cuh"
-extern "C" {
-int cs_search_create(const cs_search_cfg*, cs_search**) { cs_set_error("search_env not built yet"); return CS_ERR_UNSUPPORTED; }
-void cs_search_destroy(cs_search*) {}
-int cs_search_buffers_get(cs_search*, cs_search_buffers*) { return CS_ERR_UNSUPPORTED; }
-int cs_search_env_info(const cs_search*, int32_t*) { return CS_ERR_UNSUPPORTED; }
-int cs_search_set_targets(cs_search*, const int32_t*, void*) { return CS_ERR_UNSUPPORTED; }
-int cs_search_reset(cs_search*, const uint8_t*, uint32_t, void*) { return CS_ERR_UNSUPPORTED; }
-int cs_search_step(cs_search*, const uint8_t*, void*) { return CS_ERR_UNSUPPORTED; }
-int cs_search_step_random(cs_search*, int32_t, void*) { return CS_ERR_UNSUPPORTED; }
-int cs_search_step_host(cs_search*, const cs_search_host_io*, void*) { return CS_ERR_UNSUPPORTED; }
-int cs_search_stats(cs_search*, double*, void*) { return CS_ERR_UNSUPPORTED; }
+#include "cs_philox.cuh"
+
+namespace {
+
+constexpr int kThreads = 128;
+enum { CNT_FIND = 0, CNT_TIME = 1, CNT_FLAGS = 2, CNT_EPISODE = 3 };
+enum : int { SF_DONE = 1, SF_ILLEGAL = 2 };
+enum { MODE_STEP = 0, MODE_RESET = 1 };
+
+struct SearchParams {
+    int E, n, m, M, R, W;            // W = words per bit row
+    int S, obs_len;                  // S = 2R-1, obs_len = S*S+2
+    int agent_mode, target_mode, auto_reset;
+    uint32_t seed, env_id_base;
+    int32_t* pos;
+    uint32_t* target_bits;
+    uint32_t* unfound_bits;
+    int32_t* freq;
+    int32_t* counters;
+    const int32_t* cells;            // injected target cells [E][m][2] or nullptr
+    float* obs;
+    float* state;
+    uint8_t* avail;
+    float* reward;
+    uint8_t* terminated;
+    int32_t* target_find;
+    double* stats;
+};
+
+struct SearchSmem {
+    uint32_t* tbits;     // [M*W]
+    uint32_t* ubits;     // [M*W]
+    uint32_t* abits;     // [M*W] agent presence
+    int32_t* pos;        // [2n]
+    int32_t* cand;       // [2*kThreads] candidate cells during target placement
+    int* scal;           // [8]
+};
+
+__device__ __forceinline__ SearchSmem carve(const SearchParams& p, unsigned char* raw) {
+    SearchSmem s;
+    const int rows = p.M * p.W;
+    s.tbits = reinterpret_cast<uint32_t*>(raw);
+    s.ubits = s.tbits + rows;
+    s.abits = s.ubits + rows;
+    s.pos = reinterpret_cast<int32_t*>(s.abits + rows);
+    s.cand = s.pos + 2 * p.n;
+    s.scal = s.cand + 2 * kThreads;
+    return s;
 }
+size_t smem_bytes_for(const SearchParams& p) {
+    return sizeof(uint32_t) * (size_t)(3 * p.M * p.W) + sizeof(int32_t) * (size_t)(2 * p.n + 2 * kThreads + 8);
+}
+
+// scal slots
+enum { SC_NEWFOUND = 0, SC_ILLEGAL = 1, SC_GOT = 2, SC_NEXTK = 3 };
+
+// ---- reset of one env by its CTA (search_env.py:69-183, init=False semantics) ------------------------
+__device__ void search_reset(const SearchParams& p, const SearchSmem& s, int e, uint32_t rflags, int32_t* cnt_local) {
+    const int tid = threadIdx.x, M = p.M, W = p.W, n = p.n;
+    const int rows = M * W;
+    const uint32_t env_id = p.env_id_base + (uint32_t)e;
+    const int episode = cnt_local[CNT_EPISODE] + ((rflags & CS_RESET_KEEP_EPISODE) ? 0 : 1);
+    for (int k = tid; k < rows; k += kThreads) { s.tbits[k] = 0; s.abits[k] = 0; }
+    if (tid == 0) { s.scal[SC_GOT] = 0; s.scal[SC_NEXTK] = 0; }
+    __syncthreads();
+    if (rflags & CS_RESET_KEEP_TARGETS) {
+        const int32_t* c = p.cells + (size_t)e * p.m * 2;
+        for (int k = tid; k < p.m; k += kThreads) {
+            const int x = c[2 * k], y = c[2 * k + 1];
+            if (x >= 0 && x < M && y >= 0 && y < M) atomicOr(&s.tbits[x * W + (y >> 5)], 1u << (y & 31));
+        }
+    } else {
+        // Rejection sampling in candidate order k = 0,1,...: candidate k is Philox(env, episode, k) ->
+        // (w0 % M, w1 % M); accepted when the cell is free (mode 1: and in the edge band) -- the accept rule of
+        // search_env.py:86-104.  Philox for a batch of candidates in parallel, acceptance in order by thread 0.
+        const int lo = M / 4, hi = 3 * M / 4;
+        // the reference loops forever when the request cannot be satisfied; bound it (a hung GPU helps nobody)
+        for (int batch = 0; batch < (1 << 14); ++batch) {
+            const int base = s.scal[SC_NEXTK];
+            const cs_u4 w = cs_philox4x32_10(env_id, ((uint32_t)episode & 0xFFFFu) << 16, (uint32_t)(base + tid), 0u, p.seed,
+                                             CS_STREAM_SEARCH);
+            s.cand[2 * tid] = (int)(w.x % (uint32_t)M);
+            s.cand[2 * tid + 1] = (int)(w.y % (uint32_t)M);
+            __syncthreads();
+            if (tid == 0) {
+                int got = s.scal[SC_GOT];
+                for (int k = 0; k < kThreads && got < p.m; ++k) {
+                    const int x = s.cand[2 * k], y = s.cand[2 * k + 1];
+                    const uint32_t bit = 1u << (y & 31);
+                    uint32_t* word = &s.tbits[x * W + (y >> 5)];
+                    if (*word & bit) continue;
+                    if (p.target_mode == 1 && !(x <= lo || x >= hi || y <= lo || y >= hi)) continue;
+                    *word |= bit;
+                    ++got;
+                }
+                s.scal[SC_GOT] = got;
+                s.scal[SC_NEXTK] = base + kThreads;
+            }
+            __syncthreads();
+            if (s.scal[SC_GOT] >= p.m) break;
+        }
+    }
+    __syncthreads();
+    for (int k = tid; k < rows; k += kThreads) s.ubits[k] = s.tbits[k];
+    // agent layouts (:146-180)
+    for (int a = tid; a < n; a += kThreads) {
+        int x, y;
+        if (p.agent_mode == 0) {
+            const int L = (int)ceil(sqrt((double)n)), b = (M - L) / 2;
+            x = b + a / L; y = b + a % L;
+        } else if (p.agent_mode == 1) {
+            const int L = (int)ceil(sqrt((double)n));
+            x = M - 1 - a / L; y = a % L;
+        } else {
+            const int gap = (M - 1) / (n - 1);
+            x = M - 1; y = a * gap;
+        }
+        s.pos[2 * a] = x; s.pos[2 * a + 1] = y;
+        atomicAdd(&p.freq[(size_t)e * M * M + x * M + y], 1);         // freq_map is never cleared (:39 vs :70-80)
+    }
+    if (tid == 0) {
+        cnt_local[CNT_FIND] = 0; cnt_local[CNT_TIME] = 0; cnt_local[CNT_FLAGS] = 0; cnt_local[CNT_EPISODE] = episode;
+    }
+    __syncthreads();
+}
+
+// ---- get_obs / get_state / avail of one env (:186-243) ------------------------------------------------
+__device__ void search_emit(const SearchParams& p, const SearchSmem& s, int e) {
+    const int tid = threadIdx.x, M = p.M, W = p.W, n = p.n, R = p.R, S = p.S;
+    const int rows = M * W;
+    for (int k = tid; k < rows; k += kThreads) s.abits[k] = 0;
+    __syncthreads();
+    for (int a = tid; a < n; a += kThreads) {
+        const int x = s.pos[2 * a], y = s.pos[2 * a + 1];
+        atomicOr(&s.abits[x * W + (y >> 5)], 1u << (y & 31));
+        uint8_t* av = p.avail + ((size_t)e * n + a) * 4;
+        *reinterpret_cast<uchar4*>(av) = make_uchar4(x > 0, y > 0, x < M - 1, y < M - 1);
+    }
+    __syncthreads();
+    // state [M][M][2]: one float2 per cell, plane 0 targets (found ones stay 1), plane 1 agents
+    float2* st = reinterpret_cast<float2*>(p.state + (size_t)e * 2 * M * M);
+    for (int c = tid; c < M * M; c += kThreads) {
+        const int x = c / M, y = c - x * M;
+        const uint32_t sh = y & 31;
+        st[c] = make_float2((float)((s.tbits[x * W + (y >> 5)] >> sh) & 1u), (float)((s.abits[x * W + (y >> 5)] >> sh) & 1u));
+    }
+    // obs [n][S*S+2]
+    float* ob = p.obs + (size_t)e * n * p.obs_len;
+    const int total = n * p.obs_len;
+    const int R2 = R * R;
+    for (int idx = tid; idx < total; idx += kThreads) {
+        const int a = idx / p.obs_len, k = idx - a * p.obs_len;
+        const int x = s.pos[2 * a], y = s.pos[2 * a + 1];
+        float v;
+        if (k >= S * S) {
+            v = (float)(k == S * S ? x : y);                            // raw integer position (:205-208)
+        } else {
+            const int i = k / S, j = k - i * S;
+            const int gx = i + x - R + 1, gy = j + y - R + 1;
+            const int di = R - 1 - i, dj = R - 1 - j;
+            if (gx < 0 || gx >= M || gy < 0 || gy >= M || di * di + dj * dj > R2) v = 0.5f;     // (:220-226)
+            else v = (float)((s.tbits[gx * W + (gy >> 5)] >> (gy & 31)) & 1u);
+        }
+        ob[idx] = v;
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) search_kernel(const SearchParams p, const uint8_t* __restrict__ actions,
+                                                          const uint8_t* __restrict__ mask, uint32_t rflags, int random_policy) {
+    extern __shared__ __align__(16) unsigned char raw[];
+    __shared__ int32_t cnt[4];
+    __shared__ double s_red[kThreads / 32];
+    const SearchSmem s = carve(p, raw);
+    const int tid = threadIdx.x, e = blockIdx.x, M = p.M, W = p.W, n = p.n;
+    const int rows = M * W;
+    const uint32_t env_id = p.env_id_base + (uint32_t)e;
+    if (MODE == MODE_RESET && mask != nullptr && mask[e] == 0) return;
+
+    if (tid < 4) cnt[tid] = p.counters[(size_t)e * 4 + tid];
+    if (tid == 0) { s.scal[SC_NEWFOUND] = 0; s.scal[SC_ILLEGAL] = 0; }
+    {
+        const uint32_t* gt = p.target_bits + (size_t)e * rows;
+        const uint32_t* gu = p.unfound_bits + (size_t)e * rows;
+        for (int k = tid; k < rows; k += kThreads) { s.tbits[k] = gt[k]; s.ubits[k] = gu[k]; }
+        const int32_t* gp = p.pos + (size_t)e * 2 * n;
+        for (int k = tid; k < 2 * n; k += kThreads) s.pos[k] = gp[k];
+    }
+    __syncthreads();
+
+    bool emit = false, bits_dirty = false;
+    if (MODE == MODE_STEP) {
+        bool done = (cnt[CNT_FLAGS] & SF_DONE) != 0;
+        float rew_out = 0.f;
+        if (!done) {
+            int32_t* fq = p.freq + (size_t)e * M * M;
+            const int t1 = cnt[CNT_TIME] + 1;
+            // ---- _agent_step (:280-296)
+            for (int a = tid; a < n; a += kThreads) {
+                int x = s.pos[2 * a], y = s.pos[2 * a + 1];
+                int act;
+                if (!random_policy) {
+                    act = actions[(size_t)e * n + a];
+                } else {
+                    const cs_u4 w = cs_philox4x32_10(env_id, (((uint32_t)cnt[CNT_EPISODE] & 0xFFFFu) << 16) | ((uint32_t)t1 & 0xFFFFu),
+                                                     (uint32_t)(a >> 2), 0u, p.seed, CS_STREAM_POLICY);
+                    const int av0 = x > 0, av1 = y > 0, av2 = x < M - 1, av3 = y < M - 1;
+                    int pick = (int)(cs_word(w, a & 3) % (uint32_t)(av0 + av1 + av2 + av3));
+                    act = 0;
+                    if (av0) { if (pick == 0) act = 0; --pick; }
+                    if (av1 && pick >= 0) { if (pick == 0) act = 1; --pick; }
+                    if (av2 && pick >= 0) { if (pick == 0) act = 2; --pick; }
+                    if (av3 && pick >= 0) { if (pick == 0) act = 3; --pick; }
+                }
+                bool ok = true;
+                if (act == 0 && x > 0) x -= 1;
+                else if (act == 1 && y > 0) y -= 1;
+                else if (act == 2 && x < M - 1) x += 1;
+                else if (act == 3 && y < M - 1) y += 1;
+                else ok = false;                                    // reference raises (:293): flag, agent stays
+                if (ok) {
+                    s.pos[2 * a] = x; s.pos[2 * a + 1] = y;
+                    atomicAdd(&fq[x * M + y], 1);
+                } else {
+                    atomicOr(&s.scal[SC_ILLEGAL], 1);
+                }
+            }
+            __syncthreads();
+            // ---- reward: sum_i 1/freq[p_i] in fp64 (:257-259)
+            double part = 0.0;
+            for (int a = tid; a < n; a += kThreads) part += 1.0 / (double)__ldcg(&fq[s.pos[2 * a] * M + s.pos[2 * a + 1]]);
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            if ((tid & 31) == 0) s_red[tid >> 5] = part;
+            // ---- detection: disc rows of every agent against the unfound bit rows (:261-267)
+            const int R = p.R, R2 = R * R, span = 2 * R + 1;
+            for (int task = tid; task < n * span; task += kThreads) {
+                const int a = task / span, dx = task - a * span - R;
+                const int x = s.pos[2 * a] + dx;
+                if (x < 0 || x >= M) continue;
+                int w = 0;
+                while ((w + 1) * (w + 1) + dx * dx <= R2) ++w;      // half width of the disc row: dy^2 <= R^2 - dx^2
+                const int y0 = max(0, s.pos[2 * a + 1] - w), y1 = min(M - 1, s.pos[2 * a + 1] + w);
+                for (int wd = y0 >> 5; wd <= (y1 >> 5); ++wd) {
+                    const int lo = max(y0, wd * 32) - wd * 32, hi = min(y1, wd * 32 + 31) - wd * 32;
+                    const uint32_t m = (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
+                    if (s.ubits[x * W + wd] & m) {
+                        const uint32_t old = atomicAnd(&s.ubits[x * W + wd], ~m);
+                        const int c = __popc(old & m);
+                        if (c) atomicAdd(&s.scal[SC_NEWFOUND], c);
+                    }
+                }
+            }
+            __syncthreads();
+            const int newf = s.scal[SC_NEWFOUND];
+            double fsum = 0.0;
+            for (int k = 0; k < kThreads / 32; ++k) fsum += s_red[k];
+            const int found = cnt[CNT_FIND] + newf;
+            const bool term = found >= p.m;                                  // (:270-271)
+            rew_out = (float)(-1.0 + fsum + 10.0 * (double)newf);            // MOVE_COST + freq + REWARD_FIND (:250-265)
+            __syncthreads();
+            if (tid == 0) {
+                cnt[CNT_FIND] = found;
+                cnt[CNT_TIME] = t1;
+                cnt[CNT_FLAGS] |= (term ? SF_DONE : 0) | (s.scal[SC_ILLEGAL] ? SF_ILLEGAL : 0);
+                atomicAdd(p.stats + CS_STAT_ENV_STEPS, 1.0);
+                if (s.scal[SC_ILLEGAL]) atomicAdd(p.stats + CS_STAT_ILLEGAL, 1.0);
+                if (term) {
+                    atomicAdd(p.stats + CS_STAT_EPISODES, 1.0);
+                    atomicAdd(p.stats + CS_STAT_TARGETS_FOUND, (double)found);
+                    atomicAdd(p.stats + CS_STAT_WINS, 1.0);
+                    atomicAdd(p.stats + CS_STAT_EP_LEN, (double)t1);
+                }
+                p.reward[e] = rew_out;
+                p.terminated[e] = term ? 1 : 0;
+                p.target_find[e] = found;
+            }
+            done = term;
+            emit = true;
+            bits_dirty = true;
+            __syncthreads();
+        } else if (tid == 0) {
+            p.reward[e] = 0.f;
+            p.terminated[e] = 1;
+        }
+        if (p.auto_reset && done) {
+            search_reset(p, s, e, 0u, cnt);
+            emit = true;
+            bits_dirty = true;
+        }
+    } else {
+        search_reset(p, s, e, rflags, cnt);
+        emit = true;
+        bits_dirty = true;
+        if (tid == 0) {
+            p.reward[e] = 0.f;
+            p.terminated[e] = 0;
+            p.target_find[e] = 0;
+        }
+    }
+    if (!emit) return;
+    __syncthreads();
+    if (bits_dirty) {
+        uint32_t* gt = p.target_bits + (size_t)e * rows;
+        uint32_t* gu = p.unfound_bits + (size_t)e * rows;
+        for (int k = tid; k < rows; k += kThreads) { gt[k] = s.tbits[k]; gu[k] = s.ubits[k]; }
+        int32_t* gp = p.pos + (size_t)e * 2 * n;
+        for (int k = tid; k < 2 * n; k += kThreads) gp[k] = s.pos[k];
+        if (tid < 4) p.counters[(size_t)e * 4 + tid] = cnt[tid];
+    }
+    search_emit(p, s, e);
+}
+
+}  // namespace
+
+struct cs_search {
+    cs_search_cfg cfg;
+    SearchParams p;
+    size_t smem_bytes;
+    int32_t* d_cells;
+    uint8_t* d_actions;
+};
+
+namespace {
+cudaError_t launch_search(cs_search* h, int mode, const uint8_t* actions, const uint8_t* mask, uint32_t rflags,
+                          int random_policy, cudaStream_t st) {
+    if (mode == MODE_STEP)
+        search_kernel<MODE_STEP><<<h->p.E, kThreads, h->smem_bytes, st>>>(h->p, actions, mask, rflags, random_policy);
+    else
+        search_kernel<MODE_RESET><<<h->p.E, kThreads, h->smem_bytes, st>>>(h->p, actions, mask, rflags, random_policy);
+    cs_count_launch(1);
+    return cudaGetLastError();
+}
+}  // namespace
+
+extern "C" {
+
+int cs_search_create(const cs_search_cfg* cfg, cs_search** out) {
+    CS_REQUIRE(cfg && out, "cs_search_create: null argument");
+    CS_REQUIRE(cfg->struct_size == sizeof(cs_search_cfg), "cs_search_create: cfg.struct_size %u != %zu (ABI mismatch)",
+               cfg->struct_size, sizeof(cs_search_cfg));
+    CS_REQUIRE(cfg->num_envs > 0, "num_envs must be > 0");
+    CS_REQUIRE(cfg->n_agents >= 1 && cfg->n_agents <= 4096, "n_agents out of range");
+    CS_REQUIRE(cfg->map_size >= 2 && cfg->map_size <= 1024, "map_size out of range");
+    CS_REQUIRE(cfg->view_range >= 1 && cfg->view_range <= 64, "view_range out of range");
+    CS_REQUIRE(cfg->target_num >= 1 && cfg->target_num <= cfg->map_size * cfg->map_size, "target_num must fit the grid");
+    CS_REQUIRE(cfg->agent_mode >= 0 && cfg->agent_mode <= 2, "Unknown agent mode");          // search_env.py:180
+    CS_REQUIRE(cfg->target_mode == 0 || cfg->target_mode == 1, "Unknown target mode");        // :143 (modes 2,3: inject cells)
+    CS_REQUIRE(cfg->agent_mode != 2 || cfg->n_agents >= 2, "agent_mode 2 divides by n_agents-1 (search_env.py:171)");
+    {
+        const int L = (int)ceil(sqrt((double)cfg->n_agents));
+        CS_REQUIRE(cfg->agent_mode == 2 || L <= cfg->map_size, "agents do not fit the map");
+    }
+    cs_search* h = new (std::nothrow) cs_search();
+    if (!h) { cs_set_error("out of host memory"); return CS_ERR_NOMEM; }
+    memset(h, 0, sizeof(*h));
+    h->cfg = *cfg;
+    CS_CUDA(cudaSetDevice(cfg->device));
+    SearchParams& p = h->p;
+    p.E = cfg->num_envs; p.n = cfg->n_agents; p.m = cfg->target_num; p.M = cfg->map_size; p.R = cfg->view_range;
+    p.W = (p.M + 31) / 32; p.S = 2 * p.R - 1; p.obs_len = p.S * p.S + 2;
+    p.agent_mode = cfg->agent_mode; p.target_mode = cfg->target_mode; p.auto_reset = cfg->auto_reset;
+    p.seed = cfg->seed; p.env_id_base = cfg->env_id_base;
+    h->smem_bytes = smem_bytes_for(p);
+    CS_REQUIRE(h->smem_bytes <= 200 * 1024, "map too large for the shared-memory bit rows");
+    CS_CUDA(cudaFuncSetAttribute(search_kernel<MODE_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    CS_CUDA(cudaFuncSetAttribute(search_kernel<MODE_RESET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    const size_t E = (size_t)p.E, rows = (size_t)p.M * p.W, MM = (size_t)p.M * p.M;
+#define CS_ALLOC0(ptr, bytes)                                   \
+    CS_CUDA(cudaMalloc(reinterpret_cast<void**>(&(ptr)), (bytes))); \
+    CS_CUDA(cudaMemset((ptr), 0, (bytes)))
+    CS_ALLOC0(p.pos, E * 2 * p.n * sizeof(int32_t));
+    CS_ALLOC0(p.target_bits, E * rows * sizeof(uint32_t));
+    CS_ALLOC0(p.unfound_bits, E * rows * sizeof(uint32_t));
+    CS_ALLOC0(p.freq, E * MM * sizeof(int32_t));
+    CS_ALLOC0(p.counters, E * 4 * sizeof(int32_t));
+    CS_ALLOC0(p.obs, E * p.n * p.obs_len * sizeof(float));
+    CS_ALLOC0(p.state, E * 2 * MM * sizeof(float));
+    CS_ALLOC0(p.avail, E * p.n * 4);
+    CS_ALLOC0(p.reward, E * sizeof(float));
+    CS_ALLOC0(p.terminated, E);
+    CS_ALLOC0(p.target_find, E * sizeof(int32_t));
+    CS_ALLOC0(p.stats, CS_NUM_STATS * sizeof(double));
+    CS_ALLOC0(h->d_actions, E * p.n);
+#undef CS_ALLOC0
+    // episode counter starts at -1 so that the first reset opens episode 0
+    CS_CUDA(cudaMemset2D(p.counters + CNT_EPISODE, 4 * sizeof(int32_t), 0xFF, sizeof(int32_t), E));
+    *out = h;
+    return CS_OK;
+}
+
+void cs_search_destroy(cs_search* h) {
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    SearchParams& p = h->p;
+    cudaFree(p.pos); cudaFree(p.target_bits); cudaFree(p.unfound_bits); cudaFree(p.freq); cudaFree(p.counters);
+    cudaFree(p.obs); cudaFree(p.state); cudaFree(p.avail); cudaFree(p.reward); cudaFree(p.terminated);
+    cudaFree(p.target_find); cudaFree(p.stats); cudaFree(h->d_cells); cudaFree(h->d_actions);
+    delete h;
+}
+
+int cs_search_buffers_get(cs_search* h, cs_search_buffers* b) {
+    CS_REQUIRE(h && b, "cs_search_buffers_get: null argument");
+    const SearchParams& p = h->p;
+    b->pos = p.pos; b->target_bits = p.target_bits; b->unfound_bits = p.unfound_bits; b->freq = p.freq;
+    b->counters = p.counters; b->words_per_row = p.W; b->obs = p.obs; b->state = p.state; b->avail = p.avail;
+    b->reward = p.reward; b->terminated = p.terminated; b->target_find = p.target_find; b->stats = p.stats;
+    return CS_OK;
+}
+
+int cs_search_env_info(const cs_search* h, int32_t* out4) {
+    CS_REQUIRE(h && out4, "cs_search_env_info: null argument");
+    out4[0] = 4;                                   // n_actions      (search_env.py:62)
+    out4[1] = 2 * h->p.M * h->p.M;                 // state_shape    (:63)
+    out4[2] = h->p.obs_len;                        // obs_shape      (:64)
+    out4[3] = 500;                                 // episode_limit  (:65)
+    return CS_OK;
+}
+
+int cs_search_set_targets(cs_search* h, const int32_t* d_cells, void* stream) {
+    CS_REQUIRE(h && d_cells, "cs_search_set_targets: null argument");
+    CS_CUDA(cudaSetDevice(h->cfg.device));
+    const size_t bytes = (size_t)h->p.E * h->p.m * 2 * sizeof(int32_t);
+    if (!h->d_cells) CS_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->d_cells), bytes));
+    CS_CUDA(cudaMemcpyAsync(h->d_cells, d_cells, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    h->p.cells = h->d_cells;
+    return CS_OK;
+}
+
+int cs_search_reset(cs_search* h, const uint8_t* d_mask, uint32_t flags, void* stream) {
+    CS_REQUIRE(h, "cs_search_reset: null handle");
+    CS_REQUIRE(!(flags & CS_RESET_KEEP_TARGETS) || h->p.cells, "CS_RESET_KEEP_TARGETS needs cs_search_set_targets first");
+    CS_CUDA(launch_search(h, MODE_RESET, nullptr, d_mask, flags, 0, (cudaStream_t)stream));
+    return CS_OK;
+}
+
+int cs_search_step(cs_search* h, const uint8_t* d_actions, void* stream) {
+    CS_REQUIRE(h && d_actions, "cs_search_step: null argument");
+    CS_CUDA(launch_search(h, MODE_STEP, d_actions, nullptr, 0u, 0, (cudaStream_t)stream));
+    return CS_OK;
+}
+
+int cs_search_step_random(cs_search* h, int32_t k, void* stream) {
+    CS_REQUIRE(h && k >= 0, "cs_search_step_random: bad argument");
+    for (int i = 0; i < k; ++i) CS_CUDA(launch_search(h, MODE_STEP, nullptr, nullptr, 0u, 1, (cudaStream_t)stream));
+    return CS_OK;
+}
+
+int cs_search_step_host(cs_search* h, const cs_search_host_io* io, void* stream) {
+    CS_REQUIRE(h && io && io->actions, "cs_search_step_host: null argument");
+    const SearchParams& p = h->p;
+    const size_t E = (size_t)p.E;
+    cudaStream_t st = (cudaStream_t)stream;
+    CS_CUDA(cudaSetDevice(h->cfg.device));
+    CS_CUDA(cudaMemcpyAsync(h->d_actions, io->actions, E * p.n, cudaMemcpyHostToDevice, st));
+    CS_CUDA(launch_search(h, MODE_STEP, h->d_actions, nullptr, 0u, 0, st));
+    if (io->reward) CS_CUDA(cudaMemcpyAsync(io->reward, p.reward, E * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (io->terminated) CS_CUDA(cudaMemcpyAsync(io->terminated, p.terminated, E, cudaMemcpyDeviceToHost, st));
+    if (io->obs) CS_CUDA(cudaMemcpyAsync(io->obs, p.obs, E * p.n * p.obs_len * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (io->state) CS_CUDA(cudaMemcpyAsync(io->state, p.state, E * 2 * p.M * p.M * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (io->avail) CS_CUDA(cudaMemcpyAsync(io->avail, p.avail, E * p.n * 4, cudaMemcpyDeviceToHost, st));
+    CS_CUDA(cudaStreamSynchronize(st));
+    return CS_OK;
+}
+
+int cs_search_stats(cs_search* h, double* h_out, void* stream) {
+    CS_REQUIRE(h && h_out, "cs_search_stats: null argument");
+    CS_CUDA(cudaMemcpyAsync(h_out, h->p.stats, CS_NUM_STATS * sizeof(double), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return CS_OK;
+}
+
+}  // extern "C"

@@ -71,6 +71,11 @@ int cs_flight_lanes_per_env(const struct cs_flight* env);
 /* test hook: d_in6 [count][6] = Philox counter(4) + key(2) -> d_out4 [count][4] words */
 int cs_debug_philox(const uint32_t* d_in6, uint32_t* d_out4, int32_t count, void* stream);
 
+/* test hook, host only: evaluates the heading trig table (csrc/flight.cu: heading_sincos) a handle with this
+ * time_limit would use; returns the number of table entries.  from_table[i] = 0 where the fallback is used. */
+int cs_debug_heading_lut(int32_t time_limit, const double* h_in, int32_t count, double* sin_out, double* cos_out,
+                         int32_t* from_table);
+
 /* Pinned host memory for the *_host entry points. */
 int cs_host_alloc(void** out, uint64_t bytes);
 int cs_host_free(void* p);

@@ -1,0 +1,101 @@
+"""GPU parity of the flight (probability-map) variant: reference goldens + C oracle.
+
+Map bar: rtol 1e-5, atol 1e-37 against the float64 reference cast to float32 (north_star tolerance;
+SURVEY.md section 7 hard part 2).  Everything discrete is bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+import golden_util as gu
+from oracle import c_oracle
+from oracle.py_envs import FlightSpec
+from test_gpu_flight_easy import make_args, cpu
+
+pytestmark = pytest.mark.gpu
+MAP_RTOL, MAP_ATOL = 1e-5, 1e-37
+
+
+def assert_map_close(got, want, msg=""):
+    want32 = want.astype(np.float32)
+    np.testing.assert_allclose(got, want32, rtol=MAP_RTOL, atol=MAP_ATOL, err_msg=msg)
+
+
+@pytest.mark.parametrize("name", gu.FLIGHT_FIXTURES)
+def test_flight_matches_reference_golden(name):
+    import coopsearch_b200 as cs
+    g = gu.load(name)
+    kw, base, seed = gu.flight_spec_kwargs(g, "probmap")
+    T, E = g["reward"].shape
+    n, M = kw["n_agents"], kw["map_size"]
+    env = cs.VecFlightEnv(make_args(kw), None, num_envs=E, seed=seed, env_id_base=base, count_touched=True, reset=False)
+    env.reset(init=True, targets=g["tgt_xy"])
+    assert_map_close(cpu(env.prob_map), g["init_map"], "init map")
+    assert np.array_equal(cpu(env.found_mask).astype(np.uint32), g["init_found"])
+    for t in range(T):
+        r, term, win = env.step(g["actions"][t])
+        where = "%s step %d" % (name, t)
+        assert np.array_equal(cpu(env.found_mask).astype(np.uint32), g["found"][t]), where
+        assert np.array_equal(cpu(r), g["reward"][t].astype(np.float32)), where
+        assert np.array_equal(cpu(term), g["terminated"][t]), where
+        assert np.array_equal(cpu(win), g["win"][t]), where
+        np.testing.assert_allclose(cpu(env.agent_xy), g["xy"][t], rtol=0, atol=1e-9, err_msg=where)
+        if (t + 1) in g["map_steps"]:
+            k = list(g["map_steps"]).index(t + 1)
+            assert_map_close(cpu(env.prob_map), g["maps"][k], where)
+    assert_map_close(cpu(env.prob_map), g["final_map"], "final map")
+    # reference-shaped observation: map replicated per agent || 4 features (flight_env.py:223-230)
+    full = cpu(env.get_obs())
+    assert full.shape == (E, n, M * M + 4)
+    for a in range(n):
+        assert np.array_equal(full[:, a, :M * M], cpu(env.prob_map).reshape(E, -1))
+    assert np.array_equal(full[:, :, M * M:], cpu(env.get_obs(full=False)))
+    # second episode: reset() without init keeps the map (flight_env.py:84-86)
+    env.reset(init=False, targets=g["ep2_tgt_xy"])
+    for t in range(g["ep2_actions"].shape[0]):
+        r, _, _ = env.step(g["ep2_actions"][t])
+        assert np.array_equal(cpu(env.found_mask).astype(np.uint32), g["ep2_found"][t])
+        assert np.array_equal(cpu(r), g["ep2_reward"][t].astype(np.float32))
+    assert_map_close(cpu(env.prob_map), g["ep2_map"], "second-episode map")
+
+
+@pytest.mark.parametrize("n_agents,agent_mode,map_size,view_range", [(3, 0, 50, 7), (5, 1, 30, 5), (2, 3, 64, 9), (4, 2, 17, 3)])
+def test_flight_matches_c_oracle(n_agents, agent_mode, map_size, view_range):
+    """Fresh seeded inputs, device-drawn targets, two episodes with auto-reset, touched-cell count."""
+    import coopsearch_b200 as cs
+    E, T, seed, base = 48, 130, 21, 9000
+    spec = FlightSpec(n_agents=n_agents, agent_mode=agent_mode, map_size=map_size, view_range=view_range,
+                      time_limit=100, variant="probmap")
+    env = cs.VecFlightEnv(make_args(dict(spec.__dict__)), gu.TEMPLATE, num_envs=E, seed=seed, env_id_base=base,
+                          auto_reset=True, count_touched=True)
+    orc = c_oracle.FlightBatch(spec, gu.TEMPLATE, seed, base, E, auto_reset=True)
+    orc.reset(init=True)
+    actions = np.random.default_rng(3).integers(0, 3, size=(T, E, n_agents), dtype=np.uint8)
+    assert_map_close(cpu(env.prob_map), orc.map, "after reset")
+    for t in range(T):
+        r, term, win = env.step(actions[t])
+        orr, ot, ow = orc.step(actions[t])
+        where = "step %d" % t
+        assert np.array_equal(cpu(env.found_mask).astype(np.uint32), orc.found), where
+        assert np.array_equal(cpu(r), orr.astype(np.float32)), where
+        assert np.array_equal(cpu(term), ot) and np.array_equal(cpu(win), ow), where
+        assert np.array_equal(cpu(env.time_step), orc.time_step.astype(np.int32)), where
+        if t % 10 == 9 or t == T - 1:
+            assert_map_close(cpu(env.prob_map), orc.map, where)
+            np.testing.assert_allclose(cpu(env.agent_xy), orc.xy, rtol=0, atol=1e-9, err_msg=where)
+    assert env.stats()["map_cells_touched"] == float(orc.touched[0])
+
+
+def test_partial_reset_keeps_other_maps():
+    import coopsearch_b200 as cs
+    spec = FlightSpec(n_agents=3, variant="probmap")
+    env = cs.VecFlightEnv(make_args(dict(spec.__dict__)), gu.TEMPLATE, num_envs=6, seed=5)
+    env.step_random(20)
+    before = env.prob_map.clone()
+    mask = torch.tensor([0, 1, 0, 0, 1, 0], dtype=torch.uint8, device="cuda")
+    env.reset(init=True, mask=mask)
+    after = env.prob_map
+    for e in (0, 2, 3, 5):
+        assert torch.equal(after[e], before[e])
+    for e in (1, 4):
+        assert not torch.equal(after[e], before[e])
+        assert float(after[e].max()) <= 1.0 and float((after[e] == 0.5).float().mean()) > 0.5
