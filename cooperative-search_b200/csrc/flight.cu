@@ -192,6 +192,19 @@ __device__ __forceinline__ uint32_t fl_move(const FlightParams& p, double* S, in
     return outbits;
 }
 
+// Integer corner coordinates c with fl((c - a)^2) < R^2 -- a necessary condition for a corner in that
+// row/column to be inside the agent's disc, evaluated with the SAME floating-point expression as the corner test
+// (an agent at x = 1.0000000000000004 has corner x = 4 inside although fl(x + 3) = 4.0; bounds derived from
+// floor/ceil of a +- R alone lose such corners).  Returns [lo, hi], at most 2R wide.
+__device__ __forceinline__ void corner_span(double a, double R, double R2, int* lo, int* hi) {
+    int c = (int)floor(a - R);
+    double d = (double)c - a;
+    *lo = (d * d < R2) ? c : c + 1;
+    c = (int)ceil(a + R);
+    d = (double)c - a;
+    *hi = (d * d < R2) ? c : c - 1;
+}
+
 // ------------------------------------------------------------------------------------------------
 // belief map: _update_prob_map + _percent_in_agent_viewrange (env/flight_env.py:275-303), warp per env
 // ------------------------------------------------------------------------------------------------
@@ -202,10 +215,13 @@ __device__ __forceinline__ unsigned fl_probmap(const FlightParams& p, double* S,
     const double* T = S + p.s_tgt;
     for (int a = lane; a < n; a += 32) {
         const double ax = S[2 * a], ay = S[2 * a + 1];
-        box[4 * a + 0] = max(0, (int)floor(ax - p.R));
-        box[4 * a + 1] = min(M - 1, (int)ceil(ax + p.R) - 1);
-        box[4 * a + 2] = max(0, (int)floor(ay - p.R));
-        box[4 * a + 3] = min(M - 1, (int)ceil(ay + p.R) - 1);
+        int lo, hi;
+        corner_span(ax, p.R, p.R2, &lo, &hi);
+        box[4 * a + 0] = max(0, lo - 1);          // cell i has corners i and i+1
+        box[4 * a + 1] = min(M - 1, hi);
+        corner_span(ay, p.R, p.R2, &lo, &hi);
+        box[4 * a + 2] = max(0, lo - 1);
+        box[4 * a + 3] = min(M - 1, hi);
     }
     const int nh = __popc(newf);
     if (lane < p.m && ((newf >> lane) & 1u)) {

@@ -23,12 +23,12 @@ def test_c2_flight_easy_3a_4096_envs_bit_exact():
     import coopsearch_b200 as cs
     E, T, seed, base = 4096, 200, 42, 0
     spec = FlightSpec(n_agents=3, agent_mode=0, target_mode=0)
-    env = cs.VecFlightEasyEnv(make_args(dict(spec.__dict__)), gu.TEMPLATE, num_envs=E, seed=seed, env_id_base=base)
+    env = cs.VecFlightEasyEnv(make_args(dict(spec.__dict__)), gu.TEMPLATE, num_envs=E, seed=seed, env_id_base=base, reset=False)
     c_oracle.set_threads(8)
     orc = c_oracle.FlightBatch(spec, gu.TEMPLATE, seed, base, E)
     orc.reset(init=True)
-    # inject the oracle's libm-drawn targets so both sides start from identical float64 coordinates
-    env.reset(init=True, targets=orc.tgt, keep_episode=False)
+    # inject the oracle's libm-drawn targets so both sides start from identical float64 coordinates (episode 0 on both)
+    env.reset(init=True, targets=orc.tgt)
     actions = np.random.default_rng(1234).integers(0, 3, size=(T, E, 3), dtype=np.uint8)
     dact = torch.from_numpy(actions).cuda()
     for t in range(T):

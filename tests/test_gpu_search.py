@@ -1,5 +1,5 @@
 """GPU parity of the search_env CUDA path: reference goldens + C oracle.  Everything here is
-integer-valued except the 1/freq reward (rtol 1e-6 after the float32 cast)."""
+integer-valued except the 1/freq reward (north_star: 1e-5 relative; atol 1e-6 because -1 + sum(1/freq) can cancel to ~1e-17)."""
 import types
 
 import numpy as np
@@ -49,7 +49,7 @@ def test_search_matches_reference_golden(name):
         assert np.array_equal(cpu(env.get_avail_actions()), g["avail"][t]), where
         r, term, info = env.step(g["actions"][t])
         assert info == ''
-        np.testing.assert_allclose(cpu(r), g["reward"][t].astype(np.float32), rtol=1e-6, atol=0, err_msg=where)
+        np.testing.assert_allclose(cpu(r), g["reward"][t].astype(np.float32), rtol=1e-5, atol=1e-6, err_msg=where)
         assert np.array_equal(cpu(term), g["terminated"][t]), where
         assert np.array_equal(cpu(env.target_find), g["target_find"][t]), where
         assert np.array_equal(cpu(env.agent_pos), g["pos"][t]), where
@@ -79,7 +79,7 @@ def test_search_matches_c_oracle(n, m, M, R, am, tm):
         r, term, _ = env.step_random(1)
         orr, ot = orc.step(None)
         assert np.array_equal(cpu(env.agent_pos), orc.pos), where
-        np.testing.assert_allclose(cpu(r), orr.astype(np.float32), rtol=1e-6, atol=0, err_msg=where)
+        np.testing.assert_allclose(cpu(r), orr.astype(np.float32), rtol=1e-5, atol=1e-6, err_msg=where)
         assert np.array_equal(cpu(term), ot), where
         assert np.array_equal(cpu(env.target_find), orc.counters[:, 0]), where
         if t % 15 == 0 or t == T - 1:
