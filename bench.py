@@ -239,14 +239,15 @@ def _cpu_model():
 # ----------------------------------------------------------------------------------------------------------------
 def make_envs(cs, w, device, rank, seed=42, count_touched=False):
     envs = []
+    lpe = int(os.environ.get("CS_BENCH_LPE", "0"))      # tuning sweeps only; 0 = the library's own choice
     for b in range(w["batches"]):
         base = (rank * w["batches"] + b) * w["envs"]
         if w["kind"] == "flight_easy":
             e = cs.VecFlightEasyEnv(flight_args("flight_easy", w["n"], w["am"]), TEMPLATE, num_envs=w["envs"], device=device,
-                                    seed=seed, env_id_base=base, auto_reset=True)
+                                    seed=seed, env_id_base=base, auto_reset=True, lanes_per_env=lpe)
         elif w["kind"] == "flight":
             e = cs.VecFlightEnv(flight_args("flight", w["n"], w["am"]), TEMPLATE, num_envs=w["envs"], device=device, seed=seed,
-                                env_id_base=base, auto_reset=True, count_touched=count_touched)
+                                env_id_base=base, auto_reset=True, count_touched=count_touched, lanes_per_env=lpe)
         else:
             e = cs.VecSearchEnv(search_args(), num_envs=w["envs"], device=device, seed=seed, env_id_base=base, auto_reset=True)
         envs.append(e)

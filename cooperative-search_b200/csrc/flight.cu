@@ -26,7 +26,7 @@ namespace {
 
 constexpr int kThreads = 128;
 
-enum : uint32_t { SLOT_EMIT = 1u, SLOT_TGT_DIRTY = 2u };
+enum : uint32_t { SLOT_EMIT = 1u, SLOT_TGT_DIRTY = 2u, SLOT_MAP_PENDING = 4u, SLOT_RESULT = 8u };
 
 struct FlightParams {
     int E, n, m, M, T;
@@ -35,6 +35,9 @@ struct FlightParams {
     int rec, yaw_off, meta_off, state_len;
     // shared-memory slot geometry (doubles)
     int s_tgt, s_cs, s_out, s_res, s_am, s_box, s_hit, s_stride;
+    int s_warp;                  // doubles of shared memory per warp (EPW slots + corner-row masks)
+    int span_cap;                // power of two >= 2R: corner rows per agent in the interval pass
+    uint32_t mg_rec2, mg_m, mg_state, mg_obs;   // ceil(2^32/d) for the staging loops' index splits
     double Md, half_M, inv_half, R, R2, v, fk, fd2, near2, q_miss;
     double turn, pi, two_pi, three_pi, half_pi;
     long long thr;
@@ -82,6 +85,8 @@ __device__ __forceinline__ uint32_t* slot_meta(const FlightParams& p, double* S)
 // the pair up (one 16-byte load) -- bit-identical to the reference and cheaper than evaluating sincos().
 // Off-lattice headings (user-injected state) fall back to CUDA's sincos (<= 2 ulp).
 // ------------------------------------------------------------------------------------------------
+__device__ __noinline__ void offlattice_sincos(double h, double* sn, double* c) { sincos(h, sn, c); }
+
 __device__ __forceinline__ void heading_sincos(const FlightParams& p, double h, double* sn, double* c) {
     const int k = __double2int_rn(h * p.inv_turn);
     if (k == 0 && fabs(h) < 7.450580596923828e-09) {   // |h| < 2^-27: libm returns sin = h, cos = 1
@@ -100,7 +105,7 @@ __device__ __forceinline__ void heading_sincos(const FlightParams& p, double h, 
             return;
         }
     }
-    sincos(h, sn, c);
+    offlattice_sincos(h, sn, c);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -122,6 +127,35 @@ __device__ __forceinline__ uint32_t fl_wall(const FlightParams& p, double* S, in
     S[2 * a] = x;
     S[2 * a + 1] = y;
     return outside ? 1u : 0u;
+}
+
+// Repulsion slow path: the reference's sequential, in-place update -- agent k sees its own OLD position and the
+// already-moved j<k (env/flight_env_easy.py:271,:293-301).  Out of line: rare, and keeps the hot path compact.
+__device__ __noinline__ uint32_t fl_move_coupled(const FlightParams& p, double* S) {
+    const int n = p.n;
+    const double* cs = S + p.s_cs;
+    uint32_t outbits = 0;
+    for (int k = 0; k < n; ++k) {
+        const double x0 = S[2 * k], y0 = S[2 * k + 1];
+        double x = x0 + p.v * cs[k];
+        double y = y0 + p.v * cs[n + k];
+        double fx = 0.0, fy = 0.0;
+        for (int q = 0; q < n; ++q) {
+            if (q == k) continue;
+            const double xa = S[2 * q], ya = S[2 * q + 1];
+            const double ax = xa - x0, ay = ya - y0;
+            if (ax * ax + ay * ay < p.fd2 && (xa != x0 || ya != y0)) {
+                const double ex = x0 - xa, ey = y0 - ya;
+                const double r2 = ex * ex + ey * ey;
+                fx += p.fk * ex / r2;
+                fy += p.fk * ey / r2;
+            }
+        }
+        x += fx;
+        y += fy;
+        outbits |= fl_wall(p, S, k, x, y) << k;
+    }
+    return outbits;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -166,27 +200,7 @@ __device__ __forceinline__ uint32_t fl_move(const FlightParams& p, double* S, in
             outbits |= fl_wall(p, S, a, x, y) << a;
         }
     } else if (lane == 0) {
-        // sequential, in place: agent k sees its own OLD position and the already-moved j<k (:271,:293-301)
-        for (int k = 0; k < n; ++k) {
-            const double x0 = S[2 * k], y0 = S[2 * k + 1];
-            double x = x0 + p.v * cs[k];
-            double y = y0 + p.v * cs[n + k];
-            double fx = 0.0, fy = 0.0;
-            for (int q = 0; q < n; ++q) {
-                if (q == k) continue;
-                const double xa = S[2 * q], ya = S[2 * q + 1];
-                const double ax = xa - x0, ay = ya - y0;
-                if (ax * ax + ay * ay < p.fd2 && (xa != x0 || ya != y0)) {
-                    const double ex = x0 - xa, ey = y0 - ya;
-                    const double r2 = ex * ex + ey * ey;
-                    fx += p.fk * ex / r2;
-                    fy += p.fk * ey / r2;
-                }
-            }
-            x += fx;
-            y += fy;
-            outbits |= fl_wall(p, S, k, x, y) << k;
-        }
+        outbits = fl_move_coupled(p, S);
     }
     outbits = G::reduce_or(outbits);
     return outbits;
@@ -206,23 +220,55 @@ __device__ __forceinline__ void corner_span(double a, double R, double R2, int* 
 }
 
 // ------------------------------------------------------------------------------------------------
-// belief map: _update_prob_map + _percent_in_agent_viewrange (env/flight_env.py:275-303), warp per env
+// belief map: _update_prob_map + _percent_in_agent_viewrange (env/flight_env.py:275-303), one warp per env.
+//
+// The reference classifies the 4 corners of every cell against every agent (2500 x 4 x n fp64 tests).  Here:
+//  (1) corner classification by ROW INTERVALS: for agent a and integer corner row cx, the corner columns cy with
+//      fl(fl((cx-ax)^2) + fl((cy-ay)^2)) < R^2 form an interval (the expression is monotone in |cy-ay|).  Its
+//      ends come from one fp32 sqrt; only when an end lies within 1e-3 of an integer is the reference's exact
+//      fp64 predicate evaluated there.  One lane per (agent, corner row): <= 2R*n tasks.  The interval is OR-ed as a
+//      bit mask into rowmask[cx] (bit cy), the union over agents ("any agent", the `break` of :299-302).
+//  (2) percent of cell (i,j) = popc of bits j,j+1 of rowmask[i] and rowmask[i+1]; touched <=> any of them set.
+//  (3) sweep: per agent box, 8 lanes x float2 per map row, 4 rows per warp instruction; a cell inside several
+//      boxes belongs to the first; untouched cells are neither read nor written.  The update itself is fp32
+//      (k_c*p / (1 + (q-1)*p), fast reciprocal): measured drift vs the float64 reference over 225 steps is 3e-6
+//      relative, inside the 1e-5 bar.
+// Needs map_size <= 63 (one 64-bit mask per corner row) -- larger maps take fl_probmap_wide below.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned fl_probmap(const FlightParams& p, double* S, int lane, float* map, uint32_t newf) {
+__device__ __forceinline__ bool corner_pred(double A, double cy, double ay, double R2) {
+    const double dy = cy - ay;
+    return A + dy * dy < R2;                                   // strict '<' (:300)
+}
+
+// The reference's own grouping (1-d)*p + (1-p) matters: 1-p is exact near p = 1 (a found cell), and a cell at
+// exactly 1 must stay exactly 1 while all four corners are in view -- x/x with a correctly rounded divide --
+// because the map's derivative there is 10: any seed error would grow tenfold per step.
+__device__ __forceinline__ float belief_update(float pv, int cnt, float qf, float qm1f) {
+    (void)qm1f;
+    const float num = (0.25f * (float)cnt * qf) * pv;          // percent*(1-d)*p            (:292)
+    const float den = fmaf(qf, pv, 1.0f - pv);                 // (1-d)*p + (1-p)
+    return __fdiv_rn(num, den);
+}
+
+__device__ __noinline__ unsigned fl_probmap(const FlightParams& p, double* S, int lane, float* map, uint32_t newf,
+                                            unsigned long long* rowmask) {
     const int n = p.n, M = p.M;
-    int* box = reinterpret_cast<int*>(S + p.s_box);   // [n][4]: i0, i1, j0, j1  (cells that can have a corner inside)
+    int* box = reinterpret_cast<int*>(S + p.s_box);   // [n][6]: i0, i1, j0, j1 (cells), clo_x, chi_x (corner rows)
     int* hit = reinterpret_cast<int*>(S + p.s_hit);   // cells of the targets found by this sensing call
     const double* T = S + p.s_tgt;
     for (int a = lane; a < n; a += 32) {
         const double ax = S[2 * a], ay = S[2 * a + 1];
         int lo, hi;
         corner_span(ax, p.R, p.R2, &lo, &hi);
-        box[4 * a + 0] = max(0, lo - 1);          // cell i has corners i and i+1
-        box[4 * a + 1] = min(M - 1, hi);
+        box[6 * a + 0] = max(0, lo - 1);          // cell i has corners i and i+1
+        box[6 * a + 1] = min(M - 1, hi);
+        box[6 * a + 4] = lo;
+        box[6 * a + 5] = hi;
         corner_span(ay, p.R, p.R2, &lo, &hi);
-        box[4 * a + 2] = max(0, lo - 1);
-        box[4 * a + 3] = min(M - 1, hi);
+        box[6 * a + 2] = max(0, lo - 1);
+        box[6 * a + 3] = min(M - 1, hi);
     }
+    for (int r = lane; r <= M + 1; r += 32) rowmask[r] = 0ull;
     const int nh = __popc(newf);
     if (lane < p.m && ((newf >> lane) & 1u)) {
         const int k = __popc(newf & ((1u << lane) - 1u));
@@ -232,18 +278,115 @@ __device__ __forceinline__ unsigned fl_probmap(const FlightParams& p, double* S,
         hit[k] = (ci < 0 || cj < 0) ? -1 : ci * M + cj;
     }
     __syncwarp();
+    // (1) corner-row intervals
+    const int span = p.span_cap;                      // power of two >= 2R
+    for (int t = lane; t < n * span; t += 32) {
+        const int a = t / span, r = t - a * span;
+        const int cx = box[6 * a + 4] + r;
+        if (cx > box[6 * a + 5] || cx < 0 || cx > M) continue;
+        const double ax = S[2 * a], ay = S[2 * a + 1];
+        const double dx = (double)cx - ax;
+        const double A = dx * dx;
+        const float wf = sqrtf(fmaxf((float)(p.R2 - A), 0.0f));
+        const double yh = ay + (double)wf, yl = ay - (double)wf;
+        double fh = floor(yh), cl = ceil(yl);
+        if (yh - fh < 1e-3 || yh - fh > 1.0 - 1e-3) {          // end within 1e-3 of an integer: decide exactly
+            const double Y = rint(yh);
+            fh = corner_pred(A, Y, ay, p.R2) ? Y : Y - 1.0;
+        }
+        if (cl - yl < 1e-3 || cl - yl > 1.0 - 1e-3) {
+            const double Y = rint(yl);
+            cl = corner_pred(A, Y, ay, p.R2) ? Y : Y + 1.0;
+        }
+        const int yhi = min((int)fh, M), ylo = max((int)cl, 0);
+        if (ylo <= yhi) {
+            const unsigned long long mk = ((2ull << yhi) - 1ull) & ~((1ull << ylo) - 1ull);
+            atomicOr(&rowmask[cx], mk);
+        }
+    }
+    __syncwarp();
+    // (2)+(3) sweep
     unsigned touched = 0;
+    const float qf = (float)p.q_miss, qm1f = (float)(p.q_miss - 1.0);
+    const bool vec2 = (M & 1) == 0;
+    for (int a = 0; a < n; ++a) {
+        const int i0 = box[6 * a], i1 = box[6 * a + 1], j0 = box[6 * a + 2], j1 = box[6 * a + 3];
+        if (i0 > i1 || j0 > j1) continue;
+        const unsigned long long colmask = ((2ull << j1) - 1ull) & ~((1ull << j0) - 1ull);
+        const int rsub = vec2 ? (lane >> 3) : (lane >> 4), rstep = vec2 ? 4 : 2;
+        const int jb = vec2 ? (j0 & ~1) : j0;
+        for (int jc = jb; jc <= j1; jc += 16) {
+            const int j = vec2 ? jc + 2 * (lane & 7) : jc + (lane & 15);
+            for (int i = i0 + rsub; i <= i1; i += rstep) {
+                const unsigned long long A = rowmask[i], B = rowmask[i + 1];
+                unsigned long long Tm = (A | (A >> 1) | B | (B >> 1)) & colmask;
+                for (int b = 0; b < a; ++b)                     // a cell inside several boxes belongs to the first
+                    if (i >= box[6 * b] && i <= box[6 * b + 1])
+                        Tm &= ~(((2ull << box[6 * b + 3]) - 1ull) & ~((1ull << box[6 * b + 2]) - 1ull));
+                const unsigned t2 = (unsigned)(Tm >> j) & (vec2 ? 3u : 1u);
+                if (!t2) continue;                              // percent == 0 -> untouched (:285-286)
+                const int cell = i * M + j;
+                const unsigned a2 = (unsigned)(A >> j) & 7u, b2 = (unsigned)(B >> j) & 7u;
+                if (vec2) {
+                    float2 v = *reinterpret_cast<float2*>(map + cell);
+                    if (t2 & 1u) v.x = belief_update(v.x, __popc(a2 & 3u) + __popc(b2 & 3u), qf, qm1f);
+                    if (t2 & 2u) v.y = belief_update(v.y, __popc(a2 & 6u) + __popc(b2 & 6u), qf, qm1f);
+                    for (int k = 0; k < nh; ++k) {              // targets found by THIS call -> 1 (:288-289)
+                        if ((t2 & 1u) && hit[k] == cell) v.x = 1.0f;
+                        if ((t2 & 2u) && hit[k] == cell + 1) v.y = 1.0f;
+                    }
+                    *reinterpret_cast<float2*>(map + cell) = v;
+                    touched += __popc(t2);
+                } else {
+                    float v = belief_update(map[cell], __popc(a2 & 3u) + __popc(b2 & 3u), qf, qm1f);
+                    for (int k = 0; k < nh; ++k)
+                        if (hit[k] == cell) v = 1.0f;
+                    map[cell] = v;
+                    ++touched;
+                }
+            }
+        }
+    }
+    return touched;
+}
+
+// Fallback for map_size > 63: per-cell corner tests (same results, more arithmetic), half-warp per map row.
+__device__ __noinline__ unsigned fl_probmap_wide(const FlightParams& p, double* S, int lane, float* map, uint32_t newf) {
+    const int n = p.n, M = p.M;
+    int* box = reinterpret_cast<int*>(S + p.s_box);
+    int* hit = reinterpret_cast<int*>(S + p.s_hit);
+    const double* T = S + p.s_tgt;
+    for (int a = lane; a < n; a += 32) {
+        const double ax = S[2 * a], ay = S[2 * a + 1];
+        int lo, hi;
+        corner_span(ax, p.R, p.R2, &lo, &hi);
+        box[6 * a + 0] = max(0, lo - 1);
+        box[6 * a + 1] = min(M - 1, hi);
+        corner_span(ay, p.R, p.R2, &lo, &hi);
+        box[6 * a + 2] = max(0, lo - 1);
+        box[6 * a + 3] = min(M - 1, hi);
+    }
+    const int nh = __popc(newf);
+    if (lane < p.m && ((newf >> lane) & 1u)) {
+        const int k = __popc(newf & ((1u << lane) - 1u));
+        const int ci = min((int)fmin(T[2 * lane], p.Md), M - 1);
+        const int cj = min((int)fmin(T[2 * lane + 1], p.Md), M - 1);
+        hit[k] = (ci < 0 || cj < 0) ? -1 : ci * M + cj;
+    }
+    __syncwarp();
+    unsigned touched = 0;
+    const float qf = (float)p.q_miss, qm1f = (float)(p.q_miss - 1.0);
     const int col = lane & 15, half = lane >> 4;
     for (int a = 0; a < n; ++a) {
-        const int i0 = box[4 * a], i1 = box[4 * a + 1], j0 = box[4 * a + 2], j1 = box[4 * a + 3];
+        const int i0 = box[6 * a], i1 = box[6 * a + 1], j0 = box[6 * a + 2], j1 = box[6 * a + 3];
         for (int jc = j0; jc <= j1; jc += 16) {
             const int j = jc + col;
             if (j > j1) continue;
             const double y0 = (double)j, y1 = (double)(j + 1);
             for (int i = i0 + half; i <= i1; i += 2) {
-                bool mine = true;     // a cell inside several boxes belongs to the first of them
+                bool mine = true;
                 for (int b = 0; b < a; ++b)
-                    mine &= !(i >= box[4 * b] && i <= box[4 * b + 1] && j >= box[4 * b + 2] && j <= box[4 * b + 3]);
+                    mine &= !(i >= box[6 * b] && i <= box[6 * b + 1] && j >= box[6 * b + 2] && j <= box[6 * b + 3]);
                 if (!mine) continue;
                 const double x0 = (double)i, x1 = (double)(i + 1);
                 uint32_t bits = 0;
@@ -251,25 +394,18 @@ __device__ __forceinline__ unsigned fl_probmap(const FlightParams& p, double* S,
                     const double ax = S[2 * q], ay = S[2 * q + 1];
                     const double dx0 = x0 - ax, dx1 = x1 - ax, dy0 = y0 - ay, dy1 = y1 - ay;
                     const double sx0 = dx0 * dx0, sx1 = dx1 * dx1, sy0 = dy0 * dy0, sy1 = dy1 * dy1;
-                    bits |= (sx0 + sy0 < p.R2) ? 1u : 0u;     // strict '<' (:300)
+                    bits |= (sx0 + sy0 < p.R2) ? 1u : 0u;
                     bits |= (sx1 + sy0 < p.R2) ? 2u : 0u;
                     bits |= (sx0 + sy1 < p.R2) ? 4u : 0u;
                     bits |= (sx1 + sy1 < p.R2) ? 8u : 0u;
                 }
-                if (!bits) continue;                          // percent == 0 -> untouched (:285-286)
+                if (!bits) continue;
                 ++touched;
                 const int cell = i * M + j;
-                bool is_hit = false;
-                for (int k = 0; k < nh; ++k) is_hit |= (hit[k] == cell);
-                if (is_hit) {
-                    map[cell] = 1.0f;                         // (:288-289)
-                } else {
-                    const double pv = (double)map[cell];
-                    const double frac = 0.25 * (double)__popc(bits);
-                    const double num = frac * p.q_miss * pv;  // percent*(1-d)*p  (:292)
-                    const double den = p.q_miss * pv + (1.0 - pv);
-                    map[cell] = (float)(num / den);
-                }
+                float v = belief_update(map[cell], __popc(bits), qf, qm1f);
+                for (int k = 0; k < nh; ++k)
+                    if (hit[k] == cell) v = 1.0f;
+                map[cell] = v;
             }
         }
     }
@@ -281,7 +417,7 @@ __device__ __forceinline__ unsigned fl_probmap(const FlightParams& p, double* S,
 // ------------------------------------------------------------------------------------------------
 template <int LPE>
 __device__ __forceinline__ int fl_sense(const FlightParams& p, double* S, int lane, uint32_t env_id, uint32_t t,
-                                        uint32_t outbits, float* map, unsigned* touched) {
+                                        uint32_t outbits, SlotRes* res) {
     using G = Group<LPE>;
     const int n = p.n, m = p.m;
     uint32_t* meta = slot_meta(p, S);
@@ -336,11 +472,7 @@ __device__ __forceinline__ int fl_sense(const FlightParams& p, double* S, int la
         meta[CS_META_NEWFOUND] = newf;
         meta[CS_META_OUT] = outbits;
         meta[CS_META_FLAGS] = nflags;
-    }
-    if (LPE == 32 && p.variant) {
-        __syncwarp();
-        const unsigned tc = fl_probmap(p, S, lane, map, newf);
-        if (p.count_touched) *touched += tc;
+        res->flags |= SLOT_MAP_PENDING;      // the warp-wide belief-map pass picks this sensing call up
     }
     G::sync();
     return rew;
@@ -416,6 +548,14 @@ __device__ __forceinline__ void fl_reset(const FlightParams& p, double* S, int l
     G::sync();
 }
 
+// reset followed by the sensing call the reference makes inside reset (:182); cold, kept out of line
+template <int LPE>
+__device__ __noinline__ void fl_reset_sense(const FlightParams& p, double* S, int lane, uint32_t env_id, uint32_t rflags,
+                                            float* map, SlotRes* res) {
+    fl_reset<LPE>(p, S, lane, env_id, rflags, map, res);
+    (void)fl_sense<LPE>(p, S, lane, env_id, 0u, 0u, res);      // reward discarded
+}
+
 // get_obs / get_state rows of one env into the slot's fp32 staging area (flight_env_easy.py:190-221)
 template <int LPE>
 __device__ __forceinline__ void fl_emit(const FlightParams& p, double* S, int lane) {
@@ -440,65 +580,87 @@ __device__ __forceinline__ void fl_emit(const FlightParams& p, double* S, int la
 
 enum { MODE_STEP = 0, MODE_RESET = 1 };
 
+__device__ __forceinline__ int fastdiv(int v, uint32_t magic) { return (int)__umulhi((uint32_t)v, magic); }
+
+// Warp-wide belief-map pass over the envs of this warp whose slot carries SLOT_MAP_PENDING.
+__device__ __noinline__ unsigned map_pass(const FlightParams& p, double* W, int wcnt, int wenv0, int lane32,
+                                             unsigned long long* rowmask) {
+    unsigned touched = 0;
+    for (int le = 0; le < wcnt; ++le) {
+        double* S = W + le * p.s_stride;
+        SlotRes* res = reinterpret_cast<SlotRes*>(S + p.s_res);
+        if (!(res->flags & SLOT_MAP_PENDING)) continue;          // warp-uniform
+        float* map = p.prob_map + (size_t)(wenv0 + le) * p.M * p.M;
+        const uint32_t newf = slot_meta(p, S)[CS_META_NEWFOUND];
+        __syncwarp();
+        touched += (p.M <= 63) ? fl_probmap(p, S, lane32, map, newf, rowmask) : fl_probmap_wide(p, S, lane32, map, newf);
+        __syncwarp();
+        if (lane32 == 0) res->flags &= ~SLOT_MAP_PENDING;
+    }
+    __syncwarp();
+    return touched;
+}
+
+// One warp owns EPW = 32/LPE consecutive env instances; LPE lanes ("group") work on one env.
 // actions == nullptr in MODE_STEP: uniform-random policy drawn in-kernel (alg=random, agent/agent.py:34-36)
 template <int LPE, int MODE>
-__global__ void __launch_bounds__(kThreads) flight_kernel(const FlightParams p, const uint8_t* __restrict__ actions,
+__global__ void __launch_bounds__(kThreads) flight_kernel(const __grid_constant__ FlightParams p, const uint8_t* __restrict__ actions,
                                                           const uint8_t* __restrict__ mask, uint32_t rflags) {
     using G = Group<LPE>;
-    constexpr int EPC = kThreads / LPE;
+    constexpr int EPW = 32 / LPE;
     extern __shared__ double smem[];
-    __shared__ double s_stats[CS_NUM_STATS];
 
-    const int tid = threadIdx.x;
-    const int e0 = blockIdx.x * EPC;
-    const int cnt = min(EPC, p.E - e0);
-    if (tid < CS_NUM_STATS) s_stats[tid] = 0.0;
+    const int tid = threadIdx.x, warp = tid >> 5, lane32 = tid & 31;
+    const int wenv0 = (blockIdx.x * (kThreads / 32) + warp) * EPW;      // first env of this warp
+    const int wcnt = min(EPW, p.E - wenv0);
+    if (wcnt <= 0) return;                                               // whole warp idle: nothing is block-synchronised
+    double* W = smem + (size_t)warp * p.s_warp;
+    unsigned long long* rowmask = reinterpret_cast<unsigned long long*>(W + (size_t)EPW * p.s_stride);
 
-    // ---- stage records: global -> shared, 16-byte coalesced -------------------------------------
+    // ---- stage this warp's records: global -> shared, 16-byte coalesced ---------------------------
     {
-        const double2* gd = reinterpret_cast<const double2*>(p.dyn + (size_t)e0 * p.rec);
         const int rec2 = p.rec >> 1;
-        for (int idx = tid; idx < cnt * rec2; idx += kThreads) {
-            const int e = idx / rec2, k = idx - e * rec2;
+        const double2* gd = reinterpret_cast<const double2*>(p.dyn + (size_t)wenv0 * p.rec);
+        for (int idx = lane32; idx < wcnt * rec2; idx += 32) {
+            const int le = fastdiv(idx, p.mg_rec2), k = idx - le * rec2;
             const double2 v = gd[idx];
-            double* S = smem + e * p.s_stride;
+            double* S = W + le * p.s_stride;
             S[2 * k] = v.x;
             S[2 * k + 1] = v.y;
         }
-        const double2* gt = reinterpret_cast<const double2*>(p.tgt + (size_t)e0 * 2 * p.m);
-        const int m2 = p.m;   // 2m doubles = m double2
-        for (int idx = tid; idx < cnt * m2; idx += kThreads) {
-            const int e = idx / m2, k = idx - e * m2;
+        const double2* gt = reinterpret_cast<const double2*>(p.tgt + (size_t)wenv0 * 2 * p.m);
+        for (int idx = lane32; idx < wcnt * p.m; idx += 32) {
+            const int le = fastdiv(idx, p.mg_m), k = idx - le * p.m;
             const double2 v = gt[idx];
-            double* S = smem + e * p.s_stride + p.s_tgt;
+            double* S = W + le * p.s_stride + p.s_tgt;
             S[2 * k] = v.x;
             S[2 * k + 1] = v.y;
+        }
+        for (int le = lane32; le < wcnt; le += 32) {
+            SlotRes* res = reinterpret_cast<SlotRes*>(W + le * p.s_stride + p.s_res);
+            res->reward = 0.f; res->terminated = 0; res->win = 0; res->flags = 0;
         }
     }
-    __syncthreads();
+    __syncwarp();
 
-    const int g = tid / LPE;
-    const int lane = tid % LPE;
-    const int e = e0 + g;
-    if (g < cnt) {
-        double* S = smem + g * p.s_stride;
-        uint32_t* meta = slot_meta(p, S);
-        SlotRes* res = reinterpret_cast<SlotRes*>(S + p.s_res);
-        const uint32_t env_id = p.env_id_base + (uint32_t)e;
-        float* map = p.variant ? p.prob_map + (size_t)e * p.M * p.M : nullptr;
-        unsigned touched = 0;
-        if (lane == 0) {
-            res->reward = 0.f;
-            res->terminated = 0;
-            res->win = 0;
-            res->flags = 0;
-        }
-        G::sync();
-        if (MODE == MODE_STEP) {
+    const int g = lane32 / LPE, lane = lane32 % LPE;
+    const bool active = g < wcnt;
+    const int e = wenv0 + g;
+    double* S = W + (active ? g : 0) * p.s_stride;
+    uint32_t* meta = slot_meta(p, S);
+    SlotRes* res = reinterpret_cast<SlotRes*>(S + p.s_res);
+    const uint32_t env_id = p.env_id_base + (uint32_t)e;
+    float* map = p.variant ? p.prob_map + (size_t)e * p.M * p.M : nullptr;
+    // episode statistics of this lane's env (lane 0 of the group), reduced over the warp at the end
+    float st_eps = 0.f, st_rew = 0.f, st_found = 0.f, st_wins = 0.f, st_len = 0.f, st_steps = 0.f;
+    bool done = false;
+
+    if (MODE == MODE_STEP) {
+        if (active) {
             const uint32_t flags0 = meta[CS_META_FLAGS];
             const uint32_t time0 = meta[CS_META_TIME];
             const uint32_t episode0 = meta[CS_META_EPISODE];
-            bool done = (flags0 & CS_FLAG_DONE) != 0;
+            done = (flags0 & CS_FLAG_DONE) != 0;
             G::sync();
             if (!done) {
                 const uint8_t* act;
@@ -518,7 +680,7 @@ __global__ void __launch_bounds__(kThreads) flight_kernel(const FlightParams p, 
                 }
                 const uint32_t outbits = fl_move<LPE>(p, S, lane, act);
                 G::sync();
-                const int rew = fl_sense<LPE>(p, S, lane, env_id, time0 + 1u, outbits, map, &touched);
+                const int rew = fl_sense<LPE>(p, S, lane, env_id, time0 + 1u, outbits, res);
                 const uint32_t time1 = time0 + 1u;
                 const uint32_t fl1 = meta[CS_META_FLAGS];
                 const int nfound = __popc(meta[CS_META_FOUND]);
@@ -532,93 +694,126 @@ __global__ void __launch_bounds__(kThreads) flight_kernel(const FlightParams p, 
                     res->reward = (float)rew;
                     res->terminated = term ? 1 : 0;
                     res->win = (fl1 & CS_FLAG_WIN) ? 1 : 0;
-                    res->flags |= SLOT_EMIT;
-                    atomicAdd(&s_stats[CS_STAT_ENV_STEPS], 1.0);
+                    res->flags |= SLOT_EMIT | SLOT_RESULT;
+                    st_steps = 1.f;
                     if (term) {
-                        atomicAdd(&s_stats[CS_STAT_EPISODES], 1.0);
-                        atomicAdd(&s_stats[CS_STAT_EP_REWARD], (double)epr);
-                        atomicAdd(&s_stats[CS_STAT_TARGETS_FOUND], (double)nfound);
-                        atomicAdd(&s_stats[CS_STAT_WINS], (fl1 & CS_FLAG_WIN) ? 1.0 : 0.0);
-                        atomicAdd(&s_stats[CS_STAT_EP_LEN], (double)time1);
+                        st_eps = 1.f; st_rew = epr; st_found = (float)nfound; st_wins = (fl1 & CS_FLAG_WIN) ? 1.f : 0.f;
+                        st_len = (float)time1;
                     }
                 }
                 done = term;
-                G::sync();
             } else if (lane == 0) {
                 res->reward = 0.f;                     // masked no-op on a finished env
                 res->terminated = 1;
                 res->win = (flags0 & CS_FLAG_WIN) ? 1 : 0;
+                res->flags |= SLOT_RESULT;
             }
-            if (p.auto_reset && done) {
+        }
+        __syncwarp();
+        unsigned touched = 0;
+        if (p.variant) touched += map_pass(p, W, wcnt, wenv0, lane32, rowmask);
+        if (p.auto_reset) {
+            if (active && done) {
                 G::sync();
-                fl_reset<LPE>(p, S, lane, env_id, 0u, map, res);
-                (void)fl_sense<LPE>(p, S, lane, env_id, 0u, 0u, map, &touched);   // reward discarded (:182)
+                fl_reset_sense<LPE>(p, S, lane, env_id, 0u, map, res);
             }
-        } else {
+            __syncwarp();
+            if (p.variant) touched += map_pass(p, W, wcnt, wenv0, lane32, rowmask);
+        }
+        if (p.variant && p.count_touched) {
+            const unsigned tot = __reduce_add_sync(0xffffffffu, touched);
+            if (lane32 == 0 && tot) atomicAdd(p.stats + CS_STAT_TOUCHED, (double)tot);
+        }
+    } else {
+        if (active) {
             const bool sel = (mask == nullptr) || (mask[e] != 0);
             if (sel) {
-                fl_reset<LPE>(p, S, lane, env_id, rflags, map, res);
-                (void)fl_sense<LPE>(p, S, lane, env_id, 0u, 0u, map, &touched);
+                fl_reset_sense<LPE>(p, S, lane, env_id, rflags, map, res);
                 if (lane == 0) {
                     res->reward = 0.f;
                     res->terminated = 0;
                     res->win = (meta[CS_META_FLAGS] & CS_FLAG_WIN) ? 1 : 0;
+                    res->flags |= SLOT_RESULT;
                 }
             }
         }
-        G::sync();
-        if (res->flags & SLOT_EMIT) fl_emit<LPE>(p, S, lane);
-        if (LPE == 32 && p.variant && p.count_touched) {
-            const unsigned tot = __reduce_add_sync(0xffffffffu, touched);
-            if (lane == 0 && tot) atomicAdd(&s_stats[CS_STAT_TOUCHED], (double)tot);
-        }
-    }
-    __syncthreads();
-
-    // ---- write back: shared -> global, coalesced ------------------------------------------------
-    {
-        double2* gd = reinterpret_cast<double2*>(p.dyn + (size_t)e0 * p.rec);
-        const int rec2 = p.rec >> 1;
-        for (int idx = tid; idx < cnt * rec2; idx += kThreads) {
-            const int le = idx / rec2, k = idx - le * rec2;
-            double* S = smem + le * p.s_stride;
-            const SlotRes* res = reinterpret_cast<const SlotRes*>(S + p.s_res);
-            if (res->flags & SLOT_EMIT) gd[idx] = make_double2(S[2 * k], S[2 * k + 1]);
-        }
-        double2* gt = reinterpret_cast<double2*>(p.tgt + (size_t)e0 * 2 * p.m);
-        const int m2 = p.m;
-        for (int idx = tid; idx < cnt * m2; idx += kThreads) {
-            const int le = idx / m2, k = idx - le * m2;
-            double* S = smem + le * p.s_stride;
-            const SlotRes* res = reinterpret_cast<const SlotRes*>(S + p.s_res);
-            if (res->flags & SLOT_TGT_DIRTY) gt[idx] = make_double2(S[p.s_tgt + 2 * k], S[p.s_tgt + 2 * k + 1]);
-        }
-        float* gs = p.state + (size_t)e0 * p.state_len;
-        for (int idx = tid; idx < cnt * p.state_len; idx += kThreads) {
-            const int le = idx / p.state_len, k = idx - le * p.state_len;
-            double* S = smem + le * p.s_stride;
-            const SlotRes* res = reinterpret_cast<const SlotRes*>(S + p.s_res);
-            if (res->flags & SLOT_EMIT) gs[idx] = reinterpret_cast<const float*>(S + p.s_out)[k];
-        }
-        float* go = p.obs + (size_t)e0 * 4 * p.n;
-        const int on = 4 * p.n;
-        for (int idx = tid; idx < cnt * on; idx += kThreads) {
-            const int le = idx / on, k = idx - le * on;
-            double* S = smem + le * p.s_stride;
-            const SlotRes* res = reinterpret_cast<const SlotRes*>(S + p.s_res);
-            if (res->flags & SLOT_EMIT) go[idx] = reinterpret_cast<const float*>(S + p.s_out)[k];
-        }
-        for (int le = tid; le < cnt; le += kThreads) {
-            double* S = smem + le * p.s_stride;
-            const SlotRes* res = reinterpret_cast<const SlotRes*>(S + p.s_res);
-            if (MODE == MODE_STEP || (res->flags & SLOT_EMIT)) {
-                p.reward[e0 + le] = res->reward;
-                p.terminated[e0 + le] = res->terminated;
-                p.win[e0 + le] = res->win;
-                p.target_find[e0 + le] = __popc(slot_meta(p, S)[CS_META_FOUND]);
+        __syncwarp();
+        if (p.variant) {
+            const unsigned touched = map_pass(p, W, wcnt, wenv0, lane32, rowmask);
+            if (p.count_touched) {
+                const unsigned tot = __reduce_add_sync(0xffffffffu, touched);
+                if (lane32 == 0 && tot) atomicAdd(p.stats + CS_STAT_TOUCHED, (double)tot);
             }
         }
-        if (tid < CS_NUM_STATS && s_stats[tid] != 0.0) atomicAdd(p.stats + tid, s_stats[tid]);
+    }
+    if (active) {
+        G::sync();
+        if (res->flags & SLOT_EMIT) fl_emit<LPE>(p, S, lane);
+    }
+    __syncwarp();
+
+    // ---- write back: shared -> global, coalesced over the warp's contiguous env block --------------
+    {
+        const int rec2 = p.rec >> 1;
+        double2* gd = reinterpret_cast<double2*>(p.dyn + (size_t)wenv0 * p.rec);
+        for (int idx = lane32; idx < wcnt * rec2; idx += 32) {
+            const int le = fastdiv(idx, p.mg_rec2), k = idx - le * rec2;
+            const double* Sl = W + le * p.s_stride;
+            if (reinterpret_cast<const SlotRes*>(Sl + p.s_res)->flags & SLOT_EMIT) gd[idx] = make_double2(Sl[2 * k], Sl[2 * k + 1]);
+        }
+        float* gs = p.state + (size_t)wenv0 * p.state_len;
+        for (int idx = lane32; idx < wcnt * p.state_len; idx += 32) {
+            const int le = fastdiv(idx, p.mg_state), k = idx - le * p.state_len;
+            const double* Sl = W + le * p.s_stride;
+            if (reinterpret_cast<const SlotRes*>(Sl + p.s_res)->flags & SLOT_EMIT)
+                gs[idx] = reinterpret_cast<const float*>(Sl + p.s_out)[k];
+        }
+        const int on = 4 * p.n;
+        float* go = p.obs + (size_t)wenv0 * on;
+        for (int idx = lane32; idx < wcnt * on; idx += 32) {
+            const int le = fastdiv(idx, p.mg_obs), k = idx - le * on;
+            const double* Sl = W + le * p.s_stride;
+            if (reinterpret_cast<const SlotRes*>(Sl + p.s_res)->flags & SLOT_EMIT)
+                go[idx] = reinterpret_cast<const float*>(Sl + p.s_out)[k];
+        }
+        for (int le = lane32; le < wcnt; le += 32) {
+            double* Sl = W + le * p.s_stride;
+            const SlotRes* r = reinterpret_cast<const SlotRes*>(Sl + p.s_res);
+            if (r->flags & SLOT_RESULT) {
+                p.reward[wenv0 + le] = r->reward;
+                p.terminated[wenv0 + le] = r->terminated;
+                p.win[wenv0 + le] = r->win;
+                p.target_find[wenv0 + le] = __popc(slot_meta(p, Sl)[CS_META_FOUND]);
+            }
+            if (r->flags & SLOT_TGT_DIRTY) {                     // targets redrawn by a reset (rare)
+                double* gt = p.tgt + (size_t)(wenv0 + le) * 2 * p.m;
+                for (int k = 0; k < 2 * p.m; ++k) gt[k] = Sl[p.s_tgt + k];
+            }
+        }
+    }
+    // ---- episode statistics: warp reduction, then at most one atomic per statistic per warp ----------
+    if (MODE == MODE_STEP) {
+        const float any = st_steps + st_eps;
+        if (__any_sync(0xffffffffu, any != 0.f)) {
+            for (int o = 16; o > 0; o >>= 1) {
+                st_eps += __shfl_xor_sync(0xffffffffu, st_eps, o);
+                st_rew += __shfl_xor_sync(0xffffffffu, st_rew, o);
+                st_found += __shfl_xor_sync(0xffffffffu, st_found, o);
+                st_wins += __shfl_xor_sync(0xffffffffu, st_wins, o);
+                st_len += __shfl_xor_sync(0xffffffffu, st_len, o);
+                st_steps += __shfl_xor_sync(0xffffffffu, st_steps, o);
+            }
+            if (lane32 == 0) {
+                atomicAdd(p.stats + CS_STAT_ENV_STEPS, (double)st_steps);
+                if (st_eps != 0.f) {
+                    atomicAdd(p.stats + CS_STAT_EPISODES, (double)st_eps);
+                    atomicAdd(p.stats + CS_STAT_EP_REWARD, (double)st_rew);
+                    atomicAdd(p.stats + CS_STAT_TARGETS_FOUND, (double)st_found);
+                    atomicAdd(p.stats + CS_STAT_WINS, (double)st_wins);
+                    atomicAdd(p.stats + CS_STAT_EP_LEN, (double)st_len);
+                }
+            }
+        }
     }
 }
 
@@ -676,8 +871,8 @@ struct cs_flight {
 namespace {
 
 int pick_lpe(const cs_flight_cfg& c) {
-    if (c.variant == 1) return 32;
     if (c.lanes_per_env) return c.lanes_per_env;
+    if (c.variant == 1) return 4;     // step logic on 4 lanes; the belief-map pass is warp-wide per env either way
     // enough warps to occupy 148 SMs x 16 warps before trading lanes for instruction efficiency
     const long long want = 148LL * 16 * 32;
     int lpe = 32;
@@ -826,7 +1021,7 @@ int cs_flight_create(const cs_flight_cfg* cfg, cs_flight** out) {
     p.s_out = off; off += up2(p.state_len) / 2;
     p.s_res = off; off += 1;
     p.s_am = off; off += up2(m > (n + 3) / 4 ? m : (n + 3) / 4) / 2;
-    p.s_box = off; off += cfg->variant ? 2 * n : 0;
+    p.s_box = off; off += cfg->variant ? 3 * n : 0;
     p.s_hit = off; off += cfg->variant ? up2(m) / 2 : 0;
     p.s_stride = off | 1;      // odd stride in doubles: conflict-free slot-strided 64-bit accesses
     // constants, computed exactly as the reference's Python floats are
@@ -853,15 +1048,19 @@ int cs_flight_create(const cs_flight_cfg* cfg, cs_flight** out) {
         p.sin0 = sin(h0);
     }
 
+    p.span_cap = 1;
+    while (p.span_cap < 2 * cfg->view_range) p.span_cap <<= 1;
+    auto magic = [](int d) { return (uint32_t)((0x100000000ULL + (uint64_t)d - 1) / (uint64_t)d); };
+    p.mg_rec2 = magic(p.rec / 2); p.mg_m = magic(m); p.mg_state = magic(p.state_len); p.mg_obs = magic(4 * n);
+    const int mask_doubles = (cfg->variant && M <= 63) ? M + 2 : 0;
+    auto warp_doubles = [&](int lpe) { return (32 / lpe) * p.s_stride + mask_doubles; };
     h->lpe = pick_lpe(*cfg);
-    const int epc = kThreads / h->lpe;
-    h->smem_bytes = (size_t)epc * p.s_stride * sizeof(double);
-    if (h->smem_bytes > 200 * 1024) {
-        // fall back to more lanes per env until the CTA's slots fit
-        while (h->lpe < 32 && (size_t)(kThreads / h->lpe) * p.s_stride * sizeof(double) > 200 * 1024) h->lpe <<= 1;
-        h->smem_bytes = (size_t)(kThreads / h->lpe) * p.s_stride * sizeof(double);
-    }
-    h->grid = (p.E + (kThreads / h->lpe) - 1) / (kThreads / h->lpe);
+    // fall back to more lanes per env until the CTA's slots fit the shared memory of one SM
+    while (h->lpe < 32 && (size_t)(kThreads / 32) * warp_doubles(h->lpe) * sizeof(double) > 200 * 1024) h->lpe <<= 1;
+    p.s_warp = warp_doubles(h->lpe);
+    h->smem_bytes = (size_t)(kThreads / 32) * p.s_warp * sizeof(double);
+    const int env_per_cta = (kThreads / 32) * (32 / h->lpe);
+    h->grid = (p.E + env_per_cta - 1) / env_per_cta;
     CS_CUDA(dispatch_attr(h->lpe, h->smem_bytes));
 
     const size_t E = (size_t)p.E;

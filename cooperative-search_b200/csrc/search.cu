@@ -29,6 +29,8 @@ struct SearchParams {
     int E, n, m, M, R, W;            // W = words per bit row
     int S, obs_len;                  // S = 2R-1, obs_len = S*S+2
     int agent_mode, target_mode, auto_reset;
+    int stage_obs;                   // 1: observation block staged in shared memory (M <= 64 and it fits)
+    uint32_t mg_half, mg_M, mg_S1;   // ceil(2^32/d) for d = M/2, M, S+1
     uint32_t seed, env_id_base;
     int32_t* pos;
     uint32_t* target_bits;
@@ -52,6 +54,7 @@ struct SearchSmem {
     int32_t* pos;        // [2n]
     int32_t* cand;       // [2*kThreads] candidate cells during target placement
     int* scal;           // [8]
+    float* obs_stage;    // [n*obs_len] staging of the observation block, or nullptr (direct path)
 };
 
 __device__ __forceinline__ SearchSmem carve(const SearchParams& p, unsigned char* raw) {
@@ -63,11 +66,16 @@ __device__ __forceinline__ SearchSmem carve(const SearchParams& p, unsigned char
     s.pos = reinterpret_cast<int32_t*>(s.abits + rows);
     s.cand = s.pos + 2 * p.n;
     s.scal = s.cand + 2 * kThreads;
+    // 16-byte aligned staging block after the integer scratch
+    const size_t used = sizeof(uint32_t) * (size_t)(3 * rows) + sizeof(int32_t) * (size_t)(2 * p.n + 2 * kThreads + 8);
+    s.obs_stage = p.stage_obs ? reinterpret_cast<float*>(raw + ((used + 15) & ~(size_t)15)) : nullptr;
     return s;
 }
-size_t smem_bytes_for(const SearchParams& p) {
-    return sizeof(uint32_t) * (size_t)(3 * p.M * p.W) + sizeof(int32_t) * (size_t)(2 * p.n + 2 * kThreads + 8);
+size_t smem_base_bytes(const SearchParams& p) {
+    const size_t used = sizeof(uint32_t) * (size_t)(3 * p.M * p.W) + sizeof(int32_t) * (size_t)(2 * p.n + 2 * kThreads + 8);
+    return (used + 15) & ~(size_t)15;
 }
+__device__ __forceinline__ int fastdiv(int v, uint32_t magic) { return (int)__umulhi((uint32_t)v, magic); }
 
 // scal slots
 enum { SC_NEWFOUND = 0, SC_ILLEGAL = 1, SC_GOT = 2, SC_NEXTK = 3 };
@@ -143,6 +151,10 @@ __device__ void search_reset(const SearchParams& p, const SearchSmem& s, int e, 
 }
 
 // ---- get_obs / get_state / avail of one env (:186-243) ------------------------------------------------
+__device__ __forceinline__ uint32_t bit_at(const uint32_t* rows, int W, int x, int y) {
+    return (rows[x * W + (y >> 5)] >> (y & 31)) & 1u;
+}
+
 __device__ void search_emit(const SearchParams& p, const SearchSmem& s, int e) {
     const int tid = threadIdx.x, M = p.M, W = p.W, n = p.n, R = p.R, S = p.S;
     const int rows = M * W;
@@ -155,31 +167,79 @@ __device__ void search_emit(const SearchParams& p, const SearchSmem& s, int e) {
         *reinterpret_cast<uchar4*>(av) = make_uchar4(x > 0, y > 0, x < M - 1, y < M - 1);
     }
     __syncthreads();
-    // state [M][M][2]: one float2 per cell, plane 0 targets (found ones stay 1), plane 1 agents
-    float2* st = reinterpret_cast<float2*>(p.state + (size_t)e * 2 * M * M);
-    for (int c = tid; c < M * M; c += kThreads) {
-        const int x = c / M, y = c - x * M;
-        const uint32_t sh = y & 31;
-        st[c] = make_float2((float)((s.tbits[x * W + (y >> 5)] >> sh) & 1u), (float)((s.abits[x * W + (y >> 5)] >> sh) & 1u));
-    }
-    // obs [n][S*S+2]
-    float* ob = p.obs + (size_t)e * n * p.obs_len;
-    const int total = n * p.obs_len;
-    const int R2 = R * R;
-    for (int idx = tid; idx < total; idx += kThreads) {
-        const int a = idx / p.obs_len, k = idx - a * p.obs_len;
-        const int x = s.pos[2 * a], y = s.pos[2 * a + 1];
-        float v;
-        if (k >= S * S) {
-            v = (float)(k == S * S ? x : y);                            // raw integer position (:205-208)
-        } else {
-            const int i = k / S, j = k - i * S;
-            const int gx = i + x - R + 1, gy = j + y - R + 1;
-            const int di = R - 1 - i, dj = R - 1 - j;
-            if (gx < 0 || gx >= M || gy < 0 || gy >= M || di * di + dj * dj > R2) v = 0.5f;     // (:220-226)
-            else v = (float)((s.tbits[gx * W + (gy >> 5)] >> (gy & 31)) & 1u);
+    // state [M][M][2]: plane 0 targets (found ones stay 1), plane 1 agents; two cells = one 16-byte store
+    if ((M & 1) == 0) {
+        float4* st = reinterpret_cast<float4*>(p.state + (size_t)e * 2 * M * M);
+        const int half = M >> 1;
+        for (int c2 = tid; c2 < M * half; c2 += kThreads) {
+            const int x = fastdiv(c2, p.mg_half), y = (c2 - x * half) * 2;
+            const uint32_t tw = s.tbits[x * W + (y >> 5)] >> (y & 31), aw = s.abits[x * W + (y >> 5)] >> (y & 31);
+            st[c2] = make_float4((float)(tw & 1u), (float)(aw & 1u), (float)((tw >> 1) & 1u), (float)((aw >> 1) & 1u));
         }
-        ob[idx] = v;
+    } else {
+        float2* st = reinterpret_cast<float2*>(p.state + (size_t)e * 2 * M * M);
+        for (int c = tid; c < M * M; c += kThreads) {
+            const int x = fastdiv(c, p.mg_M), y = c - x * M;
+            st[c] = make_float2((float)bit_at(s.tbits, W, x, y), (float)bit_at(s.abits, W, x, y));
+        }
+    }
+    // obs [n][S*S+2]: one thread per (agent, window row) builds the row from the target bit row, staged in shared
+    // memory (conflict-free: consecutive tasks are S words apart, S odd), then copied out with 16-byte stores.
+    float* ob = p.obs + (size_t)e * n * p.obs_len;
+    const int R2 = R * R;
+    if (s.obs_stage != nullptr) {
+        const int tasks = n * (S + 1);
+        for (int t = tid; t < tasks; t += kThreads) {
+            const int a = fastdiv(t, p.mg_S1), i = t - a * (S + 1);
+            const int x = s.pos[2 * a], y = s.pos[2 * a + 1];
+            float* o = s.obs_stage + a * p.obs_len;
+            if (i == S) {                                              // raw integer position (:205-208)
+                o[S * S] = (float)x;
+                o[S * S + 1] = (float)y;
+                continue;
+            }
+            const int gx = i + x - R + 1, di = R - 1 - i, gy0 = y - R + 1;
+            unsigned long long field = 0ull;
+            const bool row_ok = gx >= 0 && gx < M;
+            if (row_ok) {
+                unsigned long long row = s.tbits[gx * W];
+                if (W > 1) row |= (unsigned long long)s.tbits[gx * W + 1] << 32;
+                field = gy0 >= 0 ? (row >> gy0) : (row << (-gy0));
+            }
+            float* orow = o + i * S;
+            for (int j = 0; j < S; ++j) {
+                const int gy = gy0 + j, dj = R - 1 - j;
+                const bool half = !row_ok || gy < 0 || gy >= M || di * di + dj * dj > R2;       // (:220-226)
+                orow[j] = half ? 0.5f : (float)((unsigned)(field >> j) & 1u);
+            }
+        }
+        __syncthreads();
+        const int total = n * p.obs_len;
+        if ((total & 3) == 0) {
+            const float4* src = reinterpret_cast<const float4*>(s.obs_stage);
+            float4* dst = reinterpret_cast<float4*>(ob);
+            for (int k = tid; k < (total >> 2); k += kThreads) dst[k] = src[k];
+        } else {
+            for (int k = tid; k < total; k += kThreads) ob[k] = s.obs_stage[k];
+        }
+    } else {
+        // large maps / very many agents: direct per-element path
+        const int total = n * p.obs_len;
+        for (int idx = tid; idx < total; idx += kThreads) {
+            const int a = idx / p.obs_len, k = idx - a * p.obs_len;
+            const int x = s.pos[2 * a], y = s.pos[2 * a + 1];
+            float v;
+            if (k >= S * S) {
+                v = (float)(k == S * S ? x : y);
+            } else {
+                const int i = k / S, j = k - i * S;
+                const int gx = i + x - R + 1, gy = j + y - R + 1;
+                const int di = R - 1 - i, dj = R - 1 - j;
+                if (gx < 0 || gx >= M || gy < 0 || gy >= M || di * di + dj * dj > R2) v = 0.5f;
+                else v = (float)bit_at(s.tbits, W, gx, gy);
+            }
+            ob[idx] = v;
+        }
     }
 }
 
@@ -378,7 +438,11 @@ int cs_search_create(const cs_search_cfg* cfg, cs_search** out) {
     p.W = (p.M + 31) / 32; p.S = 2 * p.R - 1; p.obs_len = p.S * p.S + 2;
     p.agent_mode = cfg->agent_mode; p.target_mode = cfg->target_mode; p.auto_reset = cfg->auto_reset;
     p.seed = cfg->seed; p.env_id_base = cfg->env_id_base;
-    h->smem_bytes = smem_bytes_for(p);
+    auto magic = [](int d) { return (uint32_t)((0x100000000ULL + (uint64_t)d - 1) / (uint64_t)d); };
+    p.mg_half = magic(p.M / 2 > 0 ? p.M / 2 : 1); p.mg_M = magic(p.M); p.mg_S1 = magic(p.S + 1);
+    const size_t stage_bytes = sizeof(float) * (size_t)p.n * p.obs_len;
+    p.stage_obs = (p.M <= 64 && smem_base_bytes(p) + stage_bytes <= 100 * 1024) ? 1 : 0;
+    h->smem_bytes = smem_base_bytes(p) + (p.stage_obs ? stage_bytes : 0);
     CS_REQUIRE(h->smem_bytes <= 200 * 1024, "map too large for the shared-memory bit rows");
     CS_CUDA(cudaFuncSetAttribute(search_kernel<MODE_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
     CS_CUDA(cudaFuncSetAttribute(search_kernel<MODE_RESET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));

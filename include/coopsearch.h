@@ -96,7 +96,7 @@ typedef struct cs_flight_cfg {
     int32_t variant;        /* 0 = flight_easy (wall test '>'), 1 = flight (prob map, '>=')*/
     int32_t auto_reset;     /* 1: a terminated env is reset inside the same step call      */
     int32_t count_touched;  /* 1: accumulate #prob-map cells updated into CS_STAT_TOUCHED  */
-    int32_t lanes_per_env;  /* 0 = choose from E; else 1,2,4,8,16,32 (variant 1 forces 32) */
+    int32_t lanes_per_env;  /* 0 = choose from E; else 1,2,4,8,16,32 lanes working on one env  */
     int32_t device;         /* CUDA device ordinal                                         */
     double velocity;        /* args.agent_velocity                                         */
     double detect_prob;     /* args.detect_prob                                            */
