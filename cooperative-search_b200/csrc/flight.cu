@@ -26,18 +26,19 @@ namespace {
 
 constexpr int kThreads = 128;
 
-enum : uint32_t { SLOT_EMIT = 1u, SLOT_TGT_DIRTY = 2u, SLOT_MAP_PENDING = 4u, SLOT_RESULT = 8u };
+enum : uint32_t { SLOT_EMIT = 1u, SLOT_TGT_DIRTY = 2u, SLOT_MAP_PENDING = 4u, SLOT_RESULT = 8u, SLOT_STATE_FULL = 16u };
 
 struct FlightParams {
     int E, n, m, M, T;
     int variant, auto_reset, agent_mode, target_mode, count_touched;
     // per-env record geometry (doubles)
     int rec, yaw_off, meta_off, state_len;
+    int state_stride;            // floats per state row in HBM (state_len rounded up to a multiple of 4)
     // shared-memory slot geometry (doubles)
     int s_tgt, s_cs, s_out, s_res, s_am, s_box, s_hit, s_stride;
     int s_warp;                  // doubles of shared memory per warp (EPW slots + corner-row masks)
     int span_cap;                // power of two >= 2R: corner rows per agent in the interval pass
-    uint32_t mg_rec2, mg_m, mg_state, mg_obs;   // ceil(2^32/d) for the staging loops' index splits
+    uint32_t mg_rec2, mg_m, mg_n;   // ceil(2^32/d) for the staging loops' index splits
     double Md, half_M, inv_half, R, R2, v, fk, fd2, near2, q_miss;
     double turn, pi, two_pi, three_pi, half_pi;
     long long thr;
@@ -250,8 +251,8 @@ __device__ __forceinline__ float belief_update(float pv, int cnt, float qf, floa
     return __fdiv_rn(num, den);
 }
 
-__device__ __noinline__ unsigned fl_probmap(const FlightParams& p, double* S, int lane, float* map, uint32_t newf,
-                                            unsigned long long* rowmask) {
+__device__ __forceinline__ unsigned fl_probmap(const FlightParams& p, double* S, int lane, float* map, uint32_t newf,
+                                               unsigned long long* rowmask) {
     const int n = p.n, M = p.M;
     int* box = reinterpret_cast<int*>(S + p.s_box);   // [n][6]: i0, i1, j0, j1 (cells), clo_x, chi_x (corner rows)
     int* hit = reinterpret_cast<int*>(S + p.s_hit);   // cells of the targets found by this sensing call
@@ -498,7 +499,7 @@ __device__ __forceinline__ void fl_reset(const FlightParams& p, double* S, int l
         meta[CS_META_FLAGS] = 0;
         meta[CS_META_EPREWARD] = 0;
         meta[CS_META_RESERVED] = 0;
-        res->flags |= SLOT_EMIT | ((rflags & CS_RESET_KEEP_TARGETS) ? 0u : SLOT_TGT_DIRTY);
+        res->flags |= SLOT_EMIT | SLOT_STATE_FULL | ((rflags & CS_RESET_KEEP_TARGETS) ? 0u : SLOT_TGT_DIRTY);
     }
     if (!(rflags & CS_RESET_KEEP_TARGETS)) {
         double* T = S + p.s_tgt;
@@ -556,31 +557,26 @@ __device__ __noinline__ void fl_reset_sense(const FlightParams& p, double* S, in
     (void)fl_sense<LPE>(p, S, lane, env_id, 0u, 0u, res);      // reward discarded
 }
 
-// get_obs / get_state rows of one env into the slot's fp32 staging area (flight_env_easy.py:190-221)
+// get_obs row of one env (= the agent part of get_state) into the slot's fp32 staging area
+// (flight_env_easy.py:218-221, :192-193).  The target part of the state row only changes at reset or when a
+// target is found; the write-back below touches it only then.
 template <int LPE>
 __device__ __forceinline__ void fl_emit(const FlightParams& p, double* S, int lane) {
-    const int n = p.n, m = p.m;
+    const int n = p.n;
     float* out = reinterpret_cast<float*>(S + p.s_out);
     const double* cs = S + p.s_cs;
-    const double* T = S + p.s_tgt;
-    const uint32_t found = slot_meta(p, S)[CS_META_FOUND];
     for (int a = lane; a < n; a += LPE) {
         out[4 * a + 0] = (float)((S[2 * a] - p.half_M) * p.inv_half);
         out[4 * a + 1] = (float)((S[2 * a + 1] - p.half_M) * p.inv_half);
         out[4 * a + 2] = (float)cs[a];
         out[4 * a + 3] = (float)cs[n + a];
     }
-    float* to = out + 4 * n;
-    for (int j = lane; j < m; j += LPE) {
-        to[3 * j + 0] = (float)((T[2 * j] - p.half_M) * p.inv_half);
-        to[3 * j + 1] = (float)((T[2 * j + 1] - p.half_M) * p.inv_half);
-        to[3 * j + 2] = ((found >> j) & 1u) ? 1.0f : 0.0f;
-    }
 }
 
 enum { MODE_STEP = 0, MODE_RESET = 1 };
 
-__device__ __forceinline__ int fastdiv(int v, uint32_t magic) { return (int)__umulhi((uint32_t)v, magic); }
+// v / d with magic = ceil(2^32 / d); d == 1 gives magic 2^32 -> stored as 0 -> identity
+__device__ __forceinline__ int fastdiv(int v, uint32_t magic) { return magic ? (int)__umulhi((uint32_t)v, magic) : v; }
 
 // Warp-wide belief-map pass over the envs of this warp whose slot carries SLOT_MAP_PENDING.
 __device__ __noinline__ unsigned map_pass(const FlightParams& p, double* W, int wcnt, int wenv0, int lane32,
@@ -761,20 +757,16 @@ __global__ void __launch_bounds__(kThreads) flight_kernel(const __grid_constant_
             const double* Sl = W + le * p.s_stride;
             if (reinterpret_cast<const SlotRes*>(Sl + p.s_res)->flags & SLOT_EMIT) gd[idx] = make_double2(Sl[2 * k], Sl[2 * k + 1]);
         }
-        float* gs = p.state + (size_t)wenv0 * p.state_len;
-        for (int idx = lane32; idx < wcnt * p.state_len; idx += 32) {
-            const int le = fastdiv(idx, p.mg_state), k = idx - le * p.state_len;
+        // obs rows and the agent prefix of the state rows: n 16-byte chunks per env
+        double2* go = reinterpret_cast<double2*>(p.obs + (size_t)wenv0 * 4 * p.n);
+        for (int idx = lane32; idx < wcnt * p.n; idx += 32) {
+            const int le = fastdiv(idx, p.mg_n), c = idx - le * p.n;
             const double* Sl = W + le * p.s_stride;
-            if (reinterpret_cast<const SlotRes*>(Sl + p.s_res)->flags & SLOT_EMIT)
-                gs[idx] = reinterpret_cast<const float*>(Sl + p.s_out)[k];
-        }
-        const int on = 4 * p.n;
-        float* go = p.obs + (size_t)wenv0 * on;
-        for (int idx = lane32; idx < wcnt * on; idx += 32) {
-            const int le = fastdiv(idx, p.mg_obs), k = idx - le * on;
-            const double* Sl = W + le * p.s_stride;
-            if (reinterpret_cast<const SlotRes*>(Sl + p.s_res)->flags & SLOT_EMIT)
-                go[idx] = reinterpret_cast<const float*>(Sl + p.s_out)[k];
+            if (reinterpret_cast<const SlotRes*>(Sl + p.s_res)->flags & SLOT_EMIT) {
+                const double2 v = make_double2(Sl[p.s_out + 2 * c], Sl[p.s_out + 2 * c + 1]);
+                go[idx] = v;
+                reinterpret_cast<double2*>(p.state + (size_t)(wenv0 + le) * p.state_stride)[c] = v;
+            }
         }
         for (int le = lane32; le < wcnt; le += 32) {
             double* Sl = W + le * p.s_stride;
@@ -788,6 +780,26 @@ __global__ void __launch_bounds__(kThreads) flight_kernel(const __grid_constant_
             if (r->flags & SLOT_TGT_DIRTY) {                     // targets redrawn by a reset (rare)
                 double* gt = p.tgt + (size_t)(wenv0 + le) * 2 * p.m;
                 for (int k = 0; k < 2 * p.m; ++k) gt[k] = Sl[p.s_tgt + k];
+            }
+            if (r->flags & SLOT_EMIT) {
+                // target part of the state row (flight_env_easy.py:201-211): rewritten in full after a reset,
+                // otherwise only the 'find' entry of targets found by this call
+                float* srow = p.state + (size_t)(wenv0 + le) * p.state_stride + 4 * p.n;
+                const uint32_t found = slot_meta(p, Sl)[CS_META_FOUND];
+                if (r->flags & SLOT_STATE_FULL) {
+                    for (int j = 0; j < p.m; ++j) {
+                        srow[3 * j + 0] = (float)((Sl[p.s_tgt + 2 * j] - p.half_M) * p.inv_half);
+                        srow[3 * j + 1] = (float)((Sl[p.s_tgt + 2 * j + 1] - p.half_M) * p.inv_half);
+                        srow[3 * j + 2] = ((found >> j) & 1u) ? 1.0f : 0.0f;
+                    }
+                } else {
+                    uint32_t nf = slot_meta(p, Sl)[CS_META_NEWFOUND];
+                    while (nf) {
+                        const int j = __ffs(nf) - 1;
+                        nf &= nf - 1;
+                        srow[3 * j + 2] = 1.0f;
+                    }
+                }
             }
         }
     }
@@ -1014,11 +1026,12 @@ int cs_flight_create(const cs_flight_cfg* cfg, cs_flight** out) {
     p.meta_off = up2(3 * n);
     p.rec = p.meta_off + CS_META_WORDS / 2;
     p.state_len = 4 * n + 3 * m;
+    p.state_stride = (p.state_len + 3) & ~3;
     // shared slot: record | targets | cos,sin | fp32 outputs | result | amask scratch | boxes | hit cells
     int off = p.rec;
     p.s_tgt = off; off += 2 * m;
     p.s_cs = off; off += 2 * n;
-    p.s_out = off; off += up2(p.state_len) / 2;
+    p.s_out = off; off += 2 * n;
     p.s_res = off; off += 1;
     p.s_am = off; off += up2(m > (n + 3) / 4 ? m : (n + 3) / 4) / 2;
     p.s_box = off; off += cfg->variant ? 3 * n : 0;
@@ -1051,7 +1064,7 @@ int cs_flight_create(const cs_flight_cfg* cfg, cs_flight** out) {
     p.span_cap = 1;
     while (p.span_cap < 2 * cfg->view_range) p.span_cap <<= 1;
     auto magic = [](int d) { return (uint32_t)((0x100000000ULL + (uint64_t)d - 1) / (uint64_t)d); };
-    p.mg_rec2 = magic(p.rec / 2); p.mg_m = magic(m); p.mg_state = magic(p.state_len); p.mg_obs = magic(4 * n);
+    p.mg_rec2 = magic(p.rec / 2); p.mg_m = magic(m); p.mg_n = magic(n);
     const int mask_doubles = (cfg->variant && M <= 63) ? M + 2 : 0;
     auto warp_doubles = [&](int lpe) { return (32 / lpe) * p.s_stride + mask_doubles; };
     h->lpe = pick_lpe(*cfg);
@@ -1073,8 +1086,8 @@ int cs_flight_create(const cs_flight_cfg* cfg, cs_flight** out) {
     CS_CUDA(cudaMemset(p.tgt, 0, E * 2 * m * sizeof(double)));
     CS_CUDA(cudaMalloc(&p.obs, E * 4 * n * sizeof(float)));
     CS_CUDA(cudaMemset(p.obs, 0, E * 4 * n * sizeof(float)));
-    CS_CUDA(cudaMalloc(&p.state, E * p.state_len * sizeof(float)));
-    CS_CUDA(cudaMemset(p.state, 0, E * p.state_len * sizeof(float)));
+    CS_CUDA(cudaMalloc(&p.state, E * p.state_stride * sizeof(float)));
+    CS_CUDA(cudaMemset(p.state, 0, E * p.state_stride * sizeof(float)));
     CS_CUDA(cudaMalloc(&p.reward, E * sizeof(float)));
     CS_CUDA(cudaMemset(p.reward, 0, E * sizeof(float)));
     CS_CUDA(cudaMalloc(&p.terminated, E));
@@ -1119,7 +1132,7 @@ void cs_flight_destroy(cs_flight* h) {
 int cs_flight_buffers_get(cs_flight* h, cs_flight_buffers* b) {
     CS_REQUIRE(h && b, "cs_flight_buffers_get: null argument");
     const FlightParams& p = h->p;
-    b->dyn = p.dyn; b->dyn_doubles = p.rec; b->yaw_off = p.yaw_off; b->meta_off = p.meta_off; b->state_len = p.state_len;
+    b->dyn = p.dyn; b->dyn_doubles = p.rec; b->yaw_off = p.yaw_off; b->meta_off = p.meta_off; b->state_len = p.state_len; b->state_stride = p.state_stride;
     b->tgt = p.tgt; b->obs = p.obs; b->state = p.state; b->reward = p.reward; b->terminated = p.terminated;
     b->win = p.win; b->target_find = p.target_find; b->prob_map = p.prob_map; b->stats = p.stats;
     return CS_OK;
@@ -1223,7 +1236,9 @@ int cs_flight_step_host(cs_flight* h, const cs_flight_host_io* io, void* stream)
     if (io->terminated) CS_CUDA(cudaMemcpyAsync(io->terminated, p.terminated, E, cudaMemcpyDeviceToHost, st));
     if (io->win) CS_CUDA(cudaMemcpyAsync(io->win, p.win, E, cudaMemcpyDeviceToHost, st));
     if (io->obs) CS_CUDA(cudaMemcpyAsync(io->obs, p.obs, E * 4 * p.n * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (io->state) CS_CUDA(cudaMemcpyAsync(io->state, p.state, E * p.state_len * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (io->state)   // compact [E][state_len] on the host, padded rows on the device
+        CS_CUDA(cudaMemcpy2DAsync(io->state, p.state_len * sizeof(float), p.state, p.state_stride * sizeof(float),
+                                  p.state_len * sizeof(float), E, cudaMemcpyDeviceToHost, st));
     CS_CUDA(cudaStreamSynchronize(st));
     return CS_OK;
 }

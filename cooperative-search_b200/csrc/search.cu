@@ -75,7 +75,8 @@ size_t smem_base_bytes(const SearchParams& p) {
     const size_t used = sizeof(uint32_t) * (size_t)(3 * p.M * p.W) + sizeof(int32_t) * (size_t)(2 * p.n + 2 * kThreads + 8);
     return (used + 15) & ~(size_t)15;
 }
-__device__ __forceinline__ int fastdiv(int v, uint32_t magic) { return (int)__umulhi((uint32_t)v, magic); }
+// v / d with magic = ceil(2^32 / d); d == 1 gives magic 2^32 -> stored as 0 -> identity
+__device__ __forceinline__ int fastdiv(int v, uint32_t magic) { return magic ? (int)__umulhi((uint32_t)v, magic) : v; }
 
 // scal slots
 enum { SC_NEWFOUND = 0, SC_ILLEGAL = 1, SC_GOT = 2, SC_NEXTK = 3 };

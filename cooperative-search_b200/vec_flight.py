@@ -121,7 +121,7 @@ class _VecFlightBase:
         self.meta = _wrap(b.dyn, (E, 2 * b.dyn_doubles), "<i4", dev, own)[:, 2 * b.meta_off:2 * b.meta_off + _lib.CS_META_WORDS]
         self.tgt_xy = _wrap(b.tgt, (E, m, 2), "<f8", dev, own)
         self._obs = _wrap(b.obs, (E, n, 4), "<f4", dev, own)
-        self._state = _wrap(b.state, (E, b.state_len), "<f4", dev, own)
+        self._state = _wrap(b.state, (E, b.state_stride), "<f4", dev, own)[:, :b.state_len]   # rows padded to 16 B
         self._reward = _wrap(b.reward, (E,), "<f4", dev, own)
         self._terminated = _wrap(b.terminated, (E,), "|u1", dev, own)
         self._win = _wrap(b.win, (E,), "|u1", dev, own)

@@ -118,9 +118,11 @@ typedef struct cs_flight_buffers {
     int32_t yaw_off;        /* = 2n   (doubles)                                            */
     int32_t meta_off;       /* doubles; meta words start at (uint32*)(rec + meta_off)      */
     int32_t state_len;      /* 4n + 3m                                                     */
+    int32_t state_stride;   /* floats between consecutive state rows (state_len rounded up
+                               to a multiple of 4 so rows start 16-byte aligned)           */
     double* tgt;
     float* obs;             /* [E][n][4]     get_obs   (flight_env_easy.py:218-221)        */
-    float* state;           /* [E][4n+3m]    get_state (:190-216)                          */
+    float* state;           /* [E][state_stride], first 4n+3m of a row = get_state (:190-216) */
     float* reward;          /* [E]           step()[0] (:314)                              */
     uint8_t* terminated;    /* [E]           step()[1]                                     */
     uint8_t* win;           /* [E]           step()[2] (win_flag)                          */
