@@ -36,9 +36,10 @@ struct FlightParams {
     int state_stride;            // floats per state row in HBM (state_len rounded up to a multiple of 4)
     // shared-memory slot geometry (doubles)
     int s_tgt, s_cs, s_out, s_res, s_am, s_box, s_hit, s_stride;
-    int s_warp;                  // doubles of shared memory per warp (EPW slots + corner-row masks)
+    int s_warp;                  // doubles of shared memory per warp (EPW slots + corner-row masks + table index)
+    int s_lut;                   // offset (doubles, even) of the warp's copy of the heading-table index
     int span_cap;                // power of two >= 2R: corner rows per agent in the interval pass
-    uint32_t mg_rec2, mg_m, mg_n;   // ceil(2^32/d) for the staging loops' index splits
+    uint32_t mg_rec2, mg_m, mg_n, mg_rows;   // ceil(2^32/d) for index splits (d = rec/2, m, n, span_cap+1)
     double Md, half_M, inv_half, R, R2, v, fk, fd2, near2, q_miss;
     double turn, pi, two_pi, three_pi, half_pi;
     long long thr;
@@ -69,6 +70,9 @@ struct SlotRes {
     uint8_t pad;
 };
 
+// v / d with magic = ceil(2^32 / d); d == 1 gives magic 2^32 -> stored as 0 -> identity
+__device__ __forceinline__ int fastdiv(int v, uint32_t magic) { return magic ? (int)__umulhi((uint32_t)v, magic) : v; }
+
 __device__ __forceinline__ uint32_t* slot_meta(const FlightParams& p, double* S) {
     return reinterpret_cast<uint32_t*>(S + p.meta_off);
 }
@@ -88,7 +92,7 @@ __device__ __forceinline__ uint32_t* slot_meta(const FlightParams& p, double* S)
 // ------------------------------------------------------------------------------------------------
 __device__ __noinline__ void offlattice_sincos(double h, double* sn, double* c) { sincos(h, sn, c); }
 
-__device__ __forceinline__ void heading_sincos(const FlightParams& p, double h, double* sn, double* c) {
+__device__ __forceinline__ void heading_sincos(const FlightParams& p, const longlong2* lutm, double h, double* sn, double* c) {
     const int k = __double2int_rn(h * p.inv_turn);
     if (k == 0 && fabs(h) < 7.450580596923828e-09) {   // |h| < 2^-27: libm returns sin = h, cos = 1
         *sn = h;
@@ -96,7 +100,7 @@ __device__ __forceinline__ void heading_sincos(const FlightParams& p, double h, 
         return;
     }
     if (k >= 1 && k <= 36) {
-        const longlong2 mt = __ldg(p.lut_meta + k);
+        const longlong2 mt = lutm[k];                      // cluster index staged in shared memory by the warp
         const long long off = __double_as_longlong(h) - mt.x;
         const long long half = mt.y >> 32;
         if (off >= -half && off <= half) {
@@ -163,7 +167,7 @@ __device__ __noinline__ uint32_t fl_move_coupled(const FlightParams& p, double* 
 // _agent_step: heading update, advance, repulsion (Gauss-Seidel), wall.  Returns the out-of-map mask.
 // ------------------------------------------------------------------------------------------------
 template <int LPE>
-__device__ __forceinline__ uint32_t fl_move(const FlightParams& p, double* S, int lane, const uint8_t* act) {
+__device__ __forceinline__ uint32_t fl_move(const FlightParams& p, double* S, int lane, const uint8_t* act, const longlong2* lutm) {
     using G = Group<LPE>;
     const int n = p.n;
     double* yaw = S + p.yaw_off;
@@ -175,7 +179,7 @@ __device__ __forceinline__ uint32_t fl_move(const FlightParams& p, double* S, in
         if (h > p.two_pi) h -= p.two_pi;                          // strict tests (:263-266)
         else if (h < 0.0) h += p.two_pi;
         double sn, c;
-        heading_sincos(p, h, &sn, &c);
+        heading_sincos(p, lutm, h, &sn, &c);
         yaw[a] = h;
         cs[a] = c;
         cs[n + a] = sn;
@@ -241,14 +245,15 @@ __device__ __forceinline__ bool corner_pred(double A, double cy, double ay, doub
     return A + dy * dy < R2;                                   // strict '<' (:300)
 }
 
-// The reference's own grouping (1-d)*p + (1-p) matters: 1-p is exact near p = 1 (a found cell), and a cell at
-// exactly 1 must stay exactly 1 while all four corners are in view -- x/x with a correctly rounded divide --
-// because the map's derivative there is 10: any seed error would grow tenfold per step.
-__device__ __forceinline__ float belief_update(float pv, int cnt, float qf, float qm1f) {
-    (void)qm1f;
-    const float num = (0.25f * (float)cnt * qf) * pv;          // percent*(1-d)*p            (:292)
+// The reference's own grouping (1-d)*p + (1-p) matters: 1-p is exact near p = 1.  A cell at exactly 1 (a found
+// target) must map to exactly percent -- in particular stay exactly 1 while all four corners are in view --
+// because the map's derivative there is 10 and any seed error would grow tenfold per step; that case is taken
+// exactly, everything else uses the fast reciprocal (values never approach 1 from below: p' <= p).
+__device__ __forceinline__ float belief_update(float pv, int cnt, float qf) {
+    const float frac = 0.25f * (float)cnt;
+    const float num = (frac * qf) * pv;                        // percent*(1-d)*p            (:292)
     const float den = fmaf(qf, pv, 1.0f - pv);                 // (1-d)*p + (1-p)
-    return __fdiv_rn(num, den);
+    return (pv == 1.0f) ? frac : __fdividef(num, den);
 }
 
 __device__ __forceinline__ unsigned fl_probmap(const FlightParams& p, double* S, int lane, float* map, uint32_t newf,
@@ -281,8 +286,10 @@ __device__ __forceinline__ unsigned fl_probmap(const FlightParams& p, double* S,
     __syncwarp();
     // (1) corner-row intervals
     const int span = p.span_cap;                      // power of two >= 2R
-    for (int t = lane; t < n * span; t += 32) {
-        const int a = t / span, r = t - a * span;
+    for (int t0 = 0; t0 < n * span; t0 += 32) {
+        const int t = t0 + lane;
+        if (t >= n * span) continue;
+        const int a = t / span, r = t - a * span;          // span is a power of two
         const int cx = box[6 * a + 4] + r;
         if (cx > box[6 * a + 5] || cx < 0 || cx > M) continue;
         const double ax = S[2 * a], ay = S[2 * a + 1];
@@ -306,40 +313,84 @@ __device__ __forceinline__ unsigned fl_probmap(const FlightParams& p, double* S,
         }
     }
     __syncwarp();
-    // (2)+(3) sweep
-    unsigned touched = 0;
-    const float qf = (float)p.q_miss, qm1f = (float)(p.q_miss - 1.0);
-    const bool vec2 = (M & 1) == 0;
-    for (int a = 0; a < n; ++a) {
-        const int i0 = box[6 * a], i1 = box[6 * a + 1], j0 = box[6 * a + 2], j1 = box[6 * a + 3];
-        if (i0 > i1 || j0 > j1) continue;
-        const unsigned long long colmask = ((2ull << j1) - 1ull) & ~((1ull << j0) - 1ull);
-        const int rsub = vec2 ? (lane >> 3) : (lane >> 4), rstep = vec2 ? 4 : 2;
-        const int jb = vec2 ? (j0 & ~1) : j0;
-        for (int jc = jb; jc <= j1; jc += 16) {
-            const int j = vec2 ? jc + 2 * (lane & 7) : jc + (lane & 15);
-            for (int i = i0 + rsub; i <= i1; i += rstep) {
+    // (2) per (agent, box row): the touched cells this agent's sweep owns.  A cell inside several boxes belongs
+    //     to the first of them.  own[a*rows_cap + r] covers map row i0_a + r.
+    const int rows_cap = p.span_cap + 1;
+    unsigned long long* own = rowmask + (M + 2);
+    for (int t0 = 0; t0 < n * rows_cap; t0 += 32) {
+        const int t = t0 + lane;
+        if (t < n * rows_cap) {
+            const int a = fastdiv(t, p.mg_rows), r = t - a * rows_cap;
+            const int i = box[6 * a] + r;
+            unsigned long long Tm = 0ull;
+            if (i <= box[6 * a + 1]) {
                 const unsigned long long A = rowmask[i], B = rowmask[i + 1];
-                unsigned long long Tm = (A | (A >> 1) | B | (B >> 1)) & colmask;
-                for (int b = 0; b < a; ++b)                     // a cell inside several boxes belongs to the first
-                    if (i >= box[6 * b] && i <= box[6 * b + 1])
-                        Tm &= ~(((2ull << box[6 * b + 3]) - 1ull) & ~((1ull << box[6 * b + 2]) - 1ull));
-                const unsigned t2 = (unsigned)(Tm >> j) & (vec2 ? 3u : 1u);
-                if (!t2) continue;                              // percent == 0 -> untouched (:285-286)
-                const int cell = i * M + j;
-                const unsigned a2 = (unsigned)(A >> j) & 7u, b2 = (unsigned)(B >> j) & 7u;
-                if (vec2) {
-                    float2 v = *reinterpret_cast<float2*>(map + cell);
-                    if (t2 & 1u) v.x = belief_update(v.x, __popc(a2 & 3u) + __popc(b2 & 3u), qf, qm1f);
-                    if (t2 & 2u) v.y = belief_update(v.y, __popc(a2 & 6u) + __popc(b2 & 6u), qf, qm1f);
-                    for (int k = 0; k < nh; ++k) {              // targets found by THIS call -> 1 (:288-289)
-                        if ((t2 & 1u) && hit[k] == cell) v.x = 1.0f;
-                        if ((t2 & 2u) && hit[k] == cell + 1) v.y = 1.0f;
+                Tm = (A | (A >> 1) | B | (B >> 1)) & (((2ull << box[6 * a + 3]) - 1ull) & ~((1ull << box[6 * a + 2]) - 1ull));
+                for (int q = 0; q < a; ++q)
+                    if (i >= box[6 * q] && i <= box[6 * q + 1])
+                        Tm &= ~(((2ull << box[6 * q + 3]) - 1ull) & ~((1ull << box[6 * q + 2]) - 1ull));
+            }
+            own[t] = Tm;
+        }
+    }
+    __syncwarp();
+    // (3) sweep: 8 lanes x float2 per map row, 4 rows per instruction, 4 instructions' loads in flight
+    unsigned touched = 0;
+    const float qf = (float)p.q_miss;
+    if ((M & 1) == 0) {
+        const int rsub = lane >> 3, jl = 2 * (lane & 7);
+        for (int a = 0; a < n; ++a) {
+            const int i0 = box[6 * a], i1 = box[6 * a + 1], j0 = box[6 * a + 2], j1 = box[6 * a + 3];
+            const int nrows = i1 - i0 + 1;
+            const unsigned long long* ow = own + a * rows_cap;
+            for (int jc = j0 & ~1; jc <= j1; jc += 16) {
+                const int j = jc + jl;
+                for (int rb = 0; rb < nrows; rb += 16) {
+                    float2 v[4];
+                    unsigned t2[4], ab[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int r = rb + 4 * u + rsub;
+                        t2[u] = 0u;
+                        if (r < nrows) {
+                            t2[u] = (unsigned)(ow[r] >> j) & 3u;
+                            if (t2[u]) {
+                                const int i = i0 + r;
+                                v[u] = *reinterpret_cast<const float2*>(map + i * M + j);
+                                ab[u] = ((unsigned)(rowmask[i] >> j) & 7u) | (((unsigned)(rowmask[i + 1] >> j) & 7u) << 3);
+                            }
+                        }
                     }
-                    *reinterpret_cast<float2*>(map + cell) = v;
-                    touched += __popc(t2);
-                } else {
-                    float v = belief_update(map[cell], __popc(a2 & 3u) + __popc(b2 & 3u), qf, qm1f);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (!t2[u]) continue;                              // percent == 0 -> untouched (:285-286)
+                        const int cell = (i0 + rb + 4 * u + rsub) * M + j;
+                        const unsigned a2 = ab[u] & 7u, b2 = ab[u] >> 3;
+                        if (t2[u] & 1u) v[u].x = belief_update(v[u].x, __popc(a2 & 3u) + __popc(b2 & 3u), qf);
+                        if (t2[u] & 2u) v[u].y = belief_update(v[u].y, __popc(a2 & 6u) + __popc(b2 & 6u), qf);
+                        for (int k = 0; k < nh; ++k) {                     // targets found by THIS call -> 1 (:288-289)
+                            if ((t2[u] & 1u) && hit[k] == cell) v[u].x = 1.0f;
+                            if ((t2[u] & 2u) && hit[k] == cell + 1) v[u].y = 1.0f;
+                        }
+                        *reinterpret_cast<float2*>(map + cell) = v[u];
+                        touched += __popc(t2[u]);
+                    }
+                }
+            }
+        }
+    } else {
+        // odd map_size: rows are only 4-byte aligned -> one cell per lane, 16 lanes per row, 2 rows per instruction
+        const int rsub = lane >> 4, jl = lane & 15;
+        for (int a = 0; a < n; ++a) {
+            const int i0 = box[6 * a], i1 = box[6 * a + 1], j0 = box[6 * a + 2], j1 = box[6 * a + 3];
+            const unsigned long long* ow = own + a * rows_cap;
+            for (int jc = j0; jc <= j1; jc += 16) {
+                const int j = jc + jl;
+                for (int r = rsub; r <= i1 - i0; r += 2) {
+                    if (!((ow[r] >> j) & 1ull)) continue;
+                    const int i = i0 + r, cell = i * M + j;
+                    const unsigned a2 = (unsigned)(rowmask[i] >> j) & 3u, b2 = (unsigned)(rowmask[i + 1] >> j) & 3u;
+                    float v = belief_update(map[cell], __popc(a2) + __popc(b2), qf);
                     for (int k = 0; k < nh; ++k)
                         if (hit[k] == cell) v = 1.0f;
                     map[cell] = v;
@@ -376,7 +427,7 @@ __device__ __noinline__ unsigned fl_probmap_wide(const FlightParams& p, double* 
     }
     __syncwarp();
     unsigned touched = 0;
-    const float qf = (float)p.q_miss, qm1f = (float)(p.q_miss - 1.0);
+    const float qf = (float)p.q_miss;
     const int col = lane & 15, half = lane >> 4;
     for (int a = 0; a < n; ++a) {
         const int i0 = box[6 * a], i1 = box[6 * a + 1], j0 = box[6 * a + 2], j1 = box[6 * a + 3];
@@ -403,7 +454,7 @@ __device__ __noinline__ unsigned fl_probmap_wide(const FlightParams& p, double* 
                 if (!bits) continue;
                 ++touched;
                 const int cell = i * M + j;
-                float v = belief_update(map[cell], __popc(bits), qf, qm1f);
+                float v = belief_update(map[cell], __popc(bits), qf);
                 for (int k = 0; k < nh; ++k)
                     if (hit[k] == cell) v = 1.0f;
                 map[cell] = v;
@@ -575,8 +626,6 @@ __device__ __forceinline__ void fl_emit(const FlightParams& p, double* S, int la
 
 enum { MODE_STEP = 0, MODE_RESET = 1 };
 
-// v / d with magic = ceil(2^32 / d); d == 1 gives magic 2^32 -> stored as 0 -> identity
-__device__ __forceinline__ int fastdiv(int v, uint32_t magic) { return magic ? (int)__umulhi((uint32_t)v, magic) : v; }
 
 // Warp-wide belief-map pass over the envs of this warp whose slot carries SLOT_MAP_PENDING.
 __device__ __noinline__ unsigned map_pass(const FlightParams& p, double* W, int wcnt, int wenv0, int lane32,
@@ -604,7 +653,7 @@ __global__ void __launch_bounds__(kThreads) flight_kernel(const __grid_constant_
                                                           const uint8_t* __restrict__ mask, uint32_t rflags) {
     using G = Group<LPE>;
     constexpr int EPW = 32 / LPE;
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) double smem[];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane32 = tid & 31;
     const int wenv0 = (blockIdx.x * (kThreads / 32) + warp) * EPW;      // first env of this warp
@@ -613,19 +662,47 @@ __global__ void __launch_bounds__(kThreads) flight_kernel(const __grid_constant_
     double* W = smem + (size_t)warp * p.s_warp;
     unsigned long long* rowmask = reinterpret_cast<unsigned long long*>(W + (size_t)EPW * p.s_stride);
 
-    // ---- stage this warp's records: global -> shared, 16-byte coalesced ---------------------------
+    // ---- stage this warp's records: global -> shared, 16-byte coalesced.  The first round of every stream
+    //      (records, targets, heading-table index) is issued before anything is consumed, so their HBM/L2
+    //      latencies overlap instead of adding up.
+    longlong2* lutm = reinterpret_cast<longlong2*>(W + p.s_lut);
     {
         const int rec2 = p.rec >> 1;
+        const int nd = wcnt * rec2, nt = wcnt * p.m;
         const double2* gd = reinterpret_cast<const double2*>(p.dyn + (size_t)wenv0 * p.rec);
-        for (int idx = lane32; idx < wcnt * rec2; idx += 32) {
+        const double2* gt = reinterpret_cast<const double2*>(p.tgt + (size_t)wenv0 * 2 * p.m);
+        double2 vd = make_double2(0.0, 0.0), vt = make_double2(0.0, 0.0);
+        longlong2 vl0 = make_longlong2(0, 0), vl1 = make_longlong2(0, 0);
+        if (lane32 < nd) vd = gd[lane32];
+        if (lane32 < nt) vt = gt[lane32];
+        if (MODE == MODE_STEP) {
+            vl0 = __ldg(p.lut_meta + lane32);
+            if (lane32 + 32 < 37) vl1 = __ldg(p.lut_meta + lane32 + 32);
+        }
+        if (lane32 < nd) {
+            const int le = fastdiv(lane32, p.mg_rec2), k = lane32 - le * rec2;
+            double* S = W + le * p.s_stride;
+            S[2 * k] = vd.x;
+            S[2 * k + 1] = vd.y;
+        }
+        if (lane32 < nt) {
+            const int le = fastdiv(lane32, p.mg_m), k = lane32 - le * p.m;
+            double* S = W + le * p.s_stride + p.s_tgt;
+            S[2 * k] = vt.x;
+            S[2 * k + 1] = vt.y;
+        }
+        if (MODE == MODE_STEP) {
+            lutm[lane32] = vl0;
+            if (lane32 + 32 < 37) lutm[lane32 + 32] = vl1;
+        }
+        for (int idx = lane32 + 32; idx < nd; idx += 32) {
             const int le = fastdiv(idx, p.mg_rec2), k = idx - le * rec2;
             const double2 v = gd[idx];
             double* S = W + le * p.s_stride;
             S[2 * k] = v.x;
             S[2 * k + 1] = v.y;
         }
-        const double2* gt = reinterpret_cast<const double2*>(p.tgt + (size_t)wenv0 * 2 * p.m);
-        for (int idx = lane32; idx < wcnt * p.m; idx += 32) {
+        for (int idx = lane32 + 32; idx < nt; idx += 32) {
             const int le = fastdiv(idx, p.mg_m), k = idx - le * p.m;
             const double2 v = gt[idx];
             double* S = W + le * p.s_stride + p.s_tgt;
@@ -674,7 +751,7 @@ __global__ void __launch_bounds__(kThreads) flight_kernel(const __grid_constant_
                     G::sync();
                     act = ra;
                 }
-                const uint32_t outbits = fl_move<LPE>(p, S, lane, act);
+                const uint32_t outbits = fl_move<LPE>(p, S, lane, act, lutm);
                 G::sync();
                 const int rew = fl_sense<LPE>(p, S, lane, env_id, time0 + 1u, outbits, res);
                 const uint32_t time1 = time0 + 1u;
@@ -1064,12 +1141,16 @@ int cs_flight_create(const cs_flight_cfg* cfg, cs_flight** out) {
     p.span_cap = 1;
     while (p.span_cap < 2 * cfg->view_range) p.span_cap <<= 1;
     auto magic = [](int d) { return (uint32_t)((0x100000000ULL + (uint64_t)d - 1) / (uint64_t)d); };
-    p.mg_rec2 = magic(p.rec / 2); p.mg_m = magic(m); p.mg_n = magic(n);
-    const int mask_doubles = (cfg->variant && M <= 63) ? M + 2 : 0;
-    auto warp_doubles = [&](int lpe) { return (32 / lpe) * p.s_stride + mask_doubles; };
+    p.mg_rec2 = magic(p.rec / 2); p.mg_m = magic(m); p.mg_n = magic(n); p.mg_rows = magic(p.span_cap + 1);
+    // corner-row masks + per-(agent,row) owned masks of the belief-map pass, then the heading-table index (37 x 16 B)
+    const int mask_doubles = ((cfg->variant && M <= 63) ? M + 2 + n * (p.span_cap + 1) : 0);
+    // per-warp layout: EPW slots | masks | (pad to 16 B) heading-table index: 37 x 16 B = 74 doubles (+2 spare)
+    auto lut_off = [&](int lpe) { return ((32 / lpe) * p.s_stride + mask_doubles + 1) & ~1; };
+    auto warp_doubles = [&](int lpe) { return lut_off(lpe) + 76; };
     h->lpe = pick_lpe(*cfg);
     // fall back to more lanes per env until the CTA's slots fit the shared memory of one SM
     while (h->lpe < 32 && (size_t)(kThreads / 32) * warp_doubles(h->lpe) * sizeof(double) > 200 * 1024) h->lpe <<= 1;
+    p.s_lut = lut_off(h->lpe);
     p.s_warp = warp_doubles(h->lpe);
     h->smem_bytes = (size_t)(kThreads / 32) * p.s_warp * sizeof(double);
     const int env_per_cta = (kThreads / 32) * (32 / h->lpe);

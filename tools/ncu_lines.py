@@ -9,6 +9,7 @@ def num(v):
 
 
 rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+SORT = 1 if (len(sys.argv) > 3 and sys.argv[3] == "inst") else 0
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 cur_file = None; hdr = None; agg = collections.OrderedDict()
@@ -27,5 +28,5 @@ for r in rows:
 tot_s = sum(a[0] for a in agg.values()) or 1; tot_i = sum(a[1] for a in agg.values()) or 1
 print("total samples %d, total warp-instr %d (over all captured launches)" % (tot_s, tot_i))
 print("%-16s %5s %7s %7s  %s" % ("file", "line", "samp%", "inst%", "source"))
-for (f, ln, src), a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+for (f, ln, src), a in sorted(agg.items(), key=lambda kv: -kv[1][SORT])[:top]:
     print("%-16s %5d %6.1f%% %6.1f%%  %s" % (f, ln, 100.0 * a[0] / tot_s, 100.0 * a[1] / tot_i, src))

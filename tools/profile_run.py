@@ -12,7 +12,7 @@ import coopsearch_b200 as cs  # noqa: E402
 name = sys.argv[1] if len(sys.argv) > 1 else "c2"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 w = dict(bench.WORKLOADS[name])
-w["batches"] = min(w["batches"], 4)
+w["batches"] = min(w["batches"], int(os.environ.get("CS_PROFILE_BATCHES", "4")))
 dev = torch.device("cuda", 0)
 envs = bench.silence(bench.make_envs, cs, w, dev, 0)
 gen = torch.Generator(device=dev).manual_seed(1)
