@@ -335,15 +335,22 @@ def run_gpu_workload(cs, torch, name, steps, warmup, device, rank, world, want_e
         for e in envs:
             e.host_buffers()
 
+        streams = [torch.cuda.Stream(device=device) for _ in range(min(4, len(envs)))]
+
         def host_step(k):
-            for b, e in enumerate(envs):
-                if w["kind"] == "search":
+            if w["kind"] == "search":
+                for b, e in enumerate(envs):
                     av = e.host_buffers()["avail"].numpy()
                     # first legal move of every agent, computed on the host from the previous step's D2H avail mask
                     acts = av.argmax(axis=2).astype(np.uint8)
                     e.step_host(acts)
-                else:
-                    e.step_host(host_actions[k % 2][b])
+                return
+            # independent env batches are pipelined over a few streams: H2D / kernel / D2H of different batches overlap
+            for b, e in enumerate(envs):
+                with torch.cuda.stream(streams[b % len(streams)]):
+                    e.step_host(host_actions[k % 2][b], sync=False)
+            for st in streams:
+                st.synchronize()
 
         if w["kind"] == "search":
             for e in envs:
@@ -360,7 +367,10 @@ def run_gpu_workload(cs, torch, name, steps, warmup, device, rank, world, want_e
         dt = time.perf_counter() - t0
         hb = envs[0].host_buffers()
         h2d = sum(hb["actions"].numel() for _ in envs)
-        d2h = sum(sum(v.numel() * v.element_size() for kname, v in e.host_buffers().items() if kname != "actions") for e in envs)
+        if "slab" in hb:
+            d2h = sum(e.host_buffers()["slab"].numel() for e in envs)      # one D2H copy of the output slab per batch
+        else:
+            d2h = sum(sum(v.numel() * v.element_size() for kname, v in e.host_buffers().items() if kname != "actions") for e in envs)
         out.update(e2e_s_per_step=dt / e2e_steps, e2e_steps=e2e_steps, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h)
     # statistics of the finished episodes on this GPU (all-reduced by the caller)
     stats = torch.zeros(8, dtype=torch.float64, device=device)
@@ -496,7 +506,7 @@ def main():
         "agent_steps_per_s": value * w["n"],
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": res["h2d_bytes_per_step"],
                 "d2h_bytes_per_step": res["d2h_bytes_per_step"], "agent_steps_per_s": e2e_value * w["n"],
-                "steps": res["e2e_steps"], "path": "cs_*_step_host: pinned host actions -> H2D -> step kernel -> D2H reward/terminated/win/obs/state -> sync, per batch"},
+                "steps": res["e2e_steps"], "path": "cs_*_step_host per batch: pinned host actions -> H2D -> step kernel -> one D2H of reward/terminated/win/target_find/obs/state; batches pipelined over 4 streams, all synchronised every step"},
         "gpu_launches": int(res["launches"] * 1),
         "gpu_launches_process_total": int(lib.cs_launch_count() - launches0),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -45,7 +45,10 @@ class FlightBuffers(C.Structure):
 
 class FlightHostIO(C.Structure):
     _fields_ = [("actions", C.c_void_p), ("reward", C.c_void_p), ("terminated", C.c_void_p), ("win", C.c_void_p),
-                ("obs", C.c_void_p), ("state", C.c_void_p)]
+                ("obs", C.c_void_p), ("state", C.c_void_p), ("slab", C.c_void_p), ("flags", C.c_uint32)]
+
+
+CS_HOST_NO_SYNC = 1
 
 
 class SearchCfg(C.Structure):
@@ -91,6 +94,7 @@ SIGNATURES = {
     "cs_flight_step_random": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "cs_flight_obs_full": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "cs_flight_step_host": (C.c_int, [C.c_void_p, C.POINTER(FlightHostIO), C.c_void_p]),
+    "cs_flight_slab_layout": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "cs_flight_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_void_p]),
     "cs_search_create": (C.c_int, [C.POINTER(SearchCfg), C.POINTER(C.c_void_p)]),
     "cs_search_destroy": (None, [C.c_void_p]),

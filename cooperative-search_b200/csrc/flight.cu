@@ -26,20 +26,18 @@ namespace {
 
 constexpr int kThreads = 128;
 
-enum : uint32_t { SLOT_EMIT = 1u, SLOT_TGT_DIRTY = 2u, SLOT_MAP_PENDING = 4u, SLOT_RESULT = 8u, SLOT_STATE_FULL = 16u };
-
 struct FlightParams {
     int E, n, m, M, T;
     int variant, auto_reset, agent_mode, target_mode, count_touched;
     // per-env record geometry (doubles)
     int rec, yaw_off, meta_off, state_len;
     int state_stride;            // floats per state row in HBM (state_len rounded up to a multiple of 4)
-    // shared-memory slot geometry (doubles)
-    int s_tgt, s_cs, s_out, s_res, s_am, s_box, s_hit, s_stride;
-    int s_warp;                  // doubles of shared memory per warp (EPW slots + corner-row masks + table index)
-    int s_lut;                   // offset (doubles, even) of the warp's copy of the heading-table index
+    // per-warp shared-memory scratch (doubles): one 5n block per group for the coupled-move path, then the
+    // belief-map scratch (agent xy | boxes | hit cells | corner-row masks | owned masks), then the table index
+    int s_cs;                    // = 3n: offset of cos/sin inside a group's 5n block (x,y | yaw | cos,sin)
+    int s_grp, s_map, s_box, s_hit, s_mask, s_lut, s_warp;
     int span_cap;                // power of two >= 2R: corner rows per agent in the interval pass
-    uint32_t mg_rec2, mg_m, mg_n, mg_rows;   // ceil(2^32/d) for index splits (d = rec/2, m, n, span_cap+1)
+    uint32_t mg_rows;            // ceil(2^32/(span_cap+1))
     double Md, half_M, inv_half, R, R2, v, fk, fd2, near2, q_miss;
     double turn, pi, two_pi, three_pi, half_pi;
     long long thr;
@@ -62,20 +60,8 @@ struct FlightParams {
     double cos0, sin0;           // cos/sin of the start heading of agent_mode, from the host libm
 };
 
-struct SlotRes {
-    float reward;
-    uint8_t terminated;
-    uint8_t win;
-    uint8_t flags;   // SLOT_*
-    uint8_t pad;
-};
-
 // v / d with magic = ceil(2^32 / d); d == 1 gives magic 2^32 -> stored as 0 -> identity
 __device__ __forceinline__ int fastdiv(int v, uint32_t magic) { return magic ? (int)__umulhi((uint32_t)v, magic) : v; }
-
-__device__ __forceinline__ uint32_t* slot_meta(const FlightParams& p, double* S) {
-    return reinterpret_cast<uint32_t*>(S + p.meta_off);
-}
 
 // ------------------------------------------------------------------------------------------------
 // cos/sin of a heading.
@@ -116,29 +102,26 @@ __device__ __forceinline__ void heading_sincos(const FlightParams& p, const long
 // ------------------------------------------------------------------------------------------------
 // wall handling of one agent: env/flight_env_easy.py:278-290 ('>' test), env/flight_env.py:328 ('>=')
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t fl_wall(const FlightParams& p, double* S, int a, double x, double y) {
+__device__ __forceinline__ bool wall_reg(const FlightParams& p, double& x, double& y, double& h, double& c) {
     const double Md = p.Md;
     const bool outside = p.variant ? (x < 0.0 || x >= Md || y < 0.0 || y >= Md)
                                    : (x < 0.0 || x > Md || y < 0.0 || y > Md);
     if (outside) {
         x = fmin(fmax(x, 0.0), Md);
         y = fmin(fmax(y, 0.0), Md);
-        double* yaw = S + p.yaw_off;
-        double* cs = S + p.s_cs;
-        const double h = yaw[a];
-        yaw[a] = (h <= p.pi) ? (p.pi - h) : (p.three_pi - h);
-        cs[a] = -cs[a];   // cos(pi - h) = cos(3pi - h) = -cos(h); sin unchanged (fp32 outputs only)
+        h = (h <= p.pi) ? (p.pi - h) : (p.three_pi - h);
+        c = -c;   // cos(pi - h) = cos(3pi - h) = -cos(h); sin unchanged (only the fp32 outputs use them)
     }
-    S[2 * a] = x;
-    S[2 * a + 1] = y;
-    return outside ? 1u : 0u;
+    return outside;
 }
 
 // Repulsion slow path: the reference's sequential, in-place update -- agent k sees its own OLD position and the
-// already-moved j<k (env/flight_env_easy.py:271,:293-301).  Out of line: rare, and keeps the hot path compact.
+// already-moved j<k (env/flight_env_easy.py:271,:293-301).  Runs on a 5n-double scratch block in shared memory
+// (x,y per agent | heading | cos | sin).  Out of line: rare, and keeps the hot path compact.
 __device__ __noinline__ uint32_t fl_move_coupled(const FlightParams& p, double* S) {
     const int n = p.n;
-    const double* cs = S + p.s_cs;
+    double* yaw = S + p.yaw_off;
+    double* cs = S + p.s_cs;
     uint32_t outbits = 0;
     for (int k = 0; k < n; ++k) {
         const double x0 = S[2 * k], y0 = S[2 * k + 1];
@@ -158,57 +141,37 @@ __device__ __noinline__ uint32_t fl_move_coupled(const FlightParams& p, double* 
         }
         x += fx;
         y += fy;
-        outbits |= fl_wall(p, S, k, x, y) << k;
+        double h = yaw[k], c = cs[k];
+        if (wall_reg(p, x, y, h, c)) outbits |= 1u << k;
+        S[2 * k] = x;
+        S[2 * k + 1] = y;
+        yaw[k] = h;
+        cs[k] = c;
     }
     return outbits;
 }
 
-// ------------------------------------------------------------------------------------------------
-// _agent_step: heading update, advance, repulsion (Gauss-Seidel), wall.  Returns the out-of-map mask.
-// ------------------------------------------------------------------------------------------------
-template <int LPE>
-__device__ __forceinline__ uint32_t fl_move(const FlightParams& p, double* S, int lane, const uint8_t* act, const longlong2* lutm) {
-    using G = Group<LPE>;
-    const int n = p.n;
-    double* yaw = S + p.yaw_off;
-    double* cs = S + p.s_cs;
-    for (int a = lane; a < n; a += LPE) {
-        const int u = act[a];
-        double h = yaw[a];
-        h += (u == 1) ? p.turn : ((u == 2) ? -p.turn : 0.0);      // dyaw = [0, pi/18, -pi/18]  (:259-262)
-        if (h > p.two_pi) h -= p.two_pi;                          // strict tests (:263-266)
-        else if (h < 0.0) h += p.two_pi;
-        double sn, c;
-        heading_sincos(p, lutm, h, &sn, &c);
-        yaw[a] = h;
-        cs[a] = c;
-        cs[n + a] = sn;
-    }
-    G::sync();
-    // Can any repulsion term be non-zero this step?  If every pair of OLD positions is farther apart
-    // than force_dist + |v| (with slack), no agent receives a force, every displacement is <= |v|, and
-    // by induction over the sequential update order no later agent does either.
-    bool close = false;
-    for (int a = lane; a < n; a += LPE) {
-        const double xa = S[2 * a], ya = S[2 * a + 1];
-        for (int q = a + 1; q < n; ++q) {
-            const double dx = S[2 * q] - xa, dy = S[2 * q + 1] - ya;
-            close |= (dx * dx + dy * dy < p.near2);
+// Reset-time target placement (env/flight_env_easy.py:95-127) from the keyed stream; cold, out of line.
+__device__ __noinline__ double2 draw_target(const FlightParams& p, uint32_t env_id, uint32_t episode, int j) {
+    const cs_u4 w = cs_philox4x32_10(env_id, (episode & 0xFFFFu) << 16, (uint32_t)j, 0u, p.seed, CS_STREAM_TARGET);
+    const double u1 = cs_u53(w.x, w.y), u2 = cs_u53(w.z, w.w);
+    double x, y;
+    if (p.target_mode == 0) {
+        const double* row = p.tmpl + 5 * j;
+        x = row[0];
+        y = row[1];
+        if (row[4] != 0.0) {                      // deter == 'f' (:106-110)
+            const double rad = sqrt(-2.0 * log(u1));
+            double sn, c;
+            sincos(2.0 * p.pi * u2, &sn, &c);
+            x += row[2] * 2.0 * (rad * c - 0.5);
+            y += row[3] * 2.0 * (rad * sn - 0.5);
         }
+    } else {                                      // target_mode 1 (:122-127)
+        x = p.Md * u1;
+        y = p.Md * u2;
     }
-    close = G::any(close);
-    uint32_t outbits = 0;
-    if (!close) {
-        for (int a = lane; a < n; a += LPE) {
-            const double x = S[2 * a] + p.v * cs[a];              // x += v*cos(yaw)   (:267-268)
-            const double y = S[2 * a + 1] + p.v * cs[n + a];
-            outbits |= fl_wall(p, S, a, x, y) << a;
-        }
-    } else if (lane == 0) {
-        outbits = fl_move_coupled(p, S);
-    }
-    outbits = G::reduce_or(outbits);
-    return outbits;
+    return make_double2(x, y);
 }
 
 // Integer corner coordinates c with fl((c - a)^2) < R^2 -- a necessary condition for a corner in that
@@ -224,22 +187,6 @@ __device__ __forceinline__ void corner_span(double a, double R, double R2, int* 
     *hi = (d * d < R2) ? c : c - 1;
 }
 
-// ------------------------------------------------------------------------------------------------
-// belief map: _update_prob_map + _percent_in_agent_viewrange (env/flight_env.py:275-303), one warp per env.
-//
-// The reference classifies the 4 corners of every cell against every agent (2500 x 4 x n fp64 tests).  Here:
-//  (1) corner classification by ROW INTERVALS: for agent a and integer corner row cx, the corner columns cy with
-//      fl(fl((cx-ax)^2) + fl((cy-ay)^2)) < R^2 form an interval (the expression is monotone in |cy-ay|).  Its
-//      ends come from one fp32 sqrt; only when an end lies within 1e-3 of an integer is the reference's exact
-//      fp64 predicate evaluated there.  One lane per (agent, corner row): <= 2R*n tasks.  The interval is OR-ed as a
-//      bit mask into rowmask[cx] (bit cy), the union over agents ("any agent", the `break` of :299-302).
-//  (2) percent of cell (i,j) = popc of bits j,j+1 of rowmask[i] and rowmask[i+1]; touched <=> any of them set.
-//  (3) sweep: per agent box, 8 lanes x float2 per map row, 4 rows per warp instruction; a cell inside several
-//      boxes belongs to the first; untouched cells are neither read nor written.  The update itself is fp32
-//      (k_c*p / (1 + (q-1)*p), fast reciprocal): measured drift vs the float64 reference over 225 steps is 3e-6
-//      relative, inside the 1e-5 bar.
-// Needs map_size <= 63 (one 64-bit mask per corner row) -- larger maps take fl_probmap_wide below.
-// ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool corner_pred(double A, double cy, double ay, double R2) {
     const double dy = cy - ay;
     return A + dy * dy < R2;                                   // strict '<' (:300)
@@ -256,14 +203,30 @@ __device__ __forceinline__ float belief_update(float pv, int cnt, float qf) {
     return (pv == 1.0f) ? frac : __fdividef(num, den);
 }
 
-__device__ __forceinline__ unsigned fl_probmap(const FlightParams& p, double* S, int lane, float* map, uint32_t newf,
-                                               unsigned long long* rowmask) {
+// ------------------------------------------------------------------------------------------------
+// belief map: _update_prob_map + _percent_in_agent_viewrange (env/flight_env.py:275-303), one warp per env.
+//
+// The reference classifies the 4 corners of every cell against every agent (2500 x 4 x n fp64 tests).  Here:
+//  (1) corner classification by ROW INTERVALS: for agent a and integer corner row cx, the corner columns cy with
+//      fl(fl((cx-ax)^2) + fl((cy-ay)^2)) < R^2 form an interval (the expression is monotone in |cy-ay|).  Its
+//      ends come from one fp32 sqrt; only when an end lies within 1e-3 of an integer is the reference's exact
+//      fp64 predicate evaluated there.  One lane per (agent, corner row): <= 2R*n tasks.  The interval is OR-ed as a
+//      bit mask into rowmask[cx] (bit cy), the union over agents ("any agent", the `break` of :299-302).
+//  (2) percent of cell (i,j) = popc of bits j,j+1 of rowmask[i] and rowmask[i+1]; touched <=> any of them set.
+//      Per (agent, box row) the touched cells that agent's sweep owns (a cell inside several boxes belongs to the
+//      first) are precomputed as one 64-bit mask.
+//  (3) sweep: per agent box, 8 lanes x float2 per map row, 4 rows per warp instruction, 4 instructions' loads in
+//      flight; untouched cells are neither read nor written.  The update itself is fp32.
+// Ms: [2n agent xy][boxes][hit cells] scratch of the warp, already filled with the agent positions and the hit
+// cells by the caller.  Needs map_size <= 63 (one 64-bit mask per corner row); larger maps take fl_probmap_wide.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned fl_probmap(const FlightParams& p, double* Ms, int lane, float* map, int nh) {
     const int n = p.n, M = p.M;
-    int* box = reinterpret_cast<int*>(S + p.s_box);   // [n][6]: i0, i1, j0, j1 (cells), clo_x, chi_x (corner rows)
-    int* hit = reinterpret_cast<int*>(S + p.s_hit);   // cells of the targets found by this sensing call
-    const double* T = S + p.s_tgt;
+    int* box = reinterpret_cast<int*>(Ms + p.s_box);   // [n][6]: i0, i1, j0, j1 (cells), clo_x, chi_x (corner rows)
+    const int* hit = reinterpret_cast<const int*>(Ms + p.s_hit);
+    unsigned long long* rowmask = reinterpret_cast<unsigned long long*>(Ms + p.s_mask);
     for (int a = lane; a < n; a += 32) {
-        const double ax = S[2 * a], ay = S[2 * a + 1];
+        const double ax = Ms[2 * a], ay = Ms[2 * a + 1];
         int lo, hi;
         corner_span(ax, p.R, p.R2, &lo, &hi);
         box[6 * a + 0] = max(0, lo - 1);          // cell i has corners i and i+1
@@ -275,14 +238,6 @@ __device__ __forceinline__ unsigned fl_probmap(const FlightParams& p, double* S,
         box[6 * a + 3] = min(M - 1, hi);
     }
     for (int r = lane; r <= M + 1; r += 32) rowmask[r] = 0ull;
-    const int nh = __popc(newf);
-    if (lane < p.m && ((newf >> lane) & 1u)) {
-        const int k = __popc(newf & ((1u << lane) - 1u));
-        // idx = min(int(x), M-1): Python int() truncates toward zero (flight_env.py:279)
-        const int ci = min((int)fmin(T[2 * lane], p.Md), M - 1);
-        const int cj = min((int)fmin(T[2 * lane + 1], p.Md), M - 1);
-        hit[k] = (ci < 0 || cj < 0) ? -1 : ci * M + cj;
-    }
     __syncwarp();
     // (1) corner-row intervals
     const int span = p.span_cap;                      // power of two >= 2R
@@ -292,7 +247,7 @@ __device__ __forceinline__ unsigned fl_probmap(const FlightParams& p, double* S,
         const int a = t / span, r = t - a * span;          // span is a power of two
         const int cx = box[6 * a + 4] + r;
         if (cx > box[6 * a + 5] || cx < 0 || cx > M) continue;
-        const double ax = S[2 * a], ay = S[2 * a + 1];
+        const double ax = Ms[2 * a], ay = Ms[2 * a + 1];
         const double dx = (double)cx - ax;
         const double A = dx * dx;
         const float wf = sqrtf(fmaxf((float)(p.R2 - A), 0.0f));
@@ -313,8 +268,7 @@ __device__ __forceinline__ unsigned fl_probmap(const FlightParams& p, double* S,
         }
     }
     __syncwarp();
-    // (2) per (agent, box row): the touched cells this agent's sweep owns.  A cell inside several boxes belongs
-    //     to the first of them.  own[a*rows_cap + r] covers map row i0_a + r.
+    // (2) owned touched cells per (agent, box row); own[a*rows_cap + r] covers map row i0_a + r
     const int rows_cap = p.span_cap + 1;
     unsigned long long* own = rowmask + (M + 2);
     for (int t0 = 0; t0 < n * rows_cap; t0 += 32) {
@@ -334,7 +288,7 @@ __device__ __forceinline__ unsigned fl_probmap(const FlightParams& p, double* S,
         }
     }
     __syncwarp();
-    // (3) sweep: 8 lanes x float2 per map row, 4 rows per instruction, 4 instructions' loads in flight
+    // (3) sweep
     unsigned touched = 0;
     const float qf = (float)p.q_miss;
     if ((M & 1) == 0) {
@@ -403,13 +357,12 @@ __device__ __forceinline__ unsigned fl_probmap(const FlightParams& p, double* S,
 }
 
 // Fallback for map_size > 63: per-cell corner tests (same results, more arithmetic), half-warp per map row.
-__device__ __noinline__ unsigned fl_probmap_wide(const FlightParams& p, double* S, int lane, float* map, uint32_t newf) {
+__device__ __noinline__ unsigned fl_probmap_wide(const FlightParams& p, double* Ms, int lane, float* map, int nh) {
     const int n = p.n, M = p.M;
-    int* box = reinterpret_cast<int*>(S + p.s_box);
-    int* hit = reinterpret_cast<int*>(S + p.s_hit);
-    const double* T = S + p.s_tgt;
+    int* box = reinterpret_cast<int*>(Ms + p.s_box);
+    const int* hit = reinterpret_cast<const int*>(Ms + p.s_hit);
     for (int a = lane; a < n; a += 32) {
-        const double ax = S[2 * a], ay = S[2 * a + 1];
+        const double ax = Ms[2 * a], ay = Ms[2 * a + 1];
         int lo, hi;
         corner_span(ax, p.R, p.R2, &lo, &hi);
         box[6 * a + 0] = max(0, lo - 1);
@@ -417,13 +370,6 @@ __device__ __noinline__ unsigned fl_probmap_wide(const FlightParams& p, double* 
         corner_span(ay, p.R, p.R2, &lo, &hi);
         box[6 * a + 2] = max(0, lo - 1);
         box[6 * a + 3] = min(M - 1, hi);
-    }
-    const int nh = __popc(newf);
-    if (lane < p.m && ((newf >> lane) & 1u)) {
-        const int k = __popc(newf & ((1u << lane) - 1u));
-        const int ci = min((int)fmin(T[2 * lane], p.Md), M - 1);
-        const int cj = min((int)fmin(T[2 * lane + 1], p.Md), M - 1);
-        hit[k] = (ci < 0 || cj < 0) ? -1 : ci * M + cj;
     }
     __syncwarp();
     unsigned touched = 0;
@@ -443,7 +389,7 @@ __device__ __noinline__ unsigned fl_probmap_wide(const FlightParams& p, double* 
                 const double x0 = (double)i, x1 = (double)(i + 1);
                 uint32_t bits = 0;
                 for (int q = 0; q < n; ++q) {
-                    const double ax = S[2 * q], ay = S[2 * q + 1];
+                    const double ax = Ms[2 * q], ay = Ms[2 * q + 1];
                     const double dx0 = x0 - ax, dx1 = x1 - ax, dy0 = y0 - ay, dy1 = y1 - ay;
                     const double sx0 = dx0 * dx0, sx1 = dx1 * dx1, sy0 = dy0 * dy0, sy1 = dy1 * dy1;
                     bits |= (sx0 + sy0 < p.R2) ? 1u : 0u;
@@ -464,433 +410,310 @@ __device__ __noinline__ unsigned fl_probmap_wide(const FlightParams& p, double* 
     return touched;
 }
 
-// ------------------------------------------------------------------------------------------------
-// _update_obs: detection + reward + win.  Returns the reward (all lanes), updates meta (lane 0).
-// ------------------------------------------------------------------------------------------------
-template <int LPE>
-__device__ __forceinline__ int fl_sense(const FlightParams& p, double* S, int lane, uint32_t env_id, uint32_t t,
-                                        uint32_t outbits, SlotRes* res) {
-    using G = Group<LPE>;
-    const int n = p.n, m = p.m;
-    uint32_t* meta = slot_meta(p, S);
-    const double* T = S + p.s_tgt;
-    uint32_t* am = reinterpret_cast<uint32_t*>(S + p.s_am);
-    const uint32_t found = meta[CS_META_FOUND];
-    const uint32_t episode = meta[CS_META_EPISODE];
-    const uint32_t flags = meta[CS_META_FLAGS];
-    uint32_t cand = 0;
-    for (int j = lane; j < m; j += LPE) {
-        if ((found >> j) & 1u) continue;                 // draw is irrelevant once found (:239)
-        const double tx = T[2 * j], ty = T[2 * j + 1];
-        uint32_t amask = 0;
-        for (int i = 0; i < n; ++i) {
-            const double dx = tx - S[2 * i], dy = ty - S[2 * i + 1];
-            if (dx * dx + dy * dy <= p.R2) amask |= 1u << i;    // '<=' (:237)
-        }
-        if (amask) {
-            am[j] = amask;
-            cand |= 1u << j;
-        }
-    }
-    uint32_t newf = 0;
-    while (cand) {
-        const int j = __ffs(cand) - 1;
-        cand &= cand - 1;
-        const uint32_t amask = am[j];
-        for (int blk = 0; 4 * blk < n; ++blk) {
-            const uint32_t bits = (amask >> (4 * blk)) & 0xFu;
-            if (!bits) continue;
-            const cs_u4 w = cs_detect_words(p.seed, env_id, episode, t, (uint32_t)blk, (uint32_t)j);
-            const bool got = ((bits & 1u) && (long long)w.x <= p.thr) || ((bits & 2u) && (long long)w.y <= p.thr) ||
-                             ((bits & 4u) && (long long)w.z <= p.thr) || ((bits & 8u) && (long long)w.w <= p.thr);
-            if (got) {
-                newf |= 1u << j;
-                break;
-            }
-        }
-    }
-    newf = G::reduce_or(newf);      // also orders every lane's reads of meta before lane 0's writes below
-    const uint32_t all = found | newf;
-    const int c = __popc(newf);
-    int rew = -1 + 10 * c;          // MOVE_COST + FIND_ONE_TGT per new target (:228,:241)
-    uint32_t nflags = flags;
-    if (c > 0 && __popc(all) == m && !(flags & CS_FLAG_WIN)) {
-        rew += 100;                 // FIND_ALL_TGT (:244-246)
-        nflags |= CS_FLAG_WIN;
-    }
-    rew -= __popc(outbits);         // OUT_PUNISH per agent outside (:249-250)
-    if (lane == 0) {
-        meta[CS_META_FOUND] = all;
-        meta[CS_META_NEWFOUND] = newf;
-        meta[CS_META_OUT] = outbits;
-        meta[CS_META_FLAGS] = nflags;
-        res->flags |= SLOT_MAP_PENDING;      // the warp-wide belief-map pass picks this sensing call up
-    }
-    G::sync();
-    return rew;
-}
-
-// ------------------------------------------------------------------------------------------------
-// reset: env/flight_env_easy.py:79-180 (without the trailing _update_obs, which the caller runs)
-// ------------------------------------------------------------------------------------------------
-template <int LPE>
-__device__ __forceinline__ void fl_reset(const FlightParams& p, double* S, int lane, uint32_t env_id, uint32_t rflags,
-                                         float* map, SlotRes* res) {
-    using G = Group<LPE>;
-    const int n = p.n, m = p.m;
-    uint32_t* meta = slot_meta(p, S);
-    const uint32_t episode = meta[CS_META_EPISODE] + ((rflags & CS_RESET_KEEP_EPISODE) ? 0u : 1u);
-    G::sync();
-    if (lane == 0) {
-        meta[CS_META_FOUND] = 0;
-        meta[CS_META_NEWFOUND] = 0;
-        meta[CS_META_OUT] = 0;
-        meta[CS_META_TIME] = 0;
-        meta[CS_META_EPISODE] = episode;
-        meta[CS_META_FLAGS] = 0;
-        meta[CS_META_EPREWARD] = 0;
-        meta[CS_META_RESERVED] = 0;
-        res->flags |= SLOT_EMIT | SLOT_STATE_FULL | ((rflags & CS_RESET_KEEP_TARGETS) ? 0u : SLOT_TGT_DIRTY);
-    }
-    if (!(rflags & CS_RESET_KEEP_TARGETS)) {
-        double* T = S + p.s_tgt;
-        for (int j = lane; j < m; j += LPE) {
-            const cs_u4 w = cs_philox4x32_10(env_id, (episode & 0xFFFFu) << 16, (uint32_t)j, 0u, p.seed, CS_STREAM_TARGET);
-            const double u1 = cs_u53(w.x, w.y), u2 = cs_u53(w.z, w.w);
-            double x, y;
-            if (p.target_mode == 0) {
-                const double* row = p.tmpl + 5 * j;
-                x = row[0];
-                y = row[1];
-                if (row[4] != 0.0) {                      // deter == 'f' (:106-110)
-                    const double rad = sqrt(-2.0 * log(u1));
-                    double sn, c;
-                    sincos(2.0 * p.pi * u2, &sn, &c);
-                    x += row[2] * 2.0 * (rad * c - 0.5);
-                    y += row[3] * 2.0 * (rad * sn - 0.5);
-                }
-            } else {                                      // target_mode 1 (:122-127)
-                x = p.Md * u1;
-                y = p.Md * u2;
-            }
-            T[2 * j] = x;
-            T[2 * j + 1] = y;
-        }
-    }
-    double* yaw = S + p.yaw_off;
-    double* cs = S + p.s_cs;
-    for (int a = lane; a < n; a += LPE) {
-        const double lin = (n != 1) ? (double)(a * p.M) / (double)(n - 1) : p.Md / 2.0;   // (:140-143)
-        double x, y, h;
-        switch (p.agent_mode) {
-            case 0: x = lin; y = 0.0; h = p.half_pi; break;
-            case 1: x = lin; y = p.Md / 2.0; h = p.half_pi; break;
-            case 2: x = 0.0; y = lin; h = 0.0; break;
-            default: x = p.Md; y = lin; h = p.pi; break;
-        }
-        S[2 * a] = x;
-        S[2 * a + 1] = y;
-        yaw[a] = h;
-        cs[a] = p.cos0;
-        cs[n + a] = p.sin0;
-    }
-    if (p.variant && (rflags & CS_RESET_INIT)) {
-        for (int c = lane; c < p.M * p.M; c += LPE) map[c] = 0.5f;       // flight_env.py:84-86
-    }
-    G::sync();
-}
-
-// reset followed by the sensing call the reference makes inside reset (:182); cold, kept out of line
-template <int LPE>
-__device__ __noinline__ void fl_reset_sense(const FlightParams& p, double* S, int lane, uint32_t env_id, uint32_t rflags,
-                                            float* map, SlotRes* res) {
-    fl_reset<LPE>(p, S, lane, env_id, rflags, map, res);
-    (void)fl_sense<LPE>(p, S, lane, env_id, 0u, 0u, res);      // reward discarded
-}
-
-// get_obs row of one env (= the agent part of get_state) into the slot's fp32 staging area
-// (flight_env_easy.py:218-221, :192-193).  The target part of the state row only changes at reset or when a
-// target is found; the write-back below touches it only then.
-template <int LPE>
-__device__ __forceinline__ void fl_emit(const FlightParams& p, double* S, int lane) {
-    const int n = p.n;
-    float* out = reinterpret_cast<float*>(S + p.s_out);
-    const double* cs = S + p.s_cs;
-    for (int a = lane; a < n; a += LPE) {
-        out[4 * a + 0] = (float)((S[2 * a] - p.half_M) * p.inv_half);
-        out[4 * a + 1] = (float)((S[2 * a + 1] - p.half_M) * p.inv_half);
-        out[4 * a + 2] = (float)cs[a];
-        out[4 * a + 3] = (float)cs[n + a];
-    }
-}
-
 enum { MODE_STEP = 0, MODE_RESET = 1 };
 
-
-// Warp-wide belief-map pass over the envs of this warp whose slot carries SLOT_MAP_PENDING.
-__device__ __noinline__ unsigned map_pass(const FlightParams& p, double* W, int wcnt, int wenv0, int lane32,
-                                             unsigned long long* rowmask) {
-    unsigned touched = 0;
-    for (int le = 0; le < wcnt; ++le) {
-        double* S = W + le * p.s_stride;
-        SlotRes* res = reinterpret_cast<SlotRes*>(S + p.s_res);
-        if (!(res->flags & SLOT_MAP_PENDING)) continue;          // warp-uniform
-        float* map = p.prob_map + (size_t)(wenv0 + le) * p.M * p.M;
-        const uint32_t newf = slot_meta(p, S)[CS_META_NEWFOUND];
-        __syncwarp();
-        touched += (p.M <= 63) ? fl_probmap(p, S, lane32, map, newf, rowmask) : fl_probmap_wide(p, S, lane32, map, newf);
-        __syncwarp();
-        if (lane32 == 0) res->flags &= ~SLOT_MAP_PENDING;
-    }
-    __syncwarp();
-    return touched;
+// group-relative ballot
+template <int LPE>
+__device__ __forceinline__ uint32_t group_ballot(bool pred) {
+    const unsigned full = __ballot_sync(Group<LPE>::mask(), pred);
+    if (LPE == 32) return full;
+    return (full >> ((threadIdx.x & 31u) & ~(unsigned)(LPE - 1))) & ((1u << (LPE & 31)) - 1u);
 }
 
-// One warp owns EPW = 32/LPE consecutive env instances; LPE lanes ("group") work on one env.
+// ------------------------------------------------------------------------------------------------
+// The step / reset kernel.  A group of LPE lanes (LPE = power of two >= max(n_agents, target_num)) owns one env:
+// lane a < n holds agent a (x, y, heading, cos, sin) and lane j < m holds target j, all in REGISTERS; positions
+// travel between lanes by warp shuffles.  Every global load is issued up front; nothing is staged through shared
+// memory except the heading-table index (per warp) and the scratch of the two cold/warp-wide parts (coupled
+// repulsion, belief map).
+//   pass 0 (STEP): _agent_step -> _update_obs -> step bookkeeping            (flight_env_easy.py:255-314)
+//   pass 1       : reset (selected envs in RESET mode; just-terminated envs under auto_reset) -> _update_obs (:79-182)
 // actions == nullptr in MODE_STEP: uniform-random policy drawn in-kernel (alg=random, agent/agent.py:34-36)
+// ------------------------------------------------------------------------------------------------
 template <int LPE, int MODE>
 __global__ void __launch_bounds__(kThreads) flight_kernel(const __grid_constant__ FlightParams p, const uint8_t* __restrict__ actions,
                                                           const uint8_t* __restrict__ mask, uint32_t rflags) {
     using G = Group<LPE>;
     constexpr int EPW = 32 / LPE;
+    constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) double smem[];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane32 = tid & 31;
     const int wenv0 = (blockIdx.x * (kThreads / 32) + warp) * EPW;      // first env of this warp
     const int wcnt = min(EPW, p.E - wenv0);
-    if (wcnt <= 0) return;                                               // whole warp idle: nothing is block-synchronised
+    if (wcnt <= 0) return;                                               // whole warp idle (nothing is block-synchronised)
     double* W = smem + (size_t)warp * p.s_warp;
-    unsigned long long* rowmask = reinterpret_cast<unsigned long long*>(W + (size_t)EPW * p.s_stride);
-
-    // ---- stage this warp's records: global -> shared, 16-byte coalesced.  The first round of every stream
-    //      (records, targets, heading-table index) is issued before anything is consumed, so their HBM/L2
-    //      latencies overlap instead of adding up.
     longlong2* lutm = reinterpret_cast<longlong2*>(W + p.s_lut);
-    {
-        const int rec2 = p.rec >> 1;
-        const int nd = wcnt * rec2, nt = wcnt * p.m;
-        const double2* gd = reinterpret_cast<const double2*>(p.dyn + (size_t)wenv0 * p.rec);
-        const double2* gt = reinterpret_cast<const double2*>(p.tgt + (size_t)wenv0 * 2 * p.m);
-        double2 vd = make_double2(0.0, 0.0), vt = make_double2(0.0, 0.0);
-        longlong2 vl0 = make_longlong2(0, 0), vl1 = make_longlong2(0, 0);
-        if (lane32 < nd) vd = gd[lane32];
-        if (lane32 < nt) vt = gt[lane32];
-        if (MODE == MODE_STEP) {
-            vl0 = __ldg(p.lut_meta + lane32);
-            if (lane32 + 32 < 37) vl1 = __ldg(p.lut_meta + lane32 + 32);
-        }
-        if (lane32 < nd) {
-            const int le = fastdiv(lane32, p.mg_rec2), k = lane32 - le * rec2;
-            double* S = W + le * p.s_stride;
-            S[2 * k] = vd.x;
-            S[2 * k + 1] = vd.y;
-        }
-        if (lane32 < nt) {
-            const int le = fastdiv(lane32, p.mg_m), k = lane32 - le * p.m;
-            double* S = W + le * p.s_stride + p.s_tgt;
-            S[2 * k] = vt.x;
-            S[2 * k + 1] = vt.y;
-        }
-        if (MODE == MODE_STEP) {
-            lutm[lane32] = vl0;
-            if (lane32 + 32 < 37) lutm[lane32 + 32] = vl1;
-        }
-        for (int idx = lane32 + 32; idx < nd; idx += 32) {
-            const int le = fastdiv(idx, p.mg_rec2), k = idx - le * rec2;
-            const double2 v = gd[idx];
-            double* S = W + le * p.s_stride;
-            S[2 * k] = v.x;
-            S[2 * k + 1] = v.y;
-        }
-        for (int idx = lane32 + 32; idx < nt; idx += 32) {
-            const int le = fastdiv(idx, p.mg_m), k = idx - le * p.m;
-            const double2 v = gt[idx];
-            double* S = W + le * p.s_stride + p.s_tgt;
-            S[2 * k] = v.x;
-            S[2 * k + 1] = v.y;
-        }
-        for (int le = lane32; le < wcnt; le += 32) {
-            SlotRes* res = reinterpret_cast<SlotRes*>(W + le * p.s_stride + p.s_res);
-            res->reward = 0.f; res->terminated = 0; res->win = 0; res->flags = 0;
-        }
-    }
-    __syncwarp();
-
+    const int n = p.n, m = p.m;
     const int g = lane32 / LPE, lane = lane32 % LPE;
     const bool active = g < wcnt;
-    const int e = wenv0 + g;
-    double* S = W + (active ? g : 0) * p.s_stride;
-    uint32_t* meta = slot_meta(p, S);
-    SlotRes* res = reinterpret_cast<SlotRes*>(S + p.s_res);
+    const int e = wenv0 + (active ? g : 0);
+    const bool is_agent = active && lane < n, is_tgt = active && lane < m;
     const uint32_t env_id = p.env_id_base + (uint32_t)e;
-    float* map = p.variant ? p.prob_map + (size_t)e * p.M * p.M : nullptr;
-    // episode statistics of this lane's env (lane 0 of the group), reduced over the warp at the end
-    float st_eps = 0.f, st_rew = 0.f, st_found = 0.f, st_wins = 0.f, st_len = 0.f, st_steps = 0.f;
-    bool done = false;
 
-    if (MODE == MODE_STEP) {
-        if (active) {
-            const uint32_t flags0 = meta[CS_META_FLAGS];
-            const uint32_t time0 = meta[CS_META_TIME];
-            const uint32_t episode0 = meta[CS_META_EPISODE];
-            done = (flags0 & CS_FLAG_DONE) != 0;
-            G::sync();
-            if (!done) {
-                const uint8_t* act;
-                if (actions != nullptr) {
-                    act = actions + (size_t)e * p.n;
-                } else {
-                    // one Philox block serves 4 agents; action = word % 3 (np.random.randint(0, 3), agent.py:36).
-                    // Staged in the slot's `am` scratch, which fl_sense only touches after fl_move consumed it.
-                    uint8_t* ra = reinterpret_cast<uint8_t*>(S + p.s_am);
-                    for (int a = lane; a < p.n; a += LPE) {
-                        const cs_u4 w = cs_philox4x32_10(env_id, ((episode0 & 0xFFFFu) << 16) | ((time0 + 1u) & 0xFFFFu),
-                                                         (uint32_t)(a >> 2), 0u, p.seed, CS_STREAM_POLICY);
-                        ra[a] = (uint8_t)(cs_word(w, a & 3) % 3u);
-                    }
-                    G::sync();
-                    act = ra;
-                }
-                const uint32_t outbits = fl_move<LPE>(p, S, lane, act, lutm);
-                G::sync();
-                const int rew = fl_sense<LPE>(p, S, lane, env_id, time0 + 1u, outbits, res);
-                const uint32_t time1 = time0 + 1u;
-                const uint32_t fl1 = meta[CS_META_FLAGS];
-                const int nfound = __popc(meta[CS_META_FOUND]);
-                const bool term = (nfound >= p.m) || ((int)time1 >= p.T);       // (:311-312)
-                G::sync();
-                if (lane == 0) {
-                    const float epr = __uint_as_float(meta[CS_META_EPREWARD]) + (float)rew;
-                    meta[CS_META_TIME] = time1;
-                    meta[CS_META_EPREWARD] = __float_as_uint(epr);
-                    meta[CS_META_FLAGS] = fl1 | (term ? CS_FLAG_DONE : 0u);
-                    res->reward = (float)rew;
-                    res->terminated = term ? 1 : 0;
-                    res->win = (fl1 & CS_FLAG_WIN) ? 1 : 0;
-                    res->flags |= SLOT_EMIT | SLOT_RESULT;
-                    st_steps = 1.f;
-                    if (term) {
-                        st_eps = 1.f; st_rew = epr; st_found = (float)nfound; st_wins = (fl1 & CS_FLAG_WIN) ? 1.f : 0.f;
-                        st_len = (float)time1;
-                    }
-                }
-                done = term;
-            } else if (lane == 0) {
-                res->reward = 0.f;                     // masked no-op on a finished env
-                res->terminated = 1;
-                res->win = (flags0 & CS_FLAG_WIN) ? 1 : 0;
-                res->flags |= SLOT_RESULT;
-            }
-        }
-        __syncwarp();
-        unsigned touched = 0;
-        if (p.variant) touched += map_pass(p, W, wcnt, wenv0, lane32, rowmask);
-        if (p.auto_reset) {
-            if (active && done) {
-                G::sync();
-                fl_reset_sense<LPE>(p, S, lane, env_id, 0u, map, res);
-            }
-            __syncwarp();
-            if (p.variant) touched += map_pass(p, W, wcnt, wenv0, lane32, rowmask);
-        }
-        if (p.variant && p.count_touched) {
-            const unsigned tot = __reduce_add_sync(0xffffffffu, touched);
-            if (lane32 == 0 && tot) atomicAdd(p.stats + CS_STAT_TOUCHED, (double)tot);
-        }
-    } else {
-        if (active) {
-            const bool sel = (mask == nullptr) || (mask[e] != 0);
-            if (sel) {
-                fl_reset_sense<LPE>(p, S, lane, env_id, rflags, map, res);
-                if (lane == 0) {
-                    res->reward = 0.f;
-                    res->terminated = 0;
-                    res->win = (meta[CS_META_FLAGS] & CS_FLAG_WIN) ? 1 : 0;
-                    res->flags |= SLOT_RESULT;
-                }
-            }
-        }
-        __syncwarp();
-        if (p.variant) {
-            const unsigned touched = map_pass(p, W, wcnt, wenv0, lane32, rowmask);
-            if (p.count_touched) {
-                const unsigned tot = __reduce_add_sync(0xffffffffu, touched);
-                if (lane32 == 0 && tot) atomicAdd(p.stats + CS_STAT_TOUCHED, (double)tot);
-            }
-        }
+    // ---- every load of the step, issued before anything is consumed ----------------------------------------
+    double* rec = p.dyn + (size_t)e * p.rec;
+    double ax = 0.0, ay = 0.0, yaw = 0.0, tx = 0.0, ty = 0.0;
+    uint4 m0 = make_uint4(0, 0, 0, 0), m1 = make_uint4(0, 0, 0, 0);
+    int act = 0;
+    if (is_agent) {
+        const double2 v = *reinterpret_cast<const double2*>(rec + 2 * lane);
+        ax = v.x; ay = v.y;
+        yaw = rec[p.yaw_off + lane];
+        if (MODE == MODE_STEP && actions != nullptr) act = actions[(size_t)e * n + lane];
+    }
+    if (is_tgt) {
+        const double2 v = *reinterpret_cast<const double2*>(p.tgt + ((size_t)e * m + lane) * 2);
+        tx = v.x; ty = v.y;
     }
     if (active) {
-        G::sync();
-        if (res->flags & SLOT_EMIT) fl_emit<LPE>(p, S, lane);
+        const uint4* mp = reinterpret_cast<const uint4*>(rec + p.meta_off);      // same address for the whole group
+        m0 = mp[0]; m1 = mp[1];
     }
-    __syncwarp();
+    if (MODE == MODE_STEP) {
+        const longlong2 v0 = __ldg(p.lut_meta + lane32);
+        longlong2 v1 = make_longlong2(0, 0);
+        if (lane32 + 32 < 37) v1 = __ldg(p.lut_meta + lane32 + 32);
+        lutm[lane32] = v0;
+        if (lane32 + 32 < 37) lutm[lane32 + 32] = v1;
+        __syncwarp();
+    }
+    uint32_t found = m0.x, newf_last = m0.y, outmask = m0.z, time_step = m0.w;
+    uint32_t episode = m1.x, flags = m1.y;
+    float ep_reward = __uint_as_float(m1.z);
 
-    // ---- write back: shared -> global, coalesced over the warp's contiguous env block --------------
-    {
-        const int rec2 = p.rec >> 1;
-        double2* gd = reinterpret_cast<double2*>(p.dyn + (size_t)wenv0 * p.rec);
-        for (int idx = lane32; idx < wcnt * rec2; idx += 32) {
-            const int le = fastdiv(idx, p.mg_rec2), k = idx - le * rec2;
-            const double* Sl = W + le * p.s_stride;
-            if (reinterpret_cast<const SlotRes*>(Sl + p.s_res)->flags & SLOT_EMIT) gd[idx] = make_double2(Sl[2 * k], Sl[2 * k + 1]);
+    double c_h = 0.0, s_h = 0.0;                 // cos/sin of the heading (agent lanes), for the fp32 outputs
+    bool done = (flags & CS_FLAG_DONE) != 0;
+    bool do_sense = false, emit = false, state_full = false, tgt_dirty = false, have_result = false;
+    float res_reward = 0.f;
+    uint32_t res_term = 0, res_win = 0, res_found = 0, t_key = 0;   // what step()/reset() report for this env
+    float st_eps = 0.f, st_rew = 0.f, st_found = 0.f, st_wins = 0.f, st_len = 0.f, st_steps = 0.f;
+    unsigned touched = 0;
+
+    // ---- _agent_step -------------------------------------------------------------------------------------------
+    if (MODE == MODE_STEP) {
+        if (active && !done) {
+            if (actions == nullptr && is_agent) {
+                // one Philox block serves 4 agents; action = word % 3 (np.random.randint(0, 3), agent.py:36)
+                const cs_u4 w = cs_philox4x32_10(env_id, ((episode & 0xFFFFu) << 16) | ((time_step + 1u) & 0xFFFFu),
+                                                 (uint32_t)(lane >> 2), 0u, p.seed, CS_STREAM_POLICY);
+                act = (int)(cs_word(w, lane & 3) % 3u);
+            }
+            if (is_agent) {
+                double h = yaw + ((act == 1) ? p.turn : ((act == 2) ? -p.turn : 0.0));   // dyaw = [0, pi/18, -pi/18] (:259-262)
+                if (h > p.two_pi) h -= p.two_pi;                                          // strict tests (:263-266)
+                else if (h < 0.0) h += p.two_pi;
+                heading_sincos(p, lutm, h, &s_h, &c_h);
+                yaw = h;
+            }
+            // Can any repulsion term be non-zero this step?  If every pair of OLD positions is farther apart than
+            // force_dist + |v| (with slack), no agent receives a force, every displacement is <= |v|, and by
+            // induction over the sequential update order no later agent does either.
+            bool close = false;
+            for (int q = 0; q < n; ++q) {
+                const double xq = __shfl_sync(G::mask(), ax, q, LPE), yq = __shfl_sync(G::mask(), ay, q, LPE);
+                const double dx = xq - ax, dy = yq - ay;
+                close |= (is_agent && q > lane && dx * dx + dy * dy < p.near2);
+            }
+            close = G::any(close);
+            bool outside = false;
+            if (!close) {
+                if (is_agent) {
+                    ax = ax + p.v * c_h;                          // x += v*cos(yaw)   (:267-268)
+                    ay = ay + p.v * s_h;
+                    outside = wall_reg(p, ax, ay, yaw, c_h);
+                }
+                outmask = group_ballot<LPE>(outside);
+            } else {
+                double* Sg = W + g * p.s_grp;
+                if (is_agent) {
+                    Sg[2 * lane] = ax; Sg[2 * lane + 1] = ay; Sg[p.yaw_off + lane] = yaw;
+                    Sg[p.s_cs + lane] = c_h; Sg[p.s_cs + n + lane] = s_h;
+                }
+                G::sync();
+                uint32_t ob = 0;
+                if (lane == 0) ob = fl_move_coupled(p, Sg);
+                G::sync();
+                outmask = __shfl_sync(G::mask(), ob, 0, LPE);
+                if (is_agent) {
+                    ax = Sg[2 * lane]; ay = Sg[2 * lane + 1]; yaw = Sg[p.yaw_off + lane]; c_h = Sg[p.s_cs + lane];
+                }
+            }
+            do_sense = true;
+            t_key = time_step + 1u;
+        } else if (active) {
+            have_result = true;                            // masked no-op on a finished env
+            res_reward = 0.f;
+            res_term = 1;
+            res_win = flags & CS_FLAG_WIN;
+            res_found = (uint32_t)__popc(found);
         }
-        // obs rows and the agent prefix of the state rows: n 16-byte chunks per env
-        double2* go = reinterpret_cast<double2*>(p.obs + (size_t)wenv0 * 4 * p.n);
-        for (int idx = lane32; idx < wcnt * p.n; idx += 32) {
-            const int le = fastdiv(idx, p.mg_n), c = idx - le * p.n;
-            const double* Sl = W + le * p.s_stride;
-            if (reinterpret_cast<const SlotRes*>(Sl + p.s_res)->flags & SLOT_EMIT) {
-                const double2 v = make_double2(Sl[p.s_out + 2 * c], Sl[p.s_out + 2 * c + 1]);
-                go[idx] = v;
-                reinterpret_cast<double2*>(p.state + (size_t)(wenv0 + le) * p.state_stride)[c] = v;
+    }
+
+    for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 1) {
+            const bool do_reset = active && ((MODE == MODE_RESET) ? (mask == nullptr || mask[e] != 0) : (p.auto_reset && done));
+            if (!__any_sync(FULL, do_reset)) break;
+            do_sense = do_reset;
+            if (do_reset) {                                                   // reset (:79-180)
+                episode += (rflags & CS_RESET_KEEP_EPISODE) ? 0u : 1u;
+                found = 0; outmask = 0; time_step = 0; flags = 0; ep_reward = 0.f; done = false;
+                if (!(rflags & CS_RESET_KEEP_TARGETS)) {
+                    if (is_tgt) {
+                        const double2 t = draw_target(p, env_id, episode, lane);
+                        tx = t.x; ty = t.y;
+                    }
+                    tgt_dirty = true;
+                }
+                if (is_agent) {
+                    const double lin = (n != 1) ? (double)(lane * p.M) / (double)(n - 1) : p.Md / 2.0;   // (:140-143)
+                    switch (p.agent_mode) {
+                        case 0: ax = lin; ay = 0.0; yaw = p.half_pi; break;
+                        case 1: ax = lin; ay = p.Md / 2.0; yaw = p.half_pi; break;
+                        case 2: ax = 0.0; ay = lin; yaw = 0.0; break;
+                        default: ax = p.Md; ay = lin; yaw = p.pi; break;
+                    }
+                    c_h = p.cos0; s_h = p.sin0;
+                }
+                if (p.variant && (rflags & CS_RESET_INIT)) {
+                    float* map = p.prob_map + (size_t)e * p.M * p.M;
+                    for (int c = lane; c < p.M * p.M; c += LPE) map[c] = 0.5f;            // flight_env.py:84-86
+                }
+                t_key = 0;
+                emit = true;
+                state_full = true;
+                if (MODE == MODE_RESET) { have_result = true; res_reward = 0.f; res_term = 0; }
+            }
+        } else if (MODE == MODE_RESET) {
+            continue;
+        }
+
+        // ---- _update_obs: detection + reward + win (:223-253) ----------------------------------------------
+        uint32_t amask = 0;
+        for (int q = 0; q < n; ++q) {
+            const double xq = __shfl_sync(G::mask(), ax, q, LPE), yq = __shfl_sync(G::mask(), ay, q, LPE);
+            const double dx = tx - xq, dy = ty - yq;
+            if (dx * dx + dy * dy <= p.R2) amask |= 1u << q;                   // '<=' (:237)
+        }
+        bool got = false;
+        if (do_sense && is_tgt && amask && !((found >> lane) & 1u)) {          // draw is irrelevant once found (:239)
+            for (int blk = 0; 4 * blk < n && !got; ++blk) {
+                const uint32_t bits = (amask >> (4 * blk)) & 0xFu;
+                if (!bits) continue;
+                const cs_u4 w = cs_detect_words(p.seed, env_id, episode, t_key, (uint32_t)blk, (uint32_t)lane);
+                got = ((bits & 1u) && (long long)w.x <= p.thr) || ((bits & 2u) && (long long)w.y <= p.thr) ||
+                      ((bits & 4u) && (long long)w.z <= p.thr) || ((bits & 8u) && (long long)w.w <= p.thr);
             }
         }
-        for (int le = lane32; le < wcnt; le += 32) {
-            double* Sl = W + le * p.s_stride;
-            const SlotRes* r = reinterpret_cast<const SlotRes*>(Sl + p.s_res);
-            if (r->flags & SLOT_RESULT) {
-                p.reward[wenv0 + le] = r->reward;
-                p.terminated[wenv0 + le] = r->terminated;
-                p.win[wenv0 + le] = r->win;
-                p.target_find[wenv0 + le] = __popc(slot_meta(p, Sl)[CS_META_FOUND]);
+        const uint32_t newf = group_ballot<LPE>(got);
+        int rew = 0;
+        if (do_sense) {
+            found |= newf;
+            newf_last = newf;
+            const int c = __popc(newf);
+            rew = -1 + 10 * c;                                                 // MOVE_COST + FIND_ONE_TGT (:228,:241)
+            if (c > 0 && __popc(found) == m && !(flags & CS_FLAG_WIN)) {
+                rew += 100;                                                    // FIND_ALL_TGT (:244-246)
+                flags |= CS_FLAG_WIN;
             }
-            if (r->flags & SLOT_TGT_DIRTY) {                     // targets redrawn by a reset (rare)
-                double* gt = p.tgt + (size_t)(wenv0 + le) * 2 * p.m;
-                for (int k = 0; k < 2 * p.m; ++k) gt[k] = Sl[p.s_tgt + k];
-            }
-            if (r->flags & SLOT_EMIT) {
-                // target part of the state row (flight_env_easy.py:201-211): rewritten in full after a reset,
-                // otherwise only the 'find' entry of targets found by this call
-                float* srow = p.state + (size_t)(wenv0 + le) * p.state_stride + 4 * p.n;
-                const uint32_t found = slot_meta(p, Sl)[CS_META_FOUND];
-                if (r->flags & SLOT_STATE_FULL) {
-                    for (int j = 0; j < p.m; ++j) {
-                        srow[3 * j + 0] = (float)((Sl[p.s_tgt + 2 * j] - p.half_M) * p.inv_half);
-                        srow[3 * j + 1] = (float)((Sl[p.s_tgt + 2 * j + 1] - p.half_M) * p.inv_half);
-                        srow[3 * j + 2] = ((found >> j) & 1u) ? 1.0f : 0.0f;
-                    }
-                } else {
-                    uint32_t nf = slot_meta(p, Sl)[CS_META_NEWFOUND];
-                    while (nf) {
-                        const int j = __ffs(nf) - 1;
-                        nf &= nf - 1;
-                        srow[3 * j + 2] = 1.0f;
-                    }
+            rew -= __popc(outmask);                                            // OUT_PUNISH per agent outside (:249-250)
+        }
+        if (MODE == MODE_RESET && do_sense) {
+            res_win = flags & CS_FLAG_WIN;
+            res_found = (uint32_t)__popc(found);
+        }
+        if (pass == 0 && do_sense) {                                           // step bookkeeping (:308-314)
+            time_step += 1u;
+            ep_reward += (float)rew;
+            const int nfound = __popc(found);
+            const bool term = (nfound >= m) || ((int)time_step >= p.T);
+            if (term) flags |= CS_FLAG_DONE;
+            done = term;
+            emit = true;
+            have_result = true;
+            res_reward = (float)rew;
+            res_term = term ? 1u : 0u;
+            res_win = flags & CS_FLAG_WIN;          // of the episode this step belongs to, also when auto_reset follows
+            res_found = (uint32_t)nfound;
+            if (lane == 0) {
+                st_steps = 1.f;
+                if (term) {
+                    st_eps = 1.f; st_rew = ep_reward; st_found = (float)nfound; st_wins = (flags & CS_FLAG_WIN) ? 1.f : 0.f;
+                    st_len = (float)time_step;
                 }
             }
         }
+        // ---- belief map of every env of this warp that was just sensed (flight_env.py:266,:275-303) ---------
+        if (p.variant) {
+            double* Ms = W + p.s_map;
+            int* hit = reinterpret_cast<int*>(Ms + p.s_hit);
+            for (int le = 0; le < EPW; ++le) {
+                const bool pend = __shfl_sync(FULL, (int)do_sense, le * LPE) != 0;
+                if (!pend) continue;                                           // warp-uniform
+                __syncwarp();
+                if (g == le) {
+                    if (is_agent) { Ms[2 * lane] = ax; Ms[2 * lane + 1] = ay; }
+                    if (is_tgt && ((newf >> lane) & 1u)) {
+                        // idx = min(int(x), M-1): Python int() truncates toward zero (flight_env.py:279)
+                        const int ci = min((int)fmin(tx, p.Md), p.M - 1), cj = min((int)fmin(ty, p.Md), p.M - 1);
+                        hit[__popc(newf & ((1u << lane) - 1u))] = (ci < 0 || cj < 0) ? -1 : ci * p.M + cj;
+                    }
+                }
+                const int nh = __popc(__shfl_sync(FULL, newf, le * LPE));
+                __syncwarp();
+                float* map = p.prob_map + (size_t)(wenv0 + le) * p.M * p.M;
+                touched += (p.M <= 63) ? fl_probmap(p, Ms, lane32, map, nh) : fl_probmap_wide(p, Ms, lane32, map, nh);
+            }
+            __syncwarp();
+        }
     }
-    // ---- episode statistics: warp reduction, then at most one atomic per statistic per warp ----------
+
+    // ---- outputs, straight from registers -------------------------------------------------------------------
+    if (active && emit) {
+        if (is_agent) {
+            *reinterpret_cast<double2*>(rec + 2 * lane) = make_double2(ax, ay);
+            rec[p.yaw_off + lane] = yaw;
+            // get_obs row = agent part of get_state (flight_env_easy.py:218-221, :192-193)
+            const float4 o = make_float4((float)((ax - p.half_M) * p.inv_half), (float)((ay - p.half_M) * p.inv_half),
+                                         (float)c_h, (float)s_h);
+            reinterpret_cast<float4*>(p.obs)[(size_t)e * n + lane] = o;
+            reinterpret_cast<float4*>(p.state + (size_t)e * p.state_stride)[lane] = o;
+        }
+        if (lane == 0) {
+            uint4* mp = reinterpret_cast<uint4*>(rec + p.meta_off);
+            mp[0] = make_uint4(found, newf_last, outmask, time_step);
+            mp[1] = make_uint4(episode, flags, __float_as_uint(ep_reward), 0u);
+        }
+        if (is_tgt) {
+            // target part of the state row (:201-211): rewritten in full after a reset, otherwise only the 'find'
+            // entry of a target found by this call
+            float* srow = p.state + (size_t)e * p.state_stride + 4 * n + 3 * lane;
+            if (state_full) {
+                srow[0] = (float)((tx - p.half_M) * p.inv_half);
+                srow[1] = (float)((ty - p.half_M) * p.inv_half);
+                srow[2] = ((found >> lane) & 1u) ? 1.0f : 0.0f;
+            } else if ((newf_last >> lane) & 1u) {
+                srow[2] = 1.0f;
+            }
+            if (tgt_dirty) *reinterpret_cast<double2*>(p.tgt + ((size_t)e * m + lane) * 2) = make_double2(tx, ty);
+        }
+    }
+    if (active && have_result && lane == 0) {
+        p.reward[e] = res_reward;
+        p.terminated[e] = (uint8_t)res_term;
+        p.win[e] = res_win ? 1 : 0;
+        p.target_find[e] = (int32_t)res_found;
+    }
+    // ---- statistics: warp reduction, then at most one atomic per statistic per warp ---------------------------
     if (MODE == MODE_STEP) {
-        const float any = st_steps + st_eps;
-        if (__any_sync(0xffffffffu, any != 0.f)) {
+        if (__any_sync(FULL, (st_steps + st_eps) != 0.f)) {
             for (int o = 16; o > 0; o >>= 1) {
-                st_eps += __shfl_xor_sync(0xffffffffu, st_eps, o);
-                st_rew += __shfl_xor_sync(0xffffffffu, st_rew, o);
-                st_found += __shfl_xor_sync(0xffffffffu, st_found, o);
-                st_wins += __shfl_xor_sync(0xffffffffu, st_wins, o);
-                st_len += __shfl_xor_sync(0xffffffffu, st_len, o);
-                st_steps += __shfl_xor_sync(0xffffffffu, st_steps, o);
+                st_eps += __shfl_xor_sync(FULL, st_eps, o);
+                st_rew += __shfl_xor_sync(FULL, st_rew, o);
+                st_found += __shfl_xor_sync(FULL, st_found, o);
+                st_wins += __shfl_xor_sync(FULL, st_wins, o);
+                st_len += __shfl_xor_sync(FULL, st_len, o);
+                st_steps += __shfl_xor_sync(FULL, st_steps, o);
             }
             if (lane32 == 0) {
                 atomicAdd(p.stats + CS_STAT_ENV_STEPS, (double)st_steps);
@@ -903,6 +726,10 @@ __global__ void __launch_bounds__(kThreads) flight_kernel(const __grid_constant_
                 }
             }
         }
+    }
+    if (p.variant && p.count_touched) {
+        const unsigned tot = __reduce_add_sync(FULL, touched);
+        if (lane32 == 0 && tot) atomicAdd(p.stats + CS_STAT_TOUCHED, (double)tot);
     }
 }
 
@@ -952,6 +779,8 @@ struct cs_flight {
     int grid;
     double* d_tmpl;
     uint8_t* d_actions;   // device staging of the *_host entry point's actions
+    uint8_t* d_slab;      // one allocation behind reward | target_find | terminated | win | obs | state
+    size_t slab_bytes, off_reward, off_tf, off_term, off_win, off_obs, off_state;
     longlong2* d_lut_meta;
     double2* d_lut;
     bool have_tmpl;
@@ -959,14 +788,13 @@ struct cs_flight {
 
 namespace {
 
+// lanes per env: the smallest power of two that gives every agent and every target its own lane
 int pick_lpe(const cs_flight_cfg& c) {
-    if (c.lanes_per_env) return c.lanes_per_env;
-    if (c.variant == 1) return 4;     // step logic on 4 lanes; the belief-map pass is warp-wide per env either way
-    // enough warps to occupy 148 SMs x 16 warps before trading lanes for instruction efficiency
-    const long long want = 148LL * 16 * 32;
-    int lpe = 32;
-    while (lpe > 1 && (long long)c.num_envs * lpe > want) lpe >>= 1;
-    return lpe;
+    int need = c.n_agents > c.target_num ? c.n_agents : c.target_num;
+    if (c.lanes_per_env > need) need = c.lanes_per_env;
+    int lpe = 1;
+    while (lpe < need) lpe <<= 1;
+    return lpe > 32 ? 32 : lpe;
 }
 
 template <int LPE>
@@ -1104,16 +932,7 @@ int cs_flight_create(const cs_flight_cfg* cfg, cs_flight** out) {
     p.rec = p.meta_off + CS_META_WORDS / 2;
     p.state_len = 4 * n + 3 * m;
     p.state_stride = (p.state_len + 3) & ~3;
-    // shared slot: record | targets | cos,sin | fp32 outputs | result | amask scratch | boxes | hit cells
-    int off = p.rec;
-    p.s_tgt = off; off += 2 * m;
-    p.s_cs = off; off += 2 * n;
-    p.s_out = off; off += 2 * n;
-    p.s_res = off; off += 1;
-    p.s_am = off; off += up2(m > (n + 3) / 4 ? m : (n + 3) / 4) / 2;
-    p.s_box = off; off += cfg->variant ? 3 * n : 0;
-    p.s_hit = off; off += cfg->variant ? up2(m) / 2 : 0;
-    p.s_stride = off | 1;      // odd stride in doubles: conflict-free slot-strided 64-bit accesses
+    p.s_cs = 3 * n;
     // constants, computed exactly as the reference's Python floats are
     p.Md = (double)M;
     p.half_M = 0.5 * (double)M;
@@ -1141,17 +960,20 @@ int cs_flight_create(const cs_flight_cfg* cfg, cs_flight** out) {
     p.span_cap = 1;
     while (p.span_cap < 2 * cfg->view_range) p.span_cap <<= 1;
     auto magic = [](int d) { return (uint32_t)((0x100000000ULL + (uint64_t)d - 1) / (uint64_t)d); };
-    p.mg_rec2 = magic(p.rec / 2); p.mg_m = magic(m); p.mg_n = magic(n); p.mg_rows = magic(p.span_cap + 1);
-    // corner-row masks + per-(agent,row) owned masks of the belief-map pass, then the heading-table index (37 x 16 B)
-    const int mask_doubles = ((cfg->variant && M <= 63) ? M + 2 + n * (p.span_cap + 1) : 0);
-    // per-warp layout: EPW slots | masks | (pad to 16 B) heading-table index: 37 x 16 B = 74 doubles (+2 spare)
-    auto lut_off = [&](int lpe) { return ((32 / lpe) * p.s_stride + mask_doubles + 1) & ~1; };
-    auto warp_doubles = [&](int lpe) { return lut_off(lpe) + 76; };
+    p.mg_rows = magic(p.span_cap + 1);
     h->lpe = pick_lpe(*cfg);
-    // fall back to more lanes per env until the CTA's slots fit the shared memory of one SM
-    while (h->lpe < 32 && (size_t)(kThreads / 32) * warp_doubles(h->lpe) * sizeof(double) > 200 * 1024) h->lpe <<= 1;
-    p.s_lut = lut_off(h->lpe);
-    p.s_warp = warp_doubles(h->lpe);
+    {
+        // per-warp shared-memory scratch (doubles): EPW x 5n (coupled move) | belief-map scratch | heading-table index
+        const int epw = 32 / h->lpe;
+        p.s_grp = 5 * n;
+        p.s_map = up2(epw * p.s_grp);
+        p.s_box = 2 * n;                                  // offsets below are relative to the belief-map scratch
+        p.s_hit = p.s_box + 3 * n;
+        p.s_mask = p.s_hit + up2(m) / 2;
+        const int map_doubles = cfg->variant ? p.s_mask + ((M <= 63) ? (M + 2) + n * (p.span_cap + 1) : 0) : 0;
+        p.s_lut = up2(p.s_map + map_doubles);
+        p.s_warp = p.s_lut + 76;                          // 37 x 16 B index, padded
+    }
     h->smem_bytes = (size_t)(kThreads / 32) * p.s_warp * sizeof(double);
     const int env_per_cta = (kThreads / 32) * (32 / h->lpe);
     h->grid = (p.E + env_per_cta - 1) / env_per_cta;
@@ -1165,18 +987,26 @@ int cs_flight_create(const cs_flight_cfg* cfg, cs_flight** out) {
                          sizeof(uint32_t), E));
     CS_CUDA(cudaMalloc(&p.tgt, E * 2 * m * sizeof(double)));
     CS_CUDA(cudaMemset(p.tgt, 0, E * 2 * m * sizeof(double)));
-    CS_CUDA(cudaMalloc(&p.obs, E * 4 * n * sizeof(float)));
-    CS_CUDA(cudaMemset(p.obs, 0, E * 4 * n * sizeof(float)));
-    CS_CUDA(cudaMalloc(&p.state, E * p.state_stride * sizeof(float)));
-    CS_CUDA(cudaMemset(p.state, 0, E * p.state_stride * sizeof(float)));
-    CS_CUDA(cudaMalloc(&p.reward, E * sizeof(float)));
-    CS_CUDA(cudaMemset(p.reward, 0, E * sizeof(float)));
-    CS_CUDA(cudaMalloc(&p.terminated, E));
-    CS_CUDA(cudaMemset(p.terminated, 0, E));
-    CS_CUDA(cudaMalloc(&p.win, E));
-    CS_CUDA(cudaMemset(p.win, 0, E));
-    CS_CUDA(cudaMalloc(&p.target_find, E * sizeof(int32_t)));
-    CS_CUDA(cudaMemset(p.target_find, 0, E * sizeof(int32_t)));
+    {
+        // all step outputs live in one slab so that the host-buffer step can fetch them with a single D2H copy
+        auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+        size_t off = 0;
+        h->off_reward = off; off = al(off + E * sizeof(float));
+        h->off_tf = off; off = al(off + E * sizeof(int32_t));
+        h->off_term = off; off = al(off + E);
+        h->off_win = off; off = al(off + E);
+        h->off_obs = off; off = al(off + E * 4 * n * sizeof(float));
+        h->off_state = off; off = al(off + E * p.state_stride * sizeof(float));
+        h->slab_bytes = off;
+        CS_CUDA(cudaMalloc(&h->d_slab, off));
+        CS_CUDA(cudaMemset(h->d_slab, 0, off));
+        p.reward = reinterpret_cast<float*>(h->d_slab + h->off_reward);
+        p.target_find = reinterpret_cast<int32_t*>(h->d_slab + h->off_tf);
+        p.terminated = h->d_slab + h->off_term;
+        p.win = h->d_slab + h->off_win;
+        p.obs = reinterpret_cast<float*>(h->d_slab + h->off_obs);
+        p.state = reinterpret_cast<float*>(h->d_slab + h->off_state);
+    }
     CS_CUDA(cudaMalloc(&p.stats, CS_NUM_STATS * sizeof(double)));
     CS_CUDA(cudaMemset(p.stats, 0, CS_NUM_STATS * sizeof(double)));
     CS_CUDA(cudaMalloc(&h->d_tmpl, (size_t)m * 5 * sizeof(double)));
@@ -1204,8 +1034,7 @@ int cs_flight_create(const cs_flight_cfg* cfg, cs_flight** out) {
 void cs_flight_destroy(cs_flight* h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
-    cudaFree(h->p.dyn); cudaFree(h->p.tgt); cudaFree(h->p.obs); cudaFree(h->p.state); cudaFree(h->p.reward);
-    cudaFree(h->p.terminated); cudaFree(h->p.win); cudaFree(h->p.target_find); cudaFree(h->p.stats);
+    cudaFree(h->p.dyn); cudaFree(h->p.tgt); cudaFree(h->d_slab); cudaFree(h->p.stats);
     cudaFree(h->d_tmpl); cudaFree(h->p.prob_map); cudaFree(h->d_actions); cudaFree(h->d_lut_meta); cudaFree(h->d_lut);
     delete h;
 }
@@ -1305,6 +1134,13 @@ int cs_flight_obs_full(cs_flight* h, float* d_out, void* stream) {
     return CS_OK;
 }
 
+int cs_flight_slab_layout(const cs_flight* h, uint64_t* out8) {
+    CS_REQUIRE(h && out8, "cs_flight_slab_layout: null argument");
+    out8[0] = h->slab_bytes; out8[1] = h->off_reward; out8[2] = h->off_tf; out8[3] = h->off_term; out8[4] = h->off_win;
+    out8[5] = h->off_obs; out8[6] = h->off_state; out8[7] = (uint64_t)h->p.state_stride * sizeof(float);
+    return CS_OK;
+}
+
 int cs_flight_step_host(cs_flight* h, const cs_flight_host_io* io, void* stream) {
     CS_REQUIRE(h && io && io->actions, "cs_flight_step_host: null argument");
     const FlightParams& p = h->p;
@@ -1313,14 +1149,19 @@ int cs_flight_step_host(cs_flight* h, const cs_flight_host_io* io, void* stream)
     CS_CUDA(cudaSetDevice(h->cfg.device));
     CS_CUDA(cudaMemcpyAsync(h->d_actions, io->actions, E * p.n, cudaMemcpyHostToDevice, st));
     CS_CUDA(dispatch(h, MODE_STEP, h->d_actions, nullptr, 0u, st));
-    if (io->reward) CS_CUDA(cudaMemcpyAsync(io->reward, p.reward, E * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (io->terminated) CS_CUDA(cudaMemcpyAsync(io->terminated, p.terminated, E, cudaMemcpyDeviceToHost, st));
-    if (io->win) CS_CUDA(cudaMemcpyAsync(io->win, p.win, E, cudaMemcpyDeviceToHost, st));
-    if (io->obs) CS_CUDA(cudaMemcpyAsync(io->obs, p.obs, E * 4 * p.n * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (io->state)   // compact [E][state_len] on the host, padded rows on the device
-        CS_CUDA(cudaMemcpy2DAsync(io->state, p.state_len * sizeof(float), p.state, p.state_stride * sizeof(float),
-                                  p.state_len * sizeof(float), E, cudaMemcpyDeviceToHost, st));
-    CS_CUDA(cudaStreamSynchronize(st));
+    if (io->slab) {
+        // one copy for everything: reward | target_find | terminated | win | obs | state (cs_flight_slab_layout)
+        CS_CUDA(cudaMemcpyAsync(io->slab, h->d_slab, h->slab_bytes, cudaMemcpyDeviceToHost, st));
+    } else {
+        if (io->reward) CS_CUDA(cudaMemcpyAsync(io->reward, p.reward, E * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (io->terminated) CS_CUDA(cudaMemcpyAsync(io->terminated, p.terminated, E, cudaMemcpyDeviceToHost, st));
+        if (io->win) CS_CUDA(cudaMemcpyAsync(io->win, p.win, E, cudaMemcpyDeviceToHost, st));
+        if (io->obs) CS_CUDA(cudaMemcpyAsync(io->obs, p.obs, E * 4 * p.n * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (io->state)   // compact [E][state_len] on the host, padded rows on the device
+            CS_CUDA(cudaMemcpy2DAsync(io->state, p.state_len * sizeof(float), p.state, p.state_stride * sizeof(float),
+                                      p.state_len * sizeof(float), E, cudaMemcpyDeviceToHost, st));
+    }
+    if (!(io->flags & CS_HOST_NO_SYNC)) CS_CUDA(cudaStreamSynchronize(st));
     return CS_OK;
 }
 

@@ -279,29 +279,39 @@ class _VecFlightBase:
             self.prob_map.copy_(d["prob_map"])
 
     def host_buffers(self):
-        """Pinned host staging used by step_host (allocated once)."""
+        """Pinned host staging used by step_host (allocated once): one slab mirroring the device output slab, so
+        a host-buffer step is one H2D copy, one kernel and ONE D2H copy."""
         if self._host is None:
             E, n = self.num_envs, self.n_agents
-            pin = lambda *shape, dtype: torch.empty(shape, dtype=dtype).pin_memory()
+            lay = (C.c_uint64 * 8)()
+            _lib.check(self.lib.cs_flight_slab_layout(self._h.ptr, lay), "cs_flight_slab_layout")
+            total, o_rew, o_tf, o_term, o_win, o_obs, o_state, pitch = [int(x) for x in lay]
+            slab = torch.empty(total, dtype=torch.uint8).pin_memory()
+            stride = pitch // 4
+            view = lambda off, nbytes, dtype: slab[off:off + nbytes].view(dtype)
             self._host = {
-                "actions": pin(E, n, dtype=torch.uint8), "reward": pin(E, dtype=torch.float32),
-                "terminated": pin(E, dtype=torch.uint8), "win": pin(E, dtype=torch.uint8),
-                "obs": pin(E, n, 4, dtype=torch.float32), "state": pin(E, self.state_shape, dtype=torch.float32),
+                "actions": torch.empty((E, n), dtype=torch.uint8).pin_memory(),
+                "slab": slab,
+                "reward": view(o_rew, 4 * E, torch.float32),
+                "target_find": view(o_tf, 4 * E, torch.int32),
+                "terminated": view(o_term, E, torch.uint8),
+                "win": view(o_win, E, torch.uint8),
+                "obs": view(o_obs, 16 * E * n, torch.float32).view(E, n, 4),
+                "state": view(o_state, pitch * E, torch.float32).view(E, stride)[:, :self.state_shape],
             }
         return self._host
 
-    def step_host(self, actions, want_obs=True, want_state=True):
+    def step_host(self, actions, want_obs=True, want_state=True, sync=True):
         """The call a CPU-side rollout makes: HOST actions in, HOST results out (numpy views of pinned
-        buffers).  H2D + kernel + D2H happen inside cs_flight_step_host."""
+        buffers).  H2D + kernel + D2H happen inside cs_flight_step_host.  sync=False only enqueues (pipelining
+        several env batches on different streams); synchronise the stream before reading the results."""
         hb = self.host_buffers()
         a = np.asarray(actions, dtype=np.uint8)
         if a.shape != (self.num_envs, self.n_agents):
             raise CoopSearchError('Act num mismatch agent')
         hb["actions"].numpy()[...] = a
-        io = _lib.FlightHostIO(
-            actions=hb["actions"].data_ptr(), reward=hb["reward"].data_ptr(), terminated=hb["terminated"].data_ptr(),
-            win=hb["win"].data_ptr(), obs=hb["obs"].data_ptr() if want_obs else None,
-            state=hb["state"].data_ptr() if want_state else None)
+        io = _lib.FlightHostIO(actions=hb["actions"].data_ptr(), slab=hb["slab"].data_ptr(),
+                               flags=0 if sync else _lib.CS_HOST_NO_SYNC)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.cs_flight_step_host(self._h.ptr, C.byref(io), self._stream()), "cs_flight_step_host")
         return (hb["reward"].numpy(), hb["terminated"].numpy(), hb["win"].numpy(),

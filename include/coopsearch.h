@@ -154,15 +154,21 @@ int cs_flight_step_random(cs_flight* env, int32_t k, void* stream);
 int cs_flight_obs_full(cs_flight* env, float* d_out, void* stream);
 /* Host-buffer step: the call a CPU-side rollout makes.  h_actions [E][n] u8.  Any output pointer
  * may be NULL (not copied).  Blocks until outputs are in host memory. */
+#define CS_HOST_NO_SYNC 1u        /* cs_*_host_io.flags: enqueue only; the caller synchronises the stream */
 typedef struct cs_flight_host_io {
     const uint8_t* actions;
     float* reward;
     uint8_t* terminated;
     uint8_t* win;
     float* obs;
-    float* state;
+    float* state;           /* compact [E][4n+3m] */
+    void* slab;             /* if non-NULL: ONE D2H copy of all outputs in the layout of
+                               cs_flight_slab_layout; the pointers above are then ignored      */
+    uint32_t flags;         /* CS_HOST_NO_SYNC */
 } cs_flight_host_io;
 int cs_flight_step_host(cs_flight* env, const cs_flight_host_io* io, void* stream);
+/* out8 = { slab bytes, offsets of reward, target_find, terminated, win, obs, state, state row pitch in bytes } */
+int cs_flight_slab_layout(const cs_flight* env, uint64_t* out8);
 /* Copies the stats vector to host (synchronises the stream). */
 int cs_flight_stats(cs_flight* env, double* h_out, void* stream);
 
