@@ -375,7 +375,7 @@ def run_gpu_workload(cs, torch, name, steps, warmup, device, rank, world, want_e
     # statistics of the finished episodes on this GPU (all-reduced by the caller)
     stats = torch.zeros(8, dtype=torch.float64, device=device)
     for e in envs:
-        stats += e.stats_tensor
+        stats += torch.tensor(list(e.stats().values()), dtype=torch.float64, device=device)
     out["stats"] = stats
     return out
 

@@ -487,7 +487,7 @@ __global__ void __launch_bounds__(kThreads) flight_kernel(const __grid_constant_
     bool do_sense = false, emit = false, state_full = false, tgt_dirty = false, have_result = false;
     float res_reward = 0.f;
     uint32_t res_term = 0, res_win = 0, res_found = 0, t_key = 0;   // what step()/reset() report for this env
-    float st_eps = 0.f, st_rew = 0.f, st_found = 0.f, st_wins = 0.f, st_len = 0.f, st_steps = 0.f;
+    float st_eps = 0.f, st_rew = 0.f, st_found = 0.f, st_wins = 0.f, st_len = 0.f;
     unsigned touched = 0;
 
     // ---- _agent_step -------------------------------------------------------------------------------------------
@@ -635,12 +635,9 @@ __global__ void __launch_bounds__(kThreads) flight_kernel(const __grid_constant_
             res_term = term ? 1u : 0u;
             res_win = flags & CS_FLAG_WIN;          // of the episode this step belongs to, also when auto_reset follows
             res_found = (uint32_t)nfound;
-            if (lane == 0) {
-                st_steps = 1.f;
-                if (term) {
-                    st_eps = 1.f; st_rew = ep_reward; st_found = (float)nfound; st_wins = (flags & CS_FLAG_WIN) ? 1.f : 0.f;
-                    st_len = (float)time_step;
-                }
+            if (lane == 0 && term) {
+                st_eps = 1.f; st_rew = ep_reward; st_found = (float)nfound; st_wins = (flags & CS_FLAG_WIN) ? 1.f : 0.f;
+                st_len = (float)time_step;
             }
         }
         // ---- belief map of every env of this warp that was just sensed (flight_env.py:266,:275-303) ---------
@@ -704,26 +701,25 @@ __global__ void __launch_bounds__(kThreads) flight_kernel(const __grid_constant_
         p.win[e] = res_win ? 1 : 0;
         p.target_find[e] = (int32_t)res_found;
     }
-    // ---- statistics: warp reduction, then at most one atomic per statistic per warp ---------------------------
+    // ---- statistics of episodes that ended in this call: warp reduction, then one atomic per statistic per warp.
+    //      Nothing is accumulated for ordinary steps (a same-address atomic per warp per step serialises in L2 and
+    //      was the floor of the small configurations); env_steps = sum of finished episode lengths + live time_steps
+    //      is assembled by cs_flight_stats.
     if (MODE == MODE_STEP) {
-        if (__any_sync(FULL, (st_steps + st_eps) != 0.f)) {
+        if (__any_sync(FULL, st_eps != 0.f)) {
             for (int o = 16; o > 0; o >>= 1) {
                 st_eps += __shfl_xor_sync(FULL, st_eps, o);
                 st_rew += __shfl_xor_sync(FULL, st_rew, o);
                 st_found += __shfl_xor_sync(FULL, st_found, o);
                 st_wins += __shfl_xor_sync(FULL, st_wins, o);
                 st_len += __shfl_xor_sync(FULL, st_len, o);
-                st_steps += __shfl_xor_sync(FULL, st_steps, o);
             }
             if (lane32 == 0) {
-                atomicAdd(p.stats + CS_STAT_ENV_STEPS, (double)st_steps);
-                if (st_eps != 0.f) {
-                    atomicAdd(p.stats + CS_STAT_EPISODES, (double)st_eps);
-                    atomicAdd(p.stats + CS_STAT_EP_REWARD, (double)st_rew);
-                    atomicAdd(p.stats + CS_STAT_TARGETS_FOUND, (double)st_found);
-                    atomicAdd(p.stats + CS_STAT_WINS, (double)st_wins);
-                    atomicAdd(p.stats + CS_STAT_EP_LEN, (double)st_len);
-                }
+                atomicAdd(p.stats + CS_STAT_EPISODES, (double)st_eps);
+                atomicAdd(p.stats + CS_STAT_EP_REWARD, (double)st_rew);
+                atomicAdd(p.stats + CS_STAT_TARGETS_FOUND, (double)st_found);
+                atomicAdd(p.stats + CS_STAT_WINS, (double)st_wins);
+                atomicAdd(p.stats + CS_STAT_EP_LEN, (double)st_len);
             }
         }
     }
@@ -731,6 +727,18 @@ __global__ void __launch_bounds__(kThreads) flight_kernel(const __grid_constant_
         const unsigned tot = __reduce_add_sync(FULL, touched);
         if (lane32 == 0 && tot) atomicAdd(p.stats + CS_STAT_TOUCHED, (double)tot);
     }
+}
+
+// sum of the time_step words of all envs (steps of the episodes still running), for cs_flight_stats
+__global__ void __launch_bounds__(256) flight_live_steps_kernel(const double* __restrict__ dyn, int E, int rec, int meta_off,
+                                                                double* __restrict__ out) {
+    unsigned long long acc = 0;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
+        const uint32_t* mt = reinterpret_cast<const uint32_t*>(dyn + (size_t)e * rec + meta_off);
+        if (!(mt[CS_META_FLAGS] & CS_FLAG_DONE)) acc += mt[CS_META_TIME];   // a finished episode is already in CS_STAT_EP_LEN
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, (double)acc);
 }
 
 // Reference-shaped observation of the flight variant: [E][n][M*M+4] (flight_env.py:223-230)
@@ -779,6 +787,7 @@ struct cs_flight {
     int grid;
     double* d_tmpl;
     uint8_t* d_actions;   // device staging of the *_host entry point's actions
+    double* d_live;       // scratch of cs_flight_stats
     uint8_t* d_slab;      // one allocation behind reward | target_find | terminated | win | obs | state
     size_t slab_bytes, off_reward, off_tf, off_term, off_win, off_obs, off_state;
     longlong2* d_lut_meta;
@@ -1007,6 +1016,7 @@ int cs_flight_create(const cs_flight_cfg* cfg, cs_flight** out) {
         p.obs = reinterpret_cast<float*>(h->d_slab + h->off_obs);
         p.state = reinterpret_cast<float*>(h->d_slab + h->off_state);
     }
+    CS_CUDA(cudaMalloc(&h->d_live, sizeof(double)));
     CS_CUDA(cudaMalloc(&p.stats, CS_NUM_STATS * sizeof(double)));
     CS_CUDA(cudaMemset(p.stats, 0, CS_NUM_STATS * sizeof(double)));
     CS_CUDA(cudaMalloc(&h->d_tmpl, (size_t)m * 5 * sizeof(double)));
@@ -1034,7 +1044,7 @@ int cs_flight_create(const cs_flight_cfg* cfg, cs_flight** out) {
 void cs_flight_destroy(cs_flight* h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
-    cudaFree(h->p.dyn); cudaFree(h->p.tgt); cudaFree(h->d_slab); cudaFree(h->p.stats);
+    cudaFree(h->p.dyn); cudaFree(h->p.tgt); cudaFree(h->d_slab); cudaFree(h->p.stats); cudaFree(h->d_live);
     cudaFree(h->d_tmpl); cudaFree(h->p.prob_map); cudaFree(h->d_actions); cudaFree(h->d_lut_meta); cudaFree(h->d_lut);
     delete h;
 }
@@ -1167,8 +1177,19 @@ int cs_flight_step_host(cs_flight* h, const cs_flight_host_io* io, void* stream)
 
 int cs_flight_stats(cs_flight* h, double* h_out, void* stream) {
     CS_REQUIRE(h && h_out, "cs_flight_stats: null argument");
-    CS_CUDA(cudaMemcpyAsync(h_out, h->p.stats, CS_NUM_STATS * sizeof(double), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
-    CS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    cudaStream_t st = (cudaStream_t)stream;
+    CS_CUDA(cudaSetDevice(h->cfg.device));
+    // env_steps = lengths of the finished episodes + steps of the episodes still running
+    CS_CUDA(cudaMemsetAsync(h->d_live, 0, sizeof(double), st));
+    const int grid = (h->p.E + 255) / 256 < CS_NUM_SMS_B200 * 4 ? (h->p.E + 255) / 256 : CS_NUM_SMS_B200 * 4;
+    flight_live_steps_kernel<<<grid, 256, 0, st>>>(h->p.dyn, h->p.E, h->p.rec, h->p.meta_off, h->d_live);
+    cs_count_launch(1);
+    CS_CUDA(cudaGetLastError());
+    double live = 0.0;
+    CS_CUDA(cudaMemcpyAsync(h_out, h->p.stats, CS_NUM_STATS * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CS_CUDA(cudaMemcpyAsync(&live, h->d_live, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CS_CUDA(cudaStreamSynchronize(st));
+    h_out[CS_STAT_ENV_STEPS] = h_out[CS_STAT_EP_LEN] + live;
     return CS_OK;
 }
 

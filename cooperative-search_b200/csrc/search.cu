@@ -30,7 +30,7 @@ struct SearchParams {
     int S, obs_len;                  // S = 2R-1, obs_len = S*S+2
     int agent_mode, target_mode, auto_reset;
     int stage_obs;                   // 1: observation block staged in shared memory (M <= 64 and it fits)
-    uint32_t mg_half, mg_M, mg_S1;   // ceil(2^32/d) for d = M/2, M, S+1
+    uint32_t mg_half, mg_M, mg_S1, mg_span;   // ceil(2^32/d) for d = M/2, M, S+1, 2R+1
     uint32_t seed, env_id_base;
     int32_t* pos;
     uint32_t* target_bits;
@@ -54,6 +54,8 @@ struct SearchSmem {
     int32_t* pos;        // [2n]
     int32_t* cand;       // [2*kThreads] candidate cells during target placement
     int* scal;           // [8]
+    uint32_t* discmask;  // [S]   bit j set: window cell (i, j) lies outside the disc -> 0.5 (search_env.py:221-222)
+    int* halfw;          // [2R+1] half width of the disc row at |dx| (detection, :263)
     float* obs_stage;    // [n*obs_len] staging of the observation block, or nullptr (direct path)
 };
 
@@ -66,13 +68,15 @@ __device__ __forceinline__ SearchSmem carve(const SearchParams& p, unsigned char
     s.pos = reinterpret_cast<int32_t*>(s.abits + rows);
     s.cand = s.pos + 2 * p.n;
     s.scal = s.cand + 2 * kThreads;
+    s.discmask = reinterpret_cast<uint32_t*>(s.scal + 8);
+    s.halfw = reinterpret_cast<int*>(s.discmask + p.S);
     // 16-byte aligned staging block after the integer scratch
-    const size_t used = sizeof(uint32_t) * (size_t)(3 * rows) + sizeof(int32_t) * (size_t)(2 * p.n + 2 * kThreads + 8);
+    const size_t used = sizeof(uint32_t) * (size_t)(3 * rows) + sizeof(int32_t) * (size_t)(2 * p.n + 2 * kThreads + 8 + p.S + 2 * p.R + 1);
     s.obs_stage = p.stage_obs ? reinterpret_cast<float*>(raw + ((used + 15) & ~(size_t)15)) : nullptr;
     return s;
 }
 size_t smem_base_bytes(const SearchParams& p) {
-    const size_t used = sizeof(uint32_t) * (size_t)(3 * p.M * p.W) + sizeof(int32_t) * (size_t)(2 * p.n + 2 * kThreads + 8);
+    const size_t used = sizeof(uint32_t) * (size_t)(3 * p.M * p.W) + sizeof(int32_t) * (size_t)(2 * p.n + 2 * kThreads + 8 + p.S + 2 * p.R + 1);
     return (used + 15) & ~(size_t)15;
 }
 // v / d with magic = ceil(2^32 / d); d == 1 gives magic 2^32 -> stored as 0 -> identity
@@ -208,10 +212,23 @@ __device__ void search_emit(const SearchParams& p, const SearchSmem& s, int e) {
                 field = gy0 >= 0 ? (row >> gy0) : (row << (-gy0));
             }
             float* orow = o + i * S;
-            for (int j = 0; j < S; ++j) {
-                const int gy = gy0 + j, dj = R - 1 - j;
-                const bool half = !row_ok || gy < 0 || gy >= M || di * di + dj * dj > R2;       // (:220-226)
-                orow[j] = half ? 0.5f : (float)((unsigned)(field >> j) & 1u);
+            if (S <= 32) {
+                // columns inside the map: j in [max(0,-gy0), min(S-1, M-1-gy0)]; everything else, everything outside the
+                // disc and every off-map row reads 0.5 (:220-226)
+                const int jlo = max(0, -gy0), jhi = min(S - 1, M - 1 - gy0);
+                uint32_t inmap = 0;
+                if (row_ok && jlo <= jhi) inmap = (jhi >= 31 ? 0xffffffffu : ((2u << jhi) - 1u)) & ~((1u << jlo) - 1u);
+                const uint32_t halfm = ~inmap | s.discmask[i];
+                const uint32_t ones = (uint32_t)field & ~halfm;
+                for (int j = 0; j < S; ++j)
+                    orow[j] = ((halfm >> j) & 1u) ? 0.5f : (float)((ones >> j) & 1u);
+            } else {
+                (void)di;
+                for (int j = 0; j < S; ++j) {
+                    const int gy = gy0 + j, dj = R - 1 - j;
+                    const bool half = !row_ok || gy < 0 || gy >= M || di * di + dj * dj > R2;
+                    orow[j] = half ? 0.5f : (float)((unsigned)(field >> j) & 1u);
+                }
             }
         }
         __syncthreads();
@@ -264,6 +281,22 @@ __global__ void __launch_bounds__(kThreads) search_kernel(const SearchParams p, 
         for (int k = tid; k < rows; k += kThreads) { s.tbits[k] = gt[k]; s.ubits[k] = gu[k]; }
         const int32_t* gp = p.pos + (size_t)e * 2 * n;
         for (int k = tid; k < 2 * n; k += kThreads) s.pos[k] = gp[k];
+        const int R = p.R, R2 = R * R;
+        for (int i = tid; i < p.S; i += kThreads) {              // window rows: which columns fall outside the disc
+            uint32_t mk = 0;
+            const int di = R - 1 - i;
+            for (int j = 0; j < p.S && j < 32; ++j) {
+                const int dj = R - 1 - j;
+                if (di * di + dj * dj > R2) mk |= 1u << j;
+            }
+            s.discmask[i] = mk;
+        }
+        for (int d = tid; d <= 2 * R; d += kThreads) {           // detection rows: half width at dx = d - R
+            const int dx = d - R;
+            int w = 0;
+            while ((w + 1) * (w + 1) + dx * dx <= R2) ++w;
+            s.halfw[d] = w;
+        }
     }
     __syncthreads();
 
@@ -313,11 +346,10 @@ __global__ void __launch_bounds__(kThreads) search_kernel(const SearchParams p, 
             // ---- detection: disc rows of every agent against the unfound bit rows (:261-267)
             const int R = p.R, R2 = R * R, span = 2 * R + 1;
             for (int task = tid; task < n * span; task += kThreads) {
-                const int a = task / span, dx = task - a * span - R;
+                const int a = fastdiv(task, p.mg_span), dx = task - a * span - R;
                 const int x = s.pos[2 * a] + dx;
                 if (x < 0 || x >= M) continue;
-                int w = 0;
-                while ((w + 1) * (w + 1) + dx * dx <= R2) ++w;      // half width of the disc row: dy^2 <= R^2 - dx^2
+                const int w = s.halfw[dx + R];                      // half width of the disc row: dy^2 <= R^2 - dx^2
                 const int y0 = max(0, s.pos[2 * a + 1] - w), y1 = min(M - 1, s.pos[2 * a + 1] + w);
                 for (int wd = y0 >> 5; wd <= (y1 >> 5); ++wd) {
                     const int lo = max(y0, wd * 32) - wd * 32, hi = min(y1, wd * 32 + 31) - wd * 32;
@@ -341,7 +373,8 @@ __global__ void __launch_bounds__(kThreads) search_kernel(const SearchParams p, 
                 cnt[CNT_FIND] = found;
                 cnt[CNT_TIME] = t1;
                 cnt[CNT_FLAGS] |= (term ? SF_DONE : 0) | (s.scal[SC_ILLEGAL] ? SF_ILLEGAL : 0);
-                atomicAdd(p.stats + CS_STAT_ENV_STEPS, 1.0);
+                // no per-step statistic: a same-address atomic per CTA per step serialises in L2; env_steps is
+                // assembled by cs_search_stats from finished-episode lengths + live time_steps
                 if (s.scal[SC_ILLEGAL]) atomicAdd(p.stats + CS_STAT_ILLEGAL, 1.0);
                 if (term) {
                     atomicAdd(p.stats + CS_STAT_EPISODES, 1.0);
@@ -389,6 +422,17 @@ __global__ void __launch_bounds__(kThreads) search_kernel(const SearchParams p, 
     search_emit(p, s, e);
 }
 
+// sum of the live time_step counters, for cs_search_stats
+__global__ void __launch_bounds__(256) search_live_steps_kernel(const int32_t* __restrict__ counters, int E, double* __restrict__ out) {
+    unsigned long long acc = 0;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
+        const int4 c = reinterpret_cast<const int4*>(counters)[e];
+        if (!(c.z & SF_DONE)) acc += (unsigned)c.y;            // a finished episode is already in CS_STAT_EP_LEN
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, (double)acc);
+}
+
 }  // namespace
 
 struct cs_search {
@@ -397,6 +441,7 @@ struct cs_search {
     size_t smem_bytes;
     int32_t* d_cells;
     uint8_t* d_actions;
+    double* d_live;
 };
 
 namespace {
@@ -440,7 +485,7 @@ int cs_search_create(const cs_search_cfg* cfg, cs_search** out) {
     p.agent_mode = cfg->agent_mode; p.target_mode = cfg->target_mode; p.auto_reset = cfg->auto_reset;
     p.seed = cfg->seed; p.env_id_base = cfg->env_id_base;
     auto magic = [](int d) { return (uint32_t)((0x100000000ULL + (uint64_t)d - 1) / (uint64_t)d); };
-    p.mg_half = magic(p.M / 2 > 0 ? p.M / 2 : 1); p.mg_M = magic(p.M); p.mg_S1 = magic(p.S + 1);
+    p.mg_half = magic(p.M / 2 > 0 ? p.M / 2 : 1); p.mg_M = magic(p.M); p.mg_S1 = magic(p.S + 1); p.mg_span = magic(2 * p.R + 1);
     const size_t stage_bytes = sizeof(float) * (size_t)p.n * p.obs_len;
     p.stage_obs = (p.M <= 64 && smem_base_bytes(p) + stage_bytes <= 100 * 1024) ? 1 : 0;
     h->smem_bytes = smem_base_bytes(p) + (p.stage_obs ? stage_bytes : 0);
@@ -464,6 +509,7 @@ int cs_search_create(const cs_search_cfg* cfg, cs_search** out) {
     CS_ALLOC0(p.target_find, E * sizeof(int32_t));
     CS_ALLOC0(p.stats, CS_NUM_STATS * sizeof(double));
     CS_ALLOC0(h->d_actions, E * p.n);
+    CS_ALLOC0(h->d_live, sizeof(double));
 #undef CS_ALLOC0
     // episode counter starts at -1 so that the first reset opens episode 0
     CS_CUDA(cudaMemset2D(p.counters + CNT_EPISODE, 4 * sizeof(int32_t), 0xFF, sizeof(int32_t), E));
@@ -477,7 +523,7 @@ void cs_search_destroy(cs_search* h) {
     SearchParams& p = h->p;
     cudaFree(p.pos); cudaFree(p.target_bits); cudaFree(p.unfound_bits); cudaFree(p.freq); cudaFree(p.counters);
     cudaFree(p.obs); cudaFree(p.state); cudaFree(p.avail); cudaFree(p.reward); cudaFree(p.terminated);
-    cudaFree(p.target_find); cudaFree(p.stats); cudaFree(h->d_cells); cudaFree(h->d_actions);
+    cudaFree(p.target_find); cudaFree(p.stats); cudaFree(h->d_cells); cudaFree(h->d_actions); cudaFree(h->d_live);
     delete h;
 }
 
@@ -547,8 +593,18 @@ int cs_search_step_host(cs_search* h, const cs_search_host_io* io, void* stream)
 
 int cs_search_stats(cs_search* h, double* h_out, void* stream) {
     CS_REQUIRE(h && h_out, "cs_search_stats: null argument");
-    CS_CUDA(cudaMemcpyAsync(h_out, h->p.stats, CS_NUM_STATS * sizeof(double), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
-    CS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    cudaStream_t st = (cudaStream_t)stream;
+    CS_CUDA(cudaSetDevice(h->cfg.device));
+    CS_CUDA(cudaMemsetAsync(h->d_live, 0, sizeof(double), st));
+    const int grid = (h->p.E + 255) / 256 < CS_NUM_SMS_B200 * 4 ? (h->p.E + 255) / 256 : CS_NUM_SMS_B200 * 4;
+    search_live_steps_kernel<<<grid, 256, 0, st>>>(h->p.counters, h->p.E, h->d_live);
+    cs_count_launch(1);
+    CS_CUDA(cudaGetLastError());
+    double live = 0.0;
+    CS_CUDA(cudaMemcpyAsync(h_out, h->p.stats, CS_NUM_STATS * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CS_CUDA(cudaMemcpyAsync(&live, h->d_live, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CS_CUDA(cudaStreamSynchronize(st));
+    h_out[CS_STAT_ENV_STEPS] = h_out[CS_STAT_EP_LEN] + live;      // finished episodes + episodes still running
     return CS_OK;
 }
 
