@@ -58,6 +58,7 @@ struct FlightParams {
     const double2* lut;          // (sin, cos) of every bit pattern in every cluster window, from the HOST libm
     double inv_turn;             // 18/pi
     double cos0, sin0;           // cos/sin of the start heading of agent_mode, from the host libm
+    double lin[CS_MAX_AGENTS];   // i*map_size/(n-1) (map_size/2 for n == 1), flight_env_easy.py:140-143
 };
 
 // v / d with magic = ceil(2^32 / d); d == 1 gives magic 2^32 -> stored as 0 -> identity
@@ -113,42 +114,6 @@ __device__ __forceinline__ bool wall_reg(const FlightParams& p, double& x, doubl
         c = -c;   // cos(pi - h) = cos(3pi - h) = -cos(h); sin unchanged (only the fp32 outputs use them)
     }
     return outside;
-}
-
-// Repulsion slow path: the reference's sequential, in-place update -- agent k sees its own OLD position and the
-// already-moved j<k (env/flight_env_easy.py:271,:293-301).  Runs on a 5n-double scratch block in shared memory
-// (x,y per agent | heading | cos | sin).  Out of line: rare, and keeps the hot path compact.
-__device__ __noinline__ uint32_t fl_move_coupled(const FlightParams& p, double* S) {
-    const int n = p.n;
-    double* yaw = S + p.yaw_off;
-    double* cs = S + p.s_cs;
-    uint32_t outbits = 0;
-    for (int k = 0; k < n; ++k) {
-        const double x0 = S[2 * k], y0 = S[2 * k + 1];
-        double x = x0 + p.v * cs[k];
-        double y = y0 + p.v * cs[n + k];
-        double fx = 0.0, fy = 0.0;
-        for (int q = 0; q < n; ++q) {
-            if (q == k) continue;
-            const double xa = S[2 * q], ya = S[2 * q + 1];
-            const double ax = xa - x0, ay = ya - y0;
-            if (ax * ax + ay * ay < p.fd2 && (xa != x0 || ya != y0)) {
-                const double ex = x0 - xa, ey = y0 - ya;
-                const double r2 = ex * ex + ey * ey;
-                fx += p.fk * ex / r2;
-                fy += p.fk * ey / r2;
-            }
-        }
-        x += fx;
-        y += fy;
-        double h = yaw[k], c = cs[k];
-        if (wall_reg(p, x, y, h, c)) outbits |= 1u << k;
-        S[2 * k] = x;
-        S[2 * k + 1] = y;
-        yaw[k] = h;
-        cs[k] = c;
-    }
-    return outbits;
 }
 
 // Reset-time target placement (env/flight_env_easy.py:95-127) from the keyed stream; cold, out of line.
@@ -220,7 +185,7 @@ __device__ __forceinline__ float belief_update(float pv, int cnt, float qf) {
 // Ms: [2n agent xy][boxes][hit cells] scratch of the warp, already filled with the agent positions and the hit
 // cells by the caller.  Needs map_size <= 63 (one 64-bit mask per corner row); larger maps take fl_probmap_wide.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned fl_probmap(const FlightParams& p, double* Ms, int lane, float* map, int nh) {
+__device__ __noinline__ unsigned fl_probmap(const FlightParams& p, double* Ms, int lane, float* map, int nh) {
     const int n = p.n, M = p.M;
     int* box = reinterpret_cast<int*>(Ms + p.s_box);   // [n][6]: i0, i1, j0, j1 (cells), clo_x, chi_x (corner rows)
     const int* hit = reinterpret_cast<const int*>(Ms + p.s_hit);
@@ -430,7 +395,7 @@ __device__ __forceinline__ uint32_t group_ballot(bool pred) {
 //   pass 1       : reset (selected envs in RESET mode; just-terminated envs under auto_reset) -> _update_obs (:79-182)
 // actions == nullptr in MODE_STEP: uniform-random policy drawn in-kernel (alg=random, agent/agent.py:34-36)
 // ------------------------------------------------------------------------------------------------
-template <int LPE, int MODE>
+template <int LPE, int MODE, bool MAP>
 __global__ void __launch_bounds__(kThreads) flight_kernel(const __grid_constant__ FlightParams p, const uint8_t* __restrict__ actions,
                                                           const uint8_t* __restrict__ mask, uint32_t rflags) {
     using G = Group<LPE>;
@@ -525,18 +490,40 @@ __global__ void __launch_bounds__(kThreads) flight_kernel(const __grid_constant_
                 }
                 outmask = group_ballot<LPE>(outside);
             } else {
-                double* Sg = W + g * p.s_grp;
-                if (is_agent) {
-                    Sg[2 * lane] = ax; Sg[2 * lane + 1] = ay; Sg[p.yaw_off + lane] = yaw;
-                    Sg[p.s_cs + lane] = c_h; Sg[p.s_cs + n + lane] = s_h;
-                }
-                G::sync();
-                uint32_t ob = 0;
-                if (lane == 0) ob = fl_move_coupled(p, Sg);
-                G::sync();
-                outmask = __shfl_sync(G::mask(), ob, 0, LPE);
-                if (is_agent) {
-                    ax = Sg[2 * lane]; ay = Sg[2 * lane + 1]; yaw = Sg[p.yaw_off + lane]; c_h = Sg[p.s_cs + lane];
+                // Repulsion path: the reference's sequential, in-place update (:271,:293-301) -- agent k sees its own
+                // OLD position and the already-moved j<k.  Lanes keep their CURRENT position in registers, so iterating
+                // k = 0..n-1 and letting every lane q evaluate its term against agent k's old position reproduces
+                // exactly that; the terms of the (few) lanes in range are added on lane k in ascending q, the
+                // reference's summation order.
+                outmask = 0;
+                for (int k = 0; k < n; ++k) {
+                    const double x0 = __shfl_sync(G::mask(), ax, k, LPE), y0 = __shfl_sync(G::mask(), ay, k, LPE);
+                    const double dxq = ax - x0, dyq = ay - y0;
+                    const bool inr = is_agent && lane != k && (dxq * dxq + dyq * dyq < p.fd2) && (ax != x0 || ay != y0);
+                    uint32_t near_mask = group_ballot<LPE>(inr);
+                    double tfx = 0.0, tfy = 0.0;
+                    if (inr) {
+                        const double ex = x0 - ax, ey = y0 - ay;
+                        const double r2 = ex * ex + ey * ey;
+                        tfx = p.fk * ex / r2;
+                        tfy = p.fk * ey / r2;
+                    }
+                    double fx = 0.0, fy = 0.0;
+                    while (near_mask) {                                         // group-uniform
+                        const int q = __ffs(near_mask) - 1;
+                        near_mask &= near_mask - 1;
+                        fx += __shfl_sync(G::mask(), tfx, q, LPE);
+                        fy += __shfl_sync(G::mask(), tfy, q, LPE);
+                    }
+                    bool outk = false;
+                    if (lane == k && is_agent) {
+                        ax = ax + p.v * c_h;
+                        ay = ay + p.v * s_h;
+                        ax += fx;
+                        ay += fy;
+                        outk = wall_reg(p, ax, ay, yaw, c_h);
+                    }
+                    outmask |= group_ballot<LPE>(outk);
                 }
             }
             do_sense = true;
@@ -566,7 +553,7 @@ __global__ void __launch_bounds__(kThreads) flight_kernel(const __grid_constant_
                     tgt_dirty = true;
                 }
                 if (is_agent) {
-                    const double lin = (n != 1) ? (double)(lane * p.M) / (double)(n - 1) : p.Md / 2.0;   // (:140-143)
+                    const double lin = p.lin[lane];                                       // (:140-143)
                     switch (p.agent_mode) {
                         case 0: ax = lin; ay = 0.0; yaw = p.half_pi; break;
                         case 1: ax = lin; ay = p.Md / 2.0; yaw = p.half_pi; break;
@@ -575,7 +562,7 @@ __global__ void __launch_bounds__(kThreads) flight_kernel(const __grid_constant_
                     }
                     c_h = p.cos0; s_h = p.sin0;
                 }
-                if (p.variant && (rflags & CS_RESET_INIT)) {
+                if (MAP && (rflags & CS_RESET_INIT)) {
                     float* map = p.prob_map + (size_t)e * p.M * p.M;
                     for (int c = lane; c < p.M * p.M; c += LPE) map[c] = 0.5f;            // flight_env.py:84-86
                 }
@@ -641,7 +628,7 @@ __global__ void __launch_bounds__(kThreads) flight_kernel(const __grid_constant_
             }
         }
         // ---- belief map of every env of this warp that was just sensed (flight_env.py:266,:275-303) ---------
-        if (p.variant) {
+        if (MAP) {
             double* Ms = W + p.s_map;
             int* hit = reinterpret_cast<int*>(Ms + p.s_hit);
             for (int le = 0; le < EPW; ++le) {
@@ -723,7 +710,7 @@ __global__ void __launch_bounds__(kThreads) flight_kernel(const __grid_constant_
             }
         }
     }
-    if (p.variant && p.count_touched) {
+    if (MAP && p.count_touched) {
         const unsigned tot = __reduce_add_sync(FULL, touched);
         if (lane32 == 0 && tot) atomicAdd(p.stats + CS_STAT_TOUCHED, (double)tot);
     }
@@ -809,19 +796,28 @@ int pick_lpe(const cs_flight_cfg& c) {
 template <int LPE>
 cudaError_t launch_flight(const cs_flight* h, int mode, const uint8_t* actions, const uint8_t* mask, uint32_t rflags,
                           cudaStream_t st) {
-    if (mode == MODE_STEP)
-        flight_kernel<LPE, MODE_STEP><<<h->grid, kThreads, h->smem_bytes, st>>>(h->p, actions, mask, rflags);
-    else
-        flight_kernel<LPE, MODE_RESET><<<h->grid, kThreads, h->smem_bytes, st>>>(h->p, actions, mask, rflags);
+    if (h->p.variant) {
+        if (mode == MODE_STEP)
+            flight_kernel<LPE, MODE_STEP, true><<<h->grid, kThreads, h->smem_bytes, st>>>(h->p, actions, mask, rflags);
+        else
+            flight_kernel<LPE, MODE_RESET, true><<<h->grid, kThreads, h->smem_bytes, st>>>(h->p, actions, mask, rflags);
+    } else {
+        if (mode == MODE_STEP)
+            flight_kernel<LPE, MODE_STEP, false><<<h->grid, kThreads, h->smem_bytes, st>>>(h->p, actions, mask, rflags);
+        else
+            flight_kernel<LPE, MODE_RESET, false><<<h->grid, kThreads, h->smem_bytes, st>>>(h->p, actions, mask, rflags);
+    }
     cs_count_launch(1);
     return cudaGetLastError();
 }
 
 template <int LPE>
 cudaError_t set_smem_attr(size_t bytes) {
-    cudaError_t e = cudaFuncSetAttribute(flight_kernel<LPE, MODE_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(flight_kernel<LPE, MODE_RESET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    cudaError_t e = cudaFuncSetAttribute(flight_kernel<LPE, MODE_STEP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(flight_kernel<LPE, MODE_RESET, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(flight_kernel<LPE, MODE_STEP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(flight_kernel<LPE, MODE_RESET, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    return e;
 }
 
 cudaError_t dispatch(const cs_flight* h, int mode, const uint8_t* actions, const uint8_t* mask, uint32_t rflags,
@@ -960,6 +956,8 @@ int cs_flight_create(const cs_flight_cfg* cfg, cs_flight** out) {
     else p.thr = (long long)floor(cfg->detect_prob * 4294967296.0);
     p.seed = cfg->seed; p.env_id_base = cfg->env_id_base;
     p.inv_turn = 18.0 / M_PI;
+    for (int a = 0; a < CS_MAX_AGENTS; ++a)
+        p.lin[a] = (n != 1) ? (double)(a * M) / (double)(n - 1) : (double)M / 2.0;
     {
         const double h0 = (cfg->agent_mode <= 1) ? M_PI / 2 : (cfg->agent_mode == 2 ? 0.0 : M_PI);
         p.cos0 = cos(h0);

@@ -56,7 +56,8 @@ struct SearchSmem {
     int* scal;           // [8]
     uint32_t* discmask;  // [S]   bit j set: window cell (i, j) lies outside the disc -> 0.5 (search_env.py:221-222)
     int* halfw;          // [2R+1] half width of the disc row at |dx| (detection, :263)
-    float* obs_stage;    // [n*obs_len] staging of the observation block, or nullptr (direct path)
+    uint8_t* obs_stage;  // [n*obs_len] bytes = 2*value of the observation block (0, 0.5, 1 and raw positions < 128),
+                         // or nullptr (direct path)
 };
 
 __device__ __forceinline__ SearchSmem carve(const SearchParams& p, unsigned char* raw) {
@@ -72,7 +73,7 @@ __device__ __forceinline__ SearchSmem carve(const SearchParams& p, unsigned char
     s.halfw = reinterpret_cast<int*>(s.discmask + p.S);
     // 16-byte aligned staging block after the integer scratch
     const size_t used = sizeof(uint32_t) * (size_t)(3 * rows) + sizeof(int32_t) * (size_t)(2 * p.n + 2 * kThreads + 8 + p.S + 2 * p.R + 1);
-    s.obs_stage = p.stage_obs ? reinterpret_cast<float*>(raw + ((used + 15) & ~(size_t)15)) : nullptr;
+    s.obs_stage = p.stage_obs ? reinterpret_cast<uint8_t*>(raw + ((used + 15) & ~(size_t)15)) : nullptr;
     return s;
 }
 size_t smem_base_bytes(const SearchParams& p) {
@@ -197,13 +198,13 @@ __device__ void search_emit(const SearchParams& p, const SearchSmem& s, int e) {
         for (int t = tid; t < tasks; t += kThreads) {
             const int a = fastdiv(t, p.mg_S1), i = t - a * (S + 1);
             const int x = s.pos[2 * a], y = s.pos[2 * a + 1];
-            float* o = s.obs_stage + a * p.obs_len;
+            uint8_t* o = s.obs_stage + a * p.obs_len;
             if (i == S) {                                              // raw integer position (:205-208)
-                o[S * S] = (float)x;
-                o[S * S + 1] = (float)y;
+                o[S * S] = (uint8_t)(2 * x);
+                o[S * S + 1] = (uint8_t)(2 * y);
                 continue;
             }
-            const int gx = i + x - R + 1, di = R - 1 - i, gy0 = y - R + 1;
+            const int gx = i + x - R + 1, gy0 = y - R + 1;
             unsigned long long field = 0ull;
             const bool row_ok = gx >= 0 && gx < M;
             if (row_ok) {
@@ -211,34 +212,29 @@ __device__ void search_emit(const SearchParams& p, const SearchSmem& s, int e) {
                 if (W > 1) row |= (unsigned long long)s.tbits[gx * W + 1] << 32;
                 field = gy0 >= 0 ? (row >> gy0) : (row << (-gy0));
             }
-            float* orow = o + i * S;
-            if (S <= 32) {
-                // columns inside the map: j in [max(0,-gy0), min(S-1, M-1-gy0)]; everything else, everything outside the
-                // disc and every off-map row reads 0.5 (:220-226)
-                const int jlo = max(0, -gy0), jhi = min(S - 1, M - 1 - gy0);
-                uint32_t inmap = 0;
-                if (row_ok && jlo <= jhi) inmap = (jhi >= 31 ? 0xffffffffu : ((2u << jhi) - 1u)) & ~((1u << jlo) - 1u);
-                const uint32_t halfm = ~inmap | s.discmask[i];
-                const uint32_t ones = (uint32_t)field & ~halfm;
-                for (int j = 0; j < S; ++j)
-                    orow[j] = ((halfm >> j) & 1u) ? 0.5f : (float)((ones >> j) & 1u);
-            } else {
-                (void)di;
-                for (int j = 0; j < S; ++j) {
-                    const int gy = gy0 + j, dj = R - 1 - j;
-                    const bool half = !row_ok || gy < 0 || gy >= M || di * di + dj * dj > R2;
-                    orow[j] = half ? 0.5f : (float)((unsigned)(field >> j) & 1u);
-                }
-            }
+            // columns inside the map: j in [max(0,-gy0), min(S-1, M-1-gy0)]; everything else, everything outside the
+            // disc and every off-map row reads 0.5 (:220-226).  Staged byte = 2*value.
+            const int jlo = max(0, -gy0), jhi = min(S - 1, M - 1 - gy0);
+            uint32_t inmap = 0;
+            if (row_ok && jlo <= jhi) inmap = (jhi >= 31 ? 0xffffffffu : ((2u << jhi) - 1u)) & ~((1u << jlo) - 1u);
+            const uint32_t halfm = ~inmap | s.discmask[i];
+            const uint32_t ones = (uint32_t)field & ~halfm;
+            uint8_t* orow = o + i * S;
+            for (int j = 0; j < S; ++j)
+                orow[j] = (uint8_t)(((halfm >> j) & 1u) + 2u * ((ones >> j) & 1u));
         }
         __syncthreads();
         const int total = n * p.obs_len;
         if ((total & 3) == 0) {
-            const float4* src = reinterpret_cast<const float4*>(s.obs_stage);
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(s.obs_stage);
             float4* dst = reinterpret_cast<float4*>(ob);
-            for (int k = tid; k < (total >> 2); k += kThreads) dst[k] = src[k];
+            for (int k = tid; k < (total >> 2); k += kThreads) {
+                const uint32_t w = src[k];
+                dst[k] = make_float4(0.5f * (float)(w & 0xffu), 0.5f * (float)((w >> 8) & 0xffu),
+                                     0.5f * (float)((w >> 16) & 0xffu), 0.5f * (float)(w >> 24));
+            }
         } else {
-            for (int k = tid; k < total; k += kThreads) ob[k] = s.obs_stage[k];
+            for (int k = tid; k < total; k += kThreads) ob[k] = 0.5f * (float)s.obs_stage[k];
         }
     } else {
         // large maps / very many agents: direct per-element path
@@ -486,8 +482,8 @@ int cs_search_create(const cs_search_cfg* cfg, cs_search** out) {
     p.seed = cfg->seed; p.env_id_base = cfg->env_id_base;
     auto magic = [](int d) { return (uint32_t)((0x100000000ULL + (uint64_t)d - 1) / (uint64_t)d); };
     p.mg_half = magic(p.M / 2 > 0 ? p.M / 2 : 1); p.mg_M = magic(p.M); p.mg_S1 = magic(p.S + 1); p.mg_span = magic(2 * p.R + 1);
-    const size_t stage_bytes = sizeof(float) * (size_t)p.n * p.obs_len;
-    p.stage_obs = (p.M <= 64 && smem_base_bytes(p) + stage_bytes <= 100 * 1024) ? 1 : 0;
+    const size_t stage_bytes = ((size_t)p.n * p.obs_len + 15) & ~(size_t)15;      // one byte (2*value) per element
+    p.stage_obs = (p.M <= 64 && p.S <= 32 && smem_base_bytes(p) + stage_bytes <= 100 * 1024) ? 1 : 0;
     h->smem_bytes = smem_base_bytes(p) + (p.stage_obs ? stage_bytes : 0);
     CS_REQUIRE(h->smem_bytes <= 200 * 1024, "map too large for the shared-memory bit rows");
     CS_CUDA(cudaFuncSetAttribute(search_kernel<MODE_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
