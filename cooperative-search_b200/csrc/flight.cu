@@ -25,6 +25,9 @@
 namespace {
 
 constexpr int kThreads = 128;
+#ifndef CS_MAP_MIN_CTAS
+#define CS_MAP_MIN_CTAS 6      // resident CTAs per SM the map-variant kernel is compiled for (register budget 65536/(128*N))
+#endif
 
 struct FlightParams {
     int E, n, m, M, T;
@@ -396,7 +399,7 @@ __device__ __forceinline__ uint32_t group_ballot(bool pred) {
 // actions == nullptr in MODE_STEP: uniform-random policy drawn in-kernel (alg=random, agent/agent.py:34-36)
 // ------------------------------------------------------------------------------------------------
 template <int LPE, int MODE, bool MAP>
-__global__ void __launch_bounds__(kThreads) flight_kernel(const __grid_constant__ FlightParams p, const uint8_t* __restrict__ actions,
+__global__ void __launch_bounds__(kThreads, MAP ? CS_MAP_MIN_CTAS : 8) flight_kernel(const __grid_constant__ FlightParams p, const uint8_t* __restrict__ actions,
                                                           const uint8_t* __restrict__ mask, uint32_t rflags) {
     using G = Group<LPE>;
     constexpr int EPW = 32 / LPE;
