@@ -380,20 +380,13 @@ __device__ __noinline__ unsigned fl_probmap_wide(const FlightParams& p, double* 
 
 enum { MODE_STEP = 0, MODE_RESET = 1 };
 
-// group-relative ballot
-template <int LPE>
-__device__ __forceinline__ uint32_t group_ballot(bool pred) {
-    const unsigned full = __ballot_sync(Group<LPE>::mask(), pred);
-    if (LPE == 32) return full;
-    return (full >> ((threadIdx.x & 31u) & ~(unsigned)(LPE - 1))) & ((1u << (LPE & 31)) - 1u);
-}
-
 // ------------------------------------------------------------------------------------------------
 // The step / reset kernel.  A group of LPE lanes (LPE = power of two >= max(n_agents, target_num)) owns one env:
 // lane a < n holds agent a (x, y, heading, cos, sin) and lane j < m holds target j, all in REGISTERS; positions
 // travel between lanes by warp shuffles.  Every global load is issued up front; nothing is staged through shared
-// memory except the heading-table index (per warp) and the scratch of the two cold/warp-wide parts (coupled
-// repulsion, belief map).
+// memory except the heading-table index (per warp) and the scratch of the warp-wide belief-map pass.
+// Every warp collective uses the FULL mask and sits in warp-uniform control flow (groups are told apart by
+// predicates, not branches), so no partial-mask MATCH/REDUX sequences or divergence barriers are generated.
 //   pass 0 (STEP): _agent_step -> _update_obs -> step bookkeeping            (flight_env_easy.py:255-314)
 //   pass 1       : reset (selected envs in RESET mode; just-terminated envs under auto_reset) -> _update_obs (:79-182)
 // actions == nullptr in MODE_STEP: uniform-random policy drawn in-kernel (alg=random, agent/agent.py:34-36)
@@ -401,9 +394,9 @@ __device__ __forceinline__ uint32_t group_ballot(bool pred) {
 template <int LPE, int MODE, bool MAP>
 __global__ void __launch_bounds__(kThreads, MAP ? CS_MAP_MIN_CTAS : 8) flight_kernel(const __grid_constant__ FlightParams p, const uint8_t* __restrict__ actions,
                                                           const uint8_t* __restrict__ mask, uint32_t rflags) {
-    using G = Group<LPE>;
     constexpr int EPW = 32 / LPE;
     constexpr unsigned FULL = 0xffffffffu;
+    constexpr unsigned GBITS = (LPE == 32) ? 0xffffffffu : ((1u << (LPE & 31)) - 1u);
     extern __shared__ __align__(16) double smem[];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane32 = tid & 31;
@@ -413,11 +406,13 @@ __global__ void __launch_bounds__(kThreads, MAP ? CS_MAP_MIN_CTAS : 8) flight_ke
     double* W = smem + (size_t)warp * p.s_warp;
     longlong2* lutm = reinterpret_cast<longlong2*>(W + p.s_lut);
     const int n = p.n, m = p.m;
-    const int g = lane32 / LPE, lane = lane32 % LPE;
+    const int g = lane32 / LPE, lane = lane32 % LPE, gbase = lane32 - lane;
     const bool active = g < wcnt;
     const int e = wenv0 + (active ? g : 0);
     const bool is_agent = active && lane < n, is_tgt = active && lane < m;
     const uint32_t env_id = p.env_id_base + (uint32_t)e;
+#define GSHFL(v, q) __shfl_sync(FULL, (v), gbase + (q))
+#define GBALLOT(pred) ((__ballot_sync(FULL, (pred)) >> gbase) & GBITS)
 
     // ---- every load of the step, issued before anything is consumed ----------------------------------------
     double* rec = p.dyn + (size_t)e * p.rec;
@@ -460,75 +455,71 @@ __global__ void __launch_bounds__(kThreads, MAP ? CS_MAP_MIN_CTAS : 8) flight_ke
 
     // ---- _agent_step -------------------------------------------------------------------------------------------
     if (MODE == MODE_STEP) {
-        if (active && !done) {
-            if (actions == nullptr && is_agent) {
+        const bool stepping = active && !done;
+        if (stepping && is_agent) {
+            if (actions == nullptr) {
                 // one Philox block serves 4 agents; action = word % 3 (np.random.randint(0, 3), agent.py:36)
                 const cs_u4 w = cs_philox4x32_10(env_id, ((episode & 0xFFFFu) << 16) | ((time_step + 1u) & 0xFFFFu),
                                                  (uint32_t)(lane >> 2), 0u, p.seed, CS_STREAM_POLICY);
                 act = (int)(cs_word(w, lane & 3) % 3u);
             }
-            if (is_agent) {
-                double h = yaw + ((act == 1) ? p.turn : ((act == 2) ? -p.turn : 0.0));   // dyaw = [0, pi/18, -pi/18] (:259-262)
-                if (h > p.two_pi) h -= p.two_pi;                                          // strict tests (:263-266)
-                else if (h < 0.0) h += p.two_pi;
-                heading_sincos(p, lutm, h, &s_h, &c_h);
-                yaw = h;
-            }
-            // Can any repulsion term be non-zero this step?  If every pair of OLD positions is farther apart than
-            // force_dist + |v| (with slack), no agent receives a force, every displacement is <= |v|, and by
-            // induction over the sequential update order no later agent does either.
-            bool close = false;
-            for (int q = 0; q < n; ++q) {
-                const double xq = __shfl_sync(G::mask(), ax, q, LPE), yq = __shfl_sync(G::mask(), ay, q, LPE);
-                const double dx = xq - ax, dy = yq - ay;
-                close |= (is_agent && q > lane && dx * dx + dy * dy < p.near2);
-            }
-            close = G::any(close);
-            bool outside = false;
-            if (!close) {
-                if (is_agent) {
-                    ax = ax + p.v * c_h;                          // x += v*cos(yaw)   (:267-268)
+            double h = yaw + ((act == 1) ? p.turn : ((act == 2) ? -p.turn : 0.0));   // dyaw = [0, pi/18, -pi/18] (:259-262)
+            if (h > p.two_pi) h -= p.two_pi;                                          // strict tests (:263-266)
+            else if (h < 0.0) h += p.two_pi;
+            heading_sincos(p, lutm, h, &s_h, &c_h);
+            yaw = h;
+        }
+        // Can any repulsion term be non-zero this step?  If every pair of OLD positions is farther apart than
+        // force_dist + |v| (with slack), no agent receives a force, every displacement is <= |v|, and by
+        // induction over the sequential update order no later agent does either.
+        bool close = false;
+        for (int q = 1; q < n; ++q) {
+            const double xq = GSHFL(ax, q), yq = GSHFL(ay, q);
+            const double dx = xq - ax, dy = yq - ay;
+            close |= (q > lane && dx * dx + dy * dy < p.near2);
+        }
+        const bool close_g = GBALLOT(close && stepping && is_agent) != 0u;     // some pair of this env is close
+        bool outside = false;
+        if (stepping && is_agent && !close_g) {
+            ax = ax + p.v * c_h;                          // x += v*cos(yaw)   (:267-268)
+            ay = ay + p.v * s_h;
+            outside = wall_reg(p, ax, ay, yaw, c_h);
+        }
+        if (__any_sync(FULL, close_g)) {
+            // Repulsion path: the reference's sequential, in-place update (:271,:293-301) -- agent k sees its own
+            // OLD position and the already-moved j<k.  Lanes keep their CURRENT position in registers, so iterating
+            // k = 0..n-1 and letting every lane q evaluate its term against agent k's old position reproduces
+            // exactly that; the terms of the (few) lanes in range are added on lane k in ascending q, the
+            // reference's summation order.
+            for (int k = 0; k < n; ++k) {
+                const double x0 = GSHFL(ax, k), y0 = GSHFL(ay, k);
+                const double dxq = ax - x0, dyq = ay - y0;
+                const bool inr = close_g && is_agent && lane != k && (dxq * dxq + dyq * dyq < p.fd2) && (ax != x0 || ay != y0);
+                uint32_t near_all = __ballot_sync(FULL, inr);
+                double tfx = 0.0, tfy = 0.0;
+                if (inr) {
+                    const double ex = x0 - ax, ey = y0 - ay;
+                    const double r2 = ex * ex + ey * ey;
+                    tfx = p.fk * ex / r2;
+                    tfy = p.fk * ey / r2;
+                }
+                double fx = 0.0, fy = 0.0;
+                while (near_all) {                                          // warp-uniform; ascending lane = ascending q
+                    const int src = __ffs(near_all) - 1;
+                    near_all &= near_all - 1;
+                    const double vx = __shfl_sync(FULL, tfx, src), vy = __shfl_sync(FULL, tfy, src);
+                    if ((src & ~(LPE - 1)) == gbase) { fx += vx; fy += vy; }
+                }
+                if (close_g && is_agent && lane == k) {
+                    ax = ax + p.v * c_h;
                     ay = ay + p.v * s_h;
+                    ax += fx;
+                    ay += fy;
                     outside = wall_reg(p, ax, ay, yaw, c_h);
                 }
-                outmask = group_ballot<LPE>(outside);
-            } else {
-                // Repulsion path: the reference's sequential, in-place update (:271,:293-301) -- agent k sees its own
-                // OLD position and the already-moved j<k.  Lanes keep their CURRENT position in registers, so iterating
-                // k = 0..n-1 and letting every lane q evaluate its term against agent k's old position reproduces
-                // exactly that; the terms of the (few) lanes in range are added on lane k in ascending q, the
-                // reference's summation order.
-                outmask = 0;
-                for (int k = 0; k < n; ++k) {
-                    const double x0 = __shfl_sync(G::mask(), ax, k, LPE), y0 = __shfl_sync(G::mask(), ay, k, LPE);
-                    const double dxq = ax - x0, dyq = ay - y0;
-                    const bool inr = is_agent && lane != k && (dxq * dxq + dyq * dyq < p.fd2) && (ax != x0 || ay != y0);
-                    uint32_t near_mask = group_ballot<LPE>(inr);
-                    double tfx = 0.0, tfy = 0.0;
-                    if (inr) {
-                        const double ex = x0 - ax, ey = y0 - ay;
-                        const double r2 = ex * ex + ey * ey;
-                        tfx = p.fk * ex / r2;
-                        tfy = p.fk * ey / r2;
-                    }
-                    double fx = 0.0, fy = 0.0;
-                    while (near_mask) {                                         // group-uniform
-                        const int q = __ffs(near_mask) - 1;
-                        near_mask &= near_mask - 1;
-                        fx += __shfl_sync(G::mask(), tfx, q, LPE);
-                        fy += __shfl_sync(G::mask(), tfy, q, LPE);
-                    }
-                    bool outk = false;
-                    if (lane == k && is_agent) {
-                        ax = ax + p.v * c_h;
-                        ay = ay + p.v * s_h;
-                        ax += fx;
-                        ay += fy;
-                        outk = wall_reg(p, ax, ay, yaw, c_h);
-                    }
-                    outmask |= group_ballot<LPE>(outk);
-                }
             }
+        }
+        if (stepping) {
             do_sense = true;
             t_key = time_step + 1u;
         } else if (active) {
@@ -538,6 +529,8 @@ __global__ void __launch_bounds__(kThreads, MAP ? CS_MAP_MIN_CTAS : 8) flight_ke
             res_win = flags & CS_FLAG_WIN;
             res_found = (uint32_t)__popc(found);
         }
+        const uint32_t ob = GBALLOT(outside);
+        if (stepping) outmask = ob;
     }
 
     for (int pass = 0; pass < 2; ++pass) {
@@ -581,7 +574,7 @@ __global__ void __launch_bounds__(kThreads, MAP ? CS_MAP_MIN_CTAS : 8) flight_ke
         // ---- _update_obs: detection + reward + win (:223-253) ----------------------------------------------
         uint32_t amask = 0;
         for (int q = 0; q < n; ++q) {
-            const double xq = __shfl_sync(G::mask(), ax, q, LPE), yq = __shfl_sync(G::mask(), ay, q, LPE);
+            const double xq = GSHFL(ax, q), yq = GSHFL(ay, q);
             const double dx = tx - xq, dy = ty - yq;
             if (dx * dx + dy * dy <= p.R2) amask |= 1u << q;                   // '<=' (:237)
         }
@@ -595,7 +588,7 @@ __global__ void __launch_bounds__(kThreads, MAP ? CS_MAP_MIN_CTAS : 8) flight_ke
                       ((bits & 4u) && (long long)w.z <= p.thr) || ((bits & 8u) && (long long)w.w <= p.thr);
             }
         }
-        const uint32_t newf = group_ballot<LPE>(got);
+        const uint32_t newf = GBALLOT(got);
         int rew = 0;
         if (do_sense) {
             found |= newf;
@@ -654,6 +647,8 @@ __global__ void __launch_bounds__(kThreads, MAP ? CS_MAP_MIN_CTAS : 8) flight_ke
             __syncwarp();
         }
     }
+#undef GSHFL
+#undef GBALLOT
 
     // ---- outputs, straight from registers -------------------------------------------------------------------
     if (active && emit) {

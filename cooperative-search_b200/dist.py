@@ -29,7 +29,9 @@ def init_from_env(backend=None):
         os.environ.setdefault("MASTER_PORT", "29533")
         if backend == "nccl":
             torch.cuda.set_device(local)
-        td.init_process_group(backend=backend, rank=rank, world_size=world)
+            td.init_process_group(backend=backend, rank=rank, world_size=world, device_id=torch.device("cuda", local))
+        else:
+            td.init_process_group(backend=backend, rank=rank, world_size=world)
     return rank, local, world
 
 
