@@ -193,6 +193,7 @@ __device__ __noinline__ unsigned fl_probmap(const FlightParams& p, double* Ms, i
     int* box = reinterpret_cast<int*>(Ms + p.s_box);   // [n][6]: i0, i1, j0, j1 (cells), clo_x, chi_x (corner rows)
     const int* hit = reinterpret_cast<const int*>(Ms + p.s_hit);
     unsigned long long* rowmask = reinterpret_cast<unsigned long long*>(Ms + p.s_mask);
+    unsigned long long* colmask = rowmask + (M + 2) + n * (p.span_cap + 1);     // [n] columns of each agent's box
     for (int a = lane; a < n; a += 32) {
         const double ax = Ms[2 * a], ay = Ms[2 * a + 1];
         int lo, hi;
@@ -202,8 +203,10 @@ __device__ __noinline__ unsigned fl_probmap(const FlightParams& p, double* Ms, i
         box[6 * a + 4] = lo;
         box[6 * a + 5] = hi;
         corner_span(ay, p.R, p.R2, &lo, &hi);
-        box[6 * a + 2] = max(0, lo - 1);
-        box[6 * a + 3] = min(M - 1, hi);
+        const int j0 = max(0, lo - 1), j1 = min(M - 1, hi);
+        box[6 * a + 2] = j0;
+        box[6 * a + 3] = j1;
+        colmask[a] = (j0 <= j1) ? (((2ull << j1) - 1ull) & ~((1ull << j0) - 1ull)) : 0ull;
     }
     for (int r = lane; r <= M + 1; r += 32) rowmask[r] = 0ull;
     __syncwarp();
@@ -218,16 +221,18 @@ __device__ __noinline__ unsigned fl_probmap(const FlightParams& p, double* Ms, i
         const double ax = Ms[2 * a], ay = Ms[2 * a + 1];
         const double dx = (double)cx - ax;
         const double A = dx * dx;
+        // candidate ends in fp32 (ay <= map_size: absolute error ~4e-6, far inside the 1e-3 guard band)
         const float wf = sqrtf(fmaxf((float)(p.R2 - A), 0.0f));
-        const double yh = ay + (double)wf, yl = ay - (double)wf;
-        double fh = floor(yh), cl = ceil(yl);
-        if (yh - fh < 1e-3 || yh - fh > 1.0 - 1e-3) {          // end within 1e-3 of an integer: decide exactly
-            const double Y = rint(yh);
-            fh = corner_pred(A, Y, ay, p.R2) ? Y : Y - 1.0;
+        const float ayf = (float)ay;
+        const float yh = ayf + wf, yl = ayf - wf;
+        float fh = floorf(yh), cl = ceilf(yl);
+        if (yh - fh < 1e-3f || yh - fh > 1.0f - 1e-3f) {       // end within 1e-3 of an integer: decide exactly
+            const double Y = (double)rintf(yh);
+            fh = (float)(corner_pred(A, Y, ay, p.R2) ? Y : Y - 1.0);
         }
-        if (cl - yl < 1e-3 || cl - yl > 1.0 - 1e-3) {
-            const double Y = rint(yl);
-            cl = corner_pred(A, Y, ay, p.R2) ? Y : Y + 1.0;
+        if (cl - yl < 1e-3f || cl - yl > 1.0f - 1e-3f) {
+            const double Y = (double)rintf(yl);
+            cl = (float)(corner_pred(A, Y, ay, p.R2) ? Y : Y + 1.0);
         }
         const int yhi = min((int)fh, M), ylo = max((int)cl, 0);
         if (ylo <= yhi) {
@@ -247,10 +252,9 @@ __device__ __noinline__ unsigned fl_probmap(const FlightParams& p, double* Ms, i
             unsigned long long Tm = 0ull;
             if (i <= box[6 * a + 1]) {
                 const unsigned long long A = rowmask[i], B = rowmask[i + 1];
-                Tm = (A | (A >> 1) | B | (B >> 1)) & (((2ull << box[6 * a + 3]) - 1ull) & ~((1ull << box[6 * a + 2]) - 1ull));
+                Tm = (A | (A >> 1) | B | (B >> 1)) & colmask[a];
                 for (int q = 0; q < a; ++q)
-                    if (i >= box[6 * q] && i <= box[6 * q + 1])
-                        Tm &= ~(((2ull << box[6 * q + 3]) - 1ull) & ~((1ull << box[6 * q + 2]) - 1ull));
+                    if (i >= box[6 * q] && i <= box[6 * q + 1]) Tm &= ~colmask[q];
             }
             own[t] = Tm;
         }
@@ -774,7 +778,7 @@ struct cs_flight {
     uint8_t* d_actions;   // device staging of the *_host entry point's actions
     double* d_live;       // scratch of cs_flight_stats
     uint8_t* d_slab;      // one allocation behind reward | target_find | terminated | win | obs | state
-    size_t slab_bytes, off_reward, off_tf, off_term, off_win, off_obs, off_state;
+    size_t slab_bytes, host_bytes, off_reward, off_tf, off_term, off_win, off_obs, off_state;
     longlong2* d_lut_meta;
     double2* d_lut;
     bool have_tmpl;
@@ -975,7 +979,7 @@ int cs_flight_create(const cs_flight_cfg* cfg, cs_flight** out) {
         p.s_box = 2 * n;                                  // offsets below are relative to the belief-map scratch
         p.s_hit = p.s_box + 3 * n;
         p.s_mask = p.s_hit + up2(m) / 2;
-        const int map_doubles = cfg->variant ? p.s_mask + ((M <= 63) ? (M + 2) + n * (p.span_cap + 1) : 0) : 0;
+        const int map_doubles = cfg->variant ? p.s_mask + ((M <= 63) ? (M + 2) + n * (p.span_cap + 1) + n : 0) : 0;
         p.s_lut = up2(p.s_map + map_doubles);
         p.s_warp = p.s_lut + 76;                          // 37 x 16 B index, padded
     }
@@ -1000,8 +1004,9 @@ int cs_flight_create(const cs_flight_cfg* cfg, cs_flight** out) {
         h->off_tf = off; off = al(off + E * sizeof(int32_t));
         h->off_term = off; off = al(off + E);
         h->off_win = off; off = al(off + E);
-        h->off_obs = off; off = al(off + E * 4 * n * sizeof(float));
         h->off_state = off; off = al(off + E * p.state_stride * sizeof(float));
+        h->host_bytes = off;                  // what the host-buffer step copies: obs rows are the state rows' first 4n floats
+        h->off_obs = off; off = al(off + E * 4 * n * sizeof(float));
         h->slab_bytes = off;
         CS_CUDA(cudaMalloc(&h->d_slab, off));
         CS_CUDA(cudaMemset(h->d_slab, 0, off));
@@ -1142,7 +1147,7 @@ int cs_flight_obs_full(cs_flight* h, float* d_out, void* stream) {
 
 int cs_flight_slab_layout(const cs_flight* h, uint64_t* out8) {
     CS_REQUIRE(h && out8, "cs_flight_slab_layout: null argument");
-    out8[0] = h->slab_bytes; out8[1] = h->off_reward; out8[2] = h->off_tf; out8[3] = h->off_term; out8[4] = h->off_win;
+    out8[0] = h->host_bytes; out8[1] = h->off_reward; out8[2] = h->off_tf; out8[3] = h->off_term; out8[4] = h->off_win;
     out8[5] = h->off_obs; out8[6] = h->off_state; out8[7] = (uint64_t)h->p.state_stride * sizeof(float);
     return CS_OK;
 }
@@ -1156,8 +1161,9 @@ int cs_flight_step_host(cs_flight* h, const cs_flight_host_io* io, void* stream)
     CS_CUDA(cudaMemcpyAsync(h->d_actions, io->actions, E * p.n, cudaMemcpyHostToDevice, st));
     CS_CUDA(dispatch(h, MODE_STEP, h->d_actions, nullptr, 0u, st));
     if (io->slab) {
-        // one copy for everything: reward | target_find | terminated | win | obs | state (cs_flight_slab_layout)
-        CS_CUDA(cudaMemcpyAsync(io->slab, h->d_slab, h->slab_bytes, cudaMemcpyDeviceToHost, st));
+        // one copy for everything: reward | target_find | terminated | win | state (cs_flight_slab_layout); the obs
+        // rows are the first 4n floats of the state rows and are not sent twice
+        CS_CUDA(cudaMemcpyAsync(io->slab, h->d_slab, h->host_bytes, cudaMemcpyDeviceToHost, st));
     } else {
         if (io->reward) CS_CUDA(cudaMemcpyAsync(io->reward, p.reward, E * sizeof(float), cudaMemcpyDeviceToHost, st));
         if (io->terminated) CS_CUDA(cudaMemcpyAsync(io->terminated, p.terminated, E, cudaMemcpyDeviceToHost, st));

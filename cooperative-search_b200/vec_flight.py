@@ -296,8 +296,9 @@ class _VecFlightBase:
                 "target_find": view(o_tf, 4 * E, torch.int32),
                 "terminated": view(o_term, E, torch.uint8),
                 "win": view(o_win, E, torch.uint8),
-                "obs": view(o_obs, 16 * E * n, torch.float32).view(E, n, 4),
                 "state": view(o_state, pitch * E, torch.float32).view(E, stride)[:, :self.state_shape],
+                # get_obs rows are the agent part of the state rows (flight_env_easy.py:192-193): not sent twice
+                "obs": view(o_state, pitch * E, torch.float32).view(E, stride)[:, :4 * n].unflatten(1, (n, 4)),
             }
         return self._host
 

@@ -162,12 +162,13 @@ typedef struct cs_flight_host_io {
     uint8_t* win;
     float* obs;
     float* state;           /* compact [E][4n+3m] */
-    void* slab;             /* if non-NULL: ONE D2H copy of all outputs in the layout of
-                               cs_flight_slab_layout; the pointers above are then ignored      */
+    void* slab;             /* if non-NULL: ONE D2H copy of reward|target_find|terminated|win|state in
+                               the layout of cs_flight_slab_layout; the pointers above are ignored */
     uint32_t flags;         /* CS_HOST_NO_SYNC */
 } cs_flight_host_io;
 int cs_flight_step_host(cs_flight* env, const cs_flight_host_io* io, void* stream);
-/* out8 = { slab bytes, offsets of reward, target_find, terminated, win, obs, state, state row pitch in bytes } */
+/* out8 = { slab bytes, offsets of reward, target_find, terminated, win, obs (unused: = slab bytes), state, state row
+ * pitch in bytes }.  The slab does not carry obs separately: obs[e][a][0..3] = state row e, floats 4a..4a+3. */
 int cs_flight_slab_layout(const cs_flight* env, uint64_t* out8);
 /* Copies the stats vector to host (synchronises the stream). */
 int cs_flight_stats(cs_flight* env, double* h_out, void* stream);

@@ -236,3 +236,42 @@ def test_single_env_adapter_types():
     assert isinstance(r, float) and isinstance(term, bool) and isinstance(info, bool)
     assert isinstance(env.target_find, int)
     assert np.array_equal(env.get_avail_agent_actions(0), np.ones(3))
+
+
+def test_config1_rollout_protocol_single_env():
+    """BASELINE.json configs[0]: flight_easy 1a15t AM0TM0, ONE env, uniform-random policy, driven through the exact
+    call sequence of RolloutWorker.generate_episode (common/rollout.py:22-140): reset, then per step get_obs,
+    get_state, get_avail_agent_actions per agent, step(actions), and finally target_find -- on the E=1 adapter,
+    against the Python oracle fed the same actions and the same injected targets."""
+    import coopsearch_b200 as cs
+    spec = FlightSpec(n_agents=1, agent_mode=0, target_mode=0)
+    args = make_args(dict(spec.__dict__))
+    vec = cs.VecFlightEasyEnv(args, TEMPLATE, num_envs=1, seed=42, env_id_base=77)
+    env = cs.SingleEnvAdapter(vec)
+    info = env.get_env_info()
+    assert info == {"n_actions": 3, "state_shape": 49, "obs_shape": 4, "episode_limit": 200}
+    orc = FlightOracle(spec, TEMPLATE, 42, 77)
+    rng = np.random.RandomState(0)
+    for episode in range(3):
+        env.reset()
+        orc.reset(targets=cpu(vec.tgt_xy)[0], init=False, episode=episode + 1)   # ctor reset was episode 0
+        terminated, step, episode_reward, win_tag = False, 0, 0.0, False
+        o, s, r = [], [], []
+        while not terminated and step < info["episode_limit"]:
+            obs, state = env.get_obs(), env.get_state()
+            np.testing.assert_allclose(obs, orc.get_obs(), rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(state, orc.get_state(), rtol=1e-5, atol=1e-6)
+            actions = []
+            for agent_id in range(1):
+                avail = env.get_avail_agent_actions(agent_id)
+                actions.append(rng.choice(np.nonzero(avail)[0]))          # agent.py:34-36 (alg=random)
+            reward, terminated, info_flag = env.step(actions)
+            wr, wterm, wwin = orc.step(actions)
+            assert (reward, terminated, info_flag) == (float(wr), bool(wterm), bool(wwin))
+            win_tag = True if terminated and info_flag else False
+            o.append(obs); s.append(state); r.append([reward])
+            episode_reward += reward
+            step += 1
+        assert env.target_find == orc.target_find
+        assert step == orc.time_step and episode_reward == orc.total_reward
+        assert win_tag == (orc.win and terminated)
