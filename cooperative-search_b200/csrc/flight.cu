@@ -38,7 +38,7 @@ struct FlightParams {
     // per-warp shared-memory scratch (doubles): one 5n block per group for the coupled-move path, then the
     // belief-map scratch (agent xy | boxes | hit cells | corner-row masks | owned masks), then the table index
     int s_cs;                    // = 3n: offset of cos/sin inside a group's 5n block (x,y | yaw | cos,sin)
-    int s_grp, s_map, s_box, s_hit, s_mask, s_lut, s_warp;
+    int s_grp, s_map, s_mapg, s_box, s_hit, s_mask, s_lut, s_warp;   // s_mapg: belief-map scratch per group
     int span_cap;                // power of two >= 2R: corner rows per agent in the interval pass
     uint32_t mg_rows;            // ceil(2^32/(span_cap+1))
     double Md, half_M, inv_half, R, R2, v, fk, fd2, near2, q_miss;
@@ -188,33 +188,39 @@ __device__ __forceinline__ float belief_update(float pv, int cnt, float qf) {
 // Ms: [2n agent xy][boxes][hit cells] scratch of the warp, already filled with the agent positions and the hit
 // cells by the caller.  Needs map_size <= 63 (one 64-bit mask per corner row); larger maps take fl_probmap_wide.
 // ------------------------------------------------------------------------------------------------
-__device__ __noinline__ unsigned fl_probmap(const FlightParams& p, double* Ms, int lane, float* map, int nh) {
+// All groups of the warp run this together (SIMT over envs): `lane` is the lane inside the group of LPE lanes that
+// owns the env, Ms is that group's scratch, `pend` tells whether this group's env was just sensed.  The barriers are
+// whole-warp, so the call site must be warp-uniform.
+template <int LPE>
+__device__ __noinline__ unsigned fl_probmap(const FlightParams& p, double* Ms, int lane, float* map, int nh, bool pend) {
     const int n = p.n, M = p.M;
     int* box = reinterpret_cast<int*>(Ms + p.s_box);   // [n][6]: i0, i1, j0, j1 (cells), clo_x, chi_x (corner rows)
     const int* hit = reinterpret_cast<const int*>(Ms + p.s_hit);
     unsigned long long* rowmask = reinterpret_cast<unsigned long long*>(Ms + p.s_mask);
     unsigned long long* colmask = rowmask + (M + 2) + n * (p.span_cap + 1);     // [n] columns of each agent's box
-    for (int a = lane; a < n; a += 32) {
-        const double ax = Ms[2 * a], ay = Ms[2 * a + 1];
-        int lo, hi;
-        corner_span(ax, p.R, p.R2, &lo, &hi);
-        box[6 * a + 0] = max(0, lo - 1);          // cell i has corners i and i+1
-        box[6 * a + 1] = min(M - 1, hi);
-        box[6 * a + 4] = lo;
-        box[6 * a + 5] = hi;
-        corner_span(ay, p.R, p.R2, &lo, &hi);
-        const int j0 = max(0, lo - 1), j1 = min(M - 1, hi);
-        box[6 * a + 2] = j0;
-        box[6 * a + 3] = j1;
-        colmask[a] = (j0 <= j1) ? (((2ull << j1) - 1ull) & ~((1ull << j0) - 1ull)) : 0ull;
+    if (pend) {
+        for (int a = lane; a < n; a += LPE) {
+            const double ax = Ms[2 * a], ay = Ms[2 * a + 1];
+            int lo, hi;
+            corner_span(ax, p.R, p.R2, &lo, &hi);
+            box[6 * a + 0] = max(0, lo - 1);          // cell i has corners i and i+1
+            box[6 * a + 1] = min(M - 1, hi);
+            box[6 * a + 4] = lo;
+            box[6 * a + 5] = hi;
+            corner_span(ay, p.R, p.R2, &lo, &hi);
+            const int j0 = max(0, lo - 1), j1 = min(M - 1, hi);
+            box[6 * a + 2] = j0;
+            box[6 * a + 3] = j1;
+            colmask[a] = (j0 <= j1) ? (((2ull << j1) - 1ull) & ~((1ull << j0) - 1ull)) : 0ull;
+        }
+        for (int r = lane; r <= M + 1; r += LPE) rowmask[r] = 0ull;
     }
-    for (int r = lane; r <= M + 1; r += 32) rowmask[r] = 0ull;
     __syncwarp();
     // (1) corner-row intervals
     const int span = p.span_cap;                      // power of two >= 2R
-    for (int t0 = 0; t0 < n * span; t0 += 32) {
+    for (int t0 = 0; t0 < n * span; t0 += LPE) {
         const int t = t0 + lane;
-        if (t >= n * span) continue;
+        if (!pend || t >= n * span) continue;
         const int a = t / span, r = t - a * span;          // span is a power of two
         const int cx = box[6 * a + 4] + r;
         if (cx > box[6 * a + 5] || cx < 0 || cx > M) continue;
@@ -244,9 +250,9 @@ __device__ __noinline__ unsigned fl_probmap(const FlightParams& p, double* Ms, i
     // (2) owned touched cells per (agent, box row); own[a*rows_cap + r] covers map row i0_a + r
     const int rows_cap = p.span_cap + 1;
     unsigned long long* own = rowmask + (M + 2);
-    for (int t0 = 0; t0 < n * rows_cap; t0 += 32) {
+    for (int t0 = 0; t0 < n * rows_cap; t0 += LPE) {
         const int t = t0 + lane;
-        if (t < n * rows_cap) {
+        if (pend && t < n * rows_cap) {
             const int a = fastdiv(t, p.mg_rows), r = t - a * rows_cap;
             const int i = box[6 * a] + r;
             unsigned long long Tm = 0ull;
@@ -262,61 +268,65 @@ __device__ __noinline__ unsigned fl_probmap(const FlightParams& p, double* Ms, i
     __syncwarp();
     // (3) sweep
     unsigned touched = 0;
+    if (!pend) return 0u;
     const float qf = (float)p.q_miss;
     if ((M & 1) == 0) {
-        const int rsub = lane >> 3, jl = 2 * (lane & 7);
+        // LPR lanes per map row, CPL cells (CPL/2 x float2) per lane; the row's masks are fetched once per CPL cells
+        // and all of a lane's loads are in flight together.  LPE = 32: 2 lanes x 8 cells, 16 rows per pass;
+        // LPE <= 16: 1 lane x 16 cells, LPE rows per pass.
+        constexpr int LPR = (LPE >= 32) ? 2 : 1, CPL = 16 / LPR, RPP = LPE / LPR, NV = CPL / 2;
+        const int rsub = lane / LPR, jl = CPL * (lane % LPR);
         for (int a = 0; a < n; ++a) {
             const int i0 = box[6 * a], i1 = box[6 * a + 1], j0 = box[6 * a + 2], j1 = box[6 * a + 3];
             const int nrows = i1 - i0 + 1;
             const unsigned long long* ow = own + a * rows_cap;
             for (int jc = j0 & ~1; jc <= j1; jc += 16) {
                 const int j = jc + jl;
-                for (int rb = 0; rb < nrows; rb += 16) {
-                    float2 v[4];
-                    unsigned t2[4], ab[4];
+                for (int rb = 0; rb < nrows; rb += RPP) {
+                    const int r = rb + rsub;
+                    if (r >= nrows) continue;
+                    const unsigned tm = (unsigned)(ow[r] >> j) & ((1u << CPL) - 1u);
+                    if (!tm) continue;                                     // percent == 0 -> untouched (:285-286)
+                    const int i = i0 + r;
+                    const unsigned Am = (unsigned)(rowmask[i] >> j) & ((2u << CPL) - 1u);
+                    const unsigned Bm = (unsigned)(rowmask[i + 1] >> j) & ((2u << CPL) - 1u);
+                    float2* rowp = reinterpret_cast<float2*>(map + i * M + j);
+                    float2 v[NV];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int r = rb + 4 * u + rsub;
-                        t2[u] = 0u;
-                        if (r < nrows) {
-                            t2[u] = (unsigned)(ow[r] >> j) & 3u;
-                            if (t2[u]) {
-                                const int i = i0 + r;
-                                v[u] = *reinterpret_cast<const float2*>(map + i * M + j);
-                                ab[u] = ((unsigned)(rowmask[i] >> j) & 7u) | (((unsigned)(rowmask[i + 1] >> j) & 7u) << 3);
+                    for (int c = 0; c < NV; ++c)
+                        if ((tm >> (2 * c)) & 3u) v[c] = rowp[c];
+#pragma unroll
+                    for (int c = 0; c < NV; ++c) {
+                        const unsigned t2 = (tm >> (2 * c)) & 3u;
+                        if (!t2) continue;
+                        const unsigned a2 = (Am >> (2 * c)) & 7u, b2 = (Bm >> (2 * c)) & 7u;
+                        if (t2 & 1u) v[c].x = belief_update(v[c].x, __popc(a2 & 3u) + __popc(b2 & 3u), qf);
+                        if (t2 & 2u) v[c].y = belief_update(v[c].y, __popc(a2 & 6u) + __popc(b2 & 6u), qf);
+                        if (nh) {                                          // targets found by THIS call -> 1 (:288-289)
+                            const int cell = i * M + j + 2 * c;
+                            for (int k = 0; k < nh; ++k) {
+                                if ((t2 & 1u) && hit[k] == cell) v[c].x = 1.0f;
+                                if ((t2 & 2u) && hit[k] == cell + 1) v[c].y = 1.0f;
                             }
                         }
+                        rowp[c] = v[c];
                     }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        if (!t2[u]) continue;                              // percent == 0 -> untouched (:285-286)
-                        const int cell = (i0 + rb + 4 * u + rsub) * M + j;
-                        const unsigned a2 = ab[u] & 7u, b2 = ab[u] >> 3;
-                        if (t2[u] & 1u) v[u].x = belief_update(v[u].x, __popc(a2 & 3u) + __popc(b2 & 3u), qf);
-                        if (t2[u] & 2u) v[u].y = belief_update(v[u].y, __popc(a2 & 6u) + __popc(b2 & 6u), qf);
-                        for (int k = 0; k < nh; ++k) {                     // targets found by THIS call -> 1 (:288-289)
-                            if ((t2[u] & 1u) && hit[k] == cell) v[u].x = 1.0f;
-                            if ((t2[u] & 2u) && hit[k] == cell + 1) v[u].y = 1.0f;
-                        }
-                        *reinterpret_cast<float2*>(map + cell) = v[u];
-                        touched += __popc(t2[u]);
-                    }
+                    touched += __popc(tm);
                 }
             }
         }
     } else {
-        // odd map_size: rows are only 4-byte aligned -> one cell per lane, 16 lanes per row, 2 rows per instruction
-        const int rsub = lane >> 4, jl = lane & 15;
+        // odd map_size: rows are only 4-byte aligned -> one cell at a time, one lane per row, 16 columns per pass
         for (int a = 0; a < n; ++a) {
             const int i0 = box[6 * a], i1 = box[6 * a + 1], j0 = box[6 * a + 2], j1 = box[6 * a + 3];
             const unsigned long long* ow = own + a * rows_cap;
-            for (int jc = j0; jc <= j1; jc += 16) {
-                const int j = jc + jl;
-                for (int r = rsub; r <= i1 - i0; r += 2) {
+            for (int r = lane; r <= i1 - i0; r += LPE) {
+                const int i = i0 + r;
+                const unsigned long long A = rowmask[i], B = rowmask[i + 1];
+                for (int j = j0; j <= j1; ++j) {
                     if (!((ow[r] >> j) & 1ull)) continue;
-                    const int i = i0 + r, cell = i * M + j;
-                    const unsigned a2 = (unsigned)(rowmask[i] >> j) & 3u, b2 = (unsigned)(rowmask[i + 1] >> j) & 3u;
-                    float v = belief_update(map[cell], __popc(a2) + __popc(b2), qf);
+                    const int cell = i * M + j;
+                    float v = belief_update(map[cell], __popc((unsigned)(A >> j) & 3u) + __popc((unsigned)(B >> j) & 3u), qf);
                     for (int k = 0; k < nh; ++k)
                         if (hit[k] == cell) v = 1.0f;
                     map[cell] = v;
@@ -629,24 +639,32 @@ __global__ void __launch_bounds__(kThreads, MAP ? CS_MAP_MIN_CTAS : 8) flight_ke
         }
         // ---- belief map of every env of this warp that was just sensed (flight_env.py:266,:275-303) ---------
         if (MAP) {
-            double* Ms = W + p.s_map;
+            // every group hands its env's agent positions and hit cells to its own scratch block; then all groups of
+            // the warp run the belief-map pass together
+            double* Ms = W + p.s_map + g * p.s_mapg;
             int* hit = reinterpret_cast<int*>(Ms + p.s_hit);
-            for (int le = 0; le < EPW; ++le) {
-                const bool pend = __shfl_sync(FULL, (int)do_sense, le * LPE) != 0;
-                if (!pend) continue;                                           // warp-uniform
-                __syncwarp();
-                if (g == le) {
-                    if (is_agent) { Ms[2 * lane] = ax; Ms[2 * lane + 1] = ay; }
-                    if (is_tgt && ((newf >> lane) & 1u)) {
-                        // idx = min(int(x), M-1): Python int() truncates toward zero (flight_env.py:279)
-                        const int ci = min((int)fmin(tx, p.Md), p.M - 1), cj = min((int)fmin(ty, p.Md), p.M - 1);
-                        hit[__popc(newf & ((1u << lane) - 1u))] = (ci < 0 || cj < 0) ? -1 : ci * p.M + cj;
-                    }
+            __syncwarp();
+            if (do_sense) {
+                if (is_agent) { Ms[2 * lane] = ax; Ms[2 * lane + 1] = ay; }
+                if (is_tgt && ((newf >> lane) & 1u)) {
+                    // idx = min(int(x), M-1): Python int() truncates toward zero (flight_env.py:279)
+                    const int ci = min((int)fmin(tx, p.Md), p.M - 1), cj = min((int)fmin(ty, p.Md), p.M - 1);
+                    hit[__popc(newf & ((1u << lane) - 1u))] = (ci < 0 || cj < 0) ? -1 : ci * p.M + cj;
                 }
-                const int nh = __popc(__shfl_sync(FULL, newf, le * LPE));
-                __syncwarp();
-                float* map = p.prob_map + (size_t)(wenv0 + le) * p.M * p.M;
-                touched += (p.M <= 63) ? fl_probmap(p, Ms, lane32, map, nh) : fl_probmap_wide(p, Ms, lane32, map, nh);
+            }
+            __syncwarp();
+            float* map = p.prob_map + (size_t)e * p.M * p.M;
+            if (p.M <= 63) {
+                touched += fl_probmap<LPE>(p, Ms, lane, map, __popc(newf), do_sense);
+            } else {
+                for (int le = 0; le < EPW; ++le) {                              // large maps: one env at a time, warp-wide
+                    const bool pend = __shfl_sync(FULL, (int)do_sense, le * LPE) != 0;
+                    if (!pend) continue;                                       // warp-uniform
+                    const int nh = __popc(__shfl_sync(FULL, newf, le * LPE));
+                    touched += fl_probmap_wide(p, W + p.s_map + le * p.s_mapg, lane32,
+                                               p.prob_map + (size_t)(wenv0 + le) * p.M * p.M, nh);
+                    __syncwarp();
+                }
             }
             __syncwarp();
         }
@@ -979,8 +997,8 @@ int cs_flight_create(const cs_flight_cfg* cfg, cs_flight** out) {
         p.s_box = 2 * n;                                  // offsets below are relative to the belief-map scratch
         p.s_hit = p.s_box + 3 * n;
         p.s_mask = p.s_hit + up2(m) / 2;
-        const int map_doubles = cfg->variant ? p.s_mask + ((M <= 63) ? (M + 2) + n * (p.span_cap + 1) + n : 0) : 0;
-        p.s_lut = up2(p.s_map + map_doubles);
+        p.s_mapg = cfg->variant ? up2(p.s_mask + ((M <= 63) ? (M + 2) + n * (p.span_cap + 1) + n : 0)) : 0;
+        p.s_lut = up2(p.s_map + epw * p.s_mapg);
         p.s_warp = p.s_lut + 76;                          // 37 x 16 B index, padded
     }
     h->smem_bytes = (size_t)(kThreads / 32) * p.s_warp * sizeof(double);
