@@ -26,7 +26,7 @@ namespace {
 
 constexpr int kThreads = 128;
 #ifndef CS_MAP_MIN_CTAS
-#define CS_MAP_MIN_CTAS 6      // resident CTAs per SM the map-variant kernel is compiled for (register budget 65536/(128*N))
+#define CS_MAP_MIN_CTAS 7      // resident CTAs per SM the map-variant kernel is compiled for (register budget 65536/(128*N))
 #endif
 
 struct FlightParams {
@@ -216,6 +216,20 @@ __device__ __noinline__ unsigned fl_probmap(const FlightParams& p, double* Ms, i
         for (int r = lane; r <= M + 1; r += LPE) rowmask[r] = 0ull;
     }
     __syncwarp();
+    // (0) the boxes are known: start pulling their map rows into L2 now, so that the sweep's loads (issued ~1500
+    //     cycles later, after the mask phases) find them there instead of paying the HBM latency
+    const int rows_cap = p.span_cap + 1;
+    for (int t0 = 0; t0 < n * rows_cap; t0 += LPE) {
+        const int t = t0 + lane;
+        if (pend && t < n * rows_cap) {
+            const int a = fastdiv(t, p.mg_rows), i = box[6 * a] + (t - a * rows_cap);
+            if (i <= box[6 * a + 1]) {
+                const float* row = map + i * M;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(row + box[6 * a + 2]));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(row + box[6 * a + 3]));
+            }
+        }
+    }
     // (1) corner-row intervals
     const int span = p.span_cap;                      // power of two >= 2R
     for (int t0 = 0; t0 < n * span; t0 += LPE) {
@@ -248,7 +262,6 @@ __device__ __noinline__ unsigned fl_probmap(const FlightParams& p, double* Ms, i
     }
     __syncwarp();
     // (2) owned touched cells per (agent, box row); own[a*rows_cap + r] covers map row i0_a + r
-    const int rows_cap = p.span_cap + 1;
     unsigned long long* own = rowmask + (M + 2);
     for (int t0 = 0; t0 < n * rows_cap; t0 += LPE) {
         const int t = t0 + lane;
