@@ -168,7 +168,7 @@ __device__ __forceinline__ float belief_update(float pv, int cnt, float qf) {
     const float frac = 0.25f * (float)cnt;
     const float num = (frac * qf) * pv;                        // percent*(1-d)*p            (:292)
     const float den = fmaf(qf, pv, 1.0f - pv);                 // (1-d)*p + (1-p)
-    return (pv == 1.0f) ? frac : __fdividef(num, den);
+    return (pv == 1.0f && qf != 0.0f) ? frac : __fdividef(num, den);     // detect_prob = 1: 0/0 = nan, like the reference
 }
 
 // ------------------------------------------------------------------------------------------------
