@@ -48,6 +48,8 @@ WORKLOADS = {
                desc="flight_easy 5a15t AM2TM0, 65536 envs per launch (configs[2])"),
     "c4": dict(kind="flight", n=3, am=0, envs=16384, batches=1,
                desc="flight (probability map) 3a15t AM0TM0, 16384 envs per GPU (configs[3])"),
+    "c2w": dict(kind="flight_easy", n=3, am=0, envs=1048576, batches=1,
+                desc="flight_easy 3a15t AM0TM0, 1048576 envs in ONE launch (throughput asymptote of the c2 kernel)"),
     "c5": dict(kind="search", n=64, am=0, envs=16384, batches=1,
                desc="search_env 64 agents / 1000 targets / map 64, 16384 envs per launch (configs[4] per-launch slice)"),
 }
@@ -532,7 +534,7 @@ def main():
     }
     if world == 1 and not args.no_extra:
         extra = {}
-        for name in ("c3", "c4", "c5"):
+        for name in ("c2w", "c3", "c4", "c5"):
             if name == args.workload:
                 continue
             try:
