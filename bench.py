@@ -393,6 +393,31 @@ def run_gpu_workload(cs, torch, name, steps, warmup, device, rank, world, want_e
     return out
 
 
+def measure_obs_full(cs, torch, device, peak):
+    """Reference-shaped flight observation (flight_env.py:223-230): 4*M*M read + 4n(M*M+4) written per env."""
+    w = dict(WORKLOADS["c4"])
+    env = silence(make_envs, cs, w, device, 0)[0]
+    env.step_random(3)
+    out = {}
+    for kind in ("tma", "plain"):
+        env.set_obs_kernel(kind)
+        for _ in range(5):
+            env.get_obs()
+        torch.cuda.synchronize(device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            env.get_obs()
+        e1.record()
+        torch.cuda.synchronize(device)
+        us = 1000.0 * e0.elapsed_time(e1) / 20
+        M2 = env.map_size ** 2
+        nbytes = env.num_envs * (4 * M2 + 4 * env.n_agents * (M2 + 4))
+        out[kind] = {"us_per_launch": us, "achieved": nbytes / (us * 1e-6) / 1e9, "frac": nbytes / (us * 1e-6) / 1e9 / peak,
+                     "bytes_per_env": nbytes // env.num_envs}
+    return out
+
+
 def measure_touched(cs, torch, device, steps=200):
     """Exact mean number of probability-map cells updated per env-step on the c4 workload (separate, untimed pass)."""
     w = dict(WORKLOADS["c4"]); w["envs"] = 2048
@@ -553,6 +578,11 @@ def main():
                                             "traffic": load_traffic(name)}}
             except Exception as exc:  # supplementary only: never lose the headline line
                 extra[name] = {"error": repr(exc)}
+        try:
+            extra["c4_obs"] = {"workload": "flight get_obs(): prob_map || features for 16384 envs x 3 agents (656 MB per call)",
+                               "unit": "GB/s", "peak": peak, **measure_obs_full(cs, torch, device, peak)}
+        except Exception as exc:
+            extra["c4_obs"] = {"error": repr(exc)}
         line["extra"] = extra
         line["cpu_baseline"] = cpu_baseline(w["kind"], w["n"], w["am"], args.cpu_seconds, 4.0)
     print(json.dumps(line))

@@ -80,6 +80,7 @@ SIGNATURES = {
     "cs_launch_count": (C.c_uint64, []),
     "cs_flight_lanes_per_env": (C.c_int, [C.c_void_p]),
     "cs_debug_philox": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "cs_debug_flight_obs_path": (C.c_int, [C.c_void_p, C.c_int32]),
     "cs_debug_heading_lut": (C.c_int, [C.c_int32, C.POINTER(C.c_double), C.c_int32, C.POINTER(C.c_double),
                                        C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "cs_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint64]),

@@ -761,7 +761,77 @@ __global__ void __launch_bounds__(256) flight_live_steps_kernel(const double* __
     if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, (double)acc);
 }
 
-// Reference-shaped observation of the flight variant: [E][n][M*M+4] (flight_env.py:223-230)
+// ------------------------------------------------------------------------------------------------
+// Reference-shaped observation of the flight variant with the TMA (bulk async copy) engine:
+// out[e][a] = prob_map[e].ravel() || (x^, y^, cos, sin)   (flight_env.py:223-230), i.e. every map is read once and
+// written n times.  One elected thread per CTA drives a ring of kStages shared-memory buffers:
+//   cp.async.bulk.shared::cluster.global (map e -> smem, completion on an mbarrier)   [SASS: UBLKCP]
+//   n x cp.async.bulk.global.shared::cta (smem -> row (e,a)), one bulk group per env
+// and refills a stage once the bulk group that read it has drained.  No SM load/store instruction touches the map;
+// the 16-byte feature tails are written by the other lanes.  Needs (M*M*4) % 16 == 0.
+// ------------------------------------------------------------------------------------------------
+constexpr int kObsStages = 4;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(32) flight_obs_full_tma_kernel(const float* __restrict__ map, const float* __restrict__ obs,
+                                                                 float* __restrict__ out, int E, int n, uint32_t map_bytes) {
+    extern __shared__ __align__(128) unsigned char tma_smem[];
+    __shared__ __align__(8) unsigned long long full_bar[kObsStages];
+    const int lane = threadIdx.x;
+    const uint32_t stage_bytes = (map_bytes + 127u) & ~127u;
+    const size_t row_bytes = (size_t)map_bytes + 16;
+    const int my_count = (E - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;      // envs of this CTA
+    if (my_count <= 0) return;
+    if (lane == 0) {
+        for (int s = 0; s < kObsStages; ++s)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&full_bar[s])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    auto issue_load = [&](int it) {                      // env of iteration `it` -> stage it % kObsStages
+        const int s = it % kObsStages;
+        const size_t e = (size_t)blockIdx.x + (size_t)it * gridDim.x;
+        const uint32_t bar = smem_u32(&full_bar[s]), dst = smem_u32(tma_smem + (size_t)s * stage_bytes);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(map_bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst), "l"(reinterpret_cast<const unsigned char*>(map) + e * map_bytes), "r"(map_bytes), "r"(bar)
+                     : "memory");
+    };
+    if (lane == 0)
+        for (int it = 0; it < kObsStages && it < my_count; ++it) issue_load(it);
+    for (int it = 0; it < my_count; ++it) {
+        const int s = it % kObsStages;
+        const size_t e = (size_t)blockIdx.x + (size_t)it * gridDim.x;
+        // feature tails of this env: lane a writes the 16 bytes after the map of row (e, a)
+        for (int a = lane; a < n; a += 32) {
+            const float4 f = reinterpret_cast<const float4*>(obs)[e * n + a];
+            *reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(out) + (e * n + a) * row_bytes + map_bytes) = f;
+        }
+        if (lane == 0) {
+            const uint32_t bar = smem_u32(&full_bar[s]), src = smem_u32(tma_smem + (size_t)s * stage_bytes);
+            const uint32_t parity = (uint32_t)(it / kObsStages) & 1u;
+            uint32_t ok = 0, spins = 0;
+            while (!ok) {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+                if (!ok && ++spins > (1u << 26)) __trap();          // a lost copy must fail loudly, not hang the GPU
+            }
+            for (int a = 0; a < n; ++a)
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             ::"l"(reinterpret_cast<unsigned char*>(out) + (e * n + a) * row_bytes), "r"(src), "r"(map_bytes) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            // the stage used by the PREVIOUS iteration may be refilled once its bulk group has finished reading it
+            if (it >= 1 && it - 1 + kObsStages < my_count) {
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                issue_load(it - 1 + kObsStages);
+            }
+        }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // all stores complete before exit
+}
+
+// Reference-shaped observation of the flight variant: [E][n][M*M+4] (flight_env.py:223-230), plain-copy form
 __global__ void __launch_bounds__(256) flight_obs_full_kernel(const float* __restrict__ map, const float* __restrict__ obs,
                                                               float* __restrict__ out, int E, int n, int cells4) {
     // one row = cells4 float4 of the map + 1 float4 of agent features; rows = E*n
@@ -808,6 +878,7 @@ struct cs_flight {
     double* d_tmpl;
     uint8_t* d_actions;   // device staging of the *_host entry point's actions
     double* d_live;       // scratch of cs_flight_stats
+    int obs_path;         // 0 = TMA bulk-copy kernel for the map observation, 1 = plain float4 copy kernel (A/B measurement)
     uint8_t* d_slab;      // one allocation behind reward | target_find | terminated | win | obs | state
     size_t slab_bytes, host_bytes, off_reward, off_tf, off_term, off_win, off_obs, off_state;
     longlong2* d_lut_meta;
@@ -1101,6 +1172,13 @@ int cs_flight_env_info(const cs_flight* h, int32_t* out4) {
 
 int cs_flight_lanes_per_env(const cs_flight* h) { return h ? h->lpe : CS_ERR_INVALID; }
 
+// tuning / measurement hook: which kernel cs_flight_obs_full uses (0 = TMA bulk copies, 1 = plain float4 copies)
+int cs_debug_flight_obs_path(cs_flight* h, int32_t path) {
+    CS_REQUIRE(h && (path == 0 || path == 1), "cs_debug_flight_obs_path: bad argument");
+    h->obs_path = path;
+    return CS_OK;
+}
+
 // test hook (host only, no GPU needed): the heading table's sin/cos for `count` headings
 int cs_debug_heading_lut(int32_t time_limit, const double* h_in, int32_t count, double* sin_out, double* cos_out,
                          int32_t* from_table) {
@@ -1163,7 +1241,18 @@ int cs_flight_obs_full(cs_flight* h, float* d_out, void* stream) {
     const FlightParams& p = h->p;
     const int cells = p.M * p.M;
     const long long total = (long long)p.E * p.n * (cells + 4);
-    if (cells % 4 == 0) {
+    const size_t stage_bytes = ((size_t)cells * 4 + 127) & ~(size_t)127;
+    if (cells % 4 == 0 && h->obs_path != 1 && kObsStages * stage_bytes <= 200 * 1024) {
+        // TMA path: persistent single-warp CTAs, a few per SM, each streaming whole maps through shared memory
+        const size_t smem = kObsStages * stage_bytes;
+        int per_sm = (int)((200 * 1024) / smem);
+        if (per_sm > 4) per_sm = 4;
+        if (per_sm < 1) per_sm = 1;
+        int grid = CS_NUM_SMS_B200 * per_sm;
+        if (grid > p.E) grid = p.E;
+        CS_CUDA(cudaFuncSetAttribute(flight_obs_full_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        flight_obs_full_tma_kernel<<<grid, 32, smem, (cudaStream_t)stream>>>(p.prob_map, p.obs, d_out, p.E, p.n, (uint32_t)cells * 4u);
+    } else if (cells % 4 == 0) {
         const long long t4 = total / 4;
         const int grid = (int)((t4 + 255) / 256 < (long long)CS_NUM_SMS_B200 * 16 ? (t4 + 255) / 256 : CS_NUM_SMS_B200 * 16);
         flight_obs_full_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p.prob_map, p.obs, d_out, p.E, p.n, cells / 4);

@@ -335,6 +335,11 @@ class VecFlightEnv(_VecFlightBase):
         super().__init__(*a, **k)
         self._obs_full = None
 
+    def set_obs_kernel(self, kind="tma"):
+        """Which kernel materialises the reference-shaped observation: "tma" (bulk async copies, default) or
+        "plain" (float4 copies); results are identical, the switch exists for A/B measurement."""
+        _lib.check(self.lib.cs_debug_flight_obs_path(self._h.ptr, {"tma": 0, "plain": 1}[kind]), "cs_debug_flight_obs_path")
+
     def get_obs(self, full=True):
         """Reference-shaped [E,n,M*M+4] = prob_map.ravel() || 4 features (flight_env.py:223-230),
         materialised by a streaming kernel.  full=False returns the [E,n,4] features only; the map

@@ -76,6 +76,9 @@ int cs_debug_philox(const uint32_t* d_in6, uint32_t* d_out4, int32_t count, void
 int cs_debug_heading_lut(int32_t time_limit, const double* h_in, int32_t count, double* sin_out, double* cos_out,
                          int32_t* from_table);
 
+/* measurement hook: kernel used by cs_flight_obs_full (0 = TMA bulk-copy kernel, default; 1 = plain copy kernel) */
+int cs_debug_flight_obs_path(struct cs_flight* env, int32_t path);
+
 /* Pinned host memory for the *_host entry points. */
 int cs_host_alloc(void** out, uint64_t bytes);
 int cs_host_free(void* p);

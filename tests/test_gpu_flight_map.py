@@ -99,3 +99,21 @@ def test_partial_reset_keeps_other_maps():
     for e in (1, 4):
         assert not torch.equal(after[e], before[e])
         assert float(after[e].max()) <= 1.0 and float((after[e] == 0.5).float().mean()) > 0.5
+
+
+@pytest.mark.parametrize("n_agents,map_size,E", [(3, 50, 1000), (5, 20, 777), (1, 62, 64), (2, 51, 33)])
+def test_map_observation_tma_equals_plain_copy(n_agents, map_size, E):
+    """get_obs() of the flight variant (flight_env.py:223-230) through the TMA bulk-copy kernel and through the plain
+    copy kernel: both equal prob_map.ravel() || features, row by row (odd map sizes take the scalar kernel)."""
+    import coopsearch_b200 as cs
+    spec = FlightSpec(n_agents=n_agents, map_size=map_size, view_range=max(2, map_size // 8), variant="probmap", target_mode=1)
+    env = cs.VecFlightEnv(make_args(dict(spec.__dict__)), None, num_envs=E, seed=9)
+    env.step_random(7)
+    env.set_obs_kernel("tma")
+    a = env.get_obs().clone()
+    env.set_obs_kernel("plain")
+    b = env.get_obs().clone()
+    assert torch.equal(a, b)
+    M2 = map_size * map_size
+    assert torch.equal(a[:, :, :M2], env.prob_map.reshape(E, 1, M2).expand(E, n_agents, M2))
+    assert torch.equal(a[:, :, M2:], env.get_obs(full=False))
