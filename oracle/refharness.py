@@ -53,7 +53,11 @@ def _install_matplotlib_stub():
     pyplot = types.ModuleType("matplotlib.pyplot")
     patches = types.ModuleType("matplotlib.patches")
     gridspec = types.ModuleType("matplotlib.gridspec")
-    pyplot.__getattr__ = lambda name: _Anything()
+    def _pyplot_attr(name):
+        if name.startswith("__"):            # keep inspect / importlib happy (torch walks sys.modules)
+            raise AttributeError(name)
+        return _Anything()
+    pyplot.__getattr__ = _pyplot_attr
     patches.Circle = _Anything
     gridspec.GridSpec = _Anything
     mpl.pyplot, mpl.patches, mpl.gridspec = pyplot, patches, gridspec

@@ -23,6 +23,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 
 from oracle import refharness as rh  # noqa: E402
+import contextlib as _ctx, io as _io  # noqa: E402
+rh.contextlib, rh.io = _ctx, _io
 
 OUT = os.path.dirname(os.path.abspath(__file__))
 SEED = 42
@@ -180,6 +182,67 @@ def run_search(n_agents, target_num, map_size, view_range, agent_mode, target_mo
     return g
 
 
+def run_rollout(n_agents, agent_mode, episodes, env_id, seed0):
+    """Episode batches produced by the reference's own RolloutWorker.generate_episode (common/rollout.py:22-141) with
+    the reference's Agents facade and alg=random (agent/agent.py:34-36) on FlightSearchEnvEasy."""
+    import types as _t
+    ref = rh.import_reference()
+    with rh.contextlib.redirect_stdout(rh.io.StringIO()):
+        from common.rollout import RolloutWorker
+        from agent.agent import Agents
+    circle = rh.load_targets_reference_semantics(TARGETS_TXT)
+    args = rh.make_args("flight_easy", n_agents=n_agents, agent_mode=agent_mode)
+    draws = rh.KeyedDraws(SEED, env_id, episode=0)
+    np.random.seed(seed0)
+    with draws:
+        draws.t = 0
+        env = rh.quiet(ref["FlightSearchEnvEasy"], args, circle)
+    info = env.get_env_info()
+    for k, v in info.items():
+        setattr(args, k, v)
+    args.alg, args.epsilon, args.anneal_epsilon, args.min_epsilon, args.epsilon_anneal_scale = "random", 0, 0, 0, "step"
+    args.last_action, args.reuse_network, args.cuda, args.evaluate_epoch = True, True, False, 20
+    agents = rh.quiet(Agents, env, args)
+    worker = rh.quiet(RolloutWorker, env, agents, args)
+    captured = []
+    orig_reset, orig_step = env.reset, env.step
+
+    def reset(init=False):
+        draws.t = 0
+        draws.episode += 1
+        out = orig_reset(init)
+        captured.append(np.array(env.target_pos, dtype=np.float64))
+        return out
+
+    def step(actions):
+        draws.t = env.time_step + 1
+        return orig_step(actions)
+    env.reset, env.step = reset, step
+    g = {}
+    T, S = info["episode_limit"], info["state_shape"]
+    keys = ["o", "s", "u", "r", "avail_u", "o_next", "s_next", "avail_u_next", "u_onehot", "padded", "terminated"]
+    for k in keys:
+        g[k] = []
+    g["episode_reward"], g["win_tag"], g["targets_find"] = [], [], []
+    with draws:
+        for ep in range(episodes):
+            np.random.seed(seed0 + 1 + ep)
+            episode, rew, win, tf = worker.generate_episode(ep)
+            for k in keys:
+                g[k].append(episode[k][0])
+            g["episode_reward"].append(rew); g["win_tag"].append(int(bool(win))); g["targets_find"].append(tf)
+    out = {k: np.array(v) for k, v in g.items()}
+    out["tgt_xy"] = np.array(captured)
+    out["meta"] = np.array([n_agents, args.target_num, args.map_size, args.view_range, T, agent_mode, 0, env_id, SEED], np.int64)
+    out["fmeta"] = np.array([args.agent_velocity, args.detect_prob, args.safe_dist, args.force_dist], np.float64)
+    # float32 is what the batched writer produces; keep the fixture small
+    for k in ("o", "s", "o_next", "s_next"):
+        out[k] = out[k].astype(np.float32)
+    for k in ("u", "avail_u", "avail_u_next", "u_onehot", "padded", "terminated"):
+        out[k] = out[k].astype(np.uint8)
+    return out
+
+
 def thin(g, keep_every, keys=("obs", "state")):
     """obs/state are derivable from xy/yaw/found; keep every k-th step to bound fixture size."""
     for k in keys:
@@ -208,6 +271,8 @@ def main():
         "flight_2a_small": lambda: thin(run_flight("FlightSearchEnv", 2, 1, E=2, T=80, env_id_base=700,
                                                      target_mode=1, map_size=20, view_range=4, time_limit=80,
                                                      second_episode=10, map_steps=(1, 2, 5, 10, 40, 80)), 20),
+        "rollout_easy_3a": lambda: run_rollout(3, 0, episodes=4, env_id=950, seed0=77),
+        "rollout_easy_5a_am3": lambda: run_rollout(5, 3, episodes=3, env_id=960, seed0=78),
         "search_3a_default": lambda: thin(run_search(3, 15, 50, 7, 0, 0, E=3, T=120, env_id_base=800), 10),
         "search_4a_am1_tm1": lambda: thin(run_search(4, 10, 20, 4, 1, 1, E=3, T=80, env_id_base=850), 10),
         "search_5a_am2": lambda: thin(run_search(5, 12, 24, 3, 2, 0, E=2, T=80, env_id_base=870), 10),
