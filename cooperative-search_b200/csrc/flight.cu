@@ -25,22 +25,20 @@
 namespace {
 
 constexpr int kThreads = 128;
-#ifndef CS_MAP_MIN_CTAS
-#define CS_MAP_MIN_CTAS 7      // resident CTAs per SM the map-variant kernel is compiled for (register budget 65536/(128*N))
-#endif
-
 struct FlightParams {
     int E, n, m, M, T;
     int variant, auto_reset, agent_mode, target_mode, count_touched;
     // per-env record geometry (doubles)
     int rec, yaw_off, meta_off, state_len;
     int state_stride;            // floats per state row in HBM (state_len rounded up to a multiple of 4)
-    // per-warp shared-memory scratch (doubles): one 5n block per group for the coupled-move path, then the
-    // belief-map scratch (agent xy | boxes | hit cells | corner-row masks | owned masks), then the table index
-    int s_cs;                    // = 3n: offset of cos/sin inside a group's 5n block (x,y | yaw | cos,sin)
-    int s_grp, s_map, s_mapg, s_box, s_hit, s_mask, s_lut, s_warp;   // s_mapg: belief-map scratch per group
-    int span_cap;                // power of two >= 2R: corner rows per agent in the interval pass
-    uint32_t mg_rows;            // ceil(2^32/(span_cap+1))
+    // per-warp shared-memory scratch of the step kernel (doubles): the heading-table index
+    int s_lut, s_warp;
+    int span_cap, span_shift;    // power of two >= 2R: corner rows per agent in the interval pass (and its log2)
+    int rs_shift;                // log2 of the row slots per agent box in the map sweep (power of two >= 2R+1)
+    int lps_shift;               // log2 of the lanes per row run in the map sweep (4 cells per lane, >= 2R+2 cells)
+    int ms_col, ms_box, ms_xy, ms_hit, ms_warp;   // map kernel: per-warp scratch offsets / size in 8-byte words
+    int pre_stride;              // doubles per env in `pre`
+    double* pre;                 // [E][pre_stride]: agent xy (2n) | int nh, hit cells -- the sensing before an in-call auto-reset
     double Md, half_M, inv_half, R, R2, v, fk, fd2, near2, q_miss;
     double turn, pi, two_pi, three_pi, half_pi;
     long long thr;
@@ -63,9 +61,6 @@ struct FlightParams {
     double cos0, sin0;           // cos/sin of the start heading of agent_mode, from the host libm
     double lin[CS_MAX_AGENTS];   // i*map_size/(n-1) (map_size/2 for n == 1), flight_env_easy.py:140-143
 };
-
-// v / d with magic = ceil(2^32 / d); d == 1 gives magic 2^32 -> stored as 0 -> identity
-__device__ __forceinline__ int fastdiv(int v, uint32_t magic) { return magic ? (int)__umulhi((uint32_t)v, magic) : v; }
 
 // ------------------------------------------------------------------------------------------------
 // cos/sin of a heading.
@@ -172,237 +167,286 @@ __device__ __forceinline__ float belief_update(float pv, int cnt, float qf) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// belief map: _update_prob_map + _percent_in_agent_viewrange (env/flight_env.py:275-303), one warp per env.
+// belief map: _update_prob_map + _percent_in_agent_viewrange (env/flight_env.py:275-303).
+//
+// Runs as its OWN kernel right after the step / reset kernel, one warp per env.  The step kernel leaves a job for
+// every env it sensed: the sensing call number in meta word CS_META_SENSE, the agent positions in the state record,
+// the targets found by that call in CS_META_NEWFOUND; an env that was auto-reset inside the call was sensed twice
+// (flight_env.py:266 runs inside reset() too) and its first job -- positions and hit cells before the reset -- sits in
+// the `pre` side buffer.  Few registers (no Philox, no fp64 state in flight) and nothing but the map traffic
+// outstanding: the SMs hold 48 warps each, which is what covers the HBM latency of the scattered 64-byte runs.
 //
 // The reference classifies the 4 corners of every cell against every agent (2500 x 4 x n fp64 tests).  Here:
 //  (1) corner classification by ROW INTERVALS: for agent a and integer corner row cx, the corner columns cy with
 //      fl(fl((cx-ax)^2) + fl((cy-ay)^2)) < R^2 form an interval (the expression is monotone in |cy-ay|).  Its
 //      ends come from one fp32 sqrt; only when an end lies within 1e-3 of an integer is the reference's exact
 //      fp64 predicate evaluated there.  One lane per (agent, corner row): <= 2R*n tasks.  The interval is OR-ed as a
-//      bit mask into rowmask[cx] (bit cy), the union over agents ("any agent", the `break` of :299-302).
-//  (2) percent of cell (i,j) = popc of bits j,j+1 of rowmask[i] and rowmask[i+1]; touched <=> any of them set.
-//      Per (agent, box row) the touched cells that agent's sweep owns (a cell inside several boxes belongs to the
-//      first) are precomputed as one 64-bit mask.
-//  (3) sweep: per agent box, 8 lanes x float2 per map row, 4 rows per warp instruction, 4 instructions' loads in
-//      flight; untouched cells are neither read nor written.  The update itself is fp32.
-// Ms: [2n agent xy][boxes][hit cells] scratch of the warp, already filled with the agent positions and the hit
-// cells by the caller.  Needs map_size <= 63 (one 64-bit mask per corner row); larger maps take fl_probmap_wide.
+//      bit mask into R[cx] (bit cy), the union over agents ("any agent", the `break` of :299-302).
+//  (2) percent of cell (i,j) = popc of bits j,j+1 of R[i] and R[i+1]; touched <=> any of them set.
+//  (3) sweep: the map rows of every agent's box are cut into runs of 4 cells, one lane each (4 lanes = one 64-byte
+//      run of a row, 8 rows per warp instruction, two such passes' loads in flight).  A pair of cells belongs to the
+//      FIRST agent whose (pair-aligned) box holds it, so every touched pair is loaded, updated and stored by exactly
+//      one lane; untouched pairs are neither read nor written.  The update itself is fp32.
+// Needs map_size <= 63 (one 64-bit mask per corner row); larger maps take flight_map_wide_kernel.
 // ------------------------------------------------------------------------------------------------
-// All groups of the warp run this together (SIMT over envs): `lane` is the lane inside the group of LPE lanes that
-// owns the env, Ms is that group's scratch, `pend` tells whether this group's env was just sensed.  The barriers are
-// whole-warp, so the call site must be warp-uniform.
-template <int LPE>
-__device__ __noinline__ unsigned fl_probmap(const FlightParams& p, double* Ms, int lane, float* map, int nh, bool pend) {
+constexpr int kMapThreads = 128;
+#ifndef CS_MAP_MIN_CTAS
+#define CS_MAP_MIN_CTAS 12     // resident CTAs per SM the map kernel is compiled for (register budget 65536/(128*N))
+#endif
+
+// cell of a target found by the sensing call: [min(int(x), M-1), min(int(y), M-1)], Python int() truncates toward
+// zero (flight_env.py:279); negative indices never match a swept cell
+__device__ __forceinline__ int hit_cell(const FlightParams& p, double tx, double ty) {
+    const int ci = min((int)fmin(tx, p.Md), p.M - 1), cj = min((int)fmin(ty, p.Md), p.M - 1);
+    return (ci < 0 || cj < 0) ? -1 : ci * p.M + cj;
+}
+
+// Loads job `job` of env e into the warp's scratch: agent positions -> xy[2n] (and the lane's registers), hit cells
+// -> hit[]; returns the number of hit cells.  job 0 = the sensing before an in-call auto-reset (side buffer),
+// job 1 = the state record as the step / reset kernel left it.
+__device__ __forceinline__ int map_job_load(const FlightParams& p, int e, int job, int lane, const double2 pos, uint32_t newf,
+                                            double* xy, int* hit, double* ax, double* ay) {
+    const int n = p.n, m = p.m;
+    int nh;
+    if (job == 0) {
+        const double* pj = p.pre + (size_t)e * p.pre_stride;
+        if (lane < n) {
+            const double2 v = reinterpret_cast<const double2*>(pj)[lane];
+            *ax = v.x; *ay = v.y;
+        }
+        const int* ph = reinterpret_cast<const int*>(pj + 2 * n);
+        nh = ph[0];
+        if (lane < nh) hit[lane] = ph[1 + lane];
+    } else {
+        *ax = pos.x; *ay = pos.y;
+        nh = __popc(newf);
+        if (lane < m && ((newf >> lane) & 1u)) {
+            const double2 t = *reinterpret_cast<const double2*>(p.tgt + ((size_t)e * m + lane) * 2);
+            hit[__popc(newf & ((1u << lane) - 1u))] = hit_cell(p, t.x, t.y);
+        }
+    }
+    if (lane < n) { xy[2 * lane] = *ax; xy[2 * lane + 1] = *ay; }
+    return nh;
+}
+
+template <bool PAIRS>
+__global__ void __launch_bounds__(kMapThreads, CS_MAP_MIN_CTAS) flight_map_kernel(const __grid_constant__ FlightParams p, uint32_t seq) {
+    extern __shared__ __align__(16) unsigned long long msm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int e = blockIdx.x * (kMapThreads / 32) + warp;
+    if (e >= p.E) return;
     const int n = p.n, M = p.M;
-    int* box = reinterpret_cast<int*>(Ms + p.s_box);   // [n][6]: i0, i1, j0, j1 (cells), clo_x, chi_x (corner rows)
-    const int* hit = reinterpret_cast<const int*>(Ms + p.s_hit);
-    unsigned long long* rowmask = reinterpret_cast<unsigned long long*>(Ms + p.s_mask);
-    unsigned long long* colmask = rowmask + (M + 2) + n * (p.span_cap + 1);     // [n] columns of each agent's box
-    if (pend) {
-        for (int a = lane; a < n; a += LPE) {
-            const double ax = Ms[2 * a], ay = Ms[2 * a + 1];
-            int lo, hi;
-            corner_span(ax, p.R, p.R2, &lo, &hi);
-            box[6 * a + 0] = max(0, lo - 1);          // cell i has corners i and i+1
-            box[6 * a + 1] = min(M - 1, hi);
-            box[6 * a + 4] = lo;
-            box[6 * a + 5] = hi;
-            corner_span(ay, p.R, p.R2, &lo, &hi);
-            const int j0 = max(0, lo - 1), j1 = min(M - 1, hi);
-            box[6 * a + 2] = j0;
-            box[6 * a + 3] = j1;
-            colmask[a] = (j0 <= j1) ? (((2ull << j1) - 1ull) & ~((1ull << j0) - 1ull)) : 0ull;
-        }
-        for (int r = lane; r <= M + 1; r += LPE) rowmask[r] = 0ull;
-    }
-    __syncwarp();
-    // (0) the boxes are known: start pulling their map rows into L2 now, so that the sweep's loads (issued ~1500
-    //     cycles later, after the mask phases) find them there instead of paying the HBM latency
-    const int rows_cap = p.span_cap + 1;
-    for (int t0 = 0; t0 < n * rows_cap; t0 += LPE) {
-        const int t = t0 + lane;
-        if (pend && t < n * rows_cap) {
-            const int a = fastdiv(t, p.mg_rows), i = box[6 * a] + (t - a * rows_cap);
-            if (i <= box[6 * a + 1]) {
-                const float* row = map + i * M;
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(row + box[6 * a + 2]));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(row + box[6 * a + 3]));
-            }
-        }
-    }
-    // (1) corner-row intervals
-    const int span = p.span_cap;                      // power of two >= 2R
-    for (int t0 = 0; t0 < n * span; t0 += LPE) {
-        const int t = t0 + lane;
-        if (!pend || t >= n * span) continue;
-        const int a = t / span, r = t - a * span;          // span is a power of two
-        const int cx = box[6 * a + 4] + r;
-        if (cx > box[6 * a + 5] || cx < 0 || cx > M) continue;
-        const double ax = Ms[2 * a], ay = Ms[2 * a + 1];
-        const double dx = (double)cx - ax;
-        const double A = dx * dx;
-        // candidate ends in fp32 (ay <= map_size: absolute error ~4e-6, far inside the 1e-3 guard band)
-        const float wf = sqrtf(fmaxf((float)(p.R2 - A), 0.0f));
-        const float ayf = (float)ay;
-        const float yh = ayf + wf, yl = ayf - wf;
-        float fh = floorf(yh), cl = ceilf(yl);
-        if (yh - fh < 1e-3f || yh - fh > 1.0f - 1e-3f) {       // end within 1e-3 of an integer: decide exactly
-            const double Y = (double)rintf(yh);
-            fh = (float)(corner_pred(A, Y, ay, p.R2) ? Y : Y - 1.0);
-        }
-        if (cl - yl < 1e-3f || cl - yl > 1.0f - 1e-3f) {
-            const double Y = (double)rintf(yl);
-            cl = (float)(corner_pred(A, Y, ay, p.R2) ? Y : Y + 1.0);
-        }
-        const int yhi = min((int)fh, M), ylo = max((int)cl, 0);
-        if (ylo <= yhi) {
-            const unsigned long long mk = ((2ull << yhi) - 1ull) & ~((1ull << ylo) - 1ull);
-            atomicOr(&rowmask[cx], mk);
-        }
-    }
-    __syncwarp();
-    // (2) owned touched cells per (agent, box row); own[a*rows_cap + r] covers map row i0_a + r
-    unsigned long long* own = rowmask + (M + 2);
-    for (int t0 = 0; t0 < n * rows_cap; t0 += LPE) {
-        const int t = t0 + lane;
-        if (pend && t < n * rows_cap) {
-            const int a = fastdiv(t, p.mg_rows), r = t - a * rows_cap;
-            const int i = box[6 * a] + r;
-            unsigned long long Tm = 0ull;
-            if (i <= box[6 * a + 1]) {
-                const unsigned long long A = rowmask[i], B = rowmask[i + 1];
-                Tm = (A | (A >> 1) | B | (B >> 1)) & colmask[a];
-                for (int q = 0; q < a; ++q)
-                    if (i >= box[6 * q] && i <= box[6 * q + 1]) Tm &= ~colmask[q];
-            }
-            own[t] = Tm;
-        }
-    }
-    __syncwarp();
-    // (3) sweep
-    unsigned touched = 0;
-    if (!pend) return 0u;
+    const double* rec = p.dyn + (size_t)e * p.rec;
+    const uint4* mp = reinterpret_cast<const uint4*>(rec + p.meta_off);
+    const uint4 m0 = mp[0], m1 = mp[1];
+    double2 pos = make_double2(0.0, 0.0);
+    if (lane < n) pos = *reinterpret_cast<const double2*>(rec + 2 * lane);
+    if ((m1.w >> 1) != seq) return;                         // not sensed by this call (finished env, masked reset)
+
+    unsigned long long* S = msm + (size_t)warp * p.ms_warp;
+    unsigned long long* R = S;                              // [M+2] corner-row masks
+    unsigned long long* col = S + p.ms_col;                 // [n]   columns of each agent's box (pair aligned)
+    int4* box = reinterpret_cast<int4*>(S + p.ms_box);      // [n]   i0, i1, first column of the window, first corner row
+    double* xy = reinterpret_cast<double*>(S + p.ms_xy);    // [2n]
+    int* hit = reinterpret_cast<int*>(S + p.ms_hit);        // [m]
+    float* map = p.prob_map + (size_t)e * M * M;
     const float qf = (float)p.q_miss;
-    if ((M & 1) == 0) {
-        // LPR lanes per map row, CPL cells (CPL/2 x float2) per lane; the row's masks are fetched once per CPL cells
-        // and all of a lane's loads are in flight together.  LPE = 32: 2 lanes x 8 cells, 16 rows per pass;
-        // LPE <= 16: 1 lane x 16 cells, LPE rows per pass.
-        constexpr int LPR = (LPE >= 32) ? 2 : 1, CPL = 16 / LPR, RPP = LPE / LPR, NV = CPL / 2;
-        const int rsub = lane / LPR, jl = CPL * (lane % LPR);
-        for (int a = 0; a < n; ++a) {
-            const int i0 = box[6 * a], i1 = box[6 * a + 1], j0 = box[6 * a + 2], j1 = box[6 * a + 3];
-            const int nrows = i1 - i0 + 1;
-            const unsigned long long* ow = own + a * rows_cap;
-            for (int jc = j0 & ~1; jc <= j1; jc += 16) {
-                const int j = jc + jl;
-                for (int rb = 0; rb < nrows; rb += RPP) {
-                    const int r = rb + rsub;
-                    if (r >= nrows) continue;
-                    const unsigned tm = (unsigned)(ow[r] >> j) & ((1u << CPL) - 1u);
-                    if (!tm) continue;                                     // percent == 0 -> untouched (:285-286)
-                    const int i = i0 + r;
-                    const unsigned Am = (unsigned)(rowmask[i] >> j) & ((2u << CPL) - 1u);
-                    const unsigned Bm = (unsigned)(rowmask[i + 1] >> j) & ((2u << CPL) - 1u);
-                    float2* rowp = reinterpret_cast<float2*>(map + i * M + j);
-                    float2 v[NV];
+    const int lps_shift = p.lps_shift, rs_shift = p.rs_shift;
+    const int sub = lane & ((1 << lps_shift) - 1), seg = lane >> lps_shift, spi = 32 >> lps_shift;
+    const int RS = 1 << rs_shift, total = n << rs_shift;
+    unsigned touched = 0;
+
+    for (int job = (m1.w & 1u) ? 0 : 1; job < 2; ++job) {
+        double ax = 0.0, ay = 0.0;
+        const int nh = map_job_load(p, e, job, lane, pos, m0.y, xy, hit, &ax, &ay);
+        for (int r = lane; r <= M + 1; r += 32) R[r] = 0ull;
+        if (lane < n) {
+            int lo, hi, clo;
+            corner_span(ax, p.R, p.R2, &lo, &hi);
+            clo = lo;
+            const int i0 = max(0, lo - 1), i1 = min(M - 1, hi);          // cell i has corners i and i+1
+            corner_span(ay, p.R, p.R2, &lo, &hi);
+            int j0 = max(0, lo - 1), j1 = min(M - 1, hi);
+            if (PAIRS) { j0 &= ~1; j1 |= 1; }                            // M is even: j1|1 <= M-1
+            box[lane] = make_int4(i0, i1, j0, clo);
+            col[lane] = (j0 <= j1 && i0 <= i1) ? (((2ull << j1) - 1ull) & ~((1ull << j0) - 1ull)) : 0ull;
+        }
+        __syncwarp();
+        // (1) corner-row intervals
+        const int span = p.span_cap;                                     // power of two >= 2R
+        for (int t = lane; t < n * span; t += 32) {
+            const int a = t >> p.span_shift, r = t & (span - 1);
+            const double axa = xy[2 * a], aya = xy[2 * a + 1];
+            const int cx = box[a].w + r;
+            const double dx = (double)cx - axa;
+            const double A = dx * dx;
+            if (!(A < p.R2) || cx < 0 || cx > M) continue;               // past the last corner row of this agent
+            // candidate ends in fp32 (ay <= map_size: absolute error ~4e-6, far inside the 1e-3 guard band)
+            const float wf = sqrtf(fmaxf((float)(p.R2 - A), 0.0f));
+            const float ayf = (float)aya;
+            const float yh = ayf + wf, yl = ayf - wf;
+            float fh = floorf(yh), cl = ceilf(yl);
+            if (yh - fh < 1e-3f || yh - fh > 1.0f - 1e-3f) {             // end within 1e-3 of an integer: decide exactly
+                const double Y = (double)rintf(yh);
+                fh = (float)(corner_pred(A, Y, aya, p.R2) ? Y : Y - 1.0);
+            }
+            if (cl - yl < 1e-3f || cl - yl > 1.0f - 1e-3f) {
+                const double Y = (double)rintf(yl);
+                cl = (float)(corner_pred(A, Y, aya, p.R2) ? Y : Y + 1.0);
+            }
+            const int yhi = min((int)fh, M), ylo = max((int)cl, 0);
+            if (ylo <= yhi) {
+                const unsigned long long mk = ((2ull << yhi) - 1ull) & ~((1ull << ylo) - 1ull);
+                unsigned* w = reinterpret_cast<unsigned*>(&R[cx]);
+                if ((unsigned)mk) atomicOr(w, (unsigned)mk);
+                if ((unsigned)(mk >> 32)) atomicOr(w + 1, (unsigned)(mk >> 32));
+            }
+        }
+        __syncwarp();
+        // (2) sweep: slot t = (agent a, box row r); lane `sub` of the slot's segment owns cells j .. j+3
+        for (int t0 = 0; t0 < total; t0 += 2 * spi) {
+            int ci[2];
+            unsigned tmv[2], ABv[2];
+            float2 v[2][2];
 #pragma unroll
-                    for (int c = 0; c < NV; ++c)
-                        if ((tm >> (2 * c)) & 3u) v[c] = rowp[c];
-#pragma unroll
-                    for (int c = 0; c < NV; ++c) {
-                        const unsigned t2 = (tm >> (2 * c)) & 3u;
-                        if (!t2) continue;
-                        const unsigned a2 = (Am >> (2 * c)) & 7u, b2 = (Bm >> (2 * c)) & 7u;
-                        if (t2 & 1u) v[c].x = belief_update(v[c].x, __popc(a2 & 3u) + __popc(b2 & 3u), qf);
-                        if (t2 & 2u) v[c].y = belief_update(v[c].y, __popc(a2 & 6u) + __popc(b2 & 6u), qf);
-                        if (nh) {                                          // targets found by THIS call -> 1 (:288-289)
-                            const int cell = i * M + j + 2 * c;
-                            for (int k = 0; k < nh; ++k) {
-                                if ((t2 & 1u) && hit[k] == cell) v[c].x = 1.0f;
-                                if ((t2 & 2u) && hit[k] == cell + 1) v[c].y = 1.0f;
-                            }
-                        }
-                        rowp[c] = v[c];
-                    }
-                    touched += __popc(tm);
+            for (int u = 0; u < 2; ++u) {
+                const int t = t0 + u * spi + seg;
+                const int a = min(t >> rs_shift, n - 1), r = t & (RS - 1);
+                const int4 bx = box[a];
+                const int i = min(bx.x + r, M - 1);
+                const bool valid = t < total && bx.x + r <= bx.y;
+                const unsigned long long Ri = R[i], Ri1 = R[i + 1];
+                unsigned long long T = (Ri | (Ri >> 1) | Ri1 | (Ri1 >> 1)) & col[a];
+                for (int q = 0; q < a; ++q) {                            // cells inside an earlier agent's box are its
+                    const int4 bq = box[q];
+                    if (i >= bq.x && i <= bq.y) T &= ~col[q];
+                }
+                const int j = bx.z + 4 * sub;
+                const unsigned tm = (valid && j < M) ? ((unsigned)(T >> j) & 0xFu) : 0u;      // percent == 0 -> untouched (:285-286)
+                tmv[u] = tm;
+                ABv[u] = ((unsigned)(Ri >> (j & 63)) & 0x1Fu) | (((unsigned)(Ri1 >> (j & 63)) & 0x1Fu) << 8);
+                ci[u] = i * M + j;
+                const float* rowp = map + ci[u];
+                if (PAIRS) {
+                    if (tm & 3u) v[u][0] = *reinterpret_cast<const float2*>(rowp);
+                    if (tm & 12u) v[u][1] = *reinterpret_cast<const float2*>(rowp + 2);
+                } else {
+                    if (tm & 1u) v[u][0].x = rowp[0];
+                    if (tm & 2u) v[u][0].y = rowp[1];
+                    if (tm & 4u) v[u][1].x = rowp[2];
+                    if (tm & 8u) v[u][1].y = rowp[3];
                 }
             }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const unsigned tm = tmv[u], AB = ABv[u];
+                if (!tm) continue;
+                if (tm & 1u) v[u][0].x = belief_update(v[u][0].x, __popc(AB & 0x0303u), qf);
+                if (tm & 2u) v[u][0].y = belief_update(v[u][0].y, __popc(AB & 0x0606u), qf);
+                if (tm & 4u) v[u][1].x = belief_update(v[u][1].x, __popc(AB & 0x0C0Cu), qf);
+                if (tm & 8u) v[u][1].y = belief_update(v[u][1].y, __popc(AB & 0x1818u), qf);
+                for (int k = 0; k < nh; ++k) {                           // targets found by THIS call -> 1 (:288-289)
+                    const unsigned d = (unsigned)(hit[k] - ci[u]);
+                    if (d < 4u && ((tm >> d) & 1u)) {
+                        if (d == 0u) v[u][0].x = 1.0f;
+                        else if (d == 1u) v[u][0].y = 1.0f;
+                        else if (d == 2u) v[u][1].x = 1.0f;
+                        else v[u][1].y = 1.0f;
+                    }
+                }
+                float* rowp = map + ci[u];
+                if (PAIRS) {
+                    if (tm & 3u) *reinterpret_cast<float2*>(rowp) = v[u][0];
+                    if (tm & 12u) *reinterpret_cast<float2*>(rowp + 2) = v[u][1];
+                } else {
+                    if (tm & 1u) rowp[0] = v[u][0].x;
+                    if (tm & 2u) rowp[1] = v[u][0].y;
+                    if (tm & 4u) rowp[2] = v[u][1].x;
+                    if (tm & 8u) rowp[3] = v[u][1].y;
+                }
+                touched += __popc(tm);
+            }
         }
-    } else {
-        // odd map_size: rows are only 4-byte aligned -> one cell at a time, one lane per row, 16 columns per pass
+        __syncwarp();                                                    // the scratch is reused by the next job
+    }
+    if (p.count_touched) {
+        const unsigned tot = __reduce_add_sync(0xffffffffu, touched);
+        if (lane == 0 && tot) atomicAdd(p.stats + CS_STAT_TOUCHED, (double)tot);
+    }
+}
+
+// map_size > 63: per-cell corner tests (same results, more arithmetic), half-warp per map row, one warp per env
+__global__ void __launch_bounds__(kMapThreads) flight_map_wide_kernel(const __grid_constant__ FlightParams p, uint32_t seq) {
+    extern __shared__ __align__(16) unsigned long long msm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int e = blockIdx.x * (kMapThreads / 32) + warp;
+    if (e >= p.E) return;
+    const int n = p.n, M = p.M;
+    const double* rec = p.dyn + (size_t)e * p.rec;
+    const uint4* mp = reinterpret_cast<const uint4*>(rec + p.meta_off);
+    const uint4 m0 = mp[0], m1 = mp[1];
+    double2 pos = make_double2(0.0, 0.0);
+    if (lane < n) pos = *reinterpret_cast<const double2*>(rec + 2 * lane);
+    if ((m1.w >> 1) != seq) return;
+    unsigned long long* S = msm + (size_t)warp * p.ms_warp;
+    int4* box = reinterpret_cast<int4*>(S + p.ms_box);
+    double* xy = reinterpret_cast<double*>(S + p.ms_xy);
+    int* hit = reinterpret_cast<int*>(S + p.ms_hit);
+    float* map = p.prob_map + (size_t)e * M * M;
+    const float qf = (float)p.q_miss;
+    const int colk = lane & 15, half = lane >> 4;
+    unsigned touched = 0;
+    for (int job = (m1.w & 1u) ? 0 : 1; job < 2; ++job) {
+        double ax = 0.0, ay = 0.0;
+        const int nh = map_job_load(p, e, job, lane, pos, m0.y, xy, hit, &ax, &ay);
+        if (lane < n) {
+            int lo, hi;
+            corner_span(ax, p.R, p.R2, &lo, &hi);
+            const int i0 = max(0, lo - 1), i1 = min(M - 1, hi);
+            corner_span(ay, p.R, p.R2, &lo, &hi);
+            box[lane] = make_int4(i0, i1, max(0, lo - 1), min(M - 1, hi));
+        }
+        __syncwarp();
         for (int a = 0; a < n; ++a) {
-            const int i0 = box[6 * a], i1 = box[6 * a + 1], j0 = box[6 * a + 2], j1 = box[6 * a + 3];
-            const unsigned long long* ow = own + a * rows_cap;
-            for (int r = lane; r <= i1 - i0; r += LPE) {
-                const int i = i0 + r;
-                const unsigned long long A = rowmask[i], B = rowmask[i + 1];
-                for (int j = j0; j <= j1; ++j) {
-                    if (!((ow[r] >> j) & 1ull)) continue;
+            const int4 bx = box[a];
+            for (int jc = bx.z; jc <= bx.w; jc += 16) {
+                const int j = jc + colk;
+                if (j > bx.w) continue;
+                const double y0 = (double)j, y1 = (double)(j + 1);
+                for (int i = bx.x + half; i <= bx.y; i += 2) {
+                    bool mine = true;
+                    for (int b = 0; b < a; ++b) {
+                        const int4 bb = box[b];
+                        mine &= !(i >= bb.x && i <= bb.y && j >= bb.z && j <= bb.w);
+                    }
+                    if (!mine) continue;
+                    const double x0 = (double)i, x1 = (double)(i + 1);
+                    uint32_t bits = 0;
+                    for (int q = 0; q < n; ++q) {
+                        const double qx = xy[2 * q], qy = xy[2 * q + 1];
+                        const double dx0 = x0 - qx, dx1 = x1 - qx, dy0 = y0 - qy, dy1 = y1 - qy;
+                        const double sx0 = dx0 * dx0, sx1 = dx1 * dx1, sy0 = dy0 * dy0, sy1 = dy1 * dy1;
+                        bits |= (sx0 + sy0 < p.R2) ? 1u : 0u;
+                        bits |= (sx1 + sy0 < p.R2) ? 2u : 0u;
+                        bits |= (sx0 + sy1 < p.R2) ? 4u : 0u;
+                        bits |= (sx1 + sy1 < p.R2) ? 8u : 0u;
+                    }
+                    if (!bits) continue;
+                    ++touched;
                     const int cell = i * M + j;
-                    float v = belief_update(map[cell], __popc((unsigned)(A >> j) & 3u) + __popc((unsigned)(B >> j) & 3u), qf);
+                    float v = belief_update(map[cell], __popc(bits), qf);
                     for (int k = 0; k < nh; ++k)
                         if (hit[k] == cell) v = 1.0f;
                     map[cell] = v;
-                    ++touched;
                 }
             }
         }
+        __syncwarp();
     }
-    return touched;
-}
-
-// Fallback for map_size > 63: per-cell corner tests (same results, more arithmetic), half-warp per map row.
-__device__ __noinline__ unsigned fl_probmap_wide(const FlightParams& p, double* Ms, int lane, float* map, int nh) {
-    const int n = p.n, M = p.M;
-    int* box = reinterpret_cast<int*>(Ms + p.s_box);
-    const int* hit = reinterpret_cast<const int*>(Ms + p.s_hit);
-    for (int a = lane; a < n; a += 32) {
-        const double ax = Ms[2 * a], ay = Ms[2 * a + 1];
-        int lo, hi;
-        corner_span(ax, p.R, p.R2, &lo, &hi);
-        box[6 * a + 0] = max(0, lo - 1);
-        box[6 * a + 1] = min(M - 1, hi);
-        corner_span(ay, p.R, p.R2, &lo, &hi);
-        box[6 * a + 2] = max(0, lo - 1);
-        box[6 * a + 3] = min(M - 1, hi);
+    if (p.count_touched) {
+        const unsigned tot = __reduce_add_sync(0xffffffffu, touched);
+        if (lane == 0 && tot) atomicAdd(p.stats + CS_STAT_TOUCHED, (double)tot);
     }
-    __syncwarp();
-    unsigned touched = 0;
-    const float qf = (float)p.q_miss;
-    const int col = lane & 15, half = lane >> 4;
-    for (int a = 0; a < n; ++a) {
-        const int i0 = box[6 * a], i1 = box[6 * a + 1], j0 = box[6 * a + 2], j1 = box[6 * a + 3];
-        for (int jc = j0; jc <= j1; jc += 16) {
-            const int j = jc + col;
-            if (j > j1) continue;
-            const double y0 = (double)j, y1 = (double)(j + 1);
-            for (int i = i0 + half; i <= i1; i += 2) {
-                bool mine = true;
-                for (int b = 0; b < a; ++b)
-                    mine &= !(i >= box[6 * b] && i <= box[6 * b + 1] && j >= box[6 * b + 2] && j <= box[6 * b + 3]);
-                if (!mine) continue;
-                const double x0 = (double)i, x1 = (double)(i + 1);
-                uint32_t bits = 0;
-                for (int q = 0; q < n; ++q) {
-                    const double ax = Ms[2 * q], ay = Ms[2 * q + 1];
-                    const double dx0 = x0 - ax, dx1 = x1 - ax, dy0 = y0 - ay, dy1 = y1 - ay;
-                    const double sx0 = dx0 * dx0, sx1 = dx1 * dx1, sy0 = dy0 * dy0, sy1 = dy1 * dy1;
-                    bits |= (sx0 + sy0 < p.R2) ? 1u : 0u;
-                    bits |= (sx1 + sy0 < p.R2) ? 2u : 0u;
-                    bits |= (sx0 + sy1 < p.R2) ? 4u : 0u;
-                    bits |= (sx1 + sy1 < p.R2) ? 8u : 0u;
-                }
-                if (!bits) continue;
-                ++touched;
-                const int cell = i * M + j;
-                float v = belief_update(map[cell], __popc(bits), qf);
-                for (int k = 0; k < nh; ++k)
-                    if (hit[k] == cell) v = 1.0f;
-                map[cell] = v;
-            }
-        }
-    }
-    return touched;
 }
 
 enum { MODE_STEP = 0, MODE_RESET = 1 };
@@ -419,8 +463,8 @@ enum { MODE_STEP = 0, MODE_RESET = 1 };
 // actions == nullptr in MODE_STEP: uniform-random policy drawn in-kernel (alg=random, agent/agent.py:34-36)
 // ------------------------------------------------------------------------------------------------
 template <int LPE, int MODE, bool MAP>
-__global__ void __launch_bounds__(kThreads, MAP ? CS_MAP_MIN_CTAS : 8) flight_kernel(const __grid_constant__ FlightParams p, const uint8_t* __restrict__ actions,
-                                                          const uint8_t* __restrict__ mask, uint32_t rflags) {
+__global__ void __launch_bounds__(kThreads, 8) flight_kernel(const __grid_constant__ FlightParams p, const uint8_t* __restrict__ actions,
+                                                             const uint8_t* __restrict__ mask, uint32_t rflags, uint32_t seq) {
     constexpr int EPW = 32 / LPE;
     constexpr unsigned FULL = 0xffffffffu;
     constexpr unsigned GBITS = (LPE == 32) ? 0xffffffffu : ((1u << (LPE & 31)) - 1u);
@@ -478,7 +522,7 @@ __global__ void __launch_bounds__(kThreads, MAP ? CS_MAP_MIN_CTAS : 8) flight_ke
     float res_reward = 0.f;
     uint32_t res_term = 0, res_win = 0, res_found = 0, t_key = 0;   // what step()/reset() report for this env
     float st_eps = 0.f, st_rew = 0.f, st_found = 0.f, st_wins = 0.f, st_len = 0.f;
-    unsigned touched = 0;
+    uint32_t sense_word = m1.w, prejob = 0;     // CS_META_SENSE: (call number << 1) | job parked in `pre`
 
     // ---- _agent_step -------------------------------------------------------------------------------------------
     if (MODE == MODE_STEP) {
@@ -650,36 +694,19 @@ __global__ void __launch_bounds__(kThreads, MAP ? CS_MAP_MIN_CTAS : 8) flight_ke
                 st_len = (float)time_step;
             }
         }
-        // ---- belief map of every env of this warp that was just sensed (flight_env.py:266,:275-303) ---------
-        if (MAP) {
-            // every group hands its env's agent positions and hit cells to its own scratch block; then all groups of
-            // the warp run the belief-map pass together
-            double* Ms = W + p.s_map + g * p.s_mapg;
-            int* hit = reinterpret_cast<int*>(Ms + p.s_hit);
-            __syncwarp();
-            if (do_sense) {
-                if (is_agent) { Ms[2 * lane] = ax; Ms[2 * lane + 1] = ay; }
-                if (is_tgt && ((newf >> lane) & 1u)) {
-                    // idx = min(int(x), M-1): Python int() truncates toward zero (flight_env.py:279)
-                    const int ci = min((int)fmin(tx, p.Md), p.M - 1), cj = min((int)fmin(ty, p.Md), p.M - 1);
-                    hit[__popc(newf & ((1u << lane) - 1u))] = (ci < 0 || cj < 0) ? -1 : ci * p.M + cj;
-                }
+        // ---- belief map (flight_env.py:266,:275-303): a job for flight_map_kernel, which runs next on the stream.
+        //      Normally the job IS the state record (positions, CS_META_NEWFOUND); an env about to be reset inside this
+        //      call parks the job of its last step in the side buffer, because pass 1 overwrites the record.
+        if (MAP && do_sense) {
+            sense_word = seq << 1;
+            if (pass == 0 && done && p.auto_reset) {
+                double* pj = p.pre + (size_t)e * p.pre_stride;
+                int* ph = reinterpret_cast<int*>(pj + 2 * n);
+                if (is_agent) *reinterpret_cast<double2*>(pj + 2 * lane) = make_double2(ax, ay);
+                if (lane == 0) ph[0] = __popc(newf);
+                if (is_tgt && ((newf >> lane) & 1u)) ph[1 + __popc(newf & ((1u << lane) - 1u))] = hit_cell(p, tx, ty);
+                prejob = 1u;
             }
-            __syncwarp();
-            float* map = p.prob_map + (size_t)e * p.M * p.M;
-            if (p.M <= 63) {
-                touched += fl_probmap<LPE>(p, Ms, lane, map, __popc(newf), do_sense);
-            } else {
-                for (int le = 0; le < EPW; ++le) {                              // large maps: one env at a time, warp-wide
-                    const bool pend = __shfl_sync(FULL, (int)do_sense, le * LPE) != 0;
-                    if (!pend) continue;                                       // warp-uniform
-                    const int nh = __popc(__shfl_sync(FULL, newf, le * LPE));
-                    touched += fl_probmap_wide(p, W + p.s_map + le * p.s_mapg, lane32,
-                                               p.prob_map + (size_t)(wenv0 + le) * p.M * p.M, nh);
-                    __syncwarp();
-                }
-            }
-            __syncwarp();
         }
     }
 #undef GSHFL
@@ -699,7 +726,7 @@ __global__ void __launch_bounds__(kThreads, MAP ? CS_MAP_MIN_CTAS : 8) flight_ke
         if (lane == 0) {
             uint4* mp = reinterpret_cast<uint4*>(rec + p.meta_off);
             mp[0] = make_uint4(found, newf_last, outmask, time_step);
-            mp[1] = make_uint4(episode, flags, __float_as_uint(ep_reward), 0u);
+            mp[1] = make_uint4(episode, flags, __float_as_uint(ep_reward), MAP ? (sense_word | prejob) : 0u);
         }
         if (is_tgt) {
             // target part of the state row (:201-211): rewritten in full after a reset, otherwise only the 'find'
@@ -742,10 +769,6 @@ __global__ void __launch_bounds__(kThreads, MAP ? CS_MAP_MIN_CTAS : 8) flight_ke
                 atomicAdd(p.stats + CS_STAT_EP_LEN, (double)st_len);
             }
         }
-    }
-    if (MAP && p.count_touched) {
-        const unsigned tot = __reduce_add_sync(FULL, touched);
-        if (lane32 == 0 && tot) atomicAdd(p.stats + CS_STAT_TOUCHED, (double)tot);
     }
 }
 
@@ -873,8 +896,9 @@ struct cs_flight {
     cs_flight_cfg cfg;
     FlightParams p;
     int lpe;
-    size_t smem_bytes;
-    int grid;
+    size_t smem_bytes, map_smem;
+    int grid, map_grid;
+    uint32_t seq;         // number of step / reset launches so far: tells the map kernel which envs the last one sensed
     double* d_tmpl;
     uint8_t* d_actions;   // device staging of the *_host entry point's actions
     double* d_live;       // scratch of cs_flight_stats
@@ -898,18 +922,28 @@ int pick_lpe(const cs_flight_cfg& c) {
 }
 
 template <int LPE>
-cudaError_t launch_flight(const cs_flight* h, int mode, const uint8_t* actions, const uint8_t* mask, uint32_t rflags,
+cudaError_t launch_flight(cs_flight* h, int mode, const uint8_t* actions, const uint8_t* mask, uint32_t rflags,
                           cudaStream_t st) {
     if (h->p.variant) {
+        h->seq = (h->seq + 1u) & 0x7FFFFFFFu;
+        if (h->seq == 0u) h->seq = 1u;                   // 0 is the never-sensed value of a fresh record
         if (mode == MODE_STEP)
-            flight_kernel<LPE, MODE_STEP, true><<<h->grid, kThreads, h->smem_bytes, st>>>(h->p, actions, mask, rflags);
+            flight_kernel<LPE, MODE_STEP, true><<<h->grid, kThreads, h->smem_bytes, st>>>(h->p, actions, mask, rflags, h->seq);
         else
-            flight_kernel<LPE, MODE_RESET, true><<<h->grid, kThreads, h->smem_bytes, st>>>(h->p, actions, mask, rflags);
+            flight_kernel<LPE, MODE_RESET, true><<<h->grid, kThreads, h->smem_bytes, st>>>(h->p, actions, mask, rflags, h->seq);
+        // the belief maps of the envs that call sensed (flight_env.py:266)
+        if (h->p.M > 63)
+            flight_map_wide_kernel<<<h->map_grid, kMapThreads, h->map_smem, st>>>(h->p, h->seq);
+        else if (h->p.M & 1)
+            flight_map_kernel<false><<<h->map_grid, kMapThreads, h->map_smem, st>>>(h->p, h->seq);
+        else
+            flight_map_kernel<true><<<h->map_grid, kMapThreads, h->map_smem, st>>>(h->p, h->seq);
+        cs_count_launch(1);
     } else {
         if (mode == MODE_STEP)
-            flight_kernel<LPE, MODE_STEP, false><<<h->grid, kThreads, h->smem_bytes, st>>>(h->p, actions, mask, rflags);
+            flight_kernel<LPE, MODE_STEP, false><<<h->grid, kThreads, h->smem_bytes, st>>>(h->p, actions, mask, rflags, 0u);
         else
-            flight_kernel<LPE, MODE_RESET, false><<<h->grid, kThreads, h->smem_bytes, st>>>(h->p, actions, mask, rflags);
+            flight_kernel<LPE, MODE_RESET, false><<<h->grid, kThreads, h->smem_bytes, st>>>(h->p, actions, mask, rflags, 0u);
     }
     cs_count_launch(1);
     return cudaGetLastError();
@@ -924,7 +958,7 @@ cudaError_t set_smem_attr(size_t bytes) {
     return e;
 }
 
-cudaError_t dispatch(const cs_flight* h, int mode, const uint8_t* actions, const uint8_t* mask, uint32_t rflags,
+cudaError_t dispatch(cs_flight* h, int mode, const uint8_t* actions, const uint8_t* mask, uint32_t rflags,
                      cudaStream_t st) {
     switch (h->lpe) {
         case 1: return launch_flight<1>(h, mode, actions, mask, rflags, st);
@@ -1041,7 +1075,6 @@ int cs_flight_create(const cs_flight_cfg* cfg, cs_flight** out) {
     p.rec = p.meta_off + CS_META_WORDS / 2;
     p.state_len = 4 * n + 3 * m;
     p.state_stride = (p.state_len + 3) & ~3;
-    p.s_cs = 3 * n;
     // constants, computed exactly as the reference's Python floats are
     p.Md = (double)M;
     p.half_M = 0.5 * (double)M;
@@ -1068,27 +1101,38 @@ int cs_flight_create(const cs_flight_cfg* cfg, cs_flight** out) {
         p.sin0 = sin(h0);
     }
 
-    p.span_cap = 1;
-    while (p.span_cap < 2 * cfg->view_range) p.span_cap <<= 1;
-    auto magic = [](int d) { return (uint32_t)((0x100000000ULL + (uint64_t)d - 1) / (uint64_t)d); };
-    p.mg_rows = magic(p.span_cap + 1);
+    p.span_cap = 1; p.span_shift = 0;
+    while (p.span_cap < 2 * cfg->view_range) { p.span_cap <<= 1; ++p.span_shift; }
     h->lpe = pick_lpe(*cfg);
+    p.s_lut = 0;
+    p.s_warp = 76;                                        // 37 x 16 B heading-table index, padded
     {
-        // per-warp shared-memory scratch (doubles): EPW x 5n (coupled move) | belief-map scratch | heading-table index
-        const int epw = 32 / h->lpe;
-        p.s_grp = 5 * n;
-        p.s_map = up2(epw * p.s_grp);
-        p.s_box = 2 * n;                                  // offsets below are relative to the belief-map scratch
-        p.s_hit = p.s_box + 3 * n;
-        p.s_mask = p.s_hit + up2(m) / 2;
-        p.s_mapg = cfg->variant ? up2(p.s_mask + ((M <= 63) ? (M + 2) + n * (p.span_cap + 1) + n : 0)) : 0;
-        p.s_lut = up2(p.s_map + epw * p.s_mapg);
-        p.s_warp = p.s_lut + 76;                          // 37 x 16 B index, padded
+        // map kernel geometry: row slots per agent box (>= 2R+1 rows), lanes per row run (4 cells each, >= 2R+2 cells,
+        // never more than the pair-aligned map row), per-warp scratch in 8-byte words
+        const int rows = 2 * cfg->view_range + 1 < M ? 2 * cfg->view_range + 1 : M;
+        const int cells = 2 * cfg->view_range + 2 < M + 1 ? 2 * cfg->view_range + 2 : M + 1;
+        p.rs_shift = 0;
+        while ((1 << p.rs_shift) < rows) ++p.rs_shift;
+        p.lps_shift = 0;
+        while ((4 << p.lps_shift) < cells && p.lps_shift < 5) ++p.lps_shift;
+        p.ms_col = (M <= 63) ? M + 2 : 0;
+        p.ms_box = up2(p.ms_col + n);
+        p.ms_xy = p.ms_box + 2 * n;
+        p.ms_hit = p.ms_xy + 2 * n;
+        p.ms_warp = up2(p.ms_hit + (m + 1) / 2);
+        h->map_smem = (size_t)(kMapThreads / 32) * p.ms_warp * sizeof(unsigned long long);
+        h->map_grid = (p.E + kMapThreads / 32 - 1) / (kMapThreads / 32);
+        p.pre_stride = up2(2 * n + (m + 2) / 2);
     }
     h->smem_bytes = (size_t)(kThreads / 32) * p.s_warp * sizeof(double);
     const int env_per_cta = (kThreads / 32) * (32 / h->lpe);
     h->grid = (p.E + env_per_cta - 1) / env_per_cta;
     CS_CUDA(dispatch_attr(h->lpe, h->smem_bytes));
+    if (cfg->variant && h->map_smem > 48 * 1024) {
+        CS_CUDA(cudaFuncSetAttribute(flight_map_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->map_smem));
+        CS_CUDA(cudaFuncSetAttribute(flight_map_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->map_smem));
+        CS_CUDA(cudaFuncSetAttribute(flight_map_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->map_smem));
+    }
 
     const size_t E = (size_t)p.E;
     CS_CUDA(cudaMalloc(&p.dyn, E * p.rec * sizeof(double)));
@@ -1128,6 +1172,8 @@ int cs_flight_create(const cs_flight_cfg* cfg, cs_flight** out) {
     if (cfg->variant) {
         CS_CUDA(cudaMalloc(&p.prob_map, E * M * M * sizeof(float)));
         CS_CUDA(cudaMemset(p.prob_map, 0, E * M * M * sizeof(float)));
+        CS_CUDA(cudaMalloc(&p.pre, E * p.pre_stride * sizeof(double)));
+        CS_CUDA(cudaMemset(p.pre, 0, E * p.pre_stride * sizeof(double)));
     }
     CS_CUDA(cudaMalloc(&h->d_actions, E * n));
     {
@@ -1148,7 +1194,7 @@ void cs_flight_destroy(cs_flight* h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     cudaFree(h->p.dyn); cudaFree(h->p.tgt); cudaFree(h->d_slab); cudaFree(h->p.stats); cudaFree(h->d_live);
-    cudaFree(h->d_tmpl); cudaFree(h->p.prob_map); cudaFree(h->d_actions); cudaFree(h->d_lut_meta); cudaFree(h->d_lut);
+    cudaFree(h->d_tmpl); cudaFree(h->p.prob_map); cudaFree(h->p.pre); cudaFree(h->d_actions); cudaFree(h->d_lut_meta); cudaFree(h->d_lut);
     delete h;
 }
 

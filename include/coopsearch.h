@@ -51,7 +51,7 @@ typedef enum cs_status {
 
 /* meta words of a flight env (uint32 each), see cs_flight_buffers.dyn */
 enum { CS_META_FOUND = 0, CS_META_NEWFOUND = 1, CS_META_OUT = 2, CS_META_TIME = 3,
-       CS_META_EPISODE = 4, CS_META_FLAGS = 5, CS_META_EPREWARD = 6, CS_META_RESERVED = 7,
+       CS_META_EPISODE = 4, CS_META_FLAGS = 5, CS_META_EPREWARD = 6, CS_META_SENSE = 7,  /* flight variant: (number of the call that last sensed the env << 1) | first-job-parked bit */
        CS_META_WORDS = 8 };
 #define CS_FLAG_WIN 1u
 #define CS_FLAG_DONE 2u
