@@ -118,6 +118,9 @@ def load(build_if_missing=True):
     if _lib is not None:
         return _lib
     path = _build.LIB_PATH
+    override = os.environ.get("COOPSEARCH_LIB")         # tuning sweeps: a variant build of the same sources
+    if override:
+        path, build_if_missing = override, False
     if build_if_missing and _build.is_stale():
         try:
             _build.build_library()

@@ -20,14 +20,19 @@ def assert_map_close(got, want, msg=""):
     np.testing.assert_allclose(got, want32, rtol=MAP_RTOL, atol=MAP_ATOL, err_msg=msg)
 
 
+# tma=True: the opt-in TMA-tile map kernel (CS_MAP_TMA=1) where it applies (even map_size in 10..63, view_range <= 7)
+@pytest.mark.parametrize("tma", [False, True])
 @pytest.mark.parametrize("name", gu.FLIGHT_FIXTURES)
-def test_flight_matches_reference_golden(name):
+def test_flight_matches_reference_golden(name, tma, monkeypatch):
     import coopsearch_b200 as cs
+    touched = not tma
+    if tma:
+        monkeypatch.setenv("CS_MAP_TMA", "1")
     g = gu.load(name)
     kw, base, seed = gu.flight_spec_kwargs(g, "probmap")
     T, E = g["reward"].shape
     n, M = kw["n_agents"], kw["map_size"]
-    env = cs.VecFlightEnv(make_args(kw), None, num_envs=E, seed=seed, env_id_base=base, count_touched=True, reset=False)
+    env = cs.VecFlightEnv(make_args(kw), None, num_envs=E, seed=seed, env_id_base=base, count_touched=touched, reset=False)
     env.reset(init=True, targets=g["tgt_xy"])
     assert_map_close(cpu(env.prob_map), g["init_map"], "init map")
     assert np.array_equal(cpu(env.found_mask).astype(np.uint32), g["init_found"])
@@ -58,15 +63,20 @@ def test_flight_matches_reference_golden(name):
     assert_map_close(cpu(env.prob_map), g["ep2_map"], "second-episode map")
 
 
-@pytest.mark.parametrize("n_agents,agent_mode,map_size,view_range", [(3, 0, 50, 7), (5, 1, 30, 5), (2, 3, 64, 9), (4, 2, 17, 3)])
-def test_flight_matches_c_oracle(n_agents, agent_mode, map_size, view_range):
+@pytest.mark.parametrize("tma", [False, True])
+@pytest.mark.parametrize("n_agents,agent_mode,map_size,view_range", [(3, 0, 50, 7), (5, 1, 30, 5), (2, 3, 64, 9), (4, 2, 17, 3),
+                                                                     (5, 0, 16, 7), (3, 2, 62, 6)])
+def test_flight_matches_c_oracle(n_agents, agent_mode, map_size, view_range, tma, monkeypatch):
     """Fresh seeded inputs, device-drawn targets, two episodes with auto-reset, touched-cell count."""
     import coopsearch_b200 as cs
+    touched = not tma
+    if tma:
+        monkeypatch.setenv("CS_MAP_TMA", "1")
     E, T, seed, base = 48, 130, 21, 9000
     spec = FlightSpec(n_agents=n_agents, agent_mode=agent_mode, map_size=map_size, view_range=view_range,
                       time_limit=100, variant="probmap")
     env = cs.VecFlightEnv(make_args(dict(spec.__dict__)), gu.TEMPLATE, num_envs=E, seed=seed, env_id_base=base,
-                          auto_reset=True, count_touched=True)
+                          auto_reset=True, count_touched=touched)
     orc = c_oracle.FlightBatch(spec, gu.TEMPLATE, seed, base, E, auto_reset=True)
     orc.reset(init=True)
     actions = np.random.default_rng(3).integers(0, 3, size=(T, E, n_agents), dtype=np.uint8)
@@ -82,7 +92,38 @@ def test_flight_matches_c_oracle(n_agents, agent_mode, map_size, view_range):
         if t % 10 == 9 or t == T - 1:
             assert_map_close(cpu(env.prob_map), orc.map, where)
             np.testing.assert_allclose(cpu(env.agent_xy), orc.xy, rtol=0, atol=1e-9, err_msg=where)
-    assert env.stats()["map_cells_touched"] == float(orc.touched[0])
+    if touched:
+        assert env.stats()["map_cells_touched"] == float(orc.touched[0])
+
+
+@pytest.mark.parametrize("n_agents,map_size,view_range,time_limit", [(3, 50, 7, 25), (5, 24, 7, 12), (8, 16, 3, 9)])
+def test_map_kernels_and_reset_paths_agree_bitwise(n_agents, map_size, view_range, time_limit, monkeypatch):
+    """The TMA-tile kernel (overlapping agent boxes updated redundantly), the direct kernel (every cell owned by one
+    box) and both ways of ending an episode -- in-call auto-reset (two sensing calls, the first parked in the side
+    buffer) and step + reset(mask=terminated) -- must leave bit-identical maps."""
+    import coopsearch_b200 as cs
+    E, T = 512, 60
+    spec = FlightSpec(n_agents=n_agents, map_size=map_size, view_range=view_range, time_limit=time_limit, variant="probmap",
+                      target_mode=1)
+    args = make_args(dict(spec.__dict__))
+    direct_auto = cs.VecFlightEnv(args, None, num_envs=E, seed=4, auto_reset=True)
+    monkeypatch.setenv("CS_MAP_TMA", "1")
+    tma_auto = cs.VecFlightEnv(args, None, num_envs=E, seed=4, auto_reset=True)
+    tma_manual = cs.VecFlightEnv(args, None, num_envs=E, seed=4, auto_reset=False)
+    monkeypatch.delenv("CS_MAP_TMA")
+    actions = torch.from_numpy(np.random.default_rng(8).integers(0, 3, size=(T, E, n_agents), dtype=np.uint8)).cuda()
+    resets = 0
+    for t in range(T):
+        tma_auto.step(actions[t])
+        direct_auto.step(actions[t])
+        _, term, _ = tma_manual.step(actions[t])
+        if bool(term.any()):
+            resets += int(term.sum())
+            tma_manual.reset(mask=term.clone())
+        assert torch.equal(tma_auto.prob_map, direct_auto.prob_map), "TMA vs direct, step %d" % t
+        assert torch.equal(tma_auto.prob_map, tma_manual.prob_map), "auto-reset vs manual reset, step %d" % t
+        assert torch.equal(tma_auto.found_mask, tma_manual.found_mask)
+    assert resets >= E
 
 
 def test_partial_reset_keeps_other_maps():

@@ -24,18 +24,35 @@ if os.environ.get("CS_L2_FETCH"):
     v = ctypes.c_size_t(0)
     rt.cudaDeviceGetLimit(ctypes.byref(v), 5)
     print("L2 fetch granularity rc", rc, "now", v.value)
+split = int(os.environ.get("CS_C4_SPLIT", "1"))       # the same envs as `split` independent batches on `split` streams
+w["batches"] = split
+w["envs"] //= split
 envs = bench.silence(bench.make_envs, cs, w, dev, 0)
-e = envs[0]
 gen = torch.Generator(device=dev).manual_seed(1)
 acts = [torch.randint(0, 3, (w["envs"], w["n"]), generator=gen, device=dev, dtype=torch.uint8) for _ in range(8)]
+streams = [torch.cuda.Stream(device=dev) for _ in envs]
+torch.cuda.synchronize()
+
+
+def step(k):
+    for e, st in zip(envs, streams):
+        with torch.cuda.stream(st):
+            e.step(acts[k % 8])
+
+
 for k in range(30):
-    e.step(acts[k % 8])
+    step(k)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
+for st in streams:
+    st.wait_stream(torch.cuda.current_stream())
 for k in range(steps):
-    e.step(acts[k % 8])
+    step(k)
+for st in streams:
+    torch.cuda.current_stream().wait_stream(st)
 e1.record()
 torch.cuda.synchronize()
 us = 1000.0 * e0.elapsed_time(e1) / steps
-print("c4 envs", w["envs"], "steps", steps, "us_per_step %.2f" % us, "env-steps/s %.3e" % (w["envs"] / us * 1e6))
+tot = w["envs"] * split
+print("c4 envs", tot, "split", split, "steps", steps, "us_per_step %.2f" % us, "env-steps/s %.3e" % (tot / us * 1e6))
