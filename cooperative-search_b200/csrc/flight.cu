@@ -1047,6 +1047,362 @@ __global__ void __launch_bounds__(kThreads, 8) flight_kernel(const __grid_consta
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The step / reset kernel, THREAD-PER-ENV form (n_agents <= kTpeMaxAgents; the default).
+//
+// flight_kernel above spends ~380 warp instructions per env-step with most lanes idle in the agent phases and every
+// reduction a shuffle or a ballot: on B200 that is issue-bound at 14 % of the HBM roofline.  Here one THREAD owns one
+// env: agent state lives in registers (arrays indexed by compile-time constants), the targets stream through from
+// global memory, the agents x targets test and the reward are plain loops, and nothing is exchanged between lanes --
+// a warp advances 32 envs per instruction.  K > 1 splits the long part, the loop over the targets, over K threads
+// that each repeat the (short) agent phase: the same latency as flight_kernel with 32/K envs per warp, for launches too
+// small to fill the GPU with one thread per env.  Only the rare heavy pieces are warp-cooperative: the Box-Muller target
+// redraw of a reset env (one lane per target) and the 0.5 fill of a belief map.
+// Same arithmetic, same operation order, same Philox counters as flight_kernel: the two are interchangeable bit for
+// bit (tests/test_gpu_flight_easy.py compares them).
+//   pass 0 (STEP): _agent_step -> _update_obs -> step bookkeeping            (flight_env_easy.py:255-314)
+//   pass 1       : reset (selected envs in RESET mode; just-terminated envs under auto_reset) -> _update_obs (:79-182)
+// ------------------------------------------------------------------------------------------------
+constexpr int kTpeThreads = 64;
+#ifndef CS_TPE_MIN_CTAS
+#define CS_TPE_MIN_CTAS 8      // resident CTAs per SM the thread-per-env kernel is compiled for (register budget 65536/(64*N))
+#endif
+constexpr int kTpeMaxAgents = 8;
+
+template <int N, int K, int MODE, bool MAP>
+__global__ void __launch_bounds__(kTpeThreads, CS_TPE_MIN_CTAS) flight_tpe_kernel(const __grid_constant__ FlightParams p, const uint8_t* __restrict__ actions,
+                                                                 const uint8_t* __restrict__ mask, uint32_t rflags, uint32_t seq) {
+    constexpr unsigned FULL = 0xffffffffu;
+    __shared__ longlong2 lutm[40];
+    static_assert(K == 1 || K == 2 || K == 4, "K");
+    constexpr uint32_t MINE = 0xFFFFFFFFu / ((1u << K) - 1u);          // targets j with j % K == 0
+    const int tid = threadIdx.x, lane32 = tid & 31, kk = tid % K;       // kk: which of the env's K threads this is
+    const int e_raw = (blockIdx.x * kTpeThreads + tid) / K;
+    const bool active = e_raw < p.E;
+    const int e = active ? e_raw : p.E - 1;
+    const int m = p.m;
+    const uint32_t env_id = p.env_id_base + (uint32_t)e;
+    if (MODE == MODE_STEP) {
+        if (tid < 37) lutm[tid] = __ldg(p.lut_meta + tid);
+        __syncthreads();
+    }
+
+    // ---- state of this env ---------------------------------------------------------------------------------
+    double* rec = p.dyn + (size_t)e * p.rec;
+    const double* tg = p.tgt + (size_t)e * m * 2;
+    if (MODE == MODE_STEP) {
+        // the targets are needed after the agent phase: start pulling this env's lines now, together with the state
+        // loads below, so that the sensing loop finds them in L1 (one HBM round trip for the whole step, not two)
+        const char* tb = reinterpret_cast<const char*>(tg);
+        for (int off = 128 * kk; off < m * 16; off += 128 * K) asm volatile("prefetch.global.L1 [%0];" ::"l"(tb + off));
+        if (kk == K - 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(tb + m * 16 - 1));
+    }
+    double ax[N], ay[N], yaw[N], c_h[N], s_h[N];
+#pragma unroll
+    for (int a = 0; a < N; ++a) {
+        const double2 v = *reinterpret_cast<const double2*>(rec + 2 * a);
+        ax[a] = v.x; ay[a] = v.y;
+        yaw[a] = rec[p.yaw_off + a];
+        c_h[a] = 0.0; s_h[a] = 0.0;
+    }
+    const uint4* mp_in = reinterpret_cast<const uint4*>(rec + p.meta_off);
+    const uint4 m0 = mp_in[0], m1 = mp_in[1];
+    uint32_t found = m0.x, newf_last = m0.y, outmask = m0.z, time_step = m0.w;
+    uint32_t episode = m1.x, flags = m1.y;
+    float ep_reward = __uint_as_float(m1.z);
+    uint32_t sense_word = m1.w, prejob = 0;     // CS_META_SENSE: (call number << 1) | job parked in `pre`
+
+    bool done = (flags & CS_FLAG_DONE) != 0;
+    bool do_sense = false, emit = false, state_full = false, have_result = false;
+    float res_reward = 0.f;
+    uint32_t res_term = 0, res_win = 0, res_found = 0, t_key = 0;   // what step()/reset() report for this env
+    float st_eps = 0.f, st_rew = 0.f, st_found = 0.f, st_wins = 0.f, st_len = 0.f;
+
+    // ---- _agent_step -------------------------------------------------------------------------------------------
+    if (MODE == MODE_STEP) {
+        const bool stepping = active && !done;
+        if (stepping) {
+            cs_u4 pw = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int a = 0; a < N; ++a) {
+                int act;
+                if (actions != nullptr) {
+                    act = actions[(size_t)e * N + a];
+                } else {
+                    // one Philox block serves 4 agents; action = word % 3 (np.random.randint(0, 3), agent.py:36)
+                    if ((a & 3) == 0)
+                        pw = cs_philox4x32_10(env_id, ((episode & 0xFFFFu) << 16) | ((time_step + 1u) & 0xFFFFu),
+                                              (uint32_t)(a >> 2), 0u, p.seed, CS_STREAM_POLICY);
+                    act = (int)(cs_word(pw, a & 3) % 3u);
+                }
+                double h = yaw[a] + ((act == 1) ? p.turn : ((act == 2) ? -p.turn : 0.0));   // dyaw = [0, pi/18, -pi/18] (:259-262)
+                if (h > p.two_pi) h -= p.two_pi;                                             // strict tests (:263-266)
+                else if (h < 0.0) h += p.two_pi;
+                double sn, cs;
+                heading_sincos(p, lutm, h, &sn, &cs);
+                s_h[a] = sn; c_h[a] = cs;
+                yaw[a] = h;
+            }
+            // Can any repulsion term be non-zero this step?  (see flight_kernel / DESIGN.md 4.2)
+            bool close = false;
+#pragma unroll
+            for (int a = 0; a < N; ++a)
+#pragma unroll
+                for (int q = a + 1; q < N; ++q) {
+                    const double dx = ax[q] - ax[a], dy = ay[q] - ay[a];
+                    close |= (dx * dx + dy * dy < p.near2);
+                }
+            uint32_t ob = 0;
+            if (!close) {
+#pragma unroll
+                for (int a = 0; a < N; ++a) {
+                    ax[a] = ax[a] + p.v * c_h[a];                 // x += v*cos(yaw)   (:267-268)
+                    ay[a] = ay[a] + p.v * s_h[a];
+                    if (wall_reg(p, ax[a], ay[a], yaw[a], c_h[a])) ob |= 1u << a;
+                }
+            } else {
+                // the reference's sequential, in-place update (:271,:293-301): agent k sees its own OLD position and the
+                // already-moved q < k; the terms are added in ascending q
+#pragma unroll
+                for (int k = 0; k < N; ++k) {
+                    const double x0 = ax[k], y0 = ay[k];
+                    double fx = 0.0, fy = 0.0;
+#pragma unroll
+                    for (int q = 0; q < N; ++q) {
+                        if (q == k) continue;
+                        const double dxq = ax[q] - x0, dyq = ay[q] - y0;
+                        if ((dxq * dxq + dyq * dyq < p.fd2) && (ax[q] != x0 || ay[q] != y0)) {
+                            const double ex = x0 - ax[q], ey = y0 - ay[q];
+                            const double r2 = ex * ex + ey * ey;
+                            fx += p.fk * ex / r2;
+                            fy += p.fk * ey / r2;
+                        }
+                    }
+                    double nx = x0 + p.v * c_h[k], ny = y0 + p.v * s_h[k];
+                    nx += fx;
+                    ny += fy;
+                    ax[k] = nx; ay[k] = ny;
+                    if (wall_reg(p, ax[k], ay[k], yaw[k], c_h[k])) ob |= 1u << k;
+                }
+            }
+            outmask = ob;
+            do_sense = true;
+            t_key = time_step + 1u;
+        } else if (active) {
+            have_result = true;                            // masked no-op on a finished env
+            res_reward = 0.f;
+            res_term = 1;
+            res_win = flags & CS_FLAG_WIN;
+            res_found = (uint32_t)__popc(found);
+        }
+    }
+
+    for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 1) {
+            const bool do_reset = active && ((MODE == MODE_RESET) ? (mask == nullptr || mask[e] != 0) : (p.auto_reset && done));
+            const unsigned rmask = __ballot_sync(FULL, do_reset && kk == 0);
+            if (!rmask) break;
+            do_sense = do_reset;
+            if (do_reset) {                                                   // reset (:79-180)
+                episode += (rflags & CS_RESET_KEEP_EPISODE) ? 0u : 1u;
+                found = 0; outmask = 0; time_step = 0; flags = 0; ep_reward = 0.f; done = false;
+#pragma unroll
+                for (int a = 0; a < N; ++a) {
+                    const double lin = p.lin[a];                                          // (:140-143)
+                    switch (p.agent_mode) {
+                        case 0: ax[a] = lin; ay[a] = 0.0; yaw[a] = p.half_pi; break;
+                        case 1: ax[a] = lin; ay[a] = p.Md / 2.0; yaw[a] = p.half_pi; break;
+                        case 2: ax[a] = 0.0; ay[a] = lin; yaw[a] = 0.0; break;
+                        default: ax[a] = p.Md; ay[a] = lin; yaw[a] = p.pi; break;
+                    }
+                    c_h[a] = p.cos0; s_h[a] = p.sin0;
+                }
+                t_key = 0;
+                emit = true;
+                state_full = true;
+                if (MODE == MODE_RESET) { have_result = true; res_reward = 0.f; res_term = 0; }
+            }
+            // warp-cooperative heavy parts of a reset, one resetting env at a time: its targets (one lane per
+            // target, :95-127) and, for reset(init=True), its belief map (flight_env.py:84-86)
+            if (!(rflags & CS_RESET_KEEP_TARGETS) || (MAP && (rflags & CS_RESET_INIT))) {
+                unsigned left = rmask;
+                const int t_first = blockIdx.x * kTpeThreads + (tid & ~31);
+                while (left) {
+                    const int src = __ffs(left) - 1;
+                    left &= left - 1;
+                    const int es = (t_first + src) / K;
+                    const uint32_t ep_s = __shfl_sync(FULL, episode, src);
+                    if (!(rflags & CS_RESET_KEEP_TARGETS)) {
+                        for (int j = lane32; j < m; j += 32) {
+                            const double2 t = draw_target(p, p.env_id_base + (uint32_t)es, ep_s, j);
+                            *reinterpret_cast<double2*>(p.tgt + ((size_t)es * m + j) * 2) = t;
+                        }
+                    }
+                    if (MAP && (rflags & CS_RESET_INIT)) {
+                        float* map = p.prob_map + (size_t)es * p.M * p.M;
+                        for (int c = lane32; c < p.M * p.M; c += 32) map[c] = 0.5f;
+                    }
+                }
+                __syncwarp();                                   // the owners read the new targets back below
+            }
+        } else if (MODE == MODE_RESET) {
+            continue;
+        }
+
+        // ---- _update_obs: detection + reward + win (:223-253) ----------------------------------------------
+        uint32_t newf = 0;
+        if (do_sense) {
+            // the env's K threads share the targets; TU of a thread's targets are loaded together so that their
+            // latency is paid once per block, not once per target
+            constexpr int TU = 5;
+            for (int j0 = kk; j0 < m; j0 += K * TU) {
+                double2 t[TU];
+#pragma unroll
+                for (int u = 0; u < TU; ++u) {
+                    const int j = min(j0 + u * K, m - 1);
+                    t[u] = *reinterpret_cast<const double2*>(tg + 2 * j);
+                }
+#pragma unroll
+                for (int u = 0; u < TU; ++u) {
+                    const int j = j0 + u * K;
+                    if (j >= m) break;
+                    uint32_t amask = 0;
+#pragma unroll
+                    for (int a = 0; a < N; ++a) {
+                        const double dx = t[u].x - ax[a], dy = t[u].y - ay[a];
+                        if (dx * dx + dy * dy <= p.R2) amask |= 1u << a;               // '<=' (:237)
+                    }
+                    if (amask && !((found >> j) & 1u)) {                               // draw is irrelevant once found (:239)
+                        bool got = false;
+#pragma unroll
+                        for (int blk = 0; 4 * blk < N; ++blk) {
+                            const uint32_t bits = (amask >> (4 * blk)) & 0xFu;
+                            if (!bits || got) continue;
+                            const cs_u4 w = cs_detect_words(p.seed, env_id, episode, t_key, (uint32_t)blk, (uint32_t)j);
+                            got = ((bits & 1u) && (long long)w.x <= p.thr) || ((bits & 2u) && (long long)w.y <= p.thr) ||
+                                  ((bits & 4u) && (long long)w.z <= p.thr) || ((bits & 8u) && (long long)w.w <= p.thr);
+                        }
+                        if (got) newf |= 1u << j;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int o = K / 2; o > 0; o >>= 1) newf |= __shfl_xor_sync(FULL, newf, o);
+        int rew = 0;
+        if (do_sense) {
+            found |= newf;
+            newf_last = newf;
+            const int c = __popc(newf);
+            rew = -1 + 10 * c;                                                 // MOVE_COST + FIND_ONE_TGT (:228,:241)
+            if (c > 0 && __popc(found) == m && !(flags & CS_FLAG_WIN)) {
+                rew += 100;                                                    // FIND_ALL_TGT (:244-246)
+                flags |= CS_FLAG_WIN;
+            }
+            rew -= __popc(outmask);                                            // OUT_PUNISH per agent outside (:249-250)
+        }
+        if (MODE == MODE_RESET && do_sense) {
+            res_win = flags & CS_FLAG_WIN;
+            res_found = (uint32_t)__popc(found);
+        }
+        if (pass == 0 && do_sense) {                                           // step bookkeeping (:308-314)
+            time_step += 1u;
+            ep_reward += (float)rew;
+            const int nfound = __popc(found);
+            const bool term = (nfound >= m) || ((int)time_step >= p.T);
+            if (term) flags |= CS_FLAG_DONE;
+            done = term;
+            emit = true;
+            have_result = true;
+            res_reward = (float)rew;
+            res_term = term ? 1u : 0u;
+            res_win = flags & CS_FLAG_WIN;          // of the episode this step belongs to, also when auto_reset follows
+            res_found = (uint32_t)nfound;
+            if (term && kk == 0) {
+                st_eps = 1.f; st_rew = ep_reward; st_found = (float)nfound; st_wins = (flags & CS_FLAG_WIN) ? 1.f : 0.f;
+                st_len = (float)time_step;
+            }
+        }
+        // ---- belief map job for flight_map_kernel (see flight_kernel) -------------------------------------------
+        if (MAP && do_sense) {
+            sense_word = seq << 1;
+            if (pass == 0 && done && p.auto_reset && kk == 0) {
+                double* pj = p.pre + (size_t)e * p.pre_stride;
+                int* ph = reinterpret_cast<int*>(pj + 2 * N);
+#pragma unroll
+                for (int a = 0; a < N; ++a) *reinterpret_cast<double2*>(pj + 2 * a) = make_double2(ax[a], ay[a]);
+                int k = 0;
+                for (uint32_t left = newf; left; left &= left - 1) {
+                    const int j = __ffs(left) - 1;
+                    const double2 t = *reinterpret_cast<const double2*>(tg + 2 * j);
+                    ph[1 + k++] = hit_cell(p, t.x, t.y);
+                }
+                ph[0] = k;
+            }
+            if (pass == 0 && done && p.auto_reset) prejob = 1u;
+        }
+    }
+
+    // ---- outputs ---------------------------------------------------------------------------------------------
+    if (active && emit) {
+        float* srow = p.state + (size_t)e * p.state_stride;
+#pragma unroll
+        for (int a = 0; a < N; ++a) {
+            if (a % K != kk) continue;                                  // the env's K threads share the rows
+            *reinterpret_cast<double2*>(rec + 2 * a) = make_double2(ax[a], ay[a]);
+            rec[p.yaw_off + a] = yaw[a];
+            // get_obs row = agent part of get_state (flight_env_easy.py:218-221, :192-193)
+            const float4 o = make_float4((float)((ax[a] - p.half_M) * p.inv_half), (float)((ay[a] - p.half_M) * p.inv_half),
+                                         (float)c_h[a], (float)s_h[a]);
+            reinterpret_cast<float4*>(p.obs)[(size_t)e * N + a] = o;
+            reinterpret_cast<float4*>(srow)[a] = o;
+        }
+        if (kk == 0) {
+            uint4* mp = reinterpret_cast<uint4*>(rec + p.meta_off);
+            mp[0] = make_uint4(found, newf_last, outmask, time_step);
+            mp[1] = make_uint4(episode, flags, __float_as_uint(ep_reward), MAP ? (sense_word | prejob) : 0u);
+        }
+        // target part of the state row (:201-211): rewritten in full after a reset, otherwise only the 'find' entry of
+        // a target found by this call
+        if (state_full) {
+            for (int j = kk; j < m; j += K) {
+                const double2 t = *reinterpret_cast<const double2*>(tg + 2 * j);
+                float* s3 = srow + 4 * N + 3 * j;
+                s3[0] = (float)((t.x - p.half_M) * p.inv_half);
+                s3[1] = (float)((t.y - p.half_M) * p.inv_half);
+                s3[2] = ((found >> j) & 1u) ? 1.0f : 0.0f;
+            }
+        } else {
+            for (uint32_t left = newf_last & (MINE << kk); left; left &= left - 1) srow[4 * N + 3 * (__ffs(left) - 1) + 2] = 1.0f;
+        }
+    }
+    if (active && have_result && kk == 0) {
+        p.reward[e] = res_reward;
+        p.terminated[e] = (uint8_t)res_term;
+        p.win[e] = res_win ? 1 : 0;
+        p.target_find[e] = (int32_t)res_found;
+    }
+    // ---- statistics of episodes that ended in this call: warp reduction, then one atomic per statistic per warp
+    if (MODE == MODE_STEP) {
+        if (__any_sync(FULL, st_eps != 0.f)) {
+            for (int o = 16; o > 0; o >>= 1) {
+                st_eps += __shfl_xor_sync(FULL, st_eps, o);
+                st_rew += __shfl_xor_sync(FULL, st_rew, o);
+                st_found += __shfl_xor_sync(FULL, st_found, o);
+                st_wins += __shfl_xor_sync(FULL, st_wins, o);
+                st_len += __shfl_xor_sync(FULL, st_len, o);
+            }
+            if (lane32 == 0) {
+                atomicAdd(p.stats + CS_STAT_EPISODES, (double)st_eps);
+                atomicAdd(p.stats + CS_STAT_EP_REWARD, (double)st_rew);
+                atomicAdd(p.stats + CS_STAT_TARGETS_FOUND, (double)st_found);
+                atomicAdd(p.stats + CS_STAT_WINS, (double)st_wins);
+                atomicAdd(p.stats + CS_STAT_EP_LEN, (double)st_len);
+            }
+        }
+    }
+}
+
 // sum of the time_step words of all envs (steps of the episodes still running), for cs_flight_stats
 __global__ void __launch_bounds__(256) flight_live_steps_kernel(const double* __restrict__ dyn, int E, int rec, int meta_off,
                                                                 double* __restrict__ out) {
@@ -1169,6 +1525,8 @@ struct cs_flight {
     cs_flight_cfg cfg;
     FlightParams p;
     int lpe;
+    bool tpe;             // thread-per-env step kernel (n_agents <= kTpeMaxAgents and no explicit lanes_per_env)
+    int tpe_k;            // threads that share one env's target loop in that kernel (1, 2, 4)
     size_t smem_bytes, map_smem;
     int grid, map_grid;
     bool map_tma;         // the TMA form of the map kernel applies (even map_size in 16..63, 2R+2 <= 16) and the tensor map exists
@@ -1198,6 +1556,40 @@ int pick_lpe(const cs_flight_cfg& c) {
     return lpe > 32 ? 32 : lpe;
 }
 
+// the belief maps of the envs the step / reset kernel just sensed (flight_env.py:266)
+void launch_map(cs_flight* h, cudaStream_t st);
+
+template <int N, int K>
+cudaError_t launch_tpe_k(cs_flight* h, int mode, const uint8_t* actions, const uint8_t* mask, uint32_t rflags, cudaStream_t st) {
+    const long long threads = (long long)h->p.E * K;
+    const int grid = (int)((threads + kTpeThreads - 1) / kTpeThreads);
+    if (h->p.variant) {
+        h->seq = (h->seq + 1u) & 0x7FFFFFFFu;
+        if (h->seq == 0u) h->seq = 1u;                   // 0 is the never-sensed value of a fresh record
+        if (mode == MODE_STEP)
+            flight_tpe_kernel<N, K, MODE_STEP, true><<<grid, kTpeThreads, 0, st>>>(h->p, actions, mask, rflags, h->seq);
+        else
+            flight_tpe_kernel<N, K, MODE_RESET, true><<<grid, kTpeThreads, 0, st>>>(h->p, actions, mask, rflags, h->seq);
+        launch_map(h, st);
+    } else {
+        if (mode == MODE_STEP)
+            flight_tpe_kernel<N, K, MODE_STEP, false><<<grid, kTpeThreads, 0, st>>>(h->p, actions, mask, rflags, 0u);
+        else
+            flight_tpe_kernel<N, K, MODE_RESET, false><<<grid, kTpeThreads, 0, st>>>(h->p, actions, mask, rflags, 0u);
+    }
+    cs_count_launch(1);
+    return cudaGetLastError();
+}
+
+template <int N>
+cudaError_t launch_tpe(cs_flight* h, int mode, const uint8_t* actions, const uint8_t* mask, uint32_t rflags, cudaStream_t st) {
+    switch (h->tpe_k) {
+        case 1: return launch_tpe_k<N, 1>(h, mode, actions, mask, rflags, st);
+        case 2: return launch_tpe_k<N, 2>(h, mode, actions, mask, rflags, st);
+        default: return launch_tpe_k<N, 4>(h, mode, actions, mask, rflags, st);
+    }
+}
+
 template <int LPE>
 cudaError_t launch_flight(cs_flight* h, int mode, const uint8_t* actions, const uint8_t* mask, uint32_t rflags,
                           cudaStream_t st) {
@@ -1208,16 +1600,7 @@ cudaError_t launch_flight(cs_flight* h, int mode, const uint8_t* actions, const 
             flight_kernel<LPE, MODE_STEP, true><<<h->grid, kThreads, h->smem_bytes, st>>>(h->p, actions, mask, rflags, h->seq);
         else
             flight_kernel<LPE, MODE_RESET, true><<<h->grid, kThreads, h->smem_bytes, st>>>(h->p, actions, mask, rflags, h->seq);
-        // the belief maps of the envs that call sensed (flight_env.py:266)
-        if (h->p.M > 63)
-            flight_map_wide_kernel<<<h->map_grid, kMapThreads, h->map_smem, st>>>(h->p, h->seq);
-        else if (h->map_tma && !h->p.count_touched && h->map_use_tma)
-            flight_map_tma_kernel<<<h->map_grid, kMapThreads, h->map_tma_smem, st>>>(h->p, h->tmap, h->seq);
-        else if (h->p.M & 1)
-            flight_map_kernel<false><<<h->map_grid, kMapThreads, h->map_smem, st>>>(h->p, h->seq);
-        else
-            flight_map_kernel<true><<<h->map_grid, kMapThreads, h->map_smem, st>>>(h->p, h->seq);
-        cs_count_launch(1);
+        launch_map(h, st);
     } else {
         if (mode == MODE_STEP)
             flight_kernel<LPE, MODE_STEP, false><<<h->grid, kThreads, h->smem_bytes, st>>>(h->p, actions, mask, rflags, 0u);
@@ -1226,6 +1609,18 @@ cudaError_t launch_flight(cs_flight* h, int mode, const uint8_t* actions, const 
     }
     cs_count_launch(1);
     return cudaGetLastError();
+}
+
+void launch_map(cs_flight* h, cudaStream_t st) {
+    if (h->p.M > 63)
+        flight_map_wide_kernel<<<h->map_grid, kMapThreads, h->map_smem, st>>>(h->p, h->seq);
+    else if (h->map_tma && !h->p.count_touched && h->map_use_tma)
+        flight_map_tma_kernel<<<h->map_grid, kMapThreads, h->map_tma_smem, st>>>(h->p, h->tmap, h->seq);
+    else if (h->p.M & 1)
+        flight_map_kernel<false><<<h->map_grid, kMapThreads, h->map_smem, st>>>(h->p, h->seq);
+    else
+        flight_map_kernel<true><<<h->map_grid, kMapThreads, h->map_smem, st>>>(h->p, h->seq);
+    cs_count_launch(1);
 }
 
 template <int LPE>
@@ -1239,6 +1634,18 @@ cudaError_t set_smem_attr(size_t bytes) {
 
 cudaError_t dispatch(cs_flight* h, int mode, const uint8_t* actions, const uint8_t* mask, uint32_t rflags,
                      cudaStream_t st) {
+    if (h->tpe) {
+        switch (h->p.n) {
+            case 1: return launch_tpe<1>(h, mode, actions, mask, rflags, st);
+            case 2: return launch_tpe<2>(h, mode, actions, mask, rflags, st);
+            case 3: return launch_tpe<3>(h, mode, actions, mask, rflags, st);
+            case 4: return launch_tpe<4>(h, mode, actions, mask, rflags, st);
+            case 5: return launch_tpe<5>(h, mode, actions, mask, rflags, st);
+            case 6: return launch_tpe<6>(h, mode, actions, mask, rflags, st);
+            case 7: return launch_tpe<7>(h, mode, actions, mask, rflags, st);
+            default: return launch_tpe<8>(h, mode, actions, mask, rflags, st);
+        }
+    }
     switch (h->lpe) {
         case 1: return launch_flight<1>(h, mode, actions, mask, rflags, st);
         case 2: return launch_flight<2>(h, mode, actions, mask, rflags, st);
@@ -1383,6 +1790,15 @@ int cs_flight_create(const cs_flight_cfg* cfg, cs_flight** out) {
     p.span_cap = 1; p.span_shift = 0;
     while (p.span_cap < 2 * cfg->view_range) { p.span_cap <<= 1; ++p.span_shift; }
     h->lpe = pick_lpe(*cfg);
+    h->tpe = cfg->lanes_per_env == 0 && n <= kTpeMaxAgents;
+    // measured on B200 (tools/sweep_step.sh): one thread per env wins from ~32k envs per launch (2.7e9 against 1.7e9
+    // env-steps/s at 65536 envs, 5.0e9 against 2.4e9 at 1M); below that a launch cannot fill the GPU with one thread
+    // per env and 4 threads per env match the lane-per-agent kernel's latency
+    h->tpe_k = p.E >= 32768 ? 1 : 4;
+    if (const char* kenv = getenv("CS_TPE_K")) {                               // tuning sweeps only
+        const int kv = atoi(kenv);
+        if (kv == 1 || kv == 2 || kv == 4) h->tpe_k = kv;
+    }
     p.s_lut = 0;
     p.s_warp = 76;                                        // 37 x 16 B heading-table index, padded
     {
@@ -1532,7 +1948,7 @@ int cs_flight_env_info(const cs_flight* h, int32_t* out4) {
     return CS_OK;
 }
 
-int cs_flight_lanes_per_env(const cs_flight* h) { return h ? h->lpe : CS_ERR_INVALID; }
+int cs_flight_lanes_per_env(const cs_flight* h) { return h ? (h->tpe ? h->tpe_k : h->lpe) : CS_ERR_INVALID; }
 
 // tuning / measurement hook: which kernel cs_flight_obs_full uses (0 = TMA bulk copies, 1 = plain float4 copies)
 int cs_debug_flight_obs_path(cs_flight* h, int32_t path) {

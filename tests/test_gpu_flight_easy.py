@@ -141,6 +141,45 @@ def test_shard_invariance_and_lane_invariance():
         assert torch.equal(whole.get_state(), torch.cat([lo.get_state(), hi.get_state()]))
 
 
+@pytest.mark.parametrize("n_agents,agent_mode,target_mode,map_size,time_limit,variant",
+                         [(3, 0, 0, 50, 40, "easy"), (5, 2, 1, 50, 30, "easy"), (8, 3, 1, 14, 25, "easy"), (1, 1, 0, 50, 20, "easy"),
+                          (3, 0, 0, 50, 40, "probmap"), (6, 1, 1, 20, 15, "probmap")])
+def test_thread_per_env_kernel_equals_lane_per_agent_kernel(n_agents, agent_mode, target_mode, map_size, time_limit, variant):
+    """flight_tpe_kernel (one thread per env, the default for n_agents <= 8) and flight_kernel (one lane per agent /
+    target, lanes_per_env > 0) are the same arithmetic in a different arrangement: every buffer must agree bit for
+    bit, through episode ends, in-call auto-resets and device-drawn targets, under device actions and the in-kernel
+    random policy."""
+    import coopsearch_b200 as cs
+    E, T = 1000, 3 * time_limit + 7
+    spec = FlightSpec(n_agents=n_agents, agent_mode=agent_mode, target_mode=target_mode, map_size=map_size,
+                      view_range=min(7, map_size // 3), time_limit=time_limit, variant=variant)
+    args = make_args(dict(spec.__dict__))
+    cls = cs.VecFlightEasyEnv if variant == "easy" else cs.VecFlightEnv
+    tpe = cls(args, TEMPLATE, num_envs=E, seed=11, env_id_base=77, auto_reset=True)
+    lpa = cls(args, TEMPLATE, num_envs=E, seed=11, env_id_base=77, auto_reset=True, lanes_per_env=16 if n_agents <= 16 else 32)
+    assert tpe.lanes_per_env <= 8 and lpa.lanes_per_env >= 16
+    actions = torch.from_numpy(np.random.default_rng(2).integers(0, 3, size=(T, E, n_agents), dtype=np.uint8)).cuda()
+    for t in range(T):
+        if t % 5 == 4:
+            ra, ta, wa = tpe.step_random(1)
+            rb, tb, wb = lpa.step_random(1)
+        else:
+            ra, ta, wa = tpe.step(actions[t])
+            rb, tb, wb = lpa.step(actions[t])
+        where = "step %d" % t
+        assert torch.equal(ra, rb) and torch.equal(ta, tb) and torch.equal(wa, wb), where
+        assert torch.equal(tpe.target_find, lpa.target_find), where
+        assert torch.equal(tpe._dyn.view(torch.int64), lpa._dyn.view(torch.int64)), where
+        assert torch.equal(tpe.tgt_xy.view(torch.int64), lpa.tgt_xy.view(torch.int64)), where
+        assert torch.equal(tpe.get_state().view(torch.int32), lpa.get_state().view(torch.int32)), where
+        assert torch.equal(tpe.get_obs(full=False).view(torch.int32) if variant != "easy" else tpe.get_obs().view(torch.int32),
+                           lpa.get_obs(full=False).view(torch.int32) if variant != "easy" else lpa.get_obs().view(torch.int32)), where
+        if variant != "easy":
+            assert torch.equal(tpe.prob_map, lpa.prob_map), where
+    sa, sb = tpe.stats(), lpa.stats()
+    assert sa == sb and sa["episodes"] >= 2 * E
+
+
 def test_auto_reset_and_stats():
     import coopsearch_b200 as cs
     spec = FlightSpec(n_agents=3, time_limit=40)
