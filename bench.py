@@ -298,8 +298,11 @@ def run_gpu_workload(cs, torch, name, steps, warmup, device, rank, world, want_e
 
     torch.cuda.synchronize(device)
     graphs = []
+    lib = cs.load_library()
     with torch.cuda.stream(side):
+        k0 = lib.cs_launch_count()
         one_step(0)
+        kernels_per_step = int(lib.cs_launch_count() - k0)     # kernels of OUR library one step launches (graph replays repeat them)
         torch.cuda.synchronize(device)
         for k in range(POOL if actions is not None else 1):
             g = torch.cuda.CUDAGraph()
@@ -335,6 +338,7 @@ def run_gpu_workload(cs, torch, name, steps, warmup, device, rank, world, want_e
     ms = ev0.elapsed_time(ev1)
     launches = steps * len(envs)
     out = dict(ms_total=ms, ms_per_step=ms / steps, env_steps_per_step=w["envs"] * len(envs), launches=launches, streams=nstreams,
+               kernels=kernels_per_step * steps,
                us_per_launch=1000.0 * ms / launches, lanes_per_env=getattr(envs[0], "lanes_per_env", None))
 
     # ---- end to end through the host-buffer C-ABI call -----------------------------------------------------
@@ -349,6 +353,12 @@ def run_gpu_workload(cs, torch, name, steps, warmup, device, rank, world, want_e
             e.host_buffers()
 
         streams = [torch.cuda.Stream(device=device) for _ in range(min(4, len(envs)))]
+        steppers = None
+        if w["kind"] != "search":
+            # this step's actions are in PINNED host memory (two alternating sets); one library call steps every batch
+            pinned = [[torch.from_numpy(a).pin_memory() for a in host_actions[k]] for k in range(2)]
+            use_graph = os.environ.get("CS_BENCH_E2E_GRAPH", "1") != "0"
+            steppers = [cs.HostStepper(envs, streams, actions=pinned[k], graph=use_graph) for k in range(2)]
 
         def host_step(k):
             if w["kind"] == "search":
@@ -358,12 +368,9 @@ def run_gpu_workload(cs, torch, name, steps, warmup, device, rank, world, want_e
                     acts = av.argmax(axis=2).astype(np.uint8)
                     e.step_host(acts)
                 return
-            # independent env batches are pipelined over a few streams: H2D / kernel / D2H of different batches overlap
-            for b, e in enumerate(envs):
-                with torch.cuda.stream(streams[b % len(streams)]):
-                    e.step_host(host_actions[k % 2][b], sync=False)
-            for st in streams:
-                st.synchronize()
+            # independent env batches are pipelined over a few streams: H2D / kernel / result traffic of different
+            # batches overlap; the call returns when every batch's results are in host memory
+            steppers[k % 2].step()
 
         if w["kind"] == "search":
             for e in envs:
@@ -427,6 +434,14 @@ def measure_touched(cs, torch, device, steps=200):
     e.step_random(steps)
     torch.cuda.synchronize(device)
     return (e.stats()["map_cells_touched"] - base) / (steps * w["envs"])
+
+
+def kernel_name(w, lanes):
+    """The dominant kernel of a workload (csrc/flight.cu, csrc/search.cu)."""
+    if w["kind"] == "search":
+        return "search_kernel<STEP>"
+    step = ("flight_tpe_kernel<N=%d,K=%d,STEP>" % (w["n"], lanes)) if lanes and lanes <= 4 else "flight_kernel<LPE=%s,STEP>" % lanes
+    return step if w["kind"] == "flight_easy" else "flight_map_kernel (after %s; two launches per env-step)" % step
 
 
 def load_peaks():
@@ -544,12 +559,13 @@ def main():
         "agent_steps_per_s": value * w["n"],
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": res["h2d_bytes_per_step"],
                 "d2h_bytes_per_step": res["d2h_bytes_per_step"], "agent_steps_per_s": e2e_value * w["n"],
-                "steps": res["e2e_steps"], "path": "cs_*_step_host per batch: pinned host actions -> H2D -> step kernel -> one D2H of reward/terminated/win/target_find/obs/state; batches pipelined over 4 streams, all synchronised every step"},
-        "gpu_launches": int(res["launches"] * 1),
+                "steps": res["e2e_steps"],
+                "path": "HostStepper.step() = cs_flight_step_host_many captured in one CUDA graph; per batch: pinned host actions -> H2D -> step kernel -> one D2H of reward/terminated/win/target_find/obs/state into the pinned slab; batches pipelined over 4 streams, all synchronised every step (search: cs_search_step_host per batch)"},
+        "gpu_launches": int(res["kernels"]),
         "gpu_launches_process_total": int(lib.cs_launch_count() - launches0),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": load_traffic(args.workload), "peak_source": peak_src,
-                     "kernel": "flight_kernel<LPE,STEP>" if w["kind"] != "search" else "search_kernel<STEP>",
+                     "kernel": kernel_name(w, res["lanes_per_env"]),
                      "algorithmic_bytes_per_env_step": per_unit, "env_steps_per_launch": w["envs"],
                      "us_per_launch": 1e6 * sec_per_launch, "map_cells_touched_per_env_step": touched,
                      "note": "duration = timed region / launches; launches of independent batches overlap when streams > 1"},
@@ -571,7 +587,7 @@ def main():
                     algorithmic_bytes("search", 64, m=1000, M=64, R=7)
                 v = r["env_steps_per_step"] / (r["ms_per_step"] / 1000.0)
                 gbs = pu * ww["envs"] / (1e-6 * r["us_per_launch"]) / 1e9
-                extra[name] = {"workload": ww["desc"], "value": v, "unit": "env-steps/s", "agent_steps_per_s": v * ww["n"],
+                extra[name] = {"workload": ww["desc"], "kernel": kernel_name(ww, r["lanes_per_env"]), "value": v, "unit": "env-steps/s", "agent_steps_per_s": v * ww["n"],
                                "us_per_launch": r["us_per_launch"], "e2e_value": r["env_steps_per_step"] / r["e2e_s_per_step"],
                                "roofline": {"achieved": gbs, "peak": peak, "frac": gbs / peak, "unit": "GB/s",
                                             "algorithmic_bytes_per_env_step": pu, "map_cells_touched_per_env_step": tch,

@@ -173,7 +173,7 @@ __device__ __forceinline__ float belief_update(float pv, int cnt, float qf) {
 // belief map: _update_prob_map + _percent_in_agent_viewrange (env/flight_env.py:275-303).
 //
 // Runs as its OWN kernel right after the step / reset kernel, 16 lanes per env (two envs per warp).  The step kernel leaves a job for
-// every env it sensed: the sensing call number in meta word CS_META_SENSE, the agent positions in the state record,
+// every env it sensed: a non-zero meta word CS_META_SENSE (cleared again by the next call that does not sense the env), the agent positions in the state record,
 // the targets found by that call in CS_META_NEWFOUND; an env that was auto-reset inside the call was sensed twice
 // (flight_env.py:266 runs inside reset() too) and its first job -- positions and hit cells before the reset -- sits in
 // the `pre` side buffer.  Few registers (no Philox, no fp64 state in flight) and nothing but the map traffic
@@ -1017,6 +1017,8 @@ __global__ void __launch_bounds__(kThreads, 8) flight_kernel(const __grid_consta
             if (tgt_dirty) *reinterpret_cast<double2*>(p.tgt + ((size_t)e * m + lane) * 2) = make_double2(tx, ty);
         }
     }
+    if (MAP && active && !emit && lane == 0 && m1.w != 0u)
+        reinterpret_cast<uint32_t*>(rec + p.meta_off)[CS_META_SENSE] = 0u;      // not sensed by THIS call: no job for the map kernel
     if (active && have_result && lane == 0) {
         p.reward[e] = res_reward;
         p.terminated[e] = (uint8_t)res_term;
@@ -1368,14 +1370,16 @@ __global__ void __launch_bounds__(kTpeThreads, CS_TPE_MIN_CTAS) flight_tpe_kerne
             for (int j = kk; j < m; j += K) {
                 const double2 t = *reinterpret_cast<const double2*>(tg + 2 * j);
                 float* s3 = srow + 4 * N + 3 * j;
-                s3[0] = (float)((t.x - p.half_M) * p.inv_half);
-                s3[1] = (float)((t.y - p.half_M) * p.inv_half);
-                s3[2] = ((found >> j) & 1u) ? 1.0f : 0.0f;
+                const float nx = (float)((t.x - p.half_M) * p.inv_half), ny = (float)((t.y - p.half_M) * p.inv_half);
+                const float fj = ((found >> j) & 1u) ? 1.0f : 0.0f;
+                s3[0] = nx; s3[1] = ny; s3[2] = fj;
             }
         } else {
             for (uint32_t left = newf_last & (MINE << kk); left; left &= left - 1) srow[4 * N + 3 * (__ffs(left) - 1) + 2] = 1.0f;
         }
     }
+    if (MAP && active && !emit && kk == 0 && m1.w != 0u)
+        reinterpret_cast<uint32_t*>(rec + p.meta_off)[CS_META_SENSE] = 0u;      // not sensed by THIS call: no job for the map kernel
     if (active && have_result && kk == 0) {
         p.reward[e] = res_reward;
         p.terminated[e] = (uint8_t)res_term;
@@ -1533,7 +1537,7 @@ struct cs_flight {
     CUtensorMap tmap;     // (2M, M/2, E) view of prob_map, box 20 x H x 1
     size_t map_tma_smem;
     bool map_use_tma;     // opt-in (CS_MAP_TMA=1): the TMA form measured 12 % slower than the direct form on the c4 workload
-    uint32_t seq;         // number of step / reset launches so far: tells the map kernel which envs the last one sensed
+    uint32_t seq;         // value of CS_META_SENSE >> 1 that marks "sensed by the latest call" (constant: launches captured in CUDA graphs replay it)
     double* d_tmpl;
     uint8_t* d_actions;   // device staging of the *_host entry point's actions
     double* d_live;       // scratch of cs_flight_stats
@@ -1564,8 +1568,6 @@ cudaError_t launch_tpe_k(cs_flight* h, int mode, const uint8_t* actions, const u
     const long long threads = (long long)h->p.E * K;
     const int grid = (int)((threads + kTpeThreads - 1) / kTpeThreads);
     if (h->p.variant) {
-        h->seq = (h->seq + 1u) & 0x7FFFFFFFu;
-        if (h->seq == 0u) h->seq = 1u;                   // 0 is the never-sensed value of a fresh record
         if (mode == MODE_STEP)
             flight_tpe_kernel<N, K, MODE_STEP, true><<<grid, kTpeThreads, 0, st>>>(h->p, actions, mask, rflags, h->seq);
         else
@@ -1594,8 +1596,6 @@ template <int LPE>
 cudaError_t launch_flight(cs_flight* h, int mode, const uint8_t* actions, const uint8_t* mask, uint32_t rflags,
                           cudaStream_t st) {
     if (h->p.variant) {
-        h->seq = (h->seq + 1u) & 0x7FFFFFFFu;
-        if (h->seq == 0u) h->seq = 1u;                   // 0 is the never-sensed value of a fresh record
         if (mode == MODE_STEP)
             flight_kernel<LPE, MODE_STEP, true><<<h->grid, kThreads, h->smem_bytes, st>>>(h->p, actions, mask, rflags, h->seq);
         else
@@ -1883,6 +1883,7 @@ int cs_flight_create(const cs_flight_cfg* cfg, cs_flight** out) {
         p.lut_meta = h->d_lut_meta;
         p.lut = h->d_lut;
     }
+    h->seq = 1u;
     h->map_use_tma = getenv("CS_MAP_TMA") != nullptr;         // A/B measurement and tests
     if (cfg->variant && !(M & 1) && M >= 10 && M <= 63 && 2 * cfg->view_range + 2 <= 16) {
         // TMA form of the map kernel: tensor map over prob_map viewed as (2M, M/2, E), tiles of 20 positions x H row pairs
@@ -2072,6 +2073,24 @@ int cs_flight_step_host(cs_flight* h, const cs_flight_host_io* io, void* stream)
                                       p.state_len * sizeof(float), E, cudaMemcpyDeviceToHost, st));
     }
     if (!(io->flags & CS_HOST_NO_SYNC)) CS_CUDA(cudaStreamSynchronize(st));
+    return CS_OK;
+}
+
+// Many independent env batches (rollout workers) in one call: batch i is enqueued on streams[i % n_streams] without
+// synchronising, then every stream is synchronised once (unless all ios carry CS_HOST_NO_SYNC).  Saves the per-call
+// overhead of the host language, which dominates a host-buffer step of a few thousand envs.
+int cs_flight_step_host_many(cs_flight* const* envs, const cs_flight_host_io* ios, int32_t count, void* const* streams, int32_t n_streams) {
+    CS_REQUIRE(envs && ios && streams && count >= 0 && n_streams >= 1, "cs_flight_step_host_many: bad argument");
+    bool sync = false;
+    for (int i = 0; i < count; ++i) {
+        cs_flight_host_io io = ios[i];
+        sync |= !(io.flags & CS_HOST_NO_SYNC);
+        io.flags |= CS_HOST_NO_SYNC;
+        const int rc = cs_flight_step_host(envs[i], &io, streams[i % n_streams]);
+        if (rc != CS_OK) return rc;
+    }
+    if (sync)
+        for (int s = 0; s < n_streams && s < count; ++s) CS_CUDA(cudaStreamSynchronize((cudaStream_t)streams[s]));
     return CS_OK;
 }
 

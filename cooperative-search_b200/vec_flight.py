@@ -319,6 +319,61 @@ class _VecFlightBase:
                 hb["obs"].numpy() if want_obs else None, hb["state"].numpy() if want_state else None)
 
 
+class HostStepper:
+    """Host-buffer steps of many independent env batches (rollout workers) with ONE library call per step
+    (cs_flight_step_host_many): batch i runs on stream i % len(streams); results land in each env's pinned
+    host_buffers().  ``actions`` (optional, at construction): pinned uint8 [E,n] tensors, one per env, that hold
+    the actions of every step; by default each env's own host_buffers()["actions"].
+
+    graph=True captures the whole step (per batch: H2D copy of the pinned actions, step kernel, D2H copy of the
+    output slab) into one CUDA graph after a first eager step, so that a step costs one graph launch on the host."""
+
+    def __init__(self, envs, streams, actions=None, graph=False):
+        self.envs = list(envs)
+        self.lib = self.envs[0].lib
+        self.device = self.envs[0].device
+        self.streams = list(streams)
+        n = len(self.envs)
+        self._handles = (C.c_void_p * n)(*[e._h.ptr for e in self.envs])
+        self._streams = (C.c_void_p * len(self.streams))(*[st.cuda_stream for st in self.streams])
+        self._ios = (_lib.FlightHostIO * n)()
+        self._keep = actions
+        for i, e in enumerate(self.envs):
+            hb = e.host_buffers()
+            self._ios[i].actions = (actions[i] if actions is not None else hb["actions"]).data_ptr()
+            self._ios[i].slab = hb["slab"].data_ptr()
+        self._want_graph = bool(graph)
+        self._graph = None
+        self._cap = torch.cuda.Stream(device=self.device) if graph else None
+
+    def _call(self, flags):
+        for i in range(len(self.envs)):
+            self._ios[i].flags = flags
+        _lib.check(self.lib.cs_flight_step_host_many(self._handles, self._ios, len(self.envs), self._streams, len(self.streams)),
+                   "cs_flight_step_host_many")
+
+    def step(self):
+        """One env-step of every batch; returns when all results are in host memory."""
+        base = 0
+        if not self._want_graph:
+            self._call(base)
+            return
+        if self._graph is None:
+            self._call(base)                     # eager first step (warm-up outside the capture)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self._cap):
+                for st in self.streams:
+                    st.wait_stream(self._cap)
+                self._call(base | _lib.CS_HOST_NO_SYNC)
+                for st in self.streams:
+                    self._cap.wait_stream(st)
+            self._graph = g
+            return
+        with torch.cuda.stream(self._cap):
+            self._graph.replay()
+        self._cap.synchronize()
+
+
 class VecFlightEasyEnv(_VecFlightBase):
     """num_envs x FlightSearchEnvEasy (env/flight_env_easy.py)."""
     VARIANT = 0

@@ -51,7 +51,7 @@ typedef enum cs_status {
 
 /* meta words of a flight env (uint32 each), see cs_flight_buffers.dyn */
 enum { CS_META_FOUND = 0, CS_META_NEWFOUND = 1, CS_META_OUT = 2, CS_META_TIME = 3,
-       CS_META_EPISODE = 4, CS_META_FLAGS = 5, CS_META_EPREWARD = 6, CS_META_SENSE = 7,  /* flight variant: (number of the call that last sensed the env << 1) | first-job-parked bit */
+       CS_META_EPISODE = 4, CS_META_FLAGS = 5, CS_META_EPREWARD = 6, CS_META_SENSE = 7,  /* flight variant: non-zero iff the latest step/reset call sensed the env (bit 0: its first job is parked in the side buffer) */
        CS_META_WORDS = 8 };
 #define CS_FLAG_WIN 1u
 #define CS_FLAG_DONE 2u
@@ -170,6 +170,10 @@ typedef struct cs_flight_host_io {
     uint32_t flags;         /* CS_HOST_NO_SYNC */
 } cs_flight_host_io;
 int cs_flight_step_host(cs_flight* env, const cs_flight_host_io* io, void* stream);
+/* cs_flight_step_host for `count` independent env batches (rollout workers) in one call: batch i is enqueued on
+ * streams[i % n_streams]; all streams are synchronised once at the end unless every io carries CS_HOST_NO_SYNC. */
+int cs_flight_step_host_many(cs_flight* const* envs, const cs_flight_host_io* ios, int32_t count, void* const* streams,
+                             int32_t n_streams);
 /* out8 = { slab bytes, offsets of reward, target_find, terminated, win, obs (unused: = slab bytes), state, state row
  * pitch in bytes }.  The slab does not carry obs separately: obs[e][a][0..3] = state row e, floats 4a..4a+3. */
 int cs_flight_slab_layout(const cs_flight* env, uint64_t* out8);

@@ -228,19 +228,58 @@ def test_masked_noop_after_termination_and_partial_reset():
     assert list(cpu(env.meta[:, 4])) == [1, 0, 0, 1, 0, 0, 0, 0]      # episode counters
 
 
-def test_host_buffer_step_equals_device_step():
+@pytest.mark.parametrize("lpe,auto_reset", [(0, True), (0, False), (16, True)])
+def test_host_buffer_step_equals_device_step(lpe, auto_reset):
+    """cs_flight_step_host: the host slab holds exactly what the device buffers hold after every step, also across
+    reset() and device-resident steps in between."""
     import coopsearch_b200 as cs
-    spec = FlightSpec(n_agents=3)
+    spec = FlightSpec(n_agents=3, time_limit=25)
     args = make_args(dict(spec.__dict__))
-    a = cs.VecFlightEasyEnv(args, TEMPLATE, num_envs=50, seed=2)
-    b = cs.VecFlightEasyEnv(args, TEMPLATE, num_envs=50, seed=2)
+    E = 300
+    a = cs.VecFlightEasyEnv(args, TEMPLATE, num_envs=E, seed=2, auto_reset=auto_reset, lanes_per_env=lpe)
+    b = cs.VecFlightEasyEnv(args, TEMPLATE, num_envs=E, seed=2, auto_reset=auto_reset, lanes_per_env=lpe)
     rng = np.random.default_rng(0)
-    for t in range(30):
-        act = rng.integers(0, 3, size=(50, 3), dtype=np.uint8)
+    for t in range(90):
+        act = rng.integers(0, 3, size=(E, 3), dtype=np.uint8)
+        if t in (40, 41):
+            a.step(act); b.step(act)
+            continue
+        if t == 60:
+            a.reset(); b.reset()
         r, term, win = a.step(act)
         hr, hterm, hwin, hobs, hstate = b.step_host(act)
-        assert np.array_equal(cpu(r), hr) and np.array_equal(cpu(term), hterm) and np.array_equal(cpu(win), hwin)
-        assert np.array_equal(cpu(a.get_obs()), hobs) and np.array_equal(cpu(a.get_state()), hstate)
+        where = "step %d" % t
+        assert np.array_equal(cpu(r), hr) and np.array_equal(cpu(term), hterm) and np.array_equal(cpu(win), hwin), where
+        assert np.array_equal(cpu(a.target_find), b.host_buffers()["target_find"].numpy()), where
+        assert np.array_equal(cpu(a.get_obs()), hobs), where
+        assert np.array_equal(cpu(a.get_state()), hstate), where
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_host_stepper_many_batches_one_call(graph):
+    """cs_flight_step_host_many: several env batches stepped from pinned host actions with one library call (or one
+    CUDA-graph launch) equal the same batches stepped one by one on the device."""
+    import coopsearch_b200 as cs
+    spec = FlightSpec(n_agents=3, time_limit=30)
+    args = make_args(dict(spec.__dict__))
+    B, E = 5, 200
+    ref = [cs.VecFlightEasyEnv(args, TEMPLATE, num_envs=E, seed=6, env_id_base=b * E, auto_reset=True) for b in range(B)]
+    envs = [cs.VecFlightEasyEnv(args, TEMPLATE, num_envs=E, seed=6, env_id_base=b * E, auto_reset=True) for b in range(B)]
+    streams = [torch.cuda.Stream() for _ in range(2)]
+    torch.cuda.synchronize()
+    pinned = [torch.empty((E, 3), dtype=torch.uint8).pin_memory() for _ in range(B)]
+    stepper = cs.HostStepper(envs, streams, actions=pinned, graph=graph)
+    rng = np.random.default_rng(1)
+    for t in range(70):
+        for b in range(B):
+            pinned[b].numpy()[...] = rng.integers(0, 3, size=(E, 3), dtype=np.uint8)
+        stepper.step()
+        for b in range(B):
+            r, term, win = ref[b].step(pinned[b].cuda())
+            hb = envs[b].host_buffers()
+            assert np.array_equal(cpu(r), hb["reward"].numpy()) and np.array_equal(cpu(term), hb["terminated"].numpy())
+            assert np.array_equal(cpu(ref[b].get_state()), hb["state"].numpy()), "batch %d step %d" % (b, t)
+            assert np.array_equal(cpu(ref[b].get_obs()), hb["obs"].numpy())
 
 
 def test_reference_error_behaviour():

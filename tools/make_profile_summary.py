@@ -1,14 +1,15 @@
 """Turns the ncu reports under gpurun_out/ into the small committed summaries under profiles/.
-usage: python tools/make_profile_summary.py r01"""
+usage: python tools/make_profile_summary.py r01 [output dir, default profiles/]
+(on the GPU box: write into gpurun_out/profiles_<tag>/ and delete the .ncu-rep files, which exceed the copy-back limit)"""
 import csv, json, os, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
 src = os.path.join(ROOT, "gpurun_out")
-dst = os.path.join(ROOT, "profiles")
+dst = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "profiles")
 os.makedirs(dst, exist_ok=True)
 traffic = {}
-for wl in ("c2", "c3", "c4", "c5"):
+for wl in ("c2", "c2w", "c3", "c4", "c4_step", "c5"):
     rep = os.path.join(src, "prof_%s.ncu-rep" % wl)
     if os.path.exists(rep):
         txt = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), rep], capture_output=True, text=True).stdout
@@ -39,5 +40,8 @@ for wl in ("c2", "c3", "c4", "c5"):
             fh.write("# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised launches)\nid,kernel,duration,unit\n")
             for r in out_rows:
                 fh.write(",".join('"%s"' % x for x in r) + "\n")
+if "c4_step" in traffic and "c4" in traffic:
+    traffic["c4_map_kernel"] = traffic["c4"]
+    traffic["c4"] = traffic["c4"] + traffic.pop("c4_step")      # one env-step = step kernel + map kernel
 json.dump(traffic, open(os.path.join(dst, "traffic.json"), "w"), indent=1)
 print("wrote", sorted(os.listdir(dst)))
