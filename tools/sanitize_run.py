@@ -9,8 +9,17 @@ import golden_util as gu
 def fargs(n, M=50, R=7, T=25, am=0):
     return types.SimpleNamespace(env="x", map_size=M, target_num=15, target_mode=0, agent_mode=am, n_agents=n, view_range=R,
                                  time_limit=T, detect_prob=0.9, safe_dist=1, agent_velocity=1, force_dist=3)
-for cls, n, M in ((cs.VecFlightEasyEnv, 3, 50), (cs.VecFlightEasyEnv, 5, 12), (cs.VecFlightEnv, 3, 50), (cs.VecFlightEnv, 2, 51), (cs.VecFlightEnv, 2, 70)):
-    env = cls(fargs(n, M=M, R=min(7, M // 3)), gu.TEMPLATE, num_envs=37, seed=1, auto_reset=True, count_touched=True)
+# (class, agents, map size, lanes_per_env: 0 = thread-per-env kernel, 16 = lane-per-agent kernel, TMA map kernel?)
+for cls, n, M, lpe, tma in ((cs.VecFlightEasyEnv, 3, 50, 0, 0), (cs.VecFlightEasyEnv, 5, 12, 0, 0), (cs.VecFlightEasyEnv, 3, 50, 16, 0),
+                            (cs.VecFlightEnv, 3, 50, 0, 0), (cs.VecFlightEnv, 3, 50, 0, 1), (cs.VecFlightEnv, 5, 50, 16, 0),
+                            (cs.VecFlightEnv, 2, 51, 0, 0), (cs.VecFlightEnv, 2, 70, 0, 0)):
+    if tma:
+        os.environ["CS_MAP_TMA"] = "1"
+    else:
+        os.environ.pop("CS_MAP_TMA", None)
+    if os.environ.get("CS_SAN_K"):
+        os.environ["CS_TPE_K"] = os.environ["CS_SAN_K"]
+    env = cls(fargs(n, M=M, R=min(7, M // 3)), gu.TEMPLATE, num_envs=37, seed=1, auto_reset=True, count_touched=not tma, lanes_per_env=lpe)
     env.step_random(40)
     acts = torch.randint(0, 3, (37, n), dtype=torch.uint8, device="cuda")
     env.step(acts)
