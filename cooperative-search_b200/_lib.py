@@ -73,6 +73,14 @@ class SearchHostIO(C.Structure):
                 ("state", C.c_void_p), ("avail", C.c_void_p)]
 
 
+EPISODE_KEYS = ("o", "s", "u", "r", "avail_u", "o_next", "s_next", "avail_u_next", "u_onehot", "padded", "terminated",
+                "episode_reward", "win_tag", "targets_find", "length")
+
+
+class EpisodeBuffers(C.Structure):      # mirrors cs_episode_buffers
+    _fields_ = [(k, C.c_void_p) for k in EPISODE_KEYS]
+
+
 # name -> (restype, argtypes); every symbol include/coopsearch.h declares
 SIGNATURES = {
     "cs_version": (C.c_int, []),
@@ -98,6 +106,8 @@ SIGNATURES = {
     "cs_flight_slab_layout": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "cs_flight_step_host_many": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(FlightHostIO), C.c_int32, C.POINTER(C.c_void_p), C.c_int32]),
     "cs_flight_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_void_p]),
+    "cs_flight_record_begin": (C.c_int, [C.c_void_p, C.POINTER(EpisodeBuffers), C.c_int32, C.c_void_p]),
+    "cs_flight_record": (C.c_int, [C.c_void_p, C.POINTER(EpisodeBuffers), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "cs_search_create": (C.c_int, [C.POINTER(SearchCfg), C.POINTER(C.c_void_p)]),
     "cs_search_destroy": (None, [C.c_void_p]),
     "cs_search_buffers_get": (C.c_int, [C.c_void_p, C.POINTER(SearchBuffers)]),

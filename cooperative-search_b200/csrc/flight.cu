@@ -1520,6 +1520,69 @@ __global__ void flight_obs_full_scalar_kernel(const float* __restrict__ map, con
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Episode-batch writer: the padded 11-array layout RolloutWorker.generate_episode builds one env and one step at a
+// time (common/rollout.py:43-132), for all envs of the handle, on the device.
+//   begin : every array <- the padding of :105-116 (zeros, padded = terminated = 1); o[:,0], s[:,0] <- obs / state
+//   record: after step t, for the envs that took it (time_step == t+1):  u, u_onehot, r, terminated, padded = 0,
+//           avail_u[t] = avail_u_next[t] = 1, o_next[t] = s_next[t] = the new obs / state, and the same rows into
+//           o[t+1], s[t+1] unless the episode ended (:79-97: "last obs" is only ever an *_next row)
+// One thread per (env, output element); rows of different envs are contiguous, so the copies are coalesced.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) flight_record_begin_kernel(const FlightParams p, cs_episode_buffers b, int T) {
+    const int n = p.n, S = p.state_len, O = 4 * n, A = 3 * n;
+    const int per_env = O + S;
+    const long long total = (long long)p.E * per_env;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int e = (int)(idx / per_env), k = (int)(idx - (long long)e * per_env);
+        if (k < O) b.o[((size_t)e * T) * O + k] = p.obs[(size_t)e * O + k];
+        else b.s[((size_t)e * T) * S + (k - O)] = p.state[(size_t)e * p.state_stride + (k - O)];
+    }
+    (void)A;
+}
+
+__global__ void __launch_bounds__(256) flight_record_kernel(const FlightParams p, cs_episode_buffers b, int t, int T,
+                                                            const uint8_t* __restrict__ actions) {
+    const int n = p.n, S = p.state_len, O = 4 * n, A = 3 * n;
+    const int per_env = O + S + 1;
+    const long long total = (long long)p.E * per_env;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int e = (int)(idx / per_env), k = (int)(idx - (long long)e * per_env);
+        const uint32_t* mt = reinterpret_cast<const uint32_t*>(p.dyn + (size_t)e * p.rec + p.meta_off);
+        if (mt[CS_META_TIME] != (uint32_t)(t + 1)) continue;           // this env did not take step t (episode over)
+        const bool over = (mt[CS_META_FLAGS] & CS_FLAG_DONE) != 0;
+        const size_t row = (size_t)e * T + t;
+        if (k < O) {
+            const float v = p.obs[(size_t)e * O + k];
+            b.o_next[row * O + k] = v;
+            if (!over && t + 1 < T) b.o[(row + 1) * O + k] = v;
+        } else if (k < O + S) {
+            const float v = p.state[(size_t)e * p.state_stride + (k - O)];
+            b.s_next[row * S + (k - O)] = v;
+            if (!over && t + 1 < T) b.s[(row + 1) * S + (k - O)] = v;
+        } else {
+            for (int a = 0; a < n; ++a) {
+                const uint8_t act = actions[(size_t)e * n + a];
+                b.u[row * n + a] = act;
+                for (int c = 0; c < 3; ++c) {
+                    b.u_onehot[row * A + 3 * a + c] = (c == act) ? 1 : 0;
+                    b.avail_u[row * A + 3 * a + c] = 1;                // get_avail_agent_actions: ones (flight_env_easy.py:184-188)
+                    b.avail_u_next[row * A + 3 * a + c] = 1;
+                }
+            }
+            b.r[row] = p.reward[e];
+            b.terminated[row] = p.terminated[e];
+            b.padded[row] = 0;
+            if (over || t + 1 == T) {                                   // episode summary (rollout.py:64,79,137-140)
+                b.episode_reward[e] = __uint_as_float(mt[CS_META_EPREWARD]);
+                b.win_tag[e] = (over && (mt[CS_META_FLAGS] & CS_FLAG_WIN)) ? 1 : 0;
+                b.targets_find[e] = p.target_find[e];
+                b.length[e] = t + 1;
+            }
+        }
+    }
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -2091,6 +2154,47 @@ int cs_flight_step_host_many(cs_flight* const* envs, const cs_flight_host_io* io
     }
     if (sync)
         for (int s = 0; s < n_streams && s < count; ++s) CS_CUDA(cudaStreamSynchronize((cudaStream_t)streams[s]));
+    return CS_OK;
+}
+
+// Episode-batch writer (see flight_record_kernel).  Buffers are caller-owned device memory.
+int cs_flight_record_begin(cs_flight* h, const cs_episode_buffers* b, int32_t T, void* stream) {
+    CS_REQUIRE(h && b && T >= 1, "cs_flight_record_begin: bad argument");
+    const FlightParams& p = h->p;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t ET = (size_t)p.E * T, O = 4 * (size_t)p.n, S = (size_t)p.state_len, A = 3 * (size_t)p.n;
+    CS_CUDA(cudaSetDevice(h->cfg.device));
+    CS_CUDA(cudaMemsetAsync(b->o, 0, ET * O * sizeof(float), st));
+    CS_CUDA(cudaMemsetAsync(b->s, 0, ET * S * sizeof(float), st));
+    CS_CUDA(cudaMemsetAsync(b->o_next, 0, ET * O * sizeof(float), st));
+    CS_CUDA(cudaMemsetAsync(b->s_next, 0, ET * S * sizeof(float), st));
+    CS_CUDA(cudaMemsetAsync(b->u, 0, ET * p.n, st));
+    CS_CUDA(cudaMemsetAsync(b->u_onehot, 0, ET * A, st));
+    CS_CUDA(cudaMemsetAsync(b->avail_u, 0, ET * A, st));
+    CS_CUDA(cudaMemsetAsync(b->avail_u_next, 0, ET * A, st));
+    CS_CUDA(cudaMemsetAsync(b->r, 0, ET * sizeof(float), st));
+    CS_CUDA(cudaMemsetAsync(b->padded, 1, ET, st));                       // rollout.py:115-116
+    CS_CUDA(cudaMemsetAsync(b->terminated, 1, ET, st));
+    CS_CUDA(cudaMemsetAsync(b->episode_reward, 0, (size_t)p.E * sizeof(float), st));
+    CS_CUDA(cudaMemsetAsync(b->win_tag, 0, (size_t)p.E, st));
+    CS_CUDA(cudaMemsetAsync(b->targets_find, 0, (size_t)p.E * sizeof(int32_t), st));
+    CS_CUDA(cudaMemsetAsync(b->length, 0, (size_t)p.E * sizeof(int32_t), st));
+    const long long total = (long long)p.E * (O + S);
+    const int grid = (int)((total + 255) / 256 < (long long)CS_NUM_SMS_B200 * 8 ? (total + 255) / 256 : CS_NUM_SMS_B200 * 8);
+    flight_record_begin_kernel<<<grid, 256, 0, st>>>(p, *b, T);
+    cs_count_launch(1);
+    CS_CUDA(cudaGetLastError());
+    return CS_OK;
+}
+
+int cs_flight_record(cs_flight* h, const cs_episode_buffers* b, int32_t t, int32_t T, const uint8_t* d_actions, void* stream) {
+    CS_REQUIRE(h && b && d_actions && t >= 0 && t < T, "cs_flight_record: bad argument");
+    const FlightParams& p = h->p;
+    const long long total = (long long)p.E * (4 * p.n + p.state_len + 1);
+    const int grid = (int)((total + 255) / 256 < (long long)CS_NUM_SMS_B200 * 8 ? (total + 255) / 256 : CS_NUM_SMS_B200 * 8);
+    flight_record_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, *b, t, T, d_actions);
+    cs_count_launch(1);
+    CS_CUDA(cudaGetLastError());
     return CS_OK;
 }
 

@@ -319,6 +319,44 @@ class _VecFlightBase:
                 hb["obs"].numpy() if want_obs else None, hb["state"].numpy() if want_state else None)
 
 
+def generate_episodes(env, actions=None, targets=None, generator=None):
+    """RolloutWorker.generate_episode (common/rollout.py:22-141) for every env of ``env`` at once: reset, then up to
+    episode_limit steps, into the padded episode arrays of :118-132 with a leading num_envs axis (device tensors;
+    float32 for o/s/r/o_next/s_next, uint8 for the rest).  ``actions``: [T,E,n] integers, or None for the
+    uniform-random policy (alg=random, agent/agent.py:34-36) drawn with ``generator``.  ``targets``: optional
+    [E,m,2] target layout to inject at the reset.  The env must not auto-reset: a finished env is a masked no-op and
+    keeps its padding rows.  Returns (episode dict, episode_reward [E], win_tag [E], targets_find [E])."""
+    if env.auto_reset:
+        raise CoopSearchError("generate_episodes needs auto_reset=False (rollout.py:43: a finished env is not stepped again)")
+    E, n, S, T, dev = env.num_envs, env.n_agents, env.state_shape, env.time_limit, env.device
+    A = env.n_actions
+    if actions is None:
+        actions = torch.randint(0, A, (T, E, n), dtype=torch.uint8, device=dev, generator=generator)
+    else:
+        actions = torch.as_tensor(np.asarray(actions) if not torch.is_tensor(actions) else actions).to(device=dev, dtype=torch.uint8)
+        if tuple(actions.shape) != (T, E, n):
+            raise CoopSearchError("actions must have shape (episode_limit, num_envs, n_agents)")
+    actions = actions.contiguous()
+    env.reset(targets=targets)
+    f32 = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+    u8 = lambda *shape: torch.empty(shape, dtype=torch.uint8, device=dev)
+    ep = {"o": f32(E, T, n, 4), "s": f32(E, T, S), "u": u8(E, T, n, 1), "r": f32(E, T, 1), "avail_u": u8(E, T, n, A),
+          "o_next": f32(E, T, n, 4), "s_next": f32(E, T, S), "avail_u_next": u8(E, T, n, A), "u_onehot": u8(E, T, n, A),
+          "padded": u8(E, T, 1), "terminated": u8(E, T, 1)}
+    summary = {"episode_reward": f32(E), "win_tag": u8(E), "targets_find": torch.empty(E, dtype=torch.int32, device=dev),
+               "length": torch.empty(E, dtype=torch.int32, device=dev)}
+    bufs = _lib.EpisodeBuffers(**{k: v.data_ptr() for k, v in {**ep, **summary}.items()})
+    with torch.cuda.device(dev):
+        _lib.check(env.lib.cs_flight_record_begin(env._h.ptr, C.byref(bufs), T, env._stream()), "cs_flight_record_begin")
+        for t in range(T):
+            a = actions[t]
+            _lib.check(env.lib.cs_flight_step(env._h.ptr, C.c_void_p(a.data_ptr()), env._stream()), "cs_flight_step")
+            _lib.check(env.lib.cs_flight_record(env._h.ptr, C.byref(bufs), t, T, C.c_void_p(a.data_ptr()), env._stream()),
+                       "cs_flight_record")
+    ep["length"] = summary["length"]
+    return ep, summary["episode_reward"], summary["win_tag"], summary["targets_find"]
+
+
 class HostStepper:
     """Host-buffer steps of many independent env batches (rollout workers) with ONE library call per step
     (cs_flight_step_host_many): batch i runs on stream i % len(streams); results land in each env's pinned

@@ -180,6 +180,30 @@ int cs_flight_slab_layout(const cs_flight* env, uint64_t* out8);
 /* Copies the stats vector to host (synchronises the stream). */
 int cs_flight_stats(cs_flight* env, double* h_out, void* stream);
 
+/* Episode-batch writer: the padded episode arrays RolloutWorker.generate_episode builds (common/rollout.py:43-132),
+ * for every env of the handle, in caller-owned DEVICE memory.  T = episode_limit; A = n_actions = 3.
+ * Usage: reset -> cs_flight_record_begin -> for t in 0..T-1: cs_flight_step(actions_t); cs_flight_record(t, actions_t)
+ * on a handle WITHOUT auto_reset (a finished env is a masked no-op and keeps its padding rows). */
+typedef struct cs_episode_buffers {
+    float* o;               /* [E][T][n][4]       obs before the step              (rollout.py:45,66)   */
+    float* s;               /* [E][T][4n+3m]      state before the step            (:46,67)             */
+    uint8_t* u;             /* [E][T][n][1]       actions                          (:68)                */
+    float* r;               /* [E][T][1]          reward                           (:71)                */
+    uint8_t* avail_u;       /* [E][T][n][A]                                        (:70)                */
+    float* o_next;          /* [E][T][n][4]       obs after the step               (:82-86)             */
+    float* s_next;          /* [E][T][4n+3m]                                                            */
+    uint8_t* avail_u_next;  /* [E][T][n][A]                                        (:90-97)             */
+    uint8_t* u_onehot;      /* [E][T][n][A]                                        (:57-58,69)          */
+    uint8_t* padded;        /* [E][T][1]          1 past the end of the episode    (:73,115)            */
+    uint8_t* terminated;    /* [E][T][1]          env flag; 1 in the padding       (:72,116)            */
+    float* episode_reward;  /* [E]                                                 (:74)                */
+    uint8_t* win_tag;       /* [E]                terminated and win               (:64)                */
+    int32_t* targets_find;  /* [E]                                                 (:79)                */
+    int32_t* length;        /* [E]                steps taken                                            */
+} cs_episode_buffers;
+int cs_flight_record_begin(cs_flight* env, const cs_episode_buffers* bufs, int32_t T, void* stream);
+int cs_flight_record(cs_flight* env, const cs_episode_buffers* bufs, int32_t t, int32_t T, const uint8_t* d_actions, void* stream);
+
 /* ===================================================================================
  * search_env  (env/search_env.py)
  * =================================================================================== */
