@@ -36,6 +36,7 @@ class FlightCfg(C.Structure):
 
 class FlightBuffers(C.Structure):
     _fields_ = [
+        ("dyn_row_stride", C.c_int64), ("dyn_env_stride", C.c_int64), ("tgt_row_stride", C.c_int64), ("tgt_env_stride", C.c_int64),
         ("dyn", C.c_void_p), ("dyn_doubles", C.c_int32), ("yaw_off", C.c_int32), ("meta_off", C.c_int32),
         ("state_len", C.c_int32), ("state_stride", C.c_int32), ("tgt", C.c_void_p), ("obs", C.c_void_p), ("state", C.c_void_p),
         ("reward", C.c_void_p), ("terminated", C.c_void_p), ("win", C.c_void_p), ("target_find", C.c_void_p),

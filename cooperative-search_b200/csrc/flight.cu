@@ -32,6 +32,7 @@ struct FlightParams {
     int variant, auto_reset, agent_mode, target_mode, count_touched;
     // per-env record geometry (doubles)
     int rec, yaw_off, meta_off, state_len;
+    long long dyn_rs, dyn_es, tgt_rs, tgt_es;   // strides (in doubles) of a row / an env in dyn and tgt
     int state_stride;            // floats per state row in HBM (state_len rounded up to a multiple of 4)
     // per-warp shared-memory scratch of the step kernel (doubles): the heading-table index
     int s_lut, s_warp;
@@ -63,6 +64,109 @@ struct FlightParams {
     double inv_turn;             // 18/pi
     double cos0, sin0;           // cos/sin of the start heading of agent_mode, from the host libm
     double lin[CS_MAX_AGENTS];   // i*map_size/(n-1) (map_size/2 for n == 1), flight_env_easy.py:140-143
+};
+
+// ------------------------------------------------------------------------------------------------
+// State layout, chosen per handle (cs_flight_create): element (row r, env e) of dyn lives at dyn[r*dyn_rs + e*dyn_es],
+// of tgt at tgt[r*tgt_rs + e*tgt_es].  Rows of dyn: 0..2n-1 = x0, y0, x1, y1, ..., 2n..3n-1 the headings,
+// meta_off..meta_off+3 the 8 uint32 meta words (two per row); rows of tgt: 2j = x of target j, 2j+1 = y.
+//   * structure of arrays (rs = E, es = 1), from 32768 envs per handle (= one thread per env, flight_tpe_kernel<N, 1>): with one thread per env every load and store
+//     of a warp is one contiguous 256-byte run (the record layout cost the thread-per-env kernel ~1100 L1 wavefronts
+//     per warp and bounded it: 1M envs 5.05e9 -> 5.5e9, 65536 envs 2.67e9 -> 2.9e9 env-steps/s);
+//   * record per env (rs = 1, es = rows), below: a launch of a few thousand envs is latency-bound and 12 % faster
+//     when a warp's state is a handful of consecutive lines instead of 43 rows 32 KB apart.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double* dyn_at(const FlightParams& p, int row, int e) {
+    return p.dyn + (size_t)row * p.dyn_rs + (size_t)e * p.dyn_es;
+}
+// record layout (row stride 1): pairs of rows are adjacent and 16-byte aligned -> one 16-byte access
+__device__ __forceinline__ double2 xy_ld(const FlightParams& p, int a, int e) {
+    const double* q = dyn_at(p, 2 * a, e);
+    if (p.dyn_rs == 1) return *reinterpret_cast<const double2*>(q);
+    return make_double2(q[0], q[p.dyn_rs]);
+}
+__device__ __forceinline__ void xy_st(const FlightParams& p, int a, int e, double x, double y) {
+    double* q = dyn_at(p, 2 * a, e);
+    if (p.dyn_rs == 1) { *reinterpret_cast<double2*>(q) = make_double2(x, y); return; }
+    q[0] = x;
+    q[p.dyn_rs] = y;
+}
+__device__ __forceinline__ double2 tgt_ld(const FlightParams& p, int j, int e) {
+    const double* t = p.tgt + (size_t)(2 * j) * p.tgt_rs + (size_t)e * p.tgt_es;
+    if (p.tgt_rs == 1) return *reinterpret_cast<const double2*>(t);
+    return make_double2(t[0], t[p.tgt_rs]);
+}
+__device__ __forceinline__ void tgt_st(const FlightParams& p, int j, int e, double2 v) {
+    double* t = p.tgt + (size_t)(2 * j) * p.tgt_rs + (size_t)e * p.tgt_es;
+    if (p.tgt_rs == 1) { *reinterpret_cast<double2*>(t) = v; return; }
+    t[0] = v.x;
+    t[p.tgt_rs] = v.y;
+}
+__device__ __forceinline__ uint2* meta_at(const FlightParams& p, int pair, int e) {       // words 2*pair, 2*pair+1
+    return reinterpret_cast<uint2*>(dyn_at(p, p.meta_off + pair, e));
+}
+__device__ __forceinline__ void meta_ld(const FlightParams& p, int e, uint4* m0, uint4* m1) {
+    if (p.dyn_rs == 1) {
+        const uint4* mp = reinterpret_cast<const uint4*>(dyn_at(p, p.meta_off, e));
+        *m0 = mp[0]; *m1 = mp[1];
+        return;
+    }
+    const uint2 a = *meta_at(p, 0, e), b = *meta_at(p, 1, e), c = *meta_at(p, 2, e), d = *meta_at(p, 3, e);
+    *m0 = make_uint4(a.x, a.y, b.x, b.y);
+    *m1 = make_uint4(c.x, c.y, d.x, d.y);
+}
+__device__ __forceinline__ void meta_st(const FlightParams& p, int e, uint4 m0, uint4 m1) {
+    if (p.dyn_rs == 1) {
+        uint4* mp = reinterpret_cast<uint4*>(dyn_at(p, p.meta_off, e));
+        mp[0] = m0; mp[1] = m1;
+        return;
+    }
+    *meta_at(p, 0, e) = make_uint2(m0.x, m0.y);
+    *meta_at(p, 1, e) = make_uint2(m0.z, m0.w);
+    *meta_at(p, 2, e) = make_uint2(m1.x, m1.y);
+    *meta_at(p, 3, e) = make_uint2(m1.z, m1.w);
+}
+
+// The same accessors with the layout known at compile time (thread-per-env kernel: structure of arrays with one thread
+// per env, record per env with 4 threads per env): no stride arithmetic, 16-byte accesses in the record layout.
+template <bool SOA>
+struct Lay {
+    static __device__ __forceinline__ double2 xy_ld(const FlightParams& p, int a, int e) {
+        if (SOA) { const double* q = p.dyn + (size_t)(2 * a) * p.E + e; return make_double2(q[0], q[p.E]); }
+        return *reinterpret_cast<const double2*>(p.dyn + (size_t)e * p.rec + 2 * a);
+    }
+    static __device__ __forceinline__ void xy_st(const FlightParams& p, int a, int e, double x, double y) {
+        if (SOA) { double* q = p.dyn + (size_t)(2 * a) * p.E + e; q[0] = x; q[p.E] = y; return; }
+        *reinterpret_cast<double2*>(p.dyn + (size_t)e * p.rec + 2 * a) = make_double2(x, y);
+    }
+    static __device__ __forceinline__ double* yaw_at(const FlightParams& p, int a, int e) {
+        return SOA ? p.dyn + (size_t)(p.yaw_off + a) * p.E + e : p.dyn + (size_t)e * p.rec + p.yaw_off + a;
+    }
+    static __device__ __forceinline__ double2 tgt_ld(const FlightParams& p, int j, int e) {
+        if (SOA) { const double* t = p.tgt + (size_t)(2 * j) * p.E + e; return make_double2(t[0], t[p.E]); }
+        return *reinterpret_cast<const double2*>(p.tgt + ((size_t)e * p.m + j) * 2);
+    }
+    static __device__ __forceinline__ void meta_ld(const FlightParams& p, int e, uint4* m0, uint4* m1) {
+        if (SOA) {
+            const uint2* q = reinterpret_cast<const uint2*>(p.dyn + (size_t)p.meta_off * p.E + e);
+            const uint2 a = q[0], b = q[p.E], c = q[2 * (size_t)p.E], d = q[3 * (size_t)p.E];
+            *m0 = make_uint4(a.x, a.y, b.x, b.y);
+            *m1 = make_uint4(c.x, c.y, d.x, d.y);
+            return;
+        }
+        const uint4* mp = reinterpret_cast<const uint4*>(p.dyn + (size_t)e * p.rec + p.meta_off);
+        *m0 = mp[0]; *m1 = mp[1];
+    }
+    static __device__ __forceinline__ void meta_st(const FlightParams& p, int e, uint4 m0, uint4 m1) {
+        if (SOA) {
+            uint2* q = reinterpret_cast<uint2*>(p.dyn + (size_t)p.meta_off * p.E + e);
+            q[0] = make_uint2(m0.x, m0.y); q[p.E] = make_uint2(m0.z, m0.w);
+            q[2 * (size_t)p.E] = make_uint2(m1.x, m1.y); q[3 * (size_t)p.E] = make_uint2(m1.z, m1.w);
+            return;
+        }
+        uint4* mp = reinterpret_cast<uint4*>(p.dyn + (size_t)e * p.rec + p.meta_off);
+        mp[0] = m0; mp[1] = m1;
+    }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -222,15 +326,14 @@ __device__ __forceinline__ int map_job_load(const FlightParams& p, int e, int jo
         nh = ph[0];
         for (int k = lane; k < nh; k += GL) hit[k] = ph[1 + k];
     } else {
-        const double* rec = p.dyn + (size_t)e * p.rec;
         for (int a = lane; a < n; a += GL) {
-            const double2 v = *reinterpret_cast<const double2*>(rec + 2 * a);
+            const double2 v = xy_ld(p, a, e);
             xy[2 * a] = v.x; xy[2 * a + 1] = v.y;
         }
         nh = __popc(newf);
         for (int j = lane; j < m; j += GL)
             if ((newf >> j) & 1u) {
-                const double2 t = *reinterpret_cast<const double2*>(p.tgt + ((size_t)e * m + j) * 2);
+                const double2 t = tgt_ld(p, j, e);
                 hit[__popc(newf & ((1u << j) - 1u))] = hit_cell(p, t.x, t.y);
             }
     }
@@ -278,8 +381,8 @@ __global__ void __launch_bounds__(kMapThreads, CS_MAP_MIN_CTAS) flight_map_kerne
     const int e_raw = blockIdx.x * kMapEnvsPerCta + grp;
     const int e = min(e_raw, p.E - 1);
     const int n = p.n, M = p.M;
-    const uint4* mp = reinterpret_cast<const uint4*>(p.dyn + (size_t)e * p.rec + p.meta_off);
-    const uint4 m0 = mp[0], m1 = mp[1];
+    uint4 m0, m1;
+    meta_ld(p, e, &m0, &m1);
     const bool sensed = e_raw < p.E && (m1.w >> 1) == seq;  // else: not sensed by this call (finished env, masked reset)
     if (!__any_sync(FULL, sensed)) return;
 
@@ -474,8 +577,8 @@ __global__ void __launch_bounds__(kMapThreads, 7) flight_map_tma_kernel(const __
     const int e_raw = blockIdx.x * kMapEnvsPerCta + grp;
     const int e = min(e_raw, p.E - 1);
     const int n = p.n, M = p.M;
-    const uint4* mp = reinterpret_cast<const uint4*>(p.dyn + (size_t)e * p.rec + p.meta_off);
-    const uint4 m0 = mp[0], m1 = mp[1];
+    uint4 m0, m1;
+    meta_ld(p, e, &m0, &m1);
     const bool sensed = e_raw < p.E && (m1.w >> 1) == seq;  // else: not sensed by this call (finished env, masked reset)
     if (!__any_sync(FULL, sensed)) return;
 
@@ -659,9 +762,8 @@ __global__ void __launch_bounds__(kMapThreads) flight_map_wide_kernel(const __gr
     const int e = blockIdx.x * (kMapThreads / 32) + warp;
     if (e >= p.E) return;
     const int n = p.n, M = p.M;
-    const double* rec = p.dyn + (size_t)e * p.rec;
-    const uint4* mp = reinterpret_cast<const uint4*>(rec + p.meta_off);
-    const uint4 m0 = mp[0], m1 = mp[1];
+    uint4 m0, m1;
+    meta_ld(p, e, &m0, &m1);
     if ((m1.w >> 1) != seq) return;
     unsigned long long* S = msm + (size_t)warp * p.ms_warp;
     int4* box = reinterpret_cast<int4*>(S + p.ms_box);
@@ -761,23 +863,21 @@ __global__ void __launch_bounds__(kThreads, 8) flight_kernel(const __grid_consta
 #define GBALLOT(pred) ((__ballot_sync(FULL, (pred)) >> gbase) & GBITS)
 
     // ---- every load of the step, issued before anything is consumed ----------------------------------------
-    double* rec = p.dyn + (size_t)e * p.rec;
     double ax = 0.0, ay = 0.0, yaw = 0.0, tx = 0.0, ty = 0.0;
     uint4 m0 = make_uint4(0, 0, 0, 0), m1 = make_uint4(0, 0, 0, 0);
     int act = 0;
     if (is_agent) {
-        const double2 v = *reinterpret_cast<const double2*>(rec + 2 * lane);
+        const double2 v = xy_ld(p, lane, e);
         ax = v.x; ay = v.y;
-        yaw = rec[p.yaw_off + lane];
+        yaw = *dyn_at(p, p.yaw_off + lane, e);
         if (MODE == MODE_STEP && actions != nullptr) act = actions[(size_t)e * n + lane];
     }
     if (is_tgt) {
-        const double2 v = *reinterpret_cast<const double2*>(p.tgt + ((size_t)e * m + lane) * 2);
+        const double2 v = tgt_ld(p, lane, e);
         tx = v.x; ty = v.y;
     }
     if (active) {
-        const uint4* mp = reinterpret_cast<const uint4*>(rec + p.meta_off);      // same address for the whole group
-        m0 = mp[0]; m1 = mp[1];
+        meta_ld(p, e, &m0, &m1);                                               // same addresses for the whole group
     }
     if (MODE == MODE_STEP) {
         const longlong2 v0 = __ldg(p.lut_meta + lane32);
@@ -990,8 +1090,8 @@ __global__ void __launch_bounds__(kThreads, 8) flight_kernel(const __grid_consta
     // ---- outputs, straight from registers -------------------------------------------------------------------
     if (active && emit) {
         if (is_agent) {
-            *reinterpret_cast<double2*>(rec + 2 * lane) = make_double2(ax, ay);
-            rec[p.yaw_off + lane] = yaw;
+            xy_st(p, lane, e, ax, ay);
+            *dyn_at(p, p.yaw_off + lane, e) = yaw;
             // get_obs row = agent part of get_state (flight_env_easy.py:218-221, :192-193)
             const float4 o = make_float4((float)((ax - p.half_M) * p.inv_half), (float)((ay - p.half_M) * p.inv_half),
                                          (float)c_h, (float)s_h);
@@ -999,9 +1099,8 @@ __global__ void __launch_bounds__(kThreads, 8) flight_kernel(const __grid_consta
             reinterpret_cast<float4*>(p.state + (size_t)e * p.state_stride)[lane] = o;
         }
         if (lane == 0) {
-            uint4* mp = reinterpret_cast<uint4*>(rec + p.meta_off);
-            mp[0] = make_uint4(found, newf_last, outmask, time_step);
-            mp[1] = make_uint4(episode, flags, __float_as_uint(ep_reward), MAP ? (sense_word | prejob) : 0u);
+            meta_st(p, e, make_uint4(found, newf_last, outmask, time_step),
+                    make_uint4(episode, flags, __float_as_uint(ep_reward), MAP ? (sense_word | prejob) : 0u));
         }
         if (is_tgt) {
             // target part of the state row (:201-211): rewritten in full after a reset, otherwise only the 'find'
@@ -1014,11 +1113,11 @@ __global__ void __launch_bounds__(kThreads, 8) flight_kernel(const __grid_consta
             } else if ((newf_last >> lane) & 1u) {
                 srow[2] = 1.0f;
             }
-            if (tgt_dirty) *reinterpret_cast<double2*>(p.tgt + ((size_t)e * m + lane) * 2) = make_double2(tx, ty);
+            if (tgt_dirty) tgt_st(p, lane, e, make_double2(tx, ty));
         }
     }
     if (MAP && active && !emit && lane == 0 && m1.w != 0u)
-        reinterpret_cast<uint32_t*>(rec + p.meta_off)[CS_META_SENSE] = 0u;      // not sensed by THIS call: no job for the map kernel
+        meta_at(p, 3, e)->y = 0u;      // not sensed by THIS call: no job for the map kernel
     if (active && have_result && lane == 0) {
         p.reward[e] = res_reward;
         p.terminated[e] = (uint8_t)res_term;
@@ -1077,6 +1176,7 @@ __global__ void __launch_bounds__(kTpeThreads, CS_TPE_MIN_CTAS) flight_tpe_kerne
     constexpr unsigned FULL = 0xffffffffu;
     __shared__ longlong2 lutm[40];
     static_assert(K == 1 || K == 2 || K == 4, "K");
+    using L = Lay<K == 1>;                                              // one thread per env <-> structure of arrays (cs_flight_create)
     constexpr uint32_t MINE = 0xFFFFFFFFu / ((1u << K) - 1u);          // targets j with j % K == 0
     const int tid = threadIdx.x, lane32 = tid & 31, kk = tid % K;       // kk: which of the env's K threads this is
     const int e_raw = (blockIdx.x * kTpeThreads + tid) / K;
@@ -1090,25 +1190,28 @@ __global__ void __launch_bounds__(kTpeThreads, CS_TPE_MIN_CTAS) flight_tpe_kerne
     }
 
     // ---- state of this env ---------------------------------------------------------------------------------
-    double* rec = p.dyn + (size_t)e * p.rec;
-    const double* tg = p.tgt + (size_t)e * m * 2;
     if (MODE == MODE_STEP) {
-        // the targets are needed after the agent phase: start pulling this env's lines now, together with the state
-        // loads below, so that the sensing loop finds them in L1 (one HBM round trip for the whole step, not two)
-        const char* tb = reinterpret_cast<const char*>(tg);
-        for (int off = 128 * kk; off < m * 16; off += 128 * K) asm volatile("prefetch.global.L1 [%0];" ::"l"(tb + off));
-        if (kk == K - 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(tb + m * 16 - 1));
+        // the targets are needed after the agent phase: start pulling this warp's target rows into L1 now, together with
+        // the state loads below, so that the sensing loop pays no further HBM round trip
+        if (K == 1) {
+            const double* tp = p.tgt + e;
+            for (int r = 0; r < 2 * m; ++r) asm volatile("prefetch.global.L1 [%0];" ::"l"(tp + (size_t)r * p.E));
+        } else {
+            const char* tb = reinterpret_cast<const char*>(p.tgt + (size_t)e * m * 2);
+            for (int off = 128 * kk; off < m * 16; off += 128 * K) asm volatile("prefetch.global.L1 [%0];" ::"l"(tb + off));
+            if (kk == K - 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(tb + m * 16 - 1));
+        }
     }
     double ax[N], ay[N], yaw[N], c_h[N], s_h[N];
 #pragma unroll
     for (int a = 0; a < N; ++a) {
-        const double2 v = *reinterpret_cast<const double2*>(rec + 2 * a);
+        const double2 v = L::xy_ld(p, a, e);
         ax[a] = v.x; ay[a] = v.y;
-        yaw[a] = rec[p.yaw_off + a];
+        yaw[a] = *L::yaw_at(p, a, e);
         c_h[a] = 0.0; s_h[a] = 0.0;
     }
-    const uint4* mp_in = reinterpret_cast<const uint4*>(rec + p.meta_off);
-    const uint4 m0 = mp_in[0], m1 = mp_in[1];
+    uint4 m0, m1;
+    L::meta_ld(p, e, &m0, &m1);
     uint32_t found = m0.x, newf_last = m0.y, outmask = m0.z, time_step = m0.w;
     uint32_t episode = m1.x, flags = m1.y;
     float ep_reward = __uint_as_float(m1.z);
@@ -1237,7 +1340,7 @@ __global__ void __launch_bounds__(kTpeThreads, CS_TPE_MIN_CTAS) flight_tpe_kerne
                     if (!(rflags & CS_RESET_KEEP_TARGETS)) {
                         for (int j = lane32; j < m; j += 32) {
                             const double2 t = draw_target(p, p.env_id_base + (uint32_t)es, ep_s, j);
-                            *reinterpret_cast<double2*>(p.tgt + ((size_t)es * m + j) * 2) = t;
+                            tgt_st(p, j, es, t);
                         }
                     }
                     if (MAP && (rflags & CS_RESET_INIT)) {
@@ -1262,7 +1365,7 @@ __global__ void __launch_bounds__(kTpeThreads, CS_TPE_MIN_CTAS) flight_tpe_kerne
 #pragma unroll
                 for (int u = 0; u < TU; ++u) {
                     const int j = min(j0 + u * K, m - 1);
-                    t[u] = *reinterpret_cast<const double2*>(tg + 2 * j);
+                    t[u] = L::tgt_ld(p, j, e);
                 }
 #pragma unroll
                 for (int u = 0; u < TU; ++u) {
@@ -1336,7 +1439,7 @@ __global__ void __launch_bounds__(kTpeThreads, CS_TPE_MIN_CTAS) flight_tpe_kerne
                 int k = 0;
                 for (uint32_t left = newf; left; left &= left - 1) {
                     const int j = __ffs(left) - 1;
-                    const double2 t = *reinterpret_cast<const double2*>(tg + 2 * j);
+                    const double2 t = L::tgt_ld(p, j, e);
                     ph[1 + k++] = hit_cell(p, t.x, t.y);
                 }
                 ph[0] = k;
@@ -1351,8 +1454,8 @@ __global__ void __launch_bounds__(kTpeThreads, CS_TPE_MIN_CTAS) flight_tpe_kerne
 #pragma unroll
         for (int a = 0; a < N; ++a) {
             if (a % K != kk) continue;                                  // the env's K threads share the rows
-            *reinterpret_cast<double2*>(rec + 2 * a) = make_double2(ax[a], ay[a]);
-            rec[p.yaw_off + a] = yaw[a];
+            L::xy_st(p, a, e, ax[a], ay[a]);
+            *L::yaw_at(p, a, e) = yaw[a];
             // get_obs row = agent part of get_state (flight_env_easy.py:218-221, :192-193)
             const float4 o = make_float4((float)((ax[a] - p.half_M) * p.inv_half), (float)((ay[a] - p.half_M) * p.inv_half),
                                          (float)c_h[a], (float)s_h[a]);
@@ -1360,15 +1463,14 @@ __global__ void __launch_bounds__(kTpeThreads, CS_TPE_MIN_CTAS) flight_tpe_kerne
             reinterpret_cast<float4*>(srow)[a] = o;
         }
         if (kk == 0) {
-            uint4* mp = reinterpret_cast<uint4*>(rec + p.meta_off);
-            mp[0] = make_uint4(found, newf_last, outmask, time_step);
-            mp[1] = make_uint4(episode, flags, __float_as_uint(ep_reward), MAP ? (sense_word | prejob) : 0u);
+            L::meta_st(p, e, make_uint4(found, newf_last, outmask, time_step),
+                    make_uint4(episode, flags, __float_as_uint(ep_reward), MAP ? (sense_word | prejob) : 0u));
         }
         // target part of the state row (:201-211): rewritten in full after a reset, otherwise only the 'find' entry of
         // a target found by this call
         if (state_full) {
             for (int j = kk; j < m; j += K) {
-                const double2 t = *reinterpret_cast<const double2*>(tg + 2 * j);
+                const double2 t = L::tgt_ld(p, j, e);
                 float* s3 = srow + 4 * N + 3 * j;
                 const float nx = (float)((t.x - p.half_M) * p.inv_half), ny = (float)((t.y - p.half_M) * p.inv_half);
                 const float fj = ((found >> j) & 1u) ? 1.0f : 0.0f;
@@ -1379,7 +1481,7 @@ __global__ void __launch_bounds__(kTpeThreads, CS_TPE_MIN_CTAS) flight_tpe_kerne
         }
     }
     if (MAP && active && !emit && kk == 0 && m1.w != 0u)
-        reinterpret_cast<uint32_t*>(rec + p.meta_off)[CS_META_SENSE] = 0u;      // not sensed by THIS call: no job for the map kernel
+        meta_at(p, 3, e)->y = 0u;      // not sensed by THIS call: no job for the map kernel
     if (active && have_result && kk == 0) {
         p.reward[e] = res_reward;
         p.terminated[e] = (uint8_t)res_term;
@@ -1408,12 +1510,13 @@ __global__ void __launch_bounds__(kTpeThreads, CS_TPE_MIN_CTAS) flight_tpe_kerne
 }
 
 // sum of the time_step words of all envs (steps of the episodes still running), for cs_flight_stats
-__global__ void __launch_bounds__(256) flight_live_steps_kernel(const double* __restrict__ dyn, int E, int rec, int meta_off,
+__global__ void __launch_bounds__(256) flight_live_steps_kernel(const double* __restrict__ dyn, int E, long long rs, long long es, int meta_off,
                                                                 double* __restrict__ out) {
     unsigned long long acc = 0;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
-        const uint32_t* mt = reinterpret_cast<const uint32_t*>(dyn + (size_t)e * rec + meta_off);
-        if (!(mt[CS_META_FLAGS] & CS_FLAG_DONE)) acc += mt[CS_META_TIME];   // a finished episode is already in CS_STAT_EP_LEN
+        const uint2 w23 = *reinterpret_cast<const uint2*>(dyn + (size_t)(meta_off + 1) * rs + (size_t)e * es);     // out mask, time_step
+        const uint2 w45 = *reinterpret_cast<const uint2*>(dyn + (size_t)(meta_off + 2) * rs + (size_t)e * es);     // episode, flags
+        if (!(w45.y & CS_FLAG_DONE)) acc += w23.y;                          // a finished episode is already in CS_STAT_EP_LEN
     }
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, (double)acc);
@@ -1548,7 +1651,9 @@ __global__ void __launch_bounds__(256) flight_record_kernel(const FlightParams p
     const long long total = (long long)p.E * per_env;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         const int e = (int)(idx / per_env), k = (int)(idx - (long long)e * per_env);
-        const uint32_t* mt = reinterpret_cast<const uint32_t*>(p.dyn + (size_t)e * p.rec + p.meta_off);
+        uint4 mq0, mq1;
+        meta_ld(p, e, &mq0, &mq1);
+        const uint32_t mt[CS_META_WORDS] = {mq0.x, mq0.y, mq0.z, mq0.w, mq1.x, mq1.y, mq1.z, mq1.w};
         if (mt[CS_META_TIME] != (uint32_t)(t + 1)) continue;           // this env did not take step t (episode over)
         const bool over = (mt[CS_META_FLAGS] & CS_FLAG_DONE) != 0;
         const size_t row = (size_t)e * T + t;
@@ -1898,8 +2003,11 @@ int cs_flight_create(const cs_flight_cfg* cfg, cs_flight** out) {
     CS_CUDA(cudaMalloc(&p.dyn, E * p.rec * sizeof(double)));
     CS_CUDA(cudaMemset(p.dyn, 0, E * p.rec * sizeof(double)));
     // episode counter starts at -1 so that the first reset opens episode 0
-    CS_CUDA(cudaMemset2D(reinterpret_cast<uint32_t*>(p.dyn + p.meta_off) + CS_META_EPISODE, p.rec * sizeof(double), 0xFF,
-                         sizeof(uint32_t), E));
+    // structure of arrays exactly where one thread owns one env (flight_tpe_kernel<N, 1>), records otherwise
+    if (h->tpe && h->tpe_k == 1) { p.dyn_rs = (long long)E; p.dyn_es = 1; p.tgt_rs = (long long)E; p.tgt_es = 1; }
+    else { p.dyn_rs = 1; p.dyn_es = p.rec; p.tgt_rs = 1; p.tgt_es = 2 * m; }
+    CS_CUDA(cudaMemset2D(reinterpret_cast<uint32_t*>(p.dyn + (size_t)(p.meta_off + CS_META_EPISODE / 2) * p.dyn_rs) + (CS_META_EPISODE & 1),
+                         (size_t)p.dyn_es * sizeof(double), 0xFF, sizeof(uint32_t), E));
     CS_CUDA(cudaMalloc(&p.tgt, E * 2 * m * sizeof(double)));
     CS_CUDA(cudaMemset(p.tgt, 0, E * 2 * m * sizeof(double)));
     {
@@ -1997,6 +2105,7 @@ void cs_flight_destroy(cs_flight* h) {
 int cs_flight_buffers_get(cs_flight* h, cs_flight_buffers* b) {
     CS_REQUIRE(h && b, "cs_flight_buffers_get: null argument");
     const FlightParams& p = h->p;
+    b->dyn_row_stride = p.dyn_rs; b->dyn_env_stride = p.dyn_es; b->tgt_row_stride = p.tgt_rs; b->tgt_env_stride = p.tgt_es;
     b->dyn = p.dyn; b->dyn_doubles = p.rec; b->yaw_off = p.yaw_off; b->meta_off = p.meta_off; b->state_len = p.state_len; b->state_stride = p.state_stride;
     b->tgt = p.tgt; b->obs = p.obs; b->state = p.state; b->reward = p.reward; b->terminated = p.terminated;
     b->win = p.win; b->target_find = p.target_find; b->prob_map = p.prob_map; b->stats = p.stats;
@@ -2205,7 +2314,7 @@ int cs_flight_stats(cs_flight* h, double* h_out, void* stream) {
     // env_steps = lengths of the finished episodes + steps of the episodes still running
     CS_CUDA(cudaMemsetAsync(h->d_live, 0, sizeof(double), st));
     const int grid = (h->p.E + 255) / 256 < CS_NUM_SMS_B200 * 4 ? (h->p.E + 255) / 256 : CS_NUM_SMS_B200 * 4;
-    flight_live_steps_kernel<<<grid, 256, 0, st>>>(h->p.dyn, h->p.E, h->p.rec, h->p.meta_off, h->d_live);
+    flight_live_steps_kernel<<<grid, 256, 0, st>>>(h->p.dyn, h->p.E, h->p.dyn_rs, h->p.dyn_es, h->p.meta_off, h->d_live);
     cs_count_launch(1);
     CS_CUDA(cudaGetLastError());
     double live = 0.0;

@@ -115,11 +115,18 @@ class _VecFlightBase:
         self._b = b
         E, n, m, M = self.num_envs, self.n_agents, self.target_num, self.map_size
         dev, own = self.device, self._h
-        self._dyn = _wrap(b.dyn, (E, b.dyn_doubles), "<f8", dev, own)
+        # the state layout is described by strides (include/coopsearch.h: record per env, or structure of arrays for
+        # large handles): these are strided zero-copy views
+        rows = b.dyn_doubles
+        flat = _wrap(b.dyn, (rows * E,), "<f8", dev, own)
+        self._dyn = flat.as_strided((E, rows), (b.dyn_env_stride, b.dyn_row_stride))              # [E,rows] f64 view
         self.agent_xy = self._dyn[:, :2 * n].unflatten(1, (n, 2))            # [E,n,2] f64 view
         self.agent_yaw = self._dyn[:, b.yaw_off:b.yaw_off + n]               # [E,n]   f64 view
-        self.meta = _wrap(b.dyn, (E, 2 * b.dyn_doubles), "<i4", dev, own)[:, 2 * b.meta_off:2 * b.meta_off + _lib.CS_META_WORDS]
-        self.tgt_xy = _wrap(b.tgt, (E, m, 2), "<f8", dev, own)
+        flat32 = _wrap(b.dyn, (rows * E * 2,), "<i4", dev, own)
+        self._meta3 = flat32.as_strided((E, _lib.CS_META_WORDS // 2, 2), (2 * b.dyn_env_stride, 2 * b.dyn_row_stride, 1),
+                                        2 * b.meta_off * b.dyn_row_stride)                        # [E,4,2] i32 view
+        self.tgt_xy = _wrap(b.tgt, (2 * m * E,), "<f8", dev, own).as_strided(
+            (E, m, 2), (b.tgt_env_stride, 2 * b.tgt_row_stride, b.tgt_row_stride))               # [E,m,2] f64 view
         self._obs = _wrap(b.obs, (E, n, 4), "<f4", dev, own)
         self._state = _wrap(b.state, (E, b.state_stride), "<f4", dev, own)[:, :b.state_len]   # rows padded to 16 B
         self._reward = _wrap(b.reward, (E,), "<f4", dev, own)
@@ -235,17 +242,25 @@ class _VecFlightBase:
     def win_flag(self):
         return self._win
 
+    def _meta_word(self, w):
+        return self._meta3[:, w >> 1, w & 1]                                 # [E] int32 view of meta word w
+
+    @property
+    def meta(self):
+        """[E, CS_META_WORDS] int32 (a copy; the words live in four [E][2] device rows)."""
+        return self._meta3.reshape(self.num_envs, _lib.CS_META_WORDS)
+
     @property
     def time_step(self):
-        return self.meta[:, _lib.META_TIME]
+        return self._meta_word(_lib.META_TIME)
 
     @property
     def found_mask(self):
-        return self.meta[:, _lib.META_FOUND]
+        return self._meta_word(_lib.META_FOUND)
 
     @property
     def out_mask(self):
-        return self.meta[:, _lib.META_OUT]
+        return self._meta_word(_lib.META_OUT)
 
     def close(self):
         pass

@@ -111,15 +111,19 @@ typedef struct cs_flight_cfg {
 
 typedef struct cs_flight cs_flight;
 
-/* Device pointers of a flight handle.  fp64 internal state, fp32/u8 outputs.
- *   dyn : [E][dyn_doubles] doubles; per env  x0,y0,..,x(n-1),y(n-1) | yaw0..yaw(n-1) |
- *         pad to meta_off | CS_META_WORDS uint32 meta words (see enum above)
- *   tgt : [E][m][2] doubles, target coordinates (target_pos, flight_env_easy.py:113)      */
+/* Device pointers of a flight handle.  fp64 internal state, fp32/u8 outputs.  The state layout is chosen per handle
+ * (structure of arrays from 32768 envs, one record per env below) and described by strides, in doubles:
+ *   dyn : element (row r, env e) at dyn[r*dyn_row_stride + e*dyn_env_stride]; rows 0..2n-1 = x0,y0,..,x(n-1),y(n-1),
+ *         rows yaw_off..yaw_off+n-1 = headings, rows meta_off..meta_off+3 = the CS_META_WORDS uint32 meta words
+ *         (two per row: word w of env e is the (w & 1)-th uint32 of element (meta_off + w/2, e))
+ *   tgt : element (row r, env e) at tgt[r*tgt_row_stride + e*tgt_env_stride]; row 2j = x of target j, row 2j+1 = y
+ *         (target_pos, flight_env_easy.py:113)                                                                    */
 typedef struct cs_flight_buffers {
+    int64_t dyn_row_stride, dyn_env_stride, tgt_row_stride, tgt_env_stride;
     double* dyn;
     int32_t dyn_doubles;
-    int32_t yaw_off;        /* = 2n   (doubles)                                            */
-    int32_t meta_off;       /* doubles; meta words start at (uint32*)(rec + meta_off)      */
+    int32_t yaw_off;        /* = 2n   (first heading row)                                  */
+    int32_t meta_off;       /* first of the four meta rows                                 */
     int32_t state_len;      /* 4n + 3m                                                     */
     int32_t state_stride;   /* floats between consecutive state rows (state_len rounded up
                                to a multiple of 4 so rows start 16-byte aligned)           */

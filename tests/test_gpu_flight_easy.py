@@ -169,8 +169,8 @@ def test_thread_per_env_kernel_equals_lane_per_agent_kernel(n_agents, agent_mode
         where = "step %d" % t
         assert torch.equal(ra, rb) and torch.equal(ta, tb) and torch.equal(wa, wb), where
         assert torch.equal(tpe.target_find, lpa.target_find), where
-        assert torch.equal(tpe._dyn.view(torch.int64), lpa._dyn.view(torch.int64)), where
-        assert torch.equal(tpe.tgt_xy.view(torch.int64), lpa.tgt_xy.view(torch.int64)), where
+        assert torch.equal(tpe._dyn.contiguous().view(torch.int64), lpa._dyn.contiguous().view(torch.int64)), where
+        assert torch.equal(tpe.tgt_xy.contiguous().view(torch.int64), lpa.tgt_xy.contiguous().view(torch.int64)), where
         assert torch.equal(tpe.get_state().view(torch.int32), lpa.get_state().view(torch.int32)), where
         assert torch.equal(tpe.get_obs(full=False).view(torch.int32) if variant != "easy" else tpe.get_obs().view(torch.int32),
                            lpa.get_obs(full=False).view(torch.int32) if variant != "easy" else lpa.get_obs().view(torch.int32)), where
