@@ -1164,7 +1164,13 @@ __global__ void __launch_bounds__(kThreads, 8) flight_kernel(const __grid_consta
 //   pass 0 (STEP): _agent_step -> _update_obs -> step bookkeeping            (flight_env_easy.py:255-314)
 //   pass 1       : reset (selected envs in RESET mode; just-terminated envs under auto_reset) -> _update_obs (:79-182)
 // ------------------------------------------------------------------------------------------------
-constexpr int kTpeThreads = 64;
+#ifndef CS_TPE_THREADS
+#define CS_TPE_THREADS 64
+#endif
+constexpr int kTpeThreads = CS_TPE_THREADS;
+#ifndef CS_TPE_TU
+#define CS_TPE_TU 5            // targets a thread loads together in the sensing loop
+#endif
 #ifndef CS_TPE_MIN_CTAS
 #define CS_TPE_MIN_CTAS 8      // resident CTAs per SM the thread-per-env kernel is compiled for (register budget 65536/(64*N))
 #endif
@@ -1175,7 +1181,7 @@ __global__ void __launch_bounds__(kTpeThreads, CS_TPE_MIN_CTAS) flight_tpe_kerne
                                                                  const uint8_t* __restrict__ mask, uint32_t rflags, uint32_t seq) {
     constexpr unsigned FULL = 0xffffffffu;
     __shared__ longlong2 lutm[40];
-    static_assert(K == 1 || K == 2 || K == 4, "K");
+    static_assert(K == 1 || K == 4, "K");
     using L = Lay<K == 1>;                                              // one thread per env <-> structure of arrays (cs_flight_create)
     constexpr uint32_t MINE = 0xFFFFFFFFu / ((1u << K) - 1u);          // targets j with j % K == 0
     const int tid = threadIdx.x, lane32 = tid & 31, kk = tid % K;       // kk: which of the env's K threads this is
@@ -1359,7 +1365,7 @@ __global__ void __launch_bounds__(kTpeThreads, CS_TPE_MIN_CTAS) flight_tpe_kerne
         if (do_sense) {
             // the env's K threads share the targets; TU of a thread's targets are loaded together so that their
             // latency is paid once per block, not once per target
-            constexpr int TU = 5;
+            constexpr int TU = CS_TPE_TU;
             for (int j0 = kk; j0 < m; j0 += K * TU) {
                 double2 t[TU];
 #pragma unroll
@@ -1698,7 +1704,7 @@ struct cs_flight {
     FlightParams p;
     int lpe;
     bool tpe;             // thread-per-env step kernel (n_agents <= kTpeMaxAgents and no explicit lanes_per_env)
-    int tpe_k;            // threads that share one env's target loop in that kernel (1, 2, 4)
+    int tpe_k;            // threads that share one env's target loop in that kernel (1 or 4)
     size_t smem_bytes, map_smem;
     int grid, map_grid;
     bool map_tma;         // the TMA form of the map kernel applies (even map_size in 16..63, 2R+2 <= 16) and the tensor map exists
@@ -1755,7 +1761,6 @@ template <int N>
 cudaError_t launch_tpe(cs_flight* h, int mode, const uint8_t* actions, const uint8_t* mask, uint32_t rflags, cudaStream_t st) {
     switch (h->tpe_k) {
         case 1: return launch_tpe_k<N, 1>(h, mode, actions, mask, rflags, st);
-        case 2: return launch_tpe_k<N, 2>(h, mode, actions, mask, rflags, st);
         default: return launch_tpe_k<N, 4>(h, mode, actions, mask, rflags, st);
     }
 }
@@ -1965,7 +1970,7 @@ int cs_flight_create(const cs_flight_cfg* cfg, cs_flight** out) {
     h->tpe_k = p.E >= 32768 ? 1 : 4;
     if (const char* kenv = getenv("CS_TPE_K")) {                               // tuning sweeps only
         const int kv = atoi(kenv);
-        if (kv == 1 || kv == 2 || kv == 4) h->tpe_k = kv;
+        if (kv == 1 || kv == 4) h->tpe_k = kv;
     }
     p.s_lut = 0;
     p.s_warp = 76;                                        // 37 x 16 B heading-table index, padded
