@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(kThreads) search_kernel(const SearchParams p, 
             for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
             if ((tid & 31) == 0) s_red[tid >> 5] = part;
             // ---- detection: disc rows of every agent against the unfound bit rows (:261-267)
-            const int R = p.R, R2 = R * R, span = 2 * R + 1;
+            const int R = p.R, span = 2 * R + 1;
             for (int task = tid; task < n * span; task += kThreads) {
                 const int a = fastdiv(task, p.mg_span), dx = task - a * span - R;
                 const int x = s.pos[2 * a] + dx;

@@ -1,11 +1,15 @@
 #!/bin/bash
-# map kernel A/B: TMA-tile vs direct sweep, timed on c4; warm-cache launch list and one full capture
-mkdir -p gpurun_out
+# map kernel variants (builds on the GPU box), timed on c4
+mkdir -p gpurun_out /tmp/csv
+cd cooperative-search_b200/csrc
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=false -Xcompiler -fPIC -shared -DCS_MAP_PREFETCH -o /tmp/csv/lib_pf.so runtime.cu flight.cu search.cu 2>/dev/null &
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=false -Xcompiler -fPIC -shared -DCS_MAP_PREFETCH -DCS_MAP_MIN_CTAS=6 -o /tmp/csv/lib_pf6.so runtime.cu flight.cu search.cu 2>/dev/null &
+wait
+cd ../..
 {
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-echo "== tma"; CS_MAP_TMA=1 python tools/exp_c4.py 300
-echo "== direct"; python tools/exp_c4.py 300
+echo "== default"; python tools/exp_c4.py 300
+echo "== L1 prefetch of the box rows"; COOPSEARCH_LIB=/tmp/csv/lib_pf.so python tools/exp_c4.py 300
+COOPSEARCH_LIB=/tmp/csv/lib_pf.so python -m pytest tests/test_gpu_flight_map.py -m gpu -x -q 2>&1 | tail -2
+echo "== L1 prefetch, 6 CTAs/SM"; COOPSEARCH_LIB=/tmp/csv/lib_pf6.so python tools/exp_c4.py 300
 } > gpurun_out/sweep_map.log 2>&1
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum --clock-control none --cache-control none -s 100 -c 4 --csv --log-file gpurun_out/c4_launches_warm.csv python tools/exp_c4.py 120 > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:flight_map -s 40 -c 1 -f -o gpurun_out/prof_c4_map python tools/exp_c4.py 60 > /dev/null 2>&1
 cat gpurun_out/sweep_map.log
