@@ -42,8 +42,11 @@ TEMPLATE = {  # flight_targets.txt of the reference (parsed as main.py:19-32 doe
 
 WORKLOADS = {
     # name: kind, n_agents, agent_mode, envs per launch, number of batches, description
-    "c2": dict(kind="flight_easy", n=3, am=0, envs=4096, batches=64,
-               desc="flight_easy 3a15t AM0TM0, 4096 envs per launch (BASELINE.json configs[1])"),
+    "c2": dict(kind="flight_easy", n=3, am=0, envs=4096, batches=64, grouped=True, lanes=1,
+               desc="flight_easy 3a15t AM0TM0, 4096 batched envs per handle (BASELINE.json configs[1]); 64 independent handles "
+                    "(rollout workers, 168 MB of state > L2) advance in ONE grouped launch (cs_flight_group_step)"),
+    "c2s": dict(kind="flight_easy", n=3, am=0, envs=4096, batches=64,
+                desc="flight_easy 3a15t AM0TM0, the same 64 handles x 4096 envs with one launch per handle (8 streams in a CUDA graph)"),
     "c3": dict(kind="flight_easy", n=5, am=2, envs=65536, batches=4,
                desc="flight_easy 5a15t AM2TM0, 65536 envs per launch (configs[2])"),
     "c4": dict(kind="flight", n=3, am=0, envs=16384, batches=1,
@@ -241,7 +244,7 @@ def _cpu_model():
 # ----------------------------------------------------------------------------------------------------------------
 def make_envs(cs, w, device, rank, seed=42, count_touched=False):
     envs = []
-    lpe = int(os.environ.get("CS_BENCH_LPE", "0"))      # tuning sweeps only; 0 = the library's own choice
+    lpe = int(os.environ.get("CS_BENCH_LPE", str(w.get("lanes", 0))))      # 0 = the library's own choice
     for b in range(w["batches"]):
         base = (rank * w["batches"] + b) * w["envs"]
         if w["kind"] == "flight_easy":
@@ -280,10 +283,19 @@ def run_gpu_workload(cs, torch, name, steps, warmup, device, rank, world, want_e
     side = torch.cuda.Stream(device=device)
     nstreams = max(1, min(int(os.environ.get("CS_BENCH_STREAMS", "8")), len(envs)))
     forks = [torch.cuda.Stream(device=device) for _ in range(nstreams)] if nstreams > 1 else []
+    grouped = None
+    if w.get("grouped") and len(envs) > 1 and os.environ.get("CS_BENCH_GROUPED", "1") != "0":
+        grouped = cs.DeviceStepper(envs)          # all batches advance in ONE launch (cs_flight_group_step)
+        nstreams, forks = 1, []
 
     def one_step(k):
-        """One env-step of every batch.  The batches are independent env sets, so their launches are forked over
-        `nstreams` streams (captured as parallel branches of the CUDA graph) and joined again."""
+        """One env-step of every batch.  The batches are independent env sets (rollout workers): either one grouped
+        launch steps them all, or their launches are forked over `nstreams` streams (captured as parallel branches of
+        the CUDA graph) and joined again."""
+        if grouped is not None:
+            with torch.cuda.stream(side):
+                grouped.step(actions[k % POOL])
+            return
         if forks:
             for f in forks:
                 f.wait_stream(side)
@@ -336,8 +348,8 @@ def run_gpu_workload(cs, torch, name, steps, warmup, device, rank, world, want_e
     if world > 1:
         torch.distributed.barrier()
     ms = ev0.elapsed_time(ev1)
-    launches = steps * len(envs)
-    out = dict(ms_total=ms, ms_per_step=ms / steps, env_steps_per_step=w["envs"] * len(envs), launches=launches, streams=nstreams,
+    launches = steps * (1 if grouped is not None else len(envs))
+    out = dict(grouped=grouped is not None, ms_total=ms, ms_per_step=ms / steps, env_steps_per_step=w["envs"] * len(envs), launches=launches, streams=nstreams,
                kernels=kernels_per_step * steps,
                us_per_launch=1000.0 * ms / launches, lanes_per_env=getattr(envs[0], "lanes_per_env", None))
 
@@ -436,10 +448,12 @@ def measure_touched(cs, torch, device, steps=200):
     return (e.stats()["map_cells_touched"] - base) / (steps * w["envs"])
 
 
-def kernel_name(w, lanes):
+def kernel_name(w, lanes, grouped=False):
     """The dominant kernel of a workload (csrc/flight.cu, csrc/search.cu)."""
     if w["kind"] == "search":
         return "search_kernel<STEP>"
+    if grouped:
+        return "flight_tpe_group_kernel<N=%d,K=%d>" % (w["n"], lanes)
     step = ("flight_tpe_kernel<N=%d,K=%d,STEP>" % (w["n"], lanes)) if lanes and lanes <= 4 else "flight_kernel<LPE=%s,STEP>" % lanes
     return step if w["kind"] == "flight_easy" else "flight_map_kernel (after %s; two launches per env-step)" % step
 
@@ -542,7 +556,7 @@ def main():
         touched = measure_touched(cs, torch, device)
     per_unit = algorithmic_bytes(w["kind"], w["n"], touched_per_step=touched or 0.0) if w["kind"] != "search" else \
         algorithmic_bytes("search", 64, m=1000, M=64, R=7)
-    bytes_per_launch = per_unit * w["envs"]
+    bytes_per_launch = per_unit * w["envs"] * (w["batches"] if res["grouped"] else 1)
     sec_per_launch = (res["ms_total"] / 1000.0) / res["launches"]
     achieved = bytes_per_launch / sec_per_launch / 1e9
     line = {
@@ -550,10 +564,12 @@ def main():
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {
-            "workload": w["desc"], "envs_per_launch": w["envs"], "batches_per_gpu": w["batches"], "launches_per_step": w["batches"],
+            "workload": w["desc"], "envs_per_handle": w["envs"], "handles_per_gpu": w["batches"],
+            "envs_per_launch": w["envs"] * (w["batches"] if res["grouped"] else 1), "launches_per_step": 1 if res["grouped"] else w["batches"],
             "env_instances_per_gpu": w["envs"] * w["batches"], "auto_reset": True,
             "actions": "pre-generated uniform-random u8 tensors resident in HBM" if w["kind"] != "search" else "uniform-random legal policy drawn in-kernel (Philox)",
-            "launch": "CUDA-graph replay of the step launches; the independent batches are forked over %d streams inside the graph" % res["streams"], "l2": "working set of all batches exceeds the 126 MB L2; batches are revisited round-robin, no flush",
+            "launch": ("CUDA-graph replay of one grouped launch that steps every handle (cs_flight_group_step)" if res["grouped"] else
+                       "CUDA-graph replay of the step launches; the independent batches are forked over %d streams inside the graph" % res["streams"]), "l2": "working set of all batches exceeds the 126 MB L2; batches are revisited round-robin, no flush",
             "lanes_per_env": res["lanes_per_env"], "parallelism": "dp%d (env instances sharded by global id, no data-path collective)" % world,
         },
         "agent_steps_per_s": value * w["n"],
@@ -565,8 +581,8 @@ def main():
         "gpu_launches_process_total": int(lib.cs_launch_count() - launches0),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": load_traffic(args.workload), "peak_source": peak_src,
-                     "kernel": kernel_name(w, res["lanes_per_env"]),
-                     "algorithmic_bytes_per_env_step": per_unit, "env_steps_per_launch": w["envs"],
+                     "kernel": kernel_name(w, res["lanes_per_env"], res["grouped"]),
+                     "algorithmic_bytes_per_env_step": per_unit, "env_steps_per_launch": w["envs"] * (w["batches"] if res["grouped"] else 1),
                      "us_per_launch": 1e6 * sec_per_launch, "map_cells_touched_per_env_step": touched,
                      "note": "duration = timed region / launches; launches of independent batches overlap when streams > 1"},
         "clocks": clocks,
@@ -575,7 +591,7 @@ def main():
     }
     if world == 1 and not args.no_extra:
         extra = {}
-        for name in ("c2w", "c3", "c4", "c5"):
+        for name in ("c2s", "c2w", "c3", "c4", "c5"):
             if name == args.workload:
                 continue
             try:
@@ -586,8 +602,8 @@ def main():
                 pu = algorithmic_bytes(ww["kind"], ww["n"], touched_per_step=tch or 0.0) if ww["kind"] != "search" else \
                     algorithmic_bytes("search", 64, m=1000, M=64, R=7)
                 v = r["env_steps_per_step"] / (r["ms_per_step"] / 1000.0)
-                gbs = pu * ww["envs"] / (1e-6 * r["us_per_launch"]) / 1e9
-                extra[name] = {"workload": ww["desc"], "kernel": kernel_name(ww, r["lanes_per_env"]), "value": v, "unit": "env-steps/s", "agent_steps_per_s": v * ww["n"],
+                gbs = pu * ww["envs"] * (ww["batches"] if r["grouped"] else 1) / (1e-6 * r["us_per_launch"]) / 1e9
+                extra[name] = {"workload": ww["desc"], "kernel": kernel_name(ww, r["lanes_per_env"], r["grouped"]), "value": v, "unit": "env-steps/s", "agent_steps_per_s": v * ww["n"],
                                "us_per_launch": r["us_per_launch"], "e2e_value": r["env_steps_per_step"] / r["e2e_s_per_step"],
                                "roofline": {"achieved": gbs, "peak": peak, "frac": gbs / peak, "unit": "GB/s",
                                             "algorithmic_bytes_per_env_step": pu, "map_cells_touched_per_env_step": tch,

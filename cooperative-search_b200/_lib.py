@@ -107,6 +107,9 @@ SIGNATURES = {
     "cs_flight_slab_layout": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "cs_flight_step_host_many": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(FlightHostIO), C.c_int32, C.POINTER(C.c_void_p), C.c_int32]),
     "cs_flight_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_void_p]),
+    "cs_flight_group_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.POINTER(C.c_void_p)]),
+    "cs_flight_group_step": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]),
+    "cs_flight_group_destroy": (None, [C.c_void_p]),
     "cs_flight_record_begin": (C.c_int, [C.c_void_p, C.POINTER(EpisodeBuffers), C.c_int32, C.c_void_p]),
     "cs_flight_record": (C.c_int, [C.c_void_p, C.POINTER(EpisodeBuffers), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "cs_search_create": (C.c_int, [C.POINTER(SearchCfg), C.POINTER(C.c_void_p)]),

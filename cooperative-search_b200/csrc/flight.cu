@@ -1177,15 +1177,15 @@ constexpr int kTpeThreads = CS_TPE_THREADS;
 constexpr int kTpeMaxAgents = 8;
 
 template <int N, int K, int MODE, bool MAP>
-__global__ void __launch_bounds__(kTpeThreads, CS_TPE_MIN_CTAS) flight_tpe_kernel(const __grid_constant__ FlightParams p, const uint8_t* __restrict__ actions,
-                                                                 const uint8_t* __restrict__ mask, uint32_t rflags, uint32_t seq) {
+__device__ __forceinline__ void flight_tpe_body(const FlightParams& p, const int block, const uint8_t* __restrict__ actions,
+                                                const uint8_t* __restrict__ mask, uint32_t rflags, uint32_t seq) {
     constexpr unsigned FULL = 0xffffffffu;
     __shared__ longlong2 lutm[40];
     static_assert(K == 1 || K == 4, "K");
     using L = Lay<K == 1>;                                              // one thread per env <-> structure of arrays (cs_flight_create)
     constexpr uint32_t MINE = 0xFFFFFFFFu / ((1u << K) - 1u);          // targets j with j % K == 0
     const int tid = threadIdx.x, lane32 = tid & 31, kk = tid % K;       // kk: which of the env's K threads this is
-    const int e_raw = (blockIdx.x * kTpeThreads + tid) / K;
+    const int e_raw = (block * kTpeThreads + tid) / K;
     const bool active = e_raw < p.E;
     const int e = active ? e_raw : p.E - 1;
     const int m = p.m;
@@ -1337,7 +1337,7 @@ __global__ void __launch_bounds__(kTpeThreads, CS_TPE_MIN_CTAS) flight_tpe_kerne
             // target, :95-127) and, for reset(init=True), its belief map (flight_env.py:84-86)
             if (!(rflags & CS_RESET_KEEP_TARGETS) || (MAP && (rflags & CS_RESET_INIT))) {
                 unsigned left = rmask;
-                const int t_first = blockIdx.x * kTpeThreads + (tid & ~31);
+                const int t_first = block * kTpeThreads + (tid & ~31);
                 while (left) {
                     const int src = __ffs(left) - 1;
                     left &= left - 1;
@@ -1513,6 +1513,33 @@ __global__ void __launch_bounds__(kTpeThreads, CS_TPE_MIN_CTAS) flight_tpe_kerne
             }
         }
     }
+}
+
+template <int N, int K, int MODE, bool MAP>
+__global__ void __launch_bounds__(kTpeThreads, CS_TPE_MIN_CTAS) flight_tpe_kernel(const __grid_constant__ FlightParams p, const uint8_t* __restrict__ actions,
+                                                                 const uint8_t* __restrict__ mask, uint32_t rflags, uint32_t seq) {
+    flight_tpe_body<N, K, MODE, MAP>(p, (int)blockIdx.x, actions, mask, rflags, seq);
+}
+
+// Grouped step of several handles (independent env batches of the same shape: rollout workers) in ONE launch:
+// blockIdx.y picks the handle, whose parameter block comes from a device table into shared memory.  A launch of a few
+// thousand envs is bound by the launch path (2.2 us per 4096-env launch inside a 64-node graph);
+// grouped, the same batches fill the GPU like one large handle.  flight_easy variant only.
+constexpr int kMaxGroup = 128;
+struct GroupActions { const uint8_t* a[kMaxGroup]; };
+
+template <int N, int K>
+__global__ void __launch_bounds__(kTpeThreads, CS_TPE_MIN_CTAS) flight_tpe_group_kernel(const FlightParams* __restrict__ table,
+                                                                                       const __grid_constant__ GroupActions acts) {
+    __shared__ FlightParams sp;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(table + blockIdx.y);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&sp);
+        for (int i = threadIdx.x; i < (int)(sizeof(FlightParams) / 4); i += kTpeThreads) dst[i] = src[i];
+    }
+    __syncthreads();
+    if ((long long)blockIdx.x * kTpeThreads >= (long long)sp.E * K) return;         // handles may differ in num_envs
+    flight_tpe_body<N, K, MODE_STEP, false>(sp, (int)blockIdx.x, acts.a[blockIdx.y], nullptr, 0u, 0u);
 }
 
 // sum of the time_step words of all envs (steps of the episodes still running), for cs_flight_stats
@@ -1723,6 +1750,12 @@ struct cs_flight {
     bool have_tmpl;
 };
 
+struct cs_flight_group {
+    int count, n, k, grid_x, device;
+    cs_flight* envs[kMaxGroup];
+    FlightParams* d_table;
+};
+
 namespace {
 
 // lanes per env: the smallest power of two that gives every agent and every target its own lane
@@ -1838,6 +1871,15 @@ cudaError_t dispatch_attr(int lpe, size_t bytes) {
         case 16: return set_smem_attr<16>(bytes);
         default: return set_smem_attr<32>(bytes);
     }
+}
+
+template <int N>
+cudaError_t launch_group(const cs_flight_group* g, const GroupActions& acts, cudaStream_t st) {
+    const dim3 grid((unsigned)g->grid_x, (unsigned)g->count);
+    if (g->k == 1) flight_tpe_group_kernel<N, 1><<<grid, kTpeThreads, 0, st>>>(g->d_table, acts);
+    else flight_tpe_group_kernel<N, 4><<<grid, kTpeThreads, 0, st>>>(g->d_table, acts);
+    cs_count_launch(1);
+    return cudaGetLastError();
 }
 
 inline int up2(int v) { return (v + 1) & ~1; }
@@ -1963,11 +2005,13 @@ int cs_flight_create(const cs_flight_cfg* cfg, cs_flight** out) {
     p.span_cap = 1; p.span_shift = 0;
     while (p.span_cap < 2 * cfg->view_range) { p.span_cap <<= 1; ++p.span_shift; }
     h->lpe = pick_lpe(*cfg);
-    h->tpe = cfg->lanes_per_env == 0 && n <= kTpeMaxAgents;
+    // lanes_per_env: 0 = automatic; 1 or 4 = thread-per-env kernel with that many threads per env; larger = lane-per-agent kernel
+    h->tpe = n <= kTpeMaxAgents && (cfg->lanes_per_env == 0 || cfg->lanes_per_env == 1 || cfg->lanes_per_env == 4);
     // measured on B200 (tools/sweep_step.sh): one thread per env wins from ~32k envs per launch (2.7e9 against 1.7e9
     // env-steps/s at 65536 envs, 5.0e9 against 2.4e9 at 1M); below that a launch cannot fill the GPU with one thread
     // per env and 4 threads per env match the lane-per-agent kernel's latency
     h->tpe_k = p.E >= 32768 ? 1 : 4;
+    if (cfg->lanes_per_env == 1 || cfg->lanes_per_env == 4) h->tpe_k = cfg->lanes_per_env;
     if (const char* kenv = getenv("CS_TPE_K")) {                               // tuning sweeps only
         const int kv = atoi(kenv);
         if (kv == 1 || kv == 4) h->tpe_k = kv;
@@ -2268,6 +2312,68 @@ int cs_flight_step_host_many(cs_flight* const* envs, const cs_flight_host_io* io
     }
     if (sync)
         for (int s = 0; s < n_streams && s < count; ++s) CS_CUDA(cudaStreamSynchronize((cudaStream_t)streams[s]));
+    return CS_OK;
+}
+
+// ---- grouped device step (flight_tpe_group_kernel) ------------------------------------------------------------
+int cs_flight_group_create(cs_flight* const* envs, int32_t count, cs_flight_group** out) {
+    CS_REQUIRE(envs && out && count >= 1 && count <= kMaxGroup, "cs_flight_group_create: count must be in 1..%d", kMaxGroup);
+    cs_flight_group* g = new (std::nothrow) cs_flight_group();
+    if (!g) { cs_set_error("out of host memory"); return CS_ERR_NOMEM; }
+    memset(g, 0, sizeof(*g));
+    std::vector<FlightParams> table((size_t)count);
+    for (int i = 0; i < count; ++i) {
+        cs_flight* h = envs[i];
+        const bool ok = h && h->tpe && h->p.variant == 0 && (i == 0 || (h->p.n == g->n && h->tpe_k == g->k && h->cfg.device == g->device));
+        if (!ok) {
+            delete g;
+            cs_set_error("cs_flight_group_create: handle %d is not a flight_easy handle with n_agents <= %d, or differs from handle 0 in n_agents / threads per env / device", i, kTpeMaxAgents);
+            return CS_ERR_INVALID;
+        }
+        if (i == 0) { g->n = h->p.n; g->k = h->tpe_k; g->device = h->cfg.device; }
+        const long long threads = (long long)h->p.E * h->tpe_k;
+        const int gx = (int)((threads + kTpeThreads - 1) / kTpeThreads);
+        if (gx > g->grid_x) g->grid_x = gx;
+        g->envs[i] = h;
+        table[(size_t)i] = h->p;
+    }
+    g->count = count;
+    cudaError_t e = cudaSetDevice(g->device);
+    if (e == cudaSuccess) e = cudaMalloc(&g->d_table, (size_t)count * sizeof(FlightParams));
+    if (e == cudaSuccess) e = cudaMemcpy(g->d_table, table.data(), (size_t)count * sizeof(FlightParams), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(g->d_table); delete g; }
+    CS_CUDA(e);
+    *out = g;
+    return CS_OK;
+}
+
+void cs_flight_group_destroy(cs_flight_group* g) {
+    if (!g) return;
+    cudaSetDevice(g->device);
+    cudaFree(g->d_table);
+    delete g;
+}
+
+int cs_flight_group_step(cs_flight_group* g, const uint8_t* const* d_actions, void* stream) {
+    CS_REQUIRE(g && d_actions, "cs_flight_group_step: null argument");
+    GroupActions acts;
+    for (int i = 0; i < g->count; ++i) {
+        CS_REQUIRE(d_actions[i] != nullptr, "cs_flight_group_step: null actions for handle %d", i);
+        acts.a[i] = d_actions[i];
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e;
+    switch (g->n) {
+        case 1: e = launch_group<1>(g, acts, st); break;
+        case 2: e = launch_group<2>(g, acts, st); break;
+        case 3: e = launch_group<3>(g, acts, st); break;
+        case 4: e = launch_group<4>(g, acts, st); break;
+        case 5: e = launch_group<5>(g, acts, st); break;
+        case 6: e = launch_group<6>(g, acts, st); break;
+        case 7: e = launch_group<7>(g, acts, st); break;
+        default: e = launch_group<8>(g, acts, st); break;
+    }
+    CS_CUDA(e);
     return CS_OK;
 }
 

@@ -372,6 +372,40 @@ def generate_episodes(env, actions=None, targets=None, generator=None):
     return ep, summary["episode_reward"], summary["win_tag"], summary["targets_find"]
 
 
+class DeviceStepper:
+    """One env-step of many independent flight_easy env batches (rollout workers) in ONE kernel launch
+    (cs_flight_group_step).  The envs must share n_agents, lanes_per_env and device; results land in each env's own
+    buffers exactly as calling ``env.step`` on each would leave them."""
+
+    def __init__(self, envs):
+        self.envs = list(envs)
+        self.lib = self.envs[0].lib
+        self.device = self.envs[0].device
+        n = len(self.envs)
+        handles = (C.c_void_p * n)(*[e._h.ptr for e in self.envs])
+        g = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.cs_flight_group_create(handles, n, C.byref(g)), "cs_flight_group_create")
+        self._g = g
+        self._ptrs = (C.c_void_p * n)()
+
+    def step(self, actions):
+        """actions: one [E,n] integer tensor per env."""
+        keep = [e._as_actions(a) for e, a in zip(self.envs, actions)]
+        for i, a in enumerate(keep):
+            self._ptrs[i] = a.data_ptr()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.cs_flight_group_step(self._g, self._ptrs, self.envs[0]._stream()), "cs_flight_group_step")
+
+    def __del__(self):
+        try:
+            if self._g:
+                self.lib.cs_flight_group_destroy(self._g)
+                self._g = None
+        except Exception:
+            pass
+
+
 class HostStepper:
     """Host-buffer steps of many independent env batches (rollout workers) with ONE library call per step
     (cs_flight_step_host_many): batch i runs on stream i % len(streams); results land in each env's pinned

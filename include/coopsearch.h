@@ -99,7 +99,8 @@ typedef struct cs_flight_cfg {
     int32_t variant;        /* 0 = flight_easy (wall test '>'), 1 = flight (prob map, '>=')*/
     int32_t auto_reset;     /* 1: a terminated env is reset inside the same step call      */
     int32_t count_touched;  /* 1: accumulate #prob-map cells updated into CS_STAT_TOUCHED  */
-    int32_t lanes_per_env;  /* 0 = choose from E; else 1,2,4,8,16,32 lanes working on one env  */
+    int32_t lanes_per_env;  /* 0 = automatic; 1 or 4 (n_agents <= 8): thread-per-env step kernel with
+                               that many threads per env; 2, 8, 16, 32: lane-per-agent kernel      */
     int32_t device;         /* CUDA device ordinal                                         */
     double velocity;        /* args.agent_velocity                                         */
     double detect_prob;     /* args.detect_prob                                            */
@@ -154,6 +155,14 @@ int cs_flight_reset(cs_flight* env, const uint8_t* d_mask, uint32_t flags, void*
 /* step(act_list) (flight_env_easy.py:303-314).  d_actions: device u8 [E][n], values 0..2.
  * Envs whose DONE flag is set are a masked no-op (reward 0, terminated 1) unless auto_reset. */
 int cs_flight_step(cs_flight* env, const uint8_t* d_actions, void* stream);
+/* Grouped device step: several flight_easy handles of the same shape (independent env batches = rollout workers,
+ * n_agents <= 8, same n_agents / lanes_per_env / device) advance one step in ONE kernel launch.  d_actions: host
+ * array of `count` device pointers, u8 [E_i][n] each.  Results land in every handle's own buffers, exactly as
+ * `count` cs_flight_step calls would leave them.  At most 128 handles per group. */
+typedef struct cs_flight_group cs_flight_group;
+int cs_flight_group_create(cs_flight* const* envs, int32_t count, cs_flight_group** out);
+int cs_flight_group_step(cs_flight_group* group, const uint8_t* const* d_actions, void* stream);
+void cs_flight_group_destroy(cs_flight_group* group);
 /* k steps under the uniform-random policy drawn in-kernel (alg=random, agent/agent.py:34-36). */
 int cs_flight_step_random(cs_flight* env, int32_t k, void* stream);
 /* Reference-shaped observation of the flight variant (flight_env.py:223-230):

@@ -282,6 +282,31 @@ def test_host_stepper_many_batches_one_call(graph):
             assert np.array_equal(cpu(ref[b].get_obs()), hb["obs"].numpy())
 
 
+@pytest.mark.parametrize("lpe,sizes", [(1, [700, 4096, 33]), (4, [256, 256, 256, 1000]), (0, [512, 512])])
+def test_grouped_device_step_equals_separate_steps(lpe, sizes):
+    """cs_flight_group_step: env batches of different sizes stepped in ONE launch end up bit-identical to the same
+    batches stepped one by one (state, targets, outputs, statistics), through episode ends and in-call auto-resets."""
+    import coopsearch_b200 as cs
+    spec = FlightSpec(n_agents=3, time_limit=20)
+    args = make_args(dict(spec.__dict__))
+    mk = lambda: [cs.VecFlightEasyEnv(args, TEMPLATE, num_envs=E, seed=9, env_id_base=1000 * b, auto_reset=True, lanes_per_env=lpe)
+                  for b, E in enumerate(sizes)]
+    ref, envs = mk(), mk()
+    stepper = cs.DeviceStepper(envs)
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    for t in range(50):
+        acts = [torch.randint(0, 3, (E, 3), dtype=torch.uint8, device="cuda", generator=gen) for E in sizes]
+        stepper.step(acts)
+        for a, e, r in zip(acts, envs, ref):
+            rr, rt, rw = r.step(a)
+            assert torch.equal(rr, e._reward) and torch.equal(rt, e._terminated) and torch.equal(rw, e._win), "step %d" % t
+            assert torch.equal(r._dyn, e._dyn) and torch.equal(r.tgt_xy, e.tgt_xy), "step %d" % t
+            assert torch.equal(r.get_state(), e.get_state()) and torch.equal(r.get_obs(), e.get_obs()), "step %d" % t
+    assert [r.stats() for r in ref] == [e.stats() for e in envs]
+    with pytest.raises(cs.CoopSearchError):
+        cs.DeviceStepper([envs[0], cs.VecFlightEasyEnv(make_args(dict(FlightSpec(n_agents=5).__dict__)), TEMPLATE, num_envs=8, seed=1)])
+
+
 def test_reference_error_behaviour():
     import coopsearch_b200 as cs
     spec = FlightSpec(n_agents=3)

@@ -9,7 +9,7 @@ src = os.path.join(ROOT, "gpurun_out")
 dst = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "profiles")
 os.makedirs(dst, exist_ok=True)
 traffic = {}
-for wl in ("c2", "c2w", "c3", "c4", "c4_step", "c5"):
+for wl in ("c2", "c2s", "c2w", "c3", "c4", "c4_step", "c5"):
     rep = os.path.join(src, "prof_%s.ncu-rep" % wl)
     if os.path.exists(rep):
         txt = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), rep], capture_output=True, text=True).stdout

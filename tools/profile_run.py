@@ -17,7 +17,11 @@ dev = torch.device("cuda", 0)
 envs = bench.silence(bench.make_envs, cs, w, dev, 0)
 gen = torch.Generator(device=dev).manual_seed(1)
 acts = [torch.randint(0, 3, (w["envs"], w["n"]), generator=gen, device=dev, dtype=torch.uint8) for _ in envs]
+grouped = cs.DeviceStepper(envs) if (w.get("grouped") and len(envs) > 1) else None
 for k in range(steps):
+    if grouped is not None:
+        grouped.step(acts)
+        continue
     for b, e in enumerate(envs):
         if w["kind"] == "search":
             e.step_random(1)
