@@ -323,8 +323,30 @@ def run_gpu_workload(cs, torch, name, steps, warmup, device, rank, world, want_e
             graphs.append(g)
     torch.cuda.synchronize(device)
 
+    gmulti = None
+    if grouped is not None and len(graphs) > 1:
+        # one grouped launch is ~57 us of GPU work: a one-node graph per step leaves ~10 us of launch gap between them, so
+        # the POOL steps are also captured back to back in one graph
+        gmulti = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(gmulti, stream=side):
+                for k in range(len(graphs)):
+                    one_step(k)
+        torch.cuda.synchronize(device)
+
     def replay(k):
         graphs[k % len(graphs)].replay()
+
+    def replay_many(count, start=0):
+        """`count` consecutive bench steps starting with action set `start`."""
+        k = start
+        if gmulti is not None:
+            while k % len(graphs) != 0 and count > 0:
+                replay(k); k += 1; count -= 1
+            while count >= len(graphs):
+                gmulti.replay(); k += len(graphs); count -= len(graphs)
+        while count > 0:
+            replay(k); k += 1; count -= 1
 
     # clock burn-in: same work, untimed, so that the sampler sees the GPU under THIS load and clocks have ramped
     t_end = time.perf_counter() + burn_in_s
@@ -341,8 +363,7 @@ def run_gpu_workload(cs, torch, name, steps, warmup, device, rank, world, want_e
     torch.cuda.synchronize(device)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    for k in range(steps):
-        replay(k)
+    replay_many(steps)
     ev1.record()
     torch.cuda.synchronize(device)
     if world > 1:
@@ -568,7 +589,7 @@ def main():
             "envs_per_launch": w["envs"] * (w["batches"] if res["grouped"] else 1), "launches_per_step": 1 if res["grouped"] else w["batches"],
             "env_instances_per_gpu": w["envs"] * w["batches"], "auto_reset": True,
             "actions": "pre-generated uniform-random u8 tensors resident in HBM" if w["kind"] != "search" else "uniform-random legal policy drawn in-kernel (Philox)",
-            "launch": ("CUDA-graph replay of one grouped launch that steps every handle (cs_flight_group_step)" if res["grouped"] else
+            "launch": ("CUDA-graph replay (8 steps per graph) of one grouped launch per step that steps every handle (cs_flight_group_step)" if res["grouped"] else
                        "CUDA-graph replay of the step launches; the independent batches are forked over %d streams inside the graph" % res["streams"]), "l2": "working set of all batches exceeds the 126 MB L2; batches are revisited round-robin, no flush",
             "lanes_per_env": res["lanes_per_env"], "parallelism": "dp%d (env instances sharded by global id, no data-path collective)" % world,
         },
