@@ -391,9 +391,15 @@ class DeviceStepper:
 
     def step(self, actions):
         """actions: one [E,n] integer tensor per env."""
-        keep = [e._as_actions(a) for e, a in zip(self.envs, actions)]
-        for i, a in enumerate(keep):
+        keep = []
+        for i, (e, a) in enumerate(zip(self.envs, actions)):
+            if not (torch.is_tensor(a) and a.dtype is torch.uint8 and a.is_cuda and a.is_contiguous()
+                    and tuple(a.shape) == (e.num_envs, e.n_agents)):
+                a = e._as_actions(a)              # any integer tensor / array -> device u8 [E,n]
+            keep.append(a)
             self._ptrs[i] = a.data_ptr()
+        if len(keep) != len(self.envs):
+            raise CoopSearchError("DeviceStepper.step needs one action tensor per env")
         with torch.cuda.device(self.device):
             _lib.check(self.lib.cs_flight_group_step(self._g, self._ptrs, self.envs[0]._stream()), "cs_flight_group_step")
 

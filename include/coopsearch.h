@@ -158,7 +158,8 @@ int cs_flight_step(cs_flight* env, const uint8_t* d_actions, void* stream);
 /* Grouped device step: several flight_easy handles of the same shape (independent env batches = rollout workers,
  * n_agents <= 8, same n_agents / lanes_per_env / device) advance one step in ONE kernel launch.  d_actions: host
  * array of `count` device pointers, u8 [E_i][n] each.  Results land in every handle's own buffers, exactly as
- * `count` cs_flight_step calls would leave them.  At most 128 handles per group. */
+ * `count` cs_flight_step calls would leave them.  At most 128 handles per group; the handles must outlive the group
+ * (it keeps their device pointers), and like a handle a group is used from one host thread / stream at a time. */
 typedef struct cs_flight_group cs_flight_group;
 int cs_flight_group_create(cs_flight* const* envs, int32_t count, cs_flight_group** out);
 int cs_flight_group_step(cs_flight_group* group, const uint8_t* const* d_actions, void* stream);
