@@ -5,6 +5,7 @@ Public surface (mirrors the reference's env protocol):
     dist.shard_range / dist.allreduce_stats for the one-process-per-GPU launch
 """
 from ._lib import CoopSearchError, load as load_library  # noqa: F401
+from .policy import BatchedRNNAgents  # noqa: F401
 from .vec_flight import VecFlightEasyEnv, VecFlightEnv, HostStepper, DeviceStepper, generate_episodes, load_targets  # noqa: F401
 from .adapter import SingleEnvAdapter  # noqa: F401
 from . import dist  # noqa: F401
@@ -14,5 +15,5 @@ try:
 except ImportError:  # pragma: no cover
     pass
 
-__all__ = ["VecFlightEasyEnv", "VecFlightEnv", "VecSearchEnv", "SingleEnvAdapter", "HostStepper", "DeviceStepper", "generate_episodes", "load_targets",
+__all__ = ["VecFlightEasyEnv", "VecFlightEnv", "VecSearchEnv", "SingleEnvAdapter", "HostStepper", "DeviceStepper", "BatchedRNNAgents", "generate_episodes", "load_targets",
            "CoopSearchError", "load_library", "dist"]

@@ -74,6 +74,24 @@ class SearchHostIO(C.Structure):
                 ("state", C.c_void_p), ("avail", C.c_void_p)]
 
 
+class PolicyCfg(C.Structure):         # mirrors cs_policy_cfg
+    _fields_ = [("struct_size", C.c_uint32), ("device", C.c_int32), ("n_agents", C.c_int32), ("obs_dim", C.c_int32),
+                ("n_actions", C.c_int32), ("hidden_dim", C.c_int32), ("last_action", C.c_int32), ("reuse_network", C.c_int32)]
+
+
+POLICY_WEIGHT_KEYS = ("fc1_w", "fc1_b", "w_ih", "w_hh", "b_ih", "b_hh", "fc2a_w", "fc2a_b", "fc2b_w", "fc2b_b")
+
+
+class PolicyWeights(C.Structure):     # mirrors cs_policy_weights
+    _fields_ = [(k, C.c_void_p) for k in POLICY_WEIGHT_KEYS]
+
+
+class PolicyIO(C.Structure):          # mirrors cs_policy_io
+    _fields_ = [("rows", C.c_int32), ("evaluate", C.c_int32), ("epsilon", C.c_float), ("seed", C.c_uint32), ("t", C.c_uint32),
+                ("obs", C.c_void_p), ("last_action", C.c_void_p), ("avail", C.c_void_p), ("hidden", C.c_void_p),
+                ("q", C.c_void_p), ("actions", C.c_void_p)]
+
+
 EPISODE_KEYS = ("o", "s", "u", "r", "avail_u", "o_next", "s_next", "avail_u_next", "u_onehot", "padded", "terminated",
                 "episode_reward", "win_tag", "targets_find", "length")
 
@@ -112,6 +130,9 @@ SIGNATURES = {
     "cs_flight_group_destroy": (None, [C.c_void_p]),
     "cs_flight_record_begin": (C.c_int, [C.c_void_p, C.POINTER(EpisodeBuffers), C.c_int32, C.c_void_p]),
     "cs_flight_record": (C.c_int, [C.c_void_p, C.POINTER(EpisodeBuffers), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "cs_policy_create": (C.c_int, [C.POINTER(PolicyCfg), C.POINTER(PolicyWeights), C.POINTER(C.c_void_p)]),
+    "cs_policy_destroy": (None, [C.c_void_p]),
+    "cs_policy_act": (C.c_int, [C.c_void_p, C.POINTER(PolicyIO), C.c_void_p]),
     "cs_search_create": (C.c_int, [C.POINTER(SearchCfg), C.POINTER(C.c_void_p)]),
     "cs_search_destroy": (None, [C.c_void_p]),
     "cs_search_buffers_get": (C.c_int, [C.c_void_p, C.POINTER(SearchBuffers)]),

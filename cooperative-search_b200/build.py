@@ -6,7 +6,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libcoopsearch.so")
-SOURCES = ["runtime.cu", "flight.cu", "search.cu"]
+SOURCES = ["runtime.cu", "flight.cu", "search.cu", "policy.cu"]
 HEADERS = ["cs_common.cuh", "cs_philox.cuh", os.path.join("..", "..", "include", "coopsearch.h")]
 
 NVCC_FLAGS = [

@@ -278,6 +278,47 @@ typedef struct cs_search_host_io {
 int cs_search_step_host(cs_search* env, const cs_search_host_io* io, void* stream);
 int cs_search_stats(cs_search* env, double* h_out, void* stream);
 
+/* ===================================================================================
+ * batched agent network + action selection  (network/base_net.py, agent/agent.py; SURVEY 8f "next" row 1)
+ * =================================================================================== */
+typedef struct cs_policy_cfg {
+    uint32_t struct_size;
+    int32_t device;
+    int32_t n_agents;       /* args.n_agents                                                   */
+    int32_t obs_dim;        /* args.obs_shape (4 for flight_easy)                              */
+    int32_t n_actions;      /* args.n_actions                                                  */
+    int32_t hidden_dim;     /* args.rnn_hidden_dim, must be 64                                 */
+    int32_t last_action;    /* args.last_action: append the last action one-hot (agent.py:44-45) */
+    int32_t reuse_network;  /* args.reuse_network: append the agent id one-hot (agent.py:46-47)  */
+} cs_policy_cfg;
+/* HOST pointers in torch's own layouts (RNN.state_dict(), network/base_net.py:22-28): Linear.weight is (out, in),
+ * GRUCell.weight_ih / weight_hh are (3*hidden, hidden) with gate order r | z | n. */
+typedef struct cs_policy_weights {
+    const float *fc1_w, *fc1_b;        /* (64, in), (64)        fc1                         */
+    const float *w_ih, *w_hh;          /* (192, 64) each        rnn.weight_ih / weight_hh   */
+    const float *b_ih, *b_hh;          /* (192) each                                        */
+    const float *fc2a_w, *fc2a_b;      /* (64, 64), (64)        fc2.0                       */
+    const float *fc2b_w, *fc2b_b;      /* (n_actions, 64), (n_actions)   fc2.2              */
+} cs_policy_weights;
+typedef struct cs_policy_io {          /* DEVICE pointers; row r = env r / n_agents, agent r % n_agents */
+    int32_t rows;
+    int32_t evaluate;                  /* 1: greedy (agent.py:71 `evaluate or ...`)                       */
+    float epsilon;                     /* probability of a uniform available action when !evaluate        */
+    uint32_t seed, t;                  /* Philox key / counter of the epsilon draws (row, t)              */
+    const float* obs;                  /* [rows][obs_dim]    = get_obs()                                  */
+    const uint8_t* last_action;        /* [rows] or NULL; 255 = no action yet (rollout.py:31 zeros)       */
+    const uint8_t* avail;              /* [rows][n_actions] or NULL (= all available)                     */
+    float* hidden;                     /* [rows][64] in/out  (policy.eval_hidden, init_hidden = zeros)    */
+    float* q;                          /* [rows][n_actions] out or NULL                                   */
+    uint8_t* actions;                  /* [rows] out; may be the same buffer as last_action               */
+} cs_policy_io;
+typedef struct cs_policy cs_policy;
+/* RNN(input_shape, args) + load_state_dict (policy/qmix.py:40-59) */
+int cs_policy_create(const cs_policy_cfg* cfg, const cs_policy_weights* host_weights, cs_policy** out);
+void cs_policy_destroy(cs_policy* policy);
+/* Agents.choose_action for every (env, agent) row at once (agent/agent.py:33-75, alg != random / reinforce) */
+int cs_policy_act(cs_policy* policy, const cs_policy_io* io, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -243,6 +243,51 @@ def run_rollout(n_agents, agent_mode, episodes, env_id, seed0):
     return out
 
 
+def run_policy(model_dir, n_agents, steps=6, rows_envs=5):
+    """The reference's own agent network (network/base_net.py: RNN) with the weights it ships (model/<dir>/*_rnn_net_params.pkl),
+    evaluated the way Agents.choose_action does (agent/agent.py:38-75, evaluate=True): inputs = obs || last action one-hot ||
+    agent id one-hot, one (1, in) row at a time, hidden state carried per agent."""
+    import glob
+    import types as _t
+    import torch
+    rh.import_reference()
+    from network.base_net import RNN
+    path = sorted(glob.glob(os.path.join(rh.REFERENCE_ROOT, "model", model_dir, "*_rnn_net_params.pkl")))[0]
+    sd = torch.load(path, map_location="cpu")
+    n_actions, obs_dim = 3, 4
+    in_dim = obs_dim + n_actions + n_agents
+    args = _t.SimpleNamespace(conv=False, rnn_hidden_dim=64, n_actions=n_actions)
+    net = RNN(in_dim, args)
+    net.load_state_dict(sd)
+    net.eval()
+    rng = np.random.default_rng(11)
+    E = rows_envs
+    obs = rng.uniform(-1, 1, size=(steps, E, n_agents, obs_dim)).astype(np.float32)
+    hidden = torch.zeros(E, n_agents, 64)
+    last = np.zeros((E, n_agents, n_actions), np.float32)
+    qs, hs, acts = [], [], []
+    with torch.no_grad():
+        for t in range(steps):
+            q_t = np.zeros((E, n_agents, n_actions), np.float32)
+            a_t = np.zeros((E, n_agents), np.uint8)
+            for e in range(E):
+                for a in range(n_agents):
+                    agent_id = np.zeros(n_agents, np.float32); agent_id[a] = 1.0
+                    inputs = np.hstack((obs[t, e, a], last[e, a], agent_id))                     # agent.py:44-47
+                    q, h = net(torch.tensor(inputs, dtype=torch.float32).unsqueeze(0), hidden[e, a].unsqueeze(0))
+                    hidden[e, a] = h[0]
+                    q_t[e, a] = q[0].numpy()
+                    act = int(torch.argmax(q))                                                    # agent.py:71-72
+                    a_t[e, a] = act
+                    last[e, a] = 0.0; last[e, a, act] = 1.0                                       # rollout.py:57-62
+            qs.append(q_t); hs.append(hidden.numpy().copy()); acts.append(a_t)
+    out = {"obs": obs, "q": np.array(qs), "hidden": np.array(hs), "actions": np.array(acts),
+           "meta": np.array([n_agents, obs_dim, n_actions], np.int64)}
+    for k, v in sd.items():
+        out["w:" + k] = v.numpy().astype(np.float32)
+    return out
+
+
 def thin(g, keep_every, keys=("obs", "state")):
     """obs/state are derivable from xy/yaw/found; keep every k-th step to bound fixture size."""
     for k in keys:
@@ -271,6 +316,7 @@ def main():
         "flight_2a_small": lambda: thin(run_flight("FlightSearchEnv", 2, 1, E=2, T=80, env_id_base=700,
                                                      target_mode=1, map_size=20, view_range=4, time_limit=80,
                                                      second_episode=10, map_steps=(1, 2, 5, 10, 40, 80)), 20),
+        "policy_qmix_3a": lambda: run_policy("flight_easy_Seed22322107_qmix_3a15t(AM0TM0)", 3),
         "rollout_easy_3a": lambda: run_rollout(3, 0, episodes=4, env_id=950, seed0=77),
         "rollout_easy_5a_am3": lambda: run_rollout(5, 3, episodes=3, env_id=960, seed0=78),
         "search_3a_default": lambda: thin(run_search(3, 15, 50, 7, 0, 0, E=3, T=120, env_id_base=800), 10),
