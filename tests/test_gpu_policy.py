@@ -115,3 +115,32 @@ def test_trained_policy_rollout_through_the_batched_env():
         found[who] = float(env.target_find.float().mean()) / 15.0
     assert found["trained"] > found["random"] + 0.08, found
     assert found["trained"] > 0.75, found
+
+
+def test_trained_policy_curve_against_reference_results():
+    """Statistical anchor shipped by the reference: result/flight_easy_Seed22322107_qmix_3a15t(AM0TM0)/average_res_60.npy is
+    the mean percentage of targets found after each step over 100 replays (runner.py:139-172 -> rollout.py:143-204:
+    reset(init=True), greedy actions, padded with 100 % after the episode ends) of qmix checkpoint 60; the weights it
+    ships in model/ are the LATER checkpoint 121 of the same run.  So this is not an exact known answer: the shipped
+    policy through BatchedRNNAgents on 8192 batched envs must be at least as good as the earlier checkpoint's curve
+    (within its N=100 sampling error) and stay close to it (measured: 69.8 / 99.4 % after steps 41 / 61 against
+    63.1 / 91.0 %).  Entries [10, 20, 40, 60, 80, 100, 150, 199] as printed by runner.py:168."""
+    import types
+    import coopsearch_b200 as cs
+    want = [0.0, 5.87, 63.07, 91.0, 100.0, 100.0, 100.0, 100.0]
+    checkpoints = [10, 20, 40, 60, 80, 100, 150, 199]
+    g = gu.load("policy_qmix_3a")
+    sd = {k[2:]: g[k] for k in g if k.startswith("w:")}
+    args = types.SimpleNamespace(env="flight_easy", map_size=50, target_num=15, target_mode=0, agent_mode=0, n_agents=3,
+                                 view_range=7, time_limit=200, detect_prob=0.9, safe_dist=1, agent_velocity=1, force_dist=3)
+    E = 8192
+    env = cs.VecFlightEasyEnv(args, gu.TEMPLATE, num_envs=E, seed=60)
+    agents = cs.BatchedRNNAgents(sd, num_envs=E, n_agents=3)
+    got = {}
+    for step in range(200):
+        env.step(agents.choose_actions(env.get_obs()))
+        if step in checkpoints:
+            got[step] = float(env.target_find.to(torch.float64).mean().item()) / 15.0 * 100.0
+    curve = np.array([got[k] for k in checkpoints])
+    diff = curve - np.array(want)
+    assert diff.min() > -7.0 and diff.max() < 12.0, "curve %s vs reference %s" % (np.round(curve, 2).tolist(), want)
