@@ -179,7 +179,9 @@ int cs_policy_create(const cs_policy_cfg* cfg, const cs_policy_weights* hw, cs_p
     cudaError_t e = cudaSetDevice(cfg->device);
     if (e == cudaSuccess) e = cudaMalloc(&h->d_w, pk.size() * sizeof(float));
     if (e == cudaSuccess) e = cudaMemcpy(h->d_w, pk.data(), pk.size() * sizeof(float), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(policy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(pk.size() * sizeof(float)));
+    // the largest weight block any policy can have, so that handles of different widths coexist
+    constexpr size_t kMaxWeights = (size_t)kMaxIn * kH + kH + 2 * (kH * 3 * kH + 3 * kH) + kH * kH + kH + kMaxActions * kH + kMaxActions;
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(policy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kMaxWeights * sizeof(float)));
     if (e != cudaSuccess) { cudaFree(h->d_w); delete h; }
     CS_CUDA(e);
     *out = h;
