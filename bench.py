@@ -458,6 +458,34 @@ def measure_obs_full(cs, torch, device, peak):
     return out
 
 
+def measure_policy(cs, torch, device, E=4096, n=3, iters=50):
+    """Batched agent network + action choice (csrc/policy.cu; SURVEY 8f rank 1, first version): rows/s of one
+    choose_actions launch on random-init weights of the reference's architecture (in 10 -> 64 -> GRU 64 -> 64 -> 3)."""
+    torch.manual_seed(0)
+    in_dim = 4 + 3 + n
+    sd = {"fc1.weight": torch.randn(64, in_dim) * 0.1, "fc1.bias": torch.zeros(64), "rnn.weight_ih": torch.randn(192, 64) * 0.1,
+          "rnn.weight_hh": torch.randn(192, 64) * 0.1, "rnn.bias_ih": torch.zeros(192), "rnn.bias_hh": torch.zeros(192),
+          "fc2.0.weight": torch.randn(64, 64) * 0.1, "fc2.0.bias": torch.zeros(64), "fc2.2.weight": torch.randn(3, 64) * 0.1,
+          "fc2.2.bias": torch.zeros(3)}
+    agents = cs.BatchedRNNAgents(sd, num_envs=E, n_agents=n, device=device)
+    obs = torch.rand(E, n, 4, device=device) * 2 - 1
+    for _ in range(5):
+        agents.choose_actions(obs)
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        agents.choose_actions(obs)
+    e1.record()
+    torch.cuda.synchronize(device)
+    us = 1000.0 * e0.elapsed_time(e1) / iters
+    rows = E * n
+    flop = 2 * (in_dim * 64 + 2 * 64 * 192 + 64 * 64 + 64 * 3)
+    return {"workload": "agent network + greedy action choice for %d envs x %d agents (random-init weights, synthetic obs)" % (E, n),
+            "rows": rows, "us_per_launch": us, "agent_steps_per_s": rows / (us * 1e-6), "gflops": rows * flop / (us * 1e-6) / 1e9,
+            "note": "first version on CUDA cores (one warp per row); not part of the headline metric"}
+
+
 def measure_touched(cs, torch, device, steps=200):
     """Exact mean number of probability-map cells updated per env-step on the c4 workload (separate, untimed pass)."""
     w = dict(WORKLOADS["c4"]); w["envs"] = 2048
@@ -636,6 +664,10 @@ def main():
                                "unit": "GB/s", "peak": peak, **measure_obs_full(cs, torch, device, peak)}
         except Exception as exc:
             extra["c4_obs"] = {"error": repr(exc)}
+        try:
+            extra["policy"] = measure_policy(cs, torch, device)
+        except Exception as exc:
+            extra["policy"] = {"error": repr(exc)}
         line["extra"] = extra
         line["cpu_baseline"] = cpu_baseline(w["kind"], w["n"], w["am"], args.cpu_seconds, 4.0)
     print(json.dumps(line))
