@@ -483,7 +483,7 @@ def measure_policy(cs, torch, device, E=4096, n=3, iters=50):
     flop = 2 * (in_dim * 64 + 2 * 64 * 192 + 64 * 64 + 64 * 3)
     return {"workload": "agent network + greedy action choice for %d envs x %d agents (random-init weights, synthetic obs)" % (E, n),
             "rows": rows, "us_per_launch": us, "agent_steps_per_s": rows / (us * 1e-6), "gflops": rows * flop / (us * 1e-6) / 1e9,
-            "note": "first version on CUDA cores (one warp per row); not part of the headline metric"}
+            "note": "first version on CUDA cores (one warp per four rows); not part of the headline metric"}
 
 
 def measure_touched(cs, torch, device, steps=200):

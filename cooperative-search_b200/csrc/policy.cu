@@ -1,4 +1,4 @@
-// Batched agent network + action selection (first version: CUDA cores, one warp per row).
+// Batched agent network + action selection (first version: CUDA cores, one warp per 4 rows).
 //
 // What is restated here (reference: WZN1ng/Cooperative-Search):
 //   RNN.forward without the conv front end   network/base_net.py:30-47   fc1 -> ReLU -> GRUCell(64) -> Linear -> ReLU -> Linear
@@ -18,6 +18,7 @@ namespace {
 constexpr int kH = 64;                 // args.rnn_hidden_dim (common/arguments.py)
 constexpr int kPolicyThreads = 256;
 constexpr int kMaxIn = 32, kMaxActions = 8;
+constexpr int kRowsPerWarp = 4;
 
 struct PolicyParams {
     int rows, n_agents, obs_dim, n_actions, in_dim, use_last, use_id, evaluate;
@@ -53,87 +54,125 @@ __global__ void __launch_bounds__(kPolicyThreads, 1) policy_kernel(const __grid_
     const float* W3 = b2 + kH;
     const float* b3 = W3 + A * kH;
 
+    // RPW consecutive rows per warp iteration: every weight read from shared memory serves RPW rows (the matvecs are
+    // bound by the 12 shared-memory loads per k, not by the FMAs)
+    constexpr int RPW = kRowsPerWarp;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = kPolicyThreads / 32;
-    for (int r = blockIdx.x * wpc + warp; r < p.rows; r += gridDim.x * wpc) {
-        const int a_id = r % p.n_agents;
-        // input element `lane` (agent/agent.py:38-50)
-        float inv = 0.f;
-        if (lane < p.obs_dim) inv = p.obs[(size_t)r * p.obs_dim + lane];
-        else if (p.use_last && lane < p.obs_dim + A) inv = (p.last_action && p.last_action[r] == lane - p.obs_dim) ? 1.f : 0.f;
-        else if (p.use_id && lane < in_dim) inv = (a_id == lane - p.obs_dim - (p.use_last ? A : 0)) ? 1.f : 0.f;
+    for (int rb = (blockIdx.x * wpc + warp) * RPW; rb < p.rows; rb += gridDim.x * wpc * RPW) {
+        int row[RPW];
+        float inv[RPW], x0[RPW], x1[RPW], h0[RPW], h1[RPW];
+#pragma unroll
+        for (int u = 0; u < RPW; ++u) {
+            const int r = min(rb + u, p.rows - 1);                      // a short last block repeats its last row (writes are guarded)
+            row[u] = r;
+            const int a_id = r % p.n_agents;
+            // input element `lane` (agent/agent.py:38-50)
+            float v = 0.f;
+            if (lane < p.obs_dim) v = p.obs[(size_t)r * p.obs_dim + lane];
+            else if (p.use_last && lane < p.obs_dim + A) v = (p.last_action && p.last_action[r] == lane - p.obs_dim) ? 1.f : 0.f;
+            else if (p.use_id && lane < in_dim) v = (a_id == lane - p.obs_dim - (p.use_last ? A : 0)) ? 1.f : 0.f;
+            inv[u] = v;
+            x0[u] = b1[lane]; x1[u] = b1[lane + 32];
+            h0[u] = p.hidden[(size_t)r * kH + lane]; h1[u] = p.hidden[(size_t)r * kH + lane + 32];
+        }
+        __syncwarp();                                                    // all rows' last actions are read before any is rewritten
         // fc1 + ReLU: outputs j = lane, lane + 32
-        float x0 = b1[lane], x1 = b1[lane + 32];
         for (int k = 0; k < in_dim; ++k) {
-            const float v = __shfl_sync(FULL, inv, k);
-            x0 = fmaf(v, W1T[k * kH + lane], x0);
-            x1 = fmaf(v, W1T[k * kH + lane + 32], x1);
+            const float w0 = W1T[k * kH + lane], w1 = W1T[k * kH + lane + 32];
+#pragma unroll
+            for (int u = 0; u < RPW; ++u) {
+                const float v = __shfl_sync(FULL, inv[u], k);
+                x0[u] = fmaf(v, w0, x0[u]);
+                x1[u] = fmaf(v, w1, x1[u]);
+            }
         }
-        x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f);
+#pragma unroll
+        for (int u = 0; u < RPW; ++u) { x0[u] = fmaxf(x0[u], 0.f); x1[u] = fmaxf(x1[u], 0.f); }
         // GRUCell: gates r | z | n, outputs j = lane + 32 * o
-        const float h0 = p.hidden[(size_t)r * kH + lane], h1 = p.hidden[(size_t)r * kH + lane + 32];
-        float gi[6], gh[6];
+        float gi[RPW][6], gh[RPW][6];
 #pragma unroll
-        for (int o = 0; o < 6; ++o) { gi[o] = bih[lane + 32 * o]; gh[o] = bhh[lane + 32 * o]; }
+        for (int u = 0; u < RPW; ++u)
+#pragma unroll
+            for (int o = 0; o < 6; ++o) { gi[u][o] = bih[lane + 32 * o]; gh[u][o] = bhh[lane + 32 * o]; }
         for (int k = 0; k < kH; ++k) {
-            const float xk = __shfl_sync(FULL, k < 32 ? x0 : x1, k & 31);
-            const float hk = __shfl_sync(FULL, k < 32 ? h0 : h1, k & 31);
-            const float* wi = WihT + k * 3 * kH + lane;
-            const float* wh = WhhT + k * 3 * kH + lane;
+            float wi[6], wh[6];
 #pragma unroll
-            for (int o = 0; o < 6; ++o) {
-                gi[o] = fmaf(xk, wi[32 * o], gi[o]);
-                gh[o] = fmaf(hk, wh[32 * o], gh[o]);
-            }
-        }
-        const float r0 = sigmoidf_(gi[0] + gh[0]), r1 = sigmoidf_(gi[1] + gh[1]);
-        const float z0 = sigmoidf_(gi[2] + gh[2]), z1 = sigmoidf_(gi[3] + gh[3]);
-        const float n0 = tanhf(gi[4] + r0 * gh[4]), n1 = tanhf(gi[5] + r1 * gh[5]);
-        const float hn0 = (1.f - z0) * n0 + z0 * h0, hn1 = (1.f - z1) * n1 + z1 * h1;
-        p.hidden[(size_t)r * kH + lane] = hn0;
-        p.hidden[(size_t)r * kH + lane + 32] = hn1;
-        // fc2: Linear + ReLU, then Linear to the action values
-        float y0 = b2[lane], y1 = b2[lane + 32];
-        for (int k = 0; k < kH; ++k) {
-            const float hk = __shfl_sync(FULL, k < 32 ? hn0 : hn1, k & 31);
-            y0 = fmaf(hk, W2T[k * kH + lane], y0);
-            y1 = fmaf(hk, W2T[k * kH + lane + 32], y1);
-        }
-        y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f);
-        float qv[kMaxActions];
+            for (int o = 0; o < 6; ++o) { wi[o] = WihT[k * 3 * kH + lane + 32 * o]; wh[o] = WhhT[k * 3 * kH + lane + 32 * o]; }
 #pragma unroll
-        for (int a = 0; a < kMaxActions; ++a) {
-            if (a >= A) { qv[a] = 0.f; continue; }
-            float part = y0 * W3[a * kH + lane] + y1 * W3[a * kH + lane + 32];
-            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
-            qv[a] = part + b3[a];
-        }
-        if (lane == 0) {
-            int best = -1, navail = 0;
-            float bq = -INFINITY;
+            for (int u = 0; u < RPW; ++u) {
+                const float xk = __shfl_sync(FULL, k < 32 ? x0[u] : x1[u], k & 31);
+                const float hk = __shfl_sync(FULL, k < 32 ? h0[u] : h1[u], k & 31);
 #pragma unroll
-            for (int a = 0; a < kMaxActions; ++a) {
-                if (a >= A) continue;
-                if (p.q) p.q[(size_t)r * A + a] = qv[a];
-                const bool ok = !p.avail || p.avail[(size_t)r * A + a] != 0;
-                navail += ok ? 1 : 0;
-                if (ok && (best < 0 || qv[a] > bq)) { best = a; bq = qv[a]; }     // first maximum, like torch.argmax
-            }
-            int act = best < 0 ? 0 : best;
-            if (!p.evaluate && p.epsilon > 0.f && navail > 0) {
-                // agent.py:71-74: np.random.rand() >= epsilon -> argmax, else a uniform available action
-                const cs_u4 w = cs_philox4x32_10((uint32_t)r, p.t, 0u, 0u, p.seed, CS_STREAM_POLICY);
-                const float u = (float)(w.x >> 8) * (1.0f / 16777216.0f);
-                if (u < p.epsilon) {
-                    int pick = (int)(w.y % (uint32_t)navail);
-#pragma unroll
-                    for (int a = 0; a < kMaxActions; ++a) {
-                        if (a >= A) continue;
-                        const bool ok = !p.avail || p.avail[(size_t)r * A + a] != 0;
-                        if (ok && pick-- == 0) act = a;
-                    }
+                for (int o = 0; o < 6; ++o) {
+                    gi[u][o] = fmaf(xk, wi[o], gi[u][o]);
+                    gh[u][o] = fmaf(hk, wh[o], gh[u][o]);
                 }
             }
-            p.actions[r] = (uint8_t)act;
+        }
+        float hn0[RPW], hn1[RPW], y0[RPW], y1[RPW];
+#pragma unroll
+        for (int u = 0; u < RPW; ++u) {
+            const float r0 = sigmoidf_(gi[u][0] + gh[u][0]), r1 = sigmoidf_(gi[u][1] + gh[u][1]);
+            const float z0 = sigmoidf_(gi[u][2] + gh[u][2]), z1 = sigmoidf_(gi[u][3] + gh[u][3]);
+            const float n0 = tanhf(gi[u][4] + r0 * gh[u][4]), n1 = tanhf(gi[u][5] + r1 * gh[u][5]);
+            hn0[u] = (1.f - z0) * n0 + z0 * h0[u];
+            hn1[u] = (1.f - z1) * n1 + z1 * h1[u];
+            if (rb + u < p.rows) {
+                p.hidden[(size_t)row[u] * kH + lane] = hn0[u];
+                p.hidden[(size_t)row[u] * kH + lane + 32] = hn1[u];
+            }
+            y0[u] = b2[lane]; y1[u] = b2[lane + 32];
+        }
+        // fc2: Linear + ReLU, then Linear to the action values
+        for (int k = 0; k < kH; ++k) {
+            const float w0 = W2T[k * kH + lane], w1 = W2T[k * kH + lane + 32];
+#pragma unroll
+            for (int u = 0; u < RPW; ++u) {
+                const float hk = __shfl_sync(FULL, k < 32 ? hn0[u] : hn1[u], k & 31);
+                y0[u] = fmaf(hk, w0, y0[u]);
+                y1[u] = fmaf(hk, w1, y1[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < RPW; ++u) {
+            const float ya = fmaxf(y0[u], 0.f), yb = fmaxf(y1[u], 0.f);
+            const int r = row[u];
+            float qv[kMaxActions];
+#pragma unroll
+            for (int a = 0; a < kMaxActions; ++a) {
+                if (a >= A) { qv[a] = 0.f; continue; }
+                float part = ya * W3[a * kH + lane] + yb * W3[a * kH + lane + 32];
+                for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
+                qv[a] = part + b3[a];
+            }
+            if (lane == 0 && rb + u < p.rows) {
+                int best = -1, navail = 0;
+                float bq = -INFINITY;
+#pragma unroll
+                for (int a = 0; a < kMaxActions; ++a) {
+                    if (a >= A) continue;
+                    if (p.q) p.q[(size_t)r * A + a] = qv[a];
+                    const bool ok = !p.avail || p.avail[(size_t)r * A + a] != 0;
+                    navail += ok ? 1 : 0;
+                    if (ok && (best < 0 || qv[a] > bq)) { best = a; bq = qv[a]; }     // first maximum, like torch.argmax
+                }
+                int act = best < 0 ? 0 : best;
+                if (!p.evaluate && p.epsilon > 0.f && navail > 0) {
+                    // agent.py:71-74: np.random.rand() >= epsilon -> argmax, else a uniform available action
+                    const cs_u4 w = cs_philox4x32_10((uint32_t)r, p.t, 0u, 0u, p.seed, CS_STREAM_POLICY);
+                    const float uu = (float)(w.x >> 8) * (1.0f / 16777216.0f);
+                    if (uu < p.epsilon) {
+                        int pick = (int)(w.y % (uint32_t)navail);
+#pragma unroll
+                        for (int a = 0; a < kMaxActions; ++a) {
+                            if (a >= A) continue;
+                            const bool ok = !p.avail || p.avail[(size_t)r * A + a] != 0;
+                            if (ok && pick-- == 0) act = a;
+                        }
+                    }
+                }
+                p.actions[r] = (uint8_t)act;
+            }
         }
     }
 }
@@ -203,7 +242,7 @@ int cs_policy_act(cs_policy* h, const cs_policy_io* io, void* stream) {
     p.use_last = h->use_last; p.use_id = h->use_id; p.evaluate = io->evaluate; p.epsilon = io->epsilon; p.seed = io->seed; p.t = io->t;
     p.w = h->d_w; p.obs = io->obs; p.last_action = io->last_action; p.avail = io->avail; p.hidden = io->hidden; p.q = io->q;
     p.actions = io->actions;
-    const int wpc = kPolicyThreads / 32;
+    const int wpc = (kPolicyThreads / 32) * kRowsPerWarp;
     int grid = (io->rows + wpc - 1) / wpc;
     if (grid > CS_NUM_SMS_B200) grid = CS_NUM_SMS_B200;                   // persistent: one CTA per SM keeps the weights resident
     policy_kernel<<<grid, kPolicyThreads, h->w_floats * sizeof(float), (cudaStream_t)stream>>>(p);
