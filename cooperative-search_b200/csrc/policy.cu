@@ -16,7 +16,7 @@
 namespace {
 
 constexpr int kH = 64;                 // args.rnn_hidden_dim (common/arguments.py)
-constexpr int kPolicyThreads = 256;
+constexpr int kPolicyThreads = 512;          // 16 warps per SM at 128 registers: one CTA per SM holds the weights
 constexpr int kMaxIn = 32, kMaxActions = 8;
 constexpr int kRowsPerWarp = 4;
 
