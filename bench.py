@@ -503,8 +503,10 @@ def kernel_name(w, lanes, grouped=False):
         return "search_kernel<STEP>"
     if grouped:
         return "flight_tpe_group_kernel<N=%d,K=%d>" % (w["n"], lanes)
-    step = ("flight_tpe_kernel<N=%d,K=%d,STEP>" % (w["n"], lanes)) if lanes and lanes <= 4 else "flight_kernel<LPE=%s,STEP>" % lanes
-    return step if w["kind"] == "flight_easy" else "flight_map_kernel (after %s; two launches per env-step)" % step
+    if w["kind"] == "flight":
+        return ("flight_fused_kernel<N=%d,STEP> (step + belief map of an env in one launch, %d lanes per env)" % (w["n"], lanes)) if lanes == 8 else \
+            "flight_kernel<LPE=%s,STEP> + flight_map_generic_kernel" % lanes
+    return ("flight_tpe_kernel<N=%d,K=%d,STEP>" % (w["n"], lanes)) if lanes and lanes <= 4 else "flight_kernel<LPE=%s,STEP>" % lanes
 
 
 def load_peaks():

@@ -40,7 +40,8 @@ class FlightBuffers(C.Structure):
         ("dyn", C.c_void_p), ("dyn_doubles", C.c_int32), ("yaw_off", C.c_int32), ("meta_off", C.c_int32),
         ("state_len", C.c_int32), ("state_stride", C.c_int32), ("tgt", C.c_void_p), ("obs", C.c_void_p), ("state", C.c_void_p),
         ("reward", C.c_void_p), ("terminated", C.c_void_p), ("win", C.c_void_p), ("target_find", C.c_void_p),
-        ("prob_map", C.c_void_p), ("stats", C.c_void_p),
+        ("prob_map", C.c_void_p), ("stats", C.c_void_p), ("map_tiles", C.c_int32), ("map_env_stride", C.c_int32),
+        ("slab", C.c_void_p), ("slab_bytes", C.c_uint64),
     ]
 
 
@@ -121,6 +122,8 @@ SIGNATURES = {
     "cs_flight_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "cs_flight_step_random": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "cs_flight_obs_full": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cs_flight_map_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cs_flight_map_import": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "cs_flight_step_host": (C.c_int, [C.c_void_p, C.POINTER(FlightHostIO), C.c_void_p]),
     "cs_flight_slab_layout": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "cs_flight_step_host_many": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(FlightHostIO), C.c_int32, C.POINTER(C.c_void_p), C.c_int32]),

@@ -1,0 +1,239 @@
+// Auxiliary kernels of the flight handles: reference-shaped map observation (de-tiling + TMA bulk stores), map
+// export / import, episode-batch writer, live-step statistics.  See flight_common.cuh for the file map.
+#include "flight_internal.h"
+
+namespace csf {
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// Reference-shaped observation of the flight variant: out[e][a] = prob_map[e].ravel() || (x^, y^, cos, sin)
+// (flight_env.py:223-230), i.e. every map is read once and written n times.  The map lives in HBM as 4x4-cell tiles
+// (flight_common.cuh); a persistent CTA de-tiles one env at a time into a row-major image in shared memory
+// (coalesced 16-byte loads, two stages) and one elected thread then writes the image to the n observation rows with
+// the TMA engine: n x cp.async.bulk.global.shared::cta [SASS: UBLKCP], one bulk group per env; a stage is refilled
+// once the bulk group that read it has drained (cp.async.bulk.wait_group.read).  The bulk form needs
+// (M*M*4) % 16 == 0; otherwise (or with obs_path = 1, the A/B hook) the image is written with plain stores.
+// ------------------------------------------------------------------------------------------------
+constexpr int kObsThreads = 256;
+
+__global__ void __launch_bounds__(kObsThreads) flight_obs_full_kernel(const float* __restrict__ map, const float* __restrict__ obs,
+                                                                      float* __restrict__ out, int E, int n, int M, int tiles,
+                                                                      int map_stride, int stage_floats, int bulk) {
+    extern __shared__ __align__(128) float img[];
+    const int tid = threadIdx.x, MM = M * M;
+    const size_t row_floats = (size_t)MM + 4;
+    int it = 0;
+    for (int e = blockIdx.x; e < E; e += gridDim.x, ++it) {
+        float* st = img + (size_t)(it & 1) * stage_floats;
+        if (bulk) {
+            // the bulk group issued two iterations ago read this stage: it must have drained before the stage is rewritten
+            if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        }
+        __syncthreads();
+        const float4* src = reinterpret_cast<const float4*>(map + (size_t)e * map_stride);
+        for (int f = tid; f < map_stride / 4; f += kObsThreads) {
+            const int tile = f >> 2, r = f & 3;
+            const int tr = tile / tiles, tc = tile - tr * tiles;
+            const int i = 4 * tr + r, j0 = 4 * tc;
+            if (i >= M) continue;
+            const float4 v = __ldcs(src + f);
+            const int d = i * M + j0;
+            if (j0 + 4 <= M && (d & 3) == 0) {
+                *reinterpret_cast<float4*>(st + d) = v;
+            } else if (j0 + 4 <= M && (d & 1) == 0) {
+                *reinterpret_cast<float2*>(st + d) = make_float2(v.x, v.y);
+                *reinterpret_cast<float2*>(st + d + 2) = make_float2(v.z, v.w);
+            } else {
+                st[d] = v.x;
+                if (j0 + 1 < M) st[d + 1] = v.y;
+                if (j0 + 2 < M) st[d + 2] = v.z;
+                if (j0 + 3 < M) st[d + 3] = v.w;
+            }
+        }
+        // feature tails of this env: thread a writes the 4 floats after the map of row (e, a)
+        for (int a = tid; a < n; a += kObsThreads) {
+            const float4 f = reinterpret_cast<const float4*>(obs)[(size_t)e * n + a];
+            float* dst = out + ((size_t)e * n + a) * row_floats + MM;
+            dst[0] = f.x; dst[1] = f.y; dst[2] = f.z; dst[3] = f.w;
+        }
+        if (bulk) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the image, before the TMA engine reads it
+        __syncthreads();
+        if (bulk) {
+            if (tid == 0) {
+                const uint32_t s32 = smem_u32(st);
+                for (int a = 0; a < n; ++a)
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 ::"l"(out + ((size_t)e * n + a) * row_floats), "r"(s32), "r"((uint32_t)MM * 4u) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        } else {
+            for (int idx = tid; idx < n * MM; idx += kObsThreads) {
+                const int a = idx / MM, k = idx - a * MM;
+                out[((size_t)e * n + a) * row_floats + k] = st[k];
+            }
+        }
+    }
+    if (bulk && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // all stores complete before exit
+}
+
+// prob_map as the reference holds it, [E][M][M] row-major (prob_map[i][j], i <-> x), from / into the tiled device layout
+__global__ void __launch_bounds__(256) flight_map_export_kernel(const float* __restrict__ map, float* __restrict__ out, int E, int M,
+                                                                int tiles, int map_stride) {
+    const long long total = (long long)E * M * M;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long e = idx / (M * M);
+        const int c = (int)(idx - e * (M * M)), i = c / M, j = c - i * M;
+        out[idx] = map[e * map_stride + tile_off(tiles, i, j)];
+    }
+}
+
+__global__ void __launch_bounds__(256) flight_map_import_kernel(float* __restrict__ map, const float* __restrict__ in, int E, int M,
+                                                                int tiles, int map_stride) {
+    const long long total = (long long)E * M * M;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long e = idx / (M * M);
+        const int c = (int)(idx - e * (M * M)), i = c / M, j = c - i * M;
+        map[e * map_stride + tile_off(tiles, i, j)] = in[idx];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Episode-batch writer: the padded 11-array layout RolloutWorker.generate_episode builds one env and one step at a
+// time (common/rollout.py:43-132), for all envs of the handle, on the device.
+//   begin : every array <- the padding of :105-116 (zeros, padded = terminated = 1); o[:,0], s[:,0] <- obs / state
+//   record: after step t, for the envs that took it (time_step == t+1):  u, u_onehot, r, terminated, padded = 0,
+//           avail_u[t] = avail_u_next[t] = 1, o_next[t] = s_next[t] = the new obs / state, and the same rows into
+//           o[t+1], s[t+1] unless the episode ended (:79-97: "last obs" is only ever an *_next row)
+// One thread per (env, output element); rows of different envs are contiguous, so the copies are coalesced.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) flight_record_begin_kernel(const FlightParams p, cs_episode_buffers b, int T) {
+    const int n = p.n, S = p.state_len, O = 4 * n, A = 3 * n;
+    const int per_env = O + S;
+    const long long total = (long long)p.E * per_env;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int e = (int)(idx / per_env), k = (int)(idx - (long long)e * per_env);
+        if (k < O) b.o[((size_t)e * T) * O + k] = p.obs[(size_t)e * O + k];
+        else b.s[((size_t)e * T) * S + (k - O)] = p.state[(size_t)e * p.state_stride + (k - O)];
+    }
+    (void)A;
+}
+
+__global__ void __launch_bounds__(256) flight_record_kernel(const FlightParams p, cs_episode_buffers b, int t, int T,
+                                                            const uint8_t* __restrict__ actions) {
+    const int n = p.n, S = p.state_len, O = 4 * n, A = 3 * n;
+    const int per_env = O + S + 1;
+    const long long total = (long long)p.E * per_env;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int e = (int)(idx / per_env), k = (int)(idx - (long long)e * per_env);
+        uint4 mq0, mq1;
+        meta_ld(p, e, &mq0, &mq1);
+        const uint32_t mt[CS_META_WORDS] = {mq0.x, mq0.y, mq0.z, mq0.w, mq1.x, mq1.y, mq1.z, mq1.w};
+        if (mt[CS_META_TIME] != (uint32_t)(t + 1)) continue;           // this env did not take step t (episode over)
+        const bool over = (mt[CS_META_FLAGS] & CS_FLAG_DONE) != 0;
+        const size_t row = (size_t)e * T + t;
+        if (k < O) {
+            const float v = p.obs[(size_t)e * O + k];
+            b.o_next[row * O + k] = v;
+            if (!over && t + 1 < T) b.o[(row + 1) * O + k] = v;
+        } else if (k < O + S) {
+            const float v = p.state[(size_t)e * p.state_stride + (k - O)];
+            b.s_next[row * S + (k - O)] = v;
+            if (!over && t + 1 < T) b.s[(row + 1) * S + (k - O)] = v;
+        } else {
+            for (int a = 0; a < n; ++a) {
+                const uint8_t act = actions[(size_t)e * n + a];
+                b.u[row * n + a] = act;
+                for (int c = 0; c < 3; ++c) {
+                    b.u_onehot[row * A + 3 * a + c] = (c == act) ? 1 : 0;
+                    b.avail_u[row * A + 3 * a + c] = 1;                // get_avail_agent_actions: ones (flight_env_easy.py:184-188)
+                    b.avail_u_next[row * A + 3 * a + c] = 1;
+                }
+            }
+            b.r[row] = p.reward[e];
+            b.terminated[row] = p.terminated[e];
+            b.padded[row] = 0;
+            if (over || t + 1 == T) {                                   // episode summary (rollout.py:64,79,137-140)
+                b.episode_reward[e] = __uint_as_float(mt[CS_META_EPREWARD]);
+                b.win_tag[e] = (over && (mt[CS_META_FLAGS] & CS_FLAG_WIN)) ? 1 : 0;
+                b.targets_find[e] = p.target_find[e];
+                b.length[e] = t + 1;
+            }
+        }
+    }
+}
+
+// sum of the time_step words of all envs (steps of the episodes still running), for cs_flight_stats
+__global__ void __launch_bounds__(256) flight_live_steps_kernel(const double* __restrict__ dyn, int E, long long rs, long long es, int meta_off,
+                                                                double* __restrict__ out) {
+    unsigned long long acc = 0;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
+        const uint2 w23 = *reinterpret_cast<const uint2*>(dyn + (size_t)(meta_off + 1) * rs + (size_t)e * es);     // out mask, time_step
+        const uint2 w45 = *reinterpret_cast<const uint2*>(dyn + (size_t)(meta_off + 2) * rs + (size_t)e * es);     // episode, flags
+        if (!(w45.y & CS_FLAG_DONE)) acc += w23.y;                          // a finished episode is already in CS_STAT_EP_LEN
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, (double)acc);
+}
+
+inline int capped_grid(long long items, int per_block, int max_blocks) {
+    const long long g = (items + per_block - 1) / per_block;
+    return (int)(g < (long long)max_blocks ? (g < 1 ? 1 : g) : max_blocks);
+}
+
+}  // namespace
+
+cudaError_t launch_obs_full(cs_flight* h, float* d_out, cudaStream_t st) {
+    const FlightParams& p = h->p;
+    const int MM = p.M * p.M;
+    const int stage_floats = (MM + 31) & ~31;                         // stages start 128-byte aligned
+    const size_t smem = 2 * (size_t)stage_floats * sizeof(float);
+    const int bulk = (MM % 4 == 0 && h->obs_path != 1) ? 1 : 0;
+    static size_t cur_limit = 48 * 1024;                              // per kernel, only ever raised
+    if (smem > cur_limit) {
+        const cudaError_t e = cudaFuncSetAttribute(flight_obs_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        cur_limit = smem;
+    }
+    int per_sm = (int)((200 * 1024) / (smem + 1024));
+    per_sm = per_sm > 4 ? 4 : (per_sm < 1 ? 1 : per_sm);
+    const int grid = p.E < CS_NUM_SMS_B200 * per_sm ? p.E : CS_NUM_SMS_B200 * per_sm;
+    flight_obs_full_kernel<<<grid, kObsThreads, smem, st>>>(p.prob_map, p.obs, d_out, p.E, p.n, p.M, p.tiles, p.map_stride, stage_floats, bulk);
+    cs_count_launch(1);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_map_export(cs_flight* h, float* d_out, cudaStream_t st) {
+    const FlightParams& p = h->p;
+    flight_map_export_kernel<<<capped_grid((long long)p.E * p.M * p.M, 256, CS_NUM_SMS_B200 * 8), 256, 0, st>>>(p.prob_map, d_out, p.E, p.M, p.tiles, p.map_stride);
+    cs_count_launch(1);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_map_import(cs_flight* h, const float* d_in, cudaStream_t st) {
+    const FlightParams& p = h->p;
+    flight_map_import_kernel<<<capped_grid((long long)p.E * p.M * p.M, 256, CS_NUM_SMS_B200 * 8), 256, 0, st>>>(p.prob_map, d_in, p.E, p.M, p.tiles, p.map_stride);
+    cs_count_launch(1);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_record_begin(cs_flight* h, const cs_episode_buffers& b, int T, cudaStream_t st) {
+    const FlightParams& p = h->p;
+    flight_record_begin_kernel<<<capped_grid((long long)p.E * (4 * p.n + p.state_len), 256, CS_NUM_SMS_B200 * 8), 256, 0, st>>>(p, b, T);
+    cs_count_launch(1);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_record(cs_flight* h, const cs_episode_buffers& b, int t, int T, const uint8_t* actions, cudaStream_t st) {
+    const FlightParams& p = h->p;
+    flight_record_kernel<<<capped_grid((long long)p.E * (4 * p.n + p.state_len + 1), 256, CS_NUM_SMS_B200 * 8), 256, 0, st>>>(p, b, t, T, actions);
+    cs_count_launch(1);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_live_steps(cs_flight* h, cudaStream_t st) {
+    flight_live_steps_kernel<<<capped_grid(h->p.E, 256, CS_NUM_SMS_B200 * 4), 256, 0, st>>>(h->p.dyn, h->p.E, h->p.dyn_rs, h->p.dyn_es, h->p.meta_off, h->d_live);
+    cs_count_launch(1);
+    return cudaGetLastError();
+}
+
+}  // namespace csf

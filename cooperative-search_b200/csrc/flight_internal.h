@@ -1,0 +1,66 @@
+// Host-side internals shared by the flight_*.cu translation units (not part of the C ABI).
+#pragma once
+#include <cuda.h>
+#include "flight_common.cuh"
+
+constexpr int kTpeMaxAgents = 8;       // thread-per-env kernels are instantiated for n_agents 1..8
+#ifndef CS_TPE_THREADS
+#define CS_TPE_THREADS 64
+#endif
+constexpr int kTpeThreads = CS_TPE_THREADS;   // threads per CTA of the thread-per-env kernels
+constexpr int kMaxGroup = 128;         // handles per grouped launch
+
+struct cs_flight {
+    cs_flight_cfg cfg;
+    csf::FlightParams p;
+    int lpe;              // lanes per env of the lane-per-agent kernel
+    bool tpe;             // thread-per-env step kernel (n_agents <= kTpeMaxAgents and lanes_per_env in {0, 1, 4})
+    int tpe_k;            // threads that share one env's target loop in that kernel (1, 4; 8 in the fused kernel)
+    bool fused;           // flight variant: step + belief map in one kernel (tpe, map_size <= 63)
+    size_t smem_bytes, map_smem;
+    int grid, map_grid;
+    uint32_t seq;         // generic map path: value of CS_META_SENSE >> 1 that marks "sensed by the latest call" (constant: launches captured in CUDA graphs replay it)
+    double* d_tmpl;
+    uint8_t* d_actions;   // device staging of the *_host entry point's actions
+    double* d_live;       // scratch of cs_flight_stats
+    int obs_path;         // 0 = TMA bulk stores for the map observation, 1 = plain stores (A/B measurement)
+    uint8_t* d_slab;      // one allocation behind reward | target_find | terminated | win | obs | state
+    size_t slab_bytes, host_bytes, off_reward, off_tf, off_term, off_win, off_obs, off_state;
+    longlong2* d_lut_meta;
+    double2* d_lut;
+    float4* d_lut_cells;
+    bool have_tmpl;
+};
+
+struct cs_flight_group {
+    int count, n, k, grid_x, device;
+    cs_flight* envs[kMaxGroup];
+    csf::FlightParams* d_table;
+};
+
+namespace csf {
+
+// flight_tpe.cu, one translation unit per pair of n_agents (part P: 2P+1, 2P+2)
+cudaError_t launch_tpe_part0(cs_flight*, int mode, const uint8_t* actions, const uint8_t* mask, uint32_t rflags, cudaStream_t);
+cudaError_t launch_tpe_part1(cs_flight*, int mode, const uint8_t* actions, const uint8_t* mask, uint32_t rflags, cudaStream_t);
+cudaError_t launch_tpe_part2(cs_flight*, int mode, const uint8_t* actions, const uint8_t* mask, uint32_t rflags, cudaStream_t);
+cudaError_t launch_tpe_part3(cs_flight*, int mode, const uint8_t* actions, const uint8_t* mask, uint32_t rflags, cudaStream_t);
+cudaError_t launch_group_part0(const cs_flight_group*, const uint8_t* const* d_actions, cudaStream_t);
+cudaError_t launch_group_part1(const cs_flight_group*, const uint8_t* const* d_actions, cudaStream_t);
+cudaError_t launch_group_part2(const cs_flight_group*, const uint8_t* const* d_actions, cudaStream_t);
+cudaError_t launch_group_part3(const cs_flight_group*, const uint8_t* const* d_actions, cudaStream_t);
+int fused_lanes_part0();
+
+// flight_lpa.cu: lane-per-agent step / reset kernel (+ the generic belief-map kernel of the flight variant)
+cudaError_t launch_lpa(cs_flight*, int mode, const uint8_t* actions, const uint8_t* mask, uint32_t rflags, cudaStream_t);
+cudaError_t lpa_set_smem_limit(size_t step_bytes, size_t map_bytes);
+
+// flight_aux.cu
+cudaError_t launch_obs_full(cs_flight*, float* d_out, cudaStream_t);
+cudaError_t launch_map_export(cs_flight*, float* d_out, cudaStream_t);
+cudaError_t launch_map_import(cs_flight*, const float* d_in, cudaStream_t);
+cudaError_t launch_record_begin(cs_flight*, const cs_episode_buffers&, int T, cudaStream_t);
+cudaError_t launch_record(cs_flight*, const cs_episode_buffers&, int t, int T, const uint8_t* actions, cudaStream_t);
+cudaError_t launch_live_steps(cs_flight*, cudaStream_t);
+
+}  // namespace csf

@@ -134,7 +134,9 @@ class _VecFlightBase:
         self._win = _wrap(b.win, (E,), "|u1", dev, own)
         self._target_find = _wrap(b.target_find, (E,), "<i4", dev, own)
         self._stats = _wrap(b.stats, (_lib.CS_NUM_STATS,), "<f8", dev, own)
-        self.prob_map = _wrap(b.prob_map, (E, M, M), "<f4", dev, own) if b.prob_map else None
+        self._slab = _wrap(b.slab, (int(b.slab_bytes),), "|u1", dev, own)      # all step outputs (checkpointing)
+        # the belief map lives on the device as 4x4-cell tiles (include/coopsearch.h): zero-copy tiled view
+        self.prob_map_tiles = _wrap(b.prob_map, (E, b.map_tiles, b.map_tiles, 4, 4), "<f4", dev, own) if b.prob_map else None
         self._avail = torch.ones((E, n, self.n_actions), dtype=torch.float32, device=dev)
         self._host = None
         print('Init Env ' + getattr(args, "env", self.ENV_NAME) + ' {}a{}t(agent mode:{}, target mode:{}) x{} envs on {}'.format(
@@ -280,18 +282,47 @@ class _VecFlightBase:
     def stats_tensor(self):
         return self._stats
 
+    @property
+    def prob_map(self):
+        """self.prob_map of the reference (flight_env.py:53): [E,M,M] float32, prob_map[e,i,j] with i <-> x -- a fresh
+        row-major copy of the tiled device map (cs_flight_map_export); None for flight_easy.  Assigning
+        (``env.prob_map = t``) converts back into the tiled map."""
+        if self.prob_map_tiles is None:
+            return None
+        out = torch.empty((self.num_envs, self.map_size, self.map_size), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.cs_flight_map_export(self._h.ptr, C.c_void_p(out.data_ptr()), self._stream()), "cs_flight_map_export")
+        return out
+
+    @prob_map.setter
+    def prob_map(self, value):
+        if self.prob_map_tiles is None:
+            raise CoopSearchError("flight_easy has no probability map")
+        t = torch.as_tensor(value, dtype=torch.float32, device=self.device).contiguous()
+        if tuple(t.shape) != (self.num_envs, self.map_size, self.map_size):
+            raise CoopSearchError("prob_map must have shape (num_envs, map_size, map_size)")
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.cs_flight_map_import(self._h.ptr, C.c_void_p(t.data_ptr()), self._stream()), "cs_flight_map_import")
+
     def get_state_dict(self):
-        """Checkpoint of the full env state (the reference never checkpoints env state)."""
-        d = {"dyn": self._dyn.clone(), "tgt": self.tgt_xy.clone()}
-        if self.prob_map is not None:
-            d["prob_map"] = self.prob_map.clone()
+        """Checkpoint of the full env state (the reference never checkpoints env state): the
+        dynamic state, the targets, the output buffers (so that get_obs / get_state / reward / target_find after a
+        restore are those of the checkpointed step) and, for the flight variant, the belief map."""
+        d = {"dyn": self._dyn.clone(), "tgt": self.tgt_xy.clone(), "outputs": self._slab.clone()}
+        if self.prob_map_tiles is not None:
+            d["prob_map_tiles"] = self.prob_map_tiles.clone()
         return d
 
     def set_state_dict(self, d):
         self._dyn.copy_(d["dyn"])
         self.tgt_xy.copy_(d["tgt"])
-        if self.prob_map is not None and "prob_map" in d:
-            self.prob_map.copy_(d["prob_map"])
+        if "outputs" in d:
+            self._slab.copy_(d["outputs"])
+        if self.prob_map_tiles is not None:
+            if "prob_map_tiles" in d:
+                self.prob_map_tiles.copy_(d["prob_map_tiles"])
+            elif "prob_map" in d:
+                self.prob_map = d["prob_map"]
 
     def host_buffers(self):
         """Pinned host staging used by step_host (allocated once): one slab mirroring the device output slab, so
@@ -484,14 +515,15 @@ class VecFlightEnv(_VecFlightBase):
         self._obs_full = None
 
     def set_obs_kernel(self, kind="tma"):
-        """Which kernel materialises the reference-shaped observation: "tma" (bulk async copies, default) or
-        "plain" (float4 copies); results are identical, the switch exists for A/B measurement."""
+        """How the de-tiling observation kernel writes the reference-shaped rows: "tma" (bulk async stores from shared
+        memory, default) or "plain" (ordinary stores); results are identical, the switch exists for A/B measurement."""
         _lib.check(self.lib.cs_debug_flight_obs_path(self._h.ptr, {"tma": 0, "plain": 1}[kind]), "cs_debug_flight_obs_path")
 
     def get_obs(self, full=True):
         """Reference-shaped [E,n,M*M+4] = prob_map.ravel() || 4 features (flight_env.py:223-230),
         materialised by a streaming kernel.  full=False returns the [E,n,4] features only; the map
-        itself is available zero-copy as ``self.prob_map`` ([E,M,M])."""
+        itself is available zero-copy in its tiled device layout as ``self.prob_map_tiles`` and as a row-major
+        copy as ``self.prob_map`` ([E,M,M])."""
         if not full:
             return self._obs
         if self._obs_full is None:

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CS_ABI_VERSION 1
+#define CS_ABI_VERSION 2
 #define CS_MAX_AGENTS 32   /* flight envs: out-of-map flags live in one 32-bit word   */
 #define CS_MAX_TARGETS 32  /* flight envs: found flags live in one 32-bit word        */
 #define CS_NUM_STATS 8
@@ -76,7 +76,7 @@ int cs_debug_philox(const uint32_t* d_in6, uint32_t* d_out4, int32_t count, void
 int cs_debug_heading_lut(int32_t time_limit, const double* h_in, int32_t count, double* sin_out, double* cos_out,
                          int32_t* from_table);
 
-/* measurement hook: kernel used by cs_flight_obs_full (0 = TMA bulk-copy kernel, default; 1 = plain copy kernel) */
+/* measurement hook: how cs_flight_obs_full writes the observation rows (0 = TMA bulk stores, default; 1 = plain stores) */
 int cs_debug_flight_obs_path(struct cs_flight* env, int32_t path);
 
 /* Pinned host memory for the *_host entry points. */
@@ -100,7 +100,9 @@ typedef struct cs_flight_cfg {
     int32_t auto_reset;     /* 1: a terminated env is reset inside the same step call      */
     int32_t count_touched;  /* 1: accumulate #prob-map cells updated into CS_STAT_TOUCHED  */
     int32_t lanes_per_env;  /* 0 = automatic; 1 or 4 (n_agents <= 8): thread-per-env step kernel with
-                               that many threads per env; 2, 8, 16, 32: lane-per-agent kernel      */
+                               that many threads per env (the flight variant then runs its fused
+                               step + belief-map kernel, 8 lanes per env); 2, 8, 16, 32:
+                               lane-per-agent kernel (flight variant: + generic map kernel)        */
     int32_t device;         /* CUDA device ordinal                                         */
     double velocity;        /* args.agent_velocity                                         */
     double detect_prob;     /* args.detect_prob                                            */
@@ -135,8 +137,15 @@ typedef struct cs_flight_buffers {
     uint8_t* terminated;    /* [E]           step()[1]                                     */
     uint8_t* win;           /* [E]           step()[2] (win_flag)                          */
     int32_t* target_find;   /* [E]           attribute target_find (rollout.py:79)         */
-    float* prob_map;        /* [E][M][M] (variant 1) else NULL; prob_map[i][j], i<->x      */
+    float* prob_map;        /* variant 1 else NULL.  TILED: 4x4-cell tiles of 64 bytes, cell prob_map[i][j]
+                               (i<->x) of env e at prob_map[e*map_env_stride + ((i>>2)*map_tiles + (j>>2))*16
+                               + (i&3)*4 + (j&3)]; cs_flight_map_export / _import convert from / to the
+                               reference's row-major [E][M][M]                              */
     double* stats;          /* [CS_NUM_STATS] running sums over finished episodes          */
+    int32_t map_tiles;      /* tiles per map side = ceil(M/4)                              */
+    int32_t map_env_stride; /* floats per env in prob_map = map_tiles^2 * 16               */
+    void* slab;             /* the one allocation behind reward..state, obs (checkpointing) */
+    uint64_t slab_bytes;
 } cs_flight_buffers;
 
 /* FlightSearchEnvEasy.__init__ / FlightSearchEnv.__init__ (flight_env_easy.py:15-69).
@@ -169,6 +178,10 @@ int cs_flight_step_random(cs_flight* env, int32_t k, void* stream);
 /* Reference-shaped observation of the flight variant (flight_env.py:223-230):
  * d_out [E][n][M*M+4] = prob_map.ravel() || (x^,y^,cos,sin). */
 int cs_flight_obs_full(cs_flight* env, float* d_out, void* stream);
+/* self.prob_map as the reference holds it (flight_env.py:53): d_out / d_in = device [E][M][M] row-major floats,
+ * converted from / into the handle's tiled map. */
+int cs_flight_map_export(cs_flight* env, float* d_out, void* stream);
+int cs_flight_map_import(cs_flight* env, const float* d_in, void* stream);
 /* Host-buffer step: the call a CPU-side rollout makes.  h_actions [E][n] u8.  Any output pointer
  * may be NULL (not copied).  Blocks until outputs are in host memory. */
 #define CS_HOST_NO_SYNC 1u        /* cs_*_host_io.flags: enqueue only; the caller synchronises the stream */

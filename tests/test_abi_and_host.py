@@ -22,7 +22,7 @@ def test_library_exports_every_symbol_of_the_header():
     for name in sorted(declared):
         assert hasattr(lib, name), "library does not export %s" % name
     assert declared == set(_lib.SIGNATURES), "ctypes table and header disagree: %s" % (declared ^ set(_lib.SIGNATURES))
-    assert lib.cs_version() == 1
+    assert lib.cs_version() == 2
     assert lib.cs_launch_count() == 0          # nothing launched by loading
 
 

@@ -169,7 +169,10 @@ def test_thread_per_env_kernel_equals_lane_per_agent_kernel(n_agents, agent_mode
         where = "step %d" % t
         assert torch.equal(ra, rb) and torch.equal(ta, tb) and torch.equal(wa, wb), where
         assert torch.equal(tpe.target_find, lpa.target_find), where
-        assert torch.equal(tpe._dyn.contiguous().view(torch.int64), lpa._dyn.contiguous().view(torch.int64)), where
+        # positions / headings bit for bit; meta words 0..6 (word 7 is the generic map kernel's job marker, unused by the fused kernel)
+        nrow = 3 * n_agents
+        assert torch.equal(tpe._dyn[:, :nrow].contiguous().view(torch.int64), lpa._dyn[:, :nrow].contiguous().view(torch.int64)), where
+        assert torch.equal(tpe.meta[:, :7], lpa.meta[:, :7]), where
         assert torch.equal(tpe.tgt_xy.contiguous().view(torch.int64), lpa.tgt_xy.contiguous().view(torch.int64)), where
         assert torch.equal(tpe.get_state().view(torch.int32), lpa.get_state().view(torch.int32)), where
         assert torch.equal(tpe.get_obs(full=False).view(torch.int32) if variant != "easy" else tpe.get_obs().view(torch.int32),

@@ -20,19 +20,20 @@ def assert_map_close(got, want, msg=""):
     np.testing.assert_allclose(got, want32, rtol=MAP_RTOL, atol=MAP_ATOL, err_msg=msg)
 
 
-# tma=True: the opt-in TMA-tile map kernel (CS_MAP_TMA=1) where it applies (even map_size in 10..63, view_range <= 7)
-@pytest.mark.parametrize("tma", [False, True])
+# lanes 0: the fused step + belief-map kernel (8 lanes per env, tiled sweep); lanes 16: lane-per-agent step kernel
+# followed by the generic per-cell map kernel
+@pytest.mark.parametrize("lanes", [0, 16])
 @pytest.mark.parametrize("name", gu.FLIGHT_FIXTURES)
-def test_flight_matches_reference_golden(name, tma, monkeypatch):
+def test_flight_matches_reference_golden(name, lanes):
     import coopsearch_b200 as cs
-    touched = not tma
-    if tma:
-        monkeypatch.setenv("CS_MAP_TMA", "1")
+    touched = True
     g = gu.load(name)
     kw, base, seed = gu.flight_spec_kwargs(g, "probmap")
     T, E = g["reward"].shape
     n, M = kw["n_agents"], kw["map_size"]
-    env = cs.VecFlightEnv(make_args(kw), None, num_envs=E, seed=seed, env_id_base=base, count_touched=touched, reset=False)
+    env = cs.VecFlightEnv(make_args(kw), None, num_envs=E, seed=seed, env_id_base=base, count_touched=touched, reset=False,
+                          lanes_per_env=lanes)
+    assert env.lanes_per_env == (8 if lanes == 0 else 16)
     env.reset(init=True, targets=g["tgt_xy"])
     assert_map_close(cpu(env.prob_map), g["init_map"], "init map")
     assert np.array_equal(cpu(env.found_mask).astype(np.uint32), g["init_found"])
@@ -63,20 +64,18 @@ def test_flight_matches_reference_golden(name, tma, monkeypatch):
     assert_map_close(cpu(env.prob_map), g["ep2_map"], "second-episode map")
 
 
-@pytest.mark.parametrize("tma", [False, True])
+@pytest.mark.parametrize("lanes", [0, 16])
 @pytest.mark.parametrize("n_agents,agent_mode,map_size,view_range", [(3, 0, 50, 7), (5, 1, 30, 5), (2, 3, 64, 9), (4, 2, 17, 3),
-                                                                     (5, 0, 16, 7), (3, 2, 62, 6)])
-def test_flight_matches_c_oracle(n_agents, agent_mode, map_size, view_range, tma, monkeypatch):
+                                                                     (5, 0, 16, 7), (3, 2, 62, 6), (8, 1, 63, 7), (1, 0, 5, 2)])
+def test_flight_matches_c_oracle(n_agents, agent_mode, map_size, view_range, lanes):
     """Fresh seeded inputs, device-drawn targets, two episodes with auto-reset, touched-cell count."""
     import coopsearch_b200 as cs
-    touched = not tma
-    if tma:
-        monkeypatch.setenv("CS_MAP_TMA", "1")
+    touched = True
     E, T, seed, base = 48, 130, 21, 9000
     spec = FlightSpec(n_agents=n_agents, agent_mode=agent_mode, map_size=map_size, view_range=view_range,
                       time_limit=100, variant="probmap")
     env = cs.VecFlightEnv(make_args(dict(spec.__dict__)), gu.TEMPLATE, num_envs=E, seed=seed, env_id_base=base,
-                          auto_reset=True, count_touched=touched)
+                          auto_reset=True, count_touched=touched, lanes_per_env=lanes)
     orc = c_oracle.FlightBatch(spec, gu.TEMPLATE, seed, base, E, auto_reset=True)
     orc.reset(init=True)
     actions = np.random.default_rng(3).integers(0, 3, size=(T, E, n_agents), dtype=np.uint8)
@@ -97,33 +96,81 @@ def test_flight_matches_c_oracle(n_agents, agent_mode, map_size, view_range, tma
 
 
 @pytest.mark.parametrize("n_agents,map_size,view_range,time_limit", [(3, 50, 7, 25), (5, 24, 7, 12), (8, 16, 3, 9)])
-def test_map_kernels_and_reset_paths_agree_bitwise(n_agents, map_size, view_range, time_limit, monkeypatch):
-    """The TMA-tile kernel (overlapping agent boxes updated redundantly), the direct kernel (every cell owned by one
-    box) and both ways of ending an episode -- in-call auto-reset (two sensing calls, the first parked in the side
-    buffer) and step + reset(mask=terminated) -- must leave bit-identical maps."""
+def test_map_kernels_and_reset_paths_agree_bitwise(n_agents, map_size, view_range, time_limit):
+    """The fused kernel (corner-row intervals, tile list, packed float4 sweep), the generic kernel (per-cell fp64 corner
+    tests, scalar update) and both ways of ending an episode -- in-call auto-reset (two sensing calls in one launch) and
+    step + reset(mask=terminated) -- must leave bit-identical maps."""
     import coopsearch_b200 as cs
     E, T = 512, 60
     spec = FlightSpec(n_agents=n_agents, map_size=map_size, view_range=view_range, time_limit=time_limit, variant="probmap",
                       target_mode=1)
     args = make_args(dict(spec.__dict__))
-    direct_auto = cs.VecFlightEnv(args, None, num_envs=E, seed=4, auto_reset=True)
-    monkeypatch.setenv("CS_MAP_TMA", "1")
-    tma_auto = cs.VecFlightEnv(args, None, num_envs=E, seed=4, auto_reset=True)
-    tma_manual = cs.VecFlightEnv(args, None, num_envs=E, seed=4, auto_reset=False)
-    monkeypatch.delenv("CS_MAP_TMA")
+    fused_auto = cs.VecFlightEnv(args, None, num_envs=E, seed=4, auto_reset=True)
+    generic_auto = cs.VecFlightEnv(args, None, num_envs=E, seed=4, auto_reset=True, lanes_per_env=16)
+    fused_manual = cs.VecFlightEnv(args, None, num_envs=E, seed=4, auto_reset=False)
+    assert fused_auto.lanes_per_env == 8 and generic_auto.lanes_per_env >= 16
     actions = torch.from_numpy(np.random.default_rng(8).integers(0, 3, size=(T, E, n_agents), dtype=np.uint8)).cuda()
     resets = 0
     for t in range(T):
-        tma_auto.step(actions[t])
-        direct_auto.step(actions[t])
-        _, term, _ = tma_manual.step(actions[t])
+        fused_auto.step(actions[t])
+        generic_auto.step(actions[t])
+        _, term, _ = fused_manual.step(actions[t])
         if bool(term.any()):
             resets += int(term.sum())
-            tma_manual.reset(mask=term.clone())
-        assert torch.equal(tma_auto.prob_map, direct_auto.prob_map), "TMA vs direct, step %d" % t
-        assert torch.equal(tma_auto.prob_map, tma_manual.prob_map), "auto-reset vs manual reset, step %d" % t
-        assert torch.equal(tma_auto.found_mask, tma_manual.found_mask)
+            fused_manual.reset(mask=term.clone())
+        assert torch.equal(fused_auto.prob_map, generic_auto.prob_map), "fused vs generic, step %d" % t
+        assert torch.equal(fused_auto.prob_map, fused_manual.prob_map), "auto-reset vs manual reset, step %d" % t
+        assert torch.equal(fused_auto.found_mask, fused_manual.found_mask)
     assert resets >= E
+
+
+def test_state_dict_round_trip_restores_outputs_and_map():
+    """get_state_dict / set_state_dict: after a restore, get_obs / get_state / reward / target_find / prob_map are those
+    of the checkpointed step, and stepping on equals an uninterrupted run."""
+    import coopsearch_b200 as cs
+    spec = FlightSpec(n_agents=3, variant="probmap", time_limit=40)
+    mk = lambda: cs.VecFlightEnv(make_args(dict(spec.__dict__)), gu.TEMPLATE, num_envs=200, seed=12, auto_reset=True)
+    a, b = mk(), mk()
+    actions = torch.from_numpy(np.random.default_rng(5).integers(0, 3, size=(90, 200, 3), dtype=np.uint8)).cuda()
+    for t in range(30):
+        a.step(actions[t])
+    ckpt = a.get_state_dict()
+    want = {"obs": a.get_obs(full=False).clone(), "state": a.get_state().clone(), "tf": a.target_find.clone(), "map": a.prob_map}
+    for t in range(30, 90):
+        a.step(actions[t])
+    for t in range(17):                       # b is somewhere else entirely (other episode, other outputs)
+        b.step(actions[60 + t])
+    b.set_state_dict(ckpt)
+    assert torch.equal(b.get_obs(full=False), want["obs"]) and torch.equal(b.get_state(), want["state"])
+    assert torch.equal(b.target_find, want["tf"]) and torch.equal(b.prob_map, want["map"])
+    for t in range(30, 90):
+        b.step(actions[t])
+    assert torch.equal(a.get_state(), b.get_state()) and torch.equal(a.prob_map, b.prob_map) and torch.equal(a._dyn, b._dyn)
+
+
+def test_prob_map_assignment_round_trips_through_the_tiled_layout():
+    import coopsearch_b200 as cs
+    for M in (50, 17, 5):
+        spec = FlightSpec(n_agents=2, map_size=M, view_range=2, variant="probmap", target_mode=1)
+        env = cs.VecFlightEnv(make_args(dict(spec.__dict__)), None, num_envs=9, seed=1)
+        ref = torch.rand(9, M, M, device="cuda")
+        env.prob_map = ref
+        assert torch.equal(env.prob_map, ref)
+        t = env.prob_map_tiles                                       # [E, tiles, tiles, 4, 4]: cell (i, j) -> [i//4, j//4, i%4, j%4]
+        assert float(t[3, 1, 0, 2, 1]) == float(ref[3, 6, 1]) if M > 6 else True
+
+
+def test_two_live_handles_of_different_size_keep_working():
+    """Dynamic shared-memory limits are per kernel: creating a second, smaller handle must not break the first."""
+    import coopsearch_b200 as cs
+    big = FlightSpec(n_agents=8, map_size=63, view_range=7, variant="probmap", target_mode=1)
+    small = FlightSpec(n_agents=2, map_size=16, view_range=3, variant="probmap", target_mode=1)
+    for lanes in (0, 32):
+        e1 = cs.VecFlightEnv(make_args(dict(big.__dict__)), None, num_envs=64, seed=1, lanes_per_env=lanes)
+        e2 = cs.VecFlightEnv(make_args(dict(small.__dict__)), None, num_envs=8, seed=1, lanes_per_env=lanes)
+        e1.step_random(3); e2.step_random(3); e1.step_random(3)
+        e1.get_obs(); e2.get_obs(); e1.get_obs()
+        torch.cuda.synchronize()
 
 
 def test_partial_reset_keeps_other_maps():
@@ -144,8 +191,8 @@ def test_partial_reset_keeps_other_maps():
 
 @pytest.mark.parametrize("n_agents,map_size,E", [(3, 50, 1000), (5, 20, 777), (1, 62, 64), (2, 51, 33)])
 def test_map_observation_tma_equals_plain_copy(n_agents, map_size, E):
-    """get_obs() of the flight variant (flight_env.py:223-230) through the TMA bulk-copy kernel and through the plain
-    copy kernel: both equal prob_map.ravel() || features, row by row (odd map sizes take the scalar kernel)."""
+    """get_obs() of the flight variant (flight_env.py:223-230): the de-tiling kernel with TMA bulk stores and with plain
+    stores -- both equal prob_map.ravel() || features, row by row (odd map sizes always take plain stores)."""
     import coopsearch_b200 as cs
     spec = FlightSpec(n_agents=n_agents, map_size=map_size, view_range=max(2, map_size // 8), variant="probmap", target_mode=1)
     env = cs.VecFlightEnv(make_args(dict(spec.__dict__)), None, num_envs=E, seed=9)
