@@ -47,14 +47,15 @@ WORKLOADS = {
                     "(rollout workers, 168 MB of state > L2) advance in ONE grouped launch (cs_flight_group_step)"),
     "c2s": dict(kind="flight_easy", n=3, am=0, envs=4096, batches=64,
                 desc="flight_easy 3a15t AM0TM0, the same 64 handles x 4096 envs with one launch per handle (8 streams in a CUDA graph)"),
-    "c3": dict(kind="flight_easy", n=5, am=2, envs=65536, batches=4,
-               desc="flight_easy 5a15t AM2TM0, 65536 envs per launch (configs[2])"),
+    "c3": dict(kind="flight_easy", n=5, am=2, envs=65536, batches=1, scaling="strong", total_envs=65536, policy="kernel",
+               desc="flight_easy 5a15t AM2TM0, 65536 envs in total sharded over the N GPUs by global env id (BASELINE.json configs[2]); "
+                    "uniform-random policy drawn in-kernel, keyed by the global env id"),
     "c4": dict(kind="flight", n=3, am=0, envs=16384, batches=1,
                desc="flight (probability map) 3a15t AM0TM0, 16384 envs per GPU (configs[3])"),
     "c2w": dict(kind="flight_easy", n=3, am=0, envs=1048576, batches=1,
                 desc="flight_easy 3a15t AM0TM0, 1048576 envs in ONE launch (throughput asymptote of the c2 kernel)"),
-    "c5": dict(kind="search", n=64, am=0, envs=16384, batches=1,
-               desc="search_env 64 agents / 1000 targets / map 64, 16384 envs per launch (configs[4] per-launch slice)"),
+    "c5": dict(kind="search", n=64, am=0, envs=131072, batches=1,
+               desc="search_env 64 agents / 1000 targets / map 64, 131072 envs per GPU (BASELINE.json configs[4]: 1M envs across 8 GPUs, NCCL episode-stat all-reduce)"),
 }
 
 
@@ -130,51 +131,134 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port on the host cores
+# CPU arm: the reference's own env classes (unmodified copies staged under oracle/_ref by __graft_entry__.build()) on
+# the host cores; the Python oracle port only where the staged reference is missing
 # ----------------------------------------------------------------------------------------------------------------
-def _py_port_worker(job):
-    """Reference-style loop on the Python oracle: reset, then per step get_obs, get_state, step (rollout.py:43-63)."""
-    kind, n, am, seconds, wid = job
-    from oracle.py_envs import FlightOracle, FlightSpec, SearchOracle, SearchSpec
-    rng = np.random.default_rng(1000 + wid)
-    steps = 0
-    t_end = time.perf_counter() + seconds
-    t0 = time.perf_counter()
+def reference_kind():
+    from oracle import refharness as rh
+    return "reference" if rh.reference_available() else "port"
+
+
+def _make_ref_env(kind, n, am):
+    """An instance of the UNMODIFIED reference env class for this workload (oracle/_ref; SURVEY.md section 8d inputs)."""
+    from oracle import refharness as rh
+    ref = rh.import_reference()
     if kind in ("flight_easy", "flight"):
-        spec = FlightSpec(n_agents=n, agent_mode=am, variant="easy" if kind == "flight_easy" else "probmap")
-        env = FlightOracle(spec, TEMPLATE, 42, wid)
-        while time.perf_counter() < t_end:
-            env.reset(init=False)
-            done = False
-            while not done and time.perf_counter() < t_end:
-                env.get_obs(); env.get_state()
-                _, done, _ = env.step(rng.integers(0, 3, size=n))
-                steps += 1
+        args = rh.make_args(kind, n_agents=n, agent_mode=am)
+        circle = rh.load_targets_reference_semantics(os.path.join(rh.REFERENCE_ROOT, "flight_targets.txt"))
+        return rh.quiet(ref["FlightSearchEnvEasy" if kind == "flight_easy" else "FlightSearchEnv"], args, circle), args
+    args = search_args() if n == 64 else search_args(n=n, m=15, M=50)
+    return rh.quiet(ref["SearchEnv"], args), args
+
+
+def _cpu_worker(job):
+    """The loop common/rollout.py:43-63 runs on one env instance: reset, then per step get_obs, get_state, step under
+    uniform-random (search: uniform-random legal) actions, for `seconds`.  impl "reference": the unmodified reference
+    class; "port": oracle/py_envs.py."""
+    import contextlib
+    import io
+    kind, n, am, seconds, wid, impl = job
+    rng = np.random.default_rng(1000 + wid)
+    np.random.seed(1000 + wid)
+    if impl == "reference":
+        env, _ = _make_ref_env(kind, n, am)
+        reset = env.reset
     else:
-        spec = SearchSpec(n_agents=n, target_num=1000 if n == 64 else 15, map_size=64 if n == 64 else 50)
-        env = SearchOracle(spec, 42, wid)
+        from oracle.py_envs import FlightOracle, FlightSpec, SearchOracle, SearchSpec
+        if kind in ("flight_easy", "flight"):
+            env = FlightOracle(FlightSpec(n_agents=n, agent_mode=am, variant="easy" if kind == "flight_easy" else "probmap"), TEMPLATE, 42, wid)
+            reset = lambda: env.reset(init=False)
+        else:
+            env = SearchOracle(SearchSpec(n_agents=n, target_num=1000 if n == 64 else 15, map_size=64 if n == 64 else 50), 42, wid)
+            reset = env.reset
+    steps, limit = 0, (500 if kind == "search" else 10 ** 9)
+    t0 = time.perf_counter()
+    t_end = t0 + seconds
+    with contextlib.redirect_stdout(io.StringIO()):              # the reference's search get_obs prints (search_env.py:206,209)
         while time.perf_counter() < t_end:
-            env.reset()
+            reset()
             done, k = False, 0
-            while not done and k < 500 and time.perf_counter() < t_end:
+            while not done and k < limit and time.perf_counter() < t_end:
                 env.get_obs(); env.get_state()
-                acts = [int(rng.choice(np.nonzero(env.get_avail_agent_actions(i))[0])) for i in range(n)]
+                if kind == "search":
+                    acts = [int(rng.choice(np.nonzero(env.get_avail_agent_actions(i))[0])) for i in range(n)]
+                else:
+                    acts = rng.integers(0, 3, size=n)
                 _, done, _ = env.step(acts)
                 steps += 1; k += 1
     return steps, time.perf_counter() - t0
 
 
-def cpu_port_throughput(kind, n, am, seconds, procs):
-    """env-steps/s of the Python oracle port with `procs` independent processes (the reference is single-threaded;
-    independent env instances are its embarrassingly-parallel upper bound)."""
+def cpu_env_throughput(kind, n, am, seconds, procs, impl=None):
+    """env-steps/s of `procs` independent single-threaded env loops (the reference is single-threaded; independent env
+    instances are its embarrassingly-parallel upper bound).  Returns (env-steps/s, env-steps)."""
     import multiprocessing as mp
-    jobs = [(kind, n, am, seconds, w) for w in range(procs)]
+    impl = impl or reference_kind()
+    jobs = [(kind, n, am, seconds, w, impl) for w in range(procs)]
     if procs == 1:
-        res = [_py_port_worker(jobs[0])]
+        res = [_cpu_worker(jobs[0])]
     else:
-        with mp.get_context("spawn").Pool(procs) as pool:
-            res = pool.map(_py_port_worker, jobs)
+        with _pool(procs) as pool:
+            res = pool.map(_cpu_worker, jobs)
     return sum(s / dt for s, dt in res), sum(s for s, _ in res)
+
+
+class _pool:
+    """One spawn-context process pool per bench run (start-up costs ~1 s per use otherwise)."""
+    _shared = None
+
+    def __init__(self, procs):
+        import multiprocessing as mp
+        if _pool._shared is None or _pool._shared[0] != procs:
+            if _pool._shared is not None:
+                _pool._shared[1].terminate()
+            _pool._shared = (procs, mp.get_context("spawn").Pool(procs))
+        self.pool = _pool._shared[1]
+
+    def __enter__(self):
+        return self.pool
+
+    def __exit__(self, *exc):
+        return False
+
+    @staticmethod
+    def close():
+        if _pool._shared is not None:
+            _pool._shared[1].terminate()
+            _pool._shared = None
+
+
+def rollout_worker_throughput(env_factory, n, seconds, seed=0):
+    """BASELINE.json configs[0]: the reference's own RolloutWorker.generate_episode (common/rollout.py:22-141) with its
+    Agents facade and alg=random (agent/agent.py:34-36), single process, driving `env_factory(args)`.  Returns
+    (env-steps/s, episodes, env-steps, mean targets found per episode)."""
+    import contextlib
+    import io
+    from oracle import refharness as rh
+    rh.import_reference()
+    with contextlib.redirect_stdout(io.StringIO()):
+        from common.rollout import RolloutWorker
+        from agent.agent import Agents
+    args = rh.make_args("flight_easy", n_agents=n, agent_mode=0)
+    env = env_factory(args)
+    for k, v in env.get_env_info().items():
+        if k != "n_envs":
+            setattr(args, k, v)
+    args.alg, args.epsilon, args.anneal_epsilon, args.min_epsilon, args.epsilon_anneal_scale = "random", 0, 0, 0, "step"
+    args.last_action, args.reuse_network, args.cuda, args.evaluate_epoch = True, True, False, 20
+    agents = rh.quiet(Agents, env, args)
+    worker = rh.quiet(RolloutWorker, env, agents, args)
+    np.random.seed(seed)
+    rh.quiet(worker.generate_episode, 0)                         # warm-up episode
+    steps = episodes = found = 0
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        ep, _, _, tf = rh.quiet(worker.generate_episode, episodes + 1)
+        steps += int((1 - ep["padded"][0]).sum())
+        found += int(tf)
+        episodes += 1
+    dt = time.perf_counter() - t0
+    return steps / dt, episodes, steps, found / max(1, episodes)
 
 
 def c_port_throughput(kind, n, am, seconds, threads):
@@ -210,23 +294,30 @@ def c_port_throughput(kind, n, am, seconds, threads):
 
 def cpu_baseline(kind, n, am, seconds_py, seconds_c):
     cores = os.cpu_count() or 1
-    v_all, steps_all = cpu_port_throughput(kind, n, am, seconds_py, cores)
-    v_one, _ = cpu_port_throughput(kind, n, am, min(seconds_py, 4.0), 1)
+    impl = reference_kind()
+    v_all, steps_all = cpu_env_throughput(kind, n, am, seconds_py, cores, impl)
+    v_one, _ = cpu_env_throughput(kind, n, am, min(seconds_py, 4.0), 1, impl)
+    out = {
+        "value": v_all, "unit": "env-steps/s", "cores": cores, "kind": impl,
+        "sample": "%s: %d independent processes x %.0f s of reset/get_obs/get_state/step with uniform-random actions, %d env-steps in total"
+                  % ("the UNMODIFIED reference env class (oracle/_ref, staged from the reference by __graft_entry__.build())" if impl == "reference"
+                     else "Python oracle port (oracle/py_envs.py, the reference's scalar float64 loop)", cores, seconds_py, steps_all),
+        "single_core": v_one, "cpu_model": _cpu_model(),
+    }
+    if impl == "reference":
+        try:
+            v_port, _ = cpu_env_throughput(kind, n, am, min(seconds_py, 4.0), 1, "port")
+            out["port_single_core"] = v_port       # the oracle restatement beside the real thing
+        except Exception as exc:
+            out["port_single_core"] = repr(exc)
     try:
         v_c, _ = c_port_throughput(kind, n, am, seconds_c, cores)
         v_c1, _ = c_port_throughput(kind, n, am, min(seconds_c, 2.0), 1)
+        out["c_port"] = {"value": v_c, "single_core": v_c1, "cores": cores,
+                         "note": "plain-C oracle (oracle/coopsearch_oracle.c), same arithmetic, batched; not what the reference runs"}
     except Exception as exc:  # the C oracle needs gcc/make on the box
-        v_c, v_c1 = None, None
         print("C oracle unavailable: %s" % exc, file=sys.stderr)
-    return {
-        "value": v_all, "unit": "env-steps/s", "cores": cores, "kind": "port",
-        "sample": "Python oracle port (oracle/py_envs.py, the reference's scalar float64 loop): %d independent processes x %.0f s of "
-                  "reset/get_obs/get_state/step with uniform-random actions, %d env-steps in total" % (cores, seconds_py, steps_all),
-        "single_core": v_one,
-        "c_port": {"value": v_c, "single_core": v_c1, "cores": cores,
-                   "note": "plain-C oracle (oracle/coopsearch_oracle.c), same arithmetic, batched; not what the reference runs"},
-        "cpu_model": _cpu_model(),
-    }
+    return out
 
 
 def _cpu_model():
@@ -242,19 +333,31 @@ def _cpu_model():
 # ----------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------------------
-def make_envs(cs, w, device, rank, seed=42, count_touched=False):
+def shard_envs(w, rank, world):
+    """(first global env id, env count) of every batch of workload `w` on this rank.  Weak-scaled workloads give every
+    GPU the same env count under its own global ids; strong-scaled ones (BASELINE.json configs[2]: 65536 envs over
+    1/2/4/8 GPUs) split the global id range [0, total_envs) into contiguous blocks (dist.shard_range)."""
+    if w.get("scaling") == "strong":
+        total = w["total_envs"]
+        base, rem = divmod(total, world)
+        lo = rank * base + min(rank, rem)
+        cnt = base + (1 if rank < rem else 0)
+        return [(lo, cnt)]
+    return [((rank * w["batches"] + b) * w["envs"], w["envs"]) for b in range(w["batches"])]
+
+
+def make_envs(cs, w, device, rank, world=1, seed=42, count_touched=False):
     envs = []
     lpe = int(os.environ.get("CS_BENCH_LPE", str(w.get("lanes", 0))))      # 0 = the library's own choice
-    for b in range(w["batches"]):
-        base = (rank * w["batches"] + b) * w["envs"]
+    for base, cnt in shard_envs(w, rank, world):
         if w["kind"] == "flight_easy":
-            e = cs.VecFlightEasyEnv(flight_args("flight_easy", w["n"], w["am"]), TEMPLATE, num_envs=w["envs"], device=device,
+            e = cs.VecFlightEasyEnv(flight_args("flight_easy", w["n"], w["am"]), TEMPLATE, num_envs=cnt, device=device,
                                     seed=seed, env_id_base=base, auto_reset=True, lanes_per_env=lpe)
         elif w["kind"] == "flight":
-            e = cs.VecFlightEnv(flight_args("flight", w["n"], w["am"]), TEMPLATE, num_envs=w["envs"], device=device, seed=seed,
+            e = cs.VecFlightEnv(flight_args("flight", w["n"], w["am"]), TEMPLATE, num_envs=cnt, device=device, seed=seed,
                                 env_id_base=base, auto_reset=True, count_touched=count_touched, lanes_per_env=lpe)
         else:
-            e = cs.VecSearchEnv(search_args(), num_envs=w["envs"], device=device, seed=seed, env_id_base=base, auto_reset=True)
+            e = cs.VecSearchEnv(search_args(), num_envs=cnt, device=device, seed=seed, env_id_base=base, auto_reset=True)
         envs.append(e)
     return envs
 
@@ -266,18 +369,24 @@ def silence(fn, *a, **k):
         return fn(*a, **k)
 
 
+MIN_TIMED_MS = 60.0       # the timed region is repeated until it is at least this long; the median repetition is reported
+
+
 def run_gpu_workload(cs, torch, name, steps, warmup, device, rank, world, want_e2e=True, burn_in_s=0.3):
-    """Returns dict(ms_per_step, env_steps_per_step, e2e_value, ...) for one workload on this rank."""
+    """One workload on this rank.  The `steps` bench steps are captured into ONE CUDA graph; the timed region replays
+    that graph R times back to back (R such that the region lasts >= MIN_TIMED_MS), every replay bracketed by CUDA
+    events on the launching stream, and the MEDIAN replay is reported: `steps` steps of a 60 us kernel are 1.4 ms,
+    which measures launch jitter, not the kernel."""
     w = WORKLOADS[name]
     n = w["n"]
     A = 4 if w["kind"] == "search" else 3
-    envs = silence(make_envs, cs, w, device, rank)
+    envs = silence(make_envs, cs, w, device, rank, world)
     POOL = 8
     gen = torch.Generator(device=device).manual_seed(1234 + rank)
-    if w["kind"] == "search":
-        actions = None          # legal moves depend on positions: the random legal policy is drawn in-kernel
+    if w["kind"] == "search" or w.get("policy") == "kernel":
+        actions = None          # the uniform-random (search: legal) policy is drawn in-kernel, keyed by the global env id
     else:
-        actions = [[torch.randint(0, A, (w["envs"], n), generator=gen, device=device, dtype=torch.uint8) for _ in envs]
+        actions = [[torch.randint(0, A, (e.num_envs, n), generator=gen, device=device, dtype=torch.uint8) for e in envs]
                    for _ in range(POOL)]
 
     side = torch.cuda.Stream(device=device)
@@ -309,70 +418,57 @@ def run_gpu_workload(cs, torch, name, steps, warmup, device, rank, world, want_e
             side.wait_stream(f)
 
     torch.cuda.synchronize(device)
-    graphs = []
     lib = cs.load_library()
     with torch.cuda.stream(side):
         k0 = lib.cs_launch_count()
         one_step(0)
         kernels_per_step = int(lib.cs_launch_count() - k0)     # kernels of OUR library one step launches (graph replays repeat them)
         torch.cuda.synchronize(device)
-        for k in range(POOL if actions is not None else 1):
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=side):
+        gsteps = torch.cuda.CUDAGraph()                        # exactly `steps` bench steps
+        with torch.cuda.graph(gsteps, stream=side):
+            for k in range(steps):
                 one_step(k)
-            graphs.append(g)
     torch.cuda.synchronize(device)
 
-    gmulti = None
-    if grouped is not None and len(graphs) > 1:
-        # one grouped launch is ~57 us of GPU work: a one-node graph per step leaves ~10 us of launch gap between them, so
-        # the POOL steps are also captured back to back in one graph
-        gmulti = torch.cuda.CUDAGraph()
-        with torch.cuda.stream(side):
-            with torch.cuda.graph(gmulti, stream=side):
-                for k in range(len(graphs)):
-                    one_step(k)
-        torch.cuda.synchronize(device)
-
-    def replay(k):
-        graphs[k % len(graphs)].replay()
-
-    def replay_many(count, start=0):
-        """`count` consecutive bench steps starting with action set `start`."""
-        k = start
-        if gmulti is not None:
-            while k % len(graphs) != 0 and count > 0:
-                replay(k); k += 1; count -= 1
-            while count >= len(graphs):
-                gmulti.replay(); k += len(graphs); count -= len(graphs)
-        while count > 0:
-            replay(k); k += 1; count -= 1
-
-    # clock burn-in: same work, untimed, so that the sampler sees the GPU under THIS load and clocks have ramped
+    # clock burn-in + warm-up: the same work, untimed, so that the sampler sees the GPU under THIS load and clocks have ramped
     t_end = time.perf_counter() + burn_in_s
-    k = 0
-    while time.perf_counter() < t_end:
-        replay(k); k += 1
-        if k % 64 == 0:
+    with torch.cuda.stream(side):
+        gsteps.replay()
+        torch.cuda.synchronize(device)
+        t0 = time.perf_counter()
+        gsteps.replay()
+        torch.cuda.synchronize(device)
+        est_ms = 1000.0 * (time.perf_counter() - t0)
+        while time.perf_counter() < t_end:
+            gsteps.replay()
             torch.cuda.synchronize(device)
-    for k in range(warmup):
-        replay(k)
+        for k in range(warmup):                                # W warm-up steps (already far exceeded by the burn-in)
+            one_step(k)
+    torch.cuda.synchronize(device)
+    reps = int(min(4000, max(1, -(-MIN_TIMED_MS // max(est_ms, 1e-3)))))
+    if world > 1:
+        reps_t = torch.tensor([reps], device=device)
+        torch.distributed.all_reduce(reps_t, op=torch.distributed.ReduceOp.MAX)     # the same replay count on every rank
+        reps = int(reps_t.item())
+        torch.distributed.barrier()
+    torch.cuda.synchronize(device)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+    with torch.cuda.stream(side):
+        evs[0].record()
+        for r in range(reps):
+            gsteps.replay()
+            evs[r + 1].record()
     torch.cuda.synchronize(device)
     if world > 1:
         torch.distributed.barrier()
-    torch.cuda.synchronize(device)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    replay_many(steps)
-    ev1.record()
-    torch.cuda.synchronize(device)
-    if world > 1:
-        torch.distributed.barrier()
-    ms = ev0.elapsed_time(ev1)
+    rep_ms = sorted(evs[r].elapsed_time(evs[r + 1]) for r in range(reps))
+    ms = rep_ms[len(rep_ms) // 2]                              # median replay of exactly `steps` steps
     launches = steps * (1 if grouped is not None else len(envs))
-    out = dict(grouped=grouped is not None, ms_total=ms, ms_per_step=ms / steps, env_steps_per_step=w["envs"] * len(envs), launches=launches, streams=nstreams,
-               kernels=kernels_per_step * steps,
-               us_per_launch=1000.0 * ms / launches, lanes_per_env=getattr(envs[0], "lanes_per_env", None))
+    env_count = sum(e.num_envs for e in envs)
+    out = dict(grouped=grouped is not None, ms_total=ms, ms_per_step=ms / steps, env_steps_per_step=env_count, launches=launches, streams=nstreams,
+               kernels=kernels_per_step * steps, timed_reps=reps, timed_region_ms=evs[0].elapsed_time(evs[reps]), ms_min=rep_ms[0], ms_max=rep_ms[-1],
+               us_per_launch=1000.0 * ms / launches, lanes_per_env=getattr(envs[0], "lanes_per_env", None),
+               envs_per_launch=env_count if grouped is not None else envs[0].num_envs)
 
     # ---- end to end through the host-buffer C-ABI call -----------------------------------------------------
     if want_e2e:
@@ -381,7 +477,7 @@ def run_gpu_workload(cs, torch, name, steps, warmup, device, rank, world, want_e
         if w["kind"] == "search":
             host_actions = None
         else:
-            host_actions = [[rng.integers(0, A, size=(w["envs"], n), dtype=np.uint8) for _ in envs] for _ in range(2)]
+            host_actions = [[rng.integers(0, A, size=(e.num_envs, n), dtype=np.uint8) for e in envs] for _ in range(2)]
         for e in envs:
             e.host_buffers()
 
@@ -411,26 +507,50 @@ def run_gpu_workload(cs, torch, name, steps, warmup, device, rank, world, want_e
         for k in range(3):
             host_step(k)
         torch.cuda.synchronize(device)
+        # repeat the e2e_steps block until >= MIN_TIMED_MS, median block
+        blocks = []
         if world > 1:
             torch.distributed.barrier()
-        t0 = time.perf_counter()
-        for k in range(e2e_steps):
-            host_step(k)
-        torch.cuda.synchronize(device)
-        dt = time.perf_counter() - t0
+        t_region = time.perf_counter()
+        while True:
+            t0 = time.perf_counter()
+            for k in range(e2e_steps):
+                host_step(k)
+            torch.cuda.synchronize(device)
+            blocks.append(time.perf_counter() - t0)
+            if (time.perf_counter() - t_region) * 1000.0 >= MIN_TIMED_MS and len(blocks) >= 3 or len(blocks) >= 200:
+                break
+        dt = sorted(blocks)[len(blocks) // 2]
         hb = envs[0].host_buffers()
-        h2d = sum(hb["actions"].numel() for _ in envs)
-        if "slab" in hb:
+        h2d = sum(e.host_buffers()["actions"].numel() for e in envs)
+        if "d2h_bytes" in hb:
+            d2h = sum(int(e.host_buffers()["d2h_bytes"]) for e in envs)
+        elif "slab" in hb:
             d2h = sum(e.host_buffers()["slab"].numel() for e in envs)      # one D2H copy of the output slab per batch
         else:
             d2h = sum(sum(v.numel() * v.element_size() for kname, v in e.host_buffers().items() if kname != "actions") for e in envs)
-        out.update(e2e_s_per_step=dt / e2e_steps, e2e_steps=e2e_steps, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h)
+        out.update(e2e_s_per_step=dt / e2e_steps, e2e_steps=e2e_steps, e2e_blocks=len(blocks), h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h)
     # statistics of the finished episodes on this GPU (all-reduced by the caller)
     stats = torch.zeros(8, dtype=torch.float64, device=device)
     for e in envs:
         stats += torch.tensor(list(e.stats().values()), dtype=torch.float64, device=device)
     out["stats"] = stats
     return out
+
+
+def shard_invariance_stats(cs, torch, dist, name, device, rank, world, steps=400):
+    """Hardware proof that sharding does not change results: a FRESH set of handles for this rank's shard of a
+    strong-scaled workload runs exactly `steps` steps under the in-kernel random policy (keyed by the global env id);
+    the NCCL all-reduced episode statistics must be identical for every world size."""
+    w = dict(WORKLOADS[name])
+    envs = silence(make_envs, cs, w, device, rank, world)
+    for e in envs:
+        e.step_random(steps)
+    stats = torch.zeros(8, dtype=torch.float64, device=device)
+    for e in envs:
+        stats += torch.tensor(list(e.stats().values()), dtype=torch.float64, device=device)
+    stats = dist.allreduce_stats(stats)
+    return dict(zip(cs._lib.STAT_NAMES, [float(x) for x in stats.tolist()]))
 
 
 def measure_obs_full(cs, torch, device, peak):
@@ -459,8 +579,8 @@ def measure_obs_full(cs, torch, device, peak):
 
 
 def measure_policy(cs, torch, device, E=4096, n=3, iters=50):
-    """Batched agent network + action choice (csrc/policy.cu; SURVEY 8f rank 1, first version): rows/s of one
-    choose_actions launch on random-init weights of the reference's architecture (in 10 -> 64 -> GRU 64 -> 64 -> 3)."""
+    """Batched agent network + action choice (csrc/policy.cu): rows/s of one choose_actions launch on
+    random-init weights of the reference's architecture (in 10 -> 64 -> GRU 64 -> 64 -> 3)."""
     torch.manual_seed(0)
     in_dim = 4 + 3 + n
     sd = {"fc1.weight": torch.randn(64, in_dim) * 0.1, "fc1.bias": torch.zeros(64), "rnn.weight_ih": torch.randn(192, 64) * 0.1,
@@ -483,7 +603,7 @@ def measure_policy(cs, torch, device, E=4096, n=3, iters=50):
     flop = 2 * (in_dim * 64 + 2 * 64 * 192 + 64 * 64 + 64 * 3)
     return {"workload": "agent network + greedy action choice for %d envs x %d agents (random-init weights, synthetic obs)" % (E, n),
             "rows": rows, "us_per_launch": us, "agent_steps_per_s": rows / (us * 1e-6), "gflops": rows * flop / (us * 1e-6) / 1e9,
-            "note": "first version on CUDA cores (one warp per four rows); not part of the headline metric"}
+            "kernel": getattr(agents, "kernel_name", "policy_kernel")}
 
 
 def measure_touched(cs, torch, device, steps=200):
@@ -497,8 +617,27 @@ def measure_touched(cs, torch, device, steps=200):
     return (e.stats()["map_cells_touched"] - base) / (steps * w["envs"])
 
 
+def measure_c1(cs, torch, device, seconds=4.0):
+    """BASELINE.json configs[0] (flight_easy 1a15t AM0TM0, single env, random policy via common/rollout.py): the
+    reference's own RolloutWorker + Agents(alg=random) driving (i) the reference env on one host core and (ii) our
+    E=1 SingleEnvAdapter (one kernel launch per call: the latency floor of the drop-in, not a throughput figure)."""
+    from oracle import refharness as rh
+    if not rh.reference_available():
+        return {"unavailable": "oracle/_ref is not staged on this box (run __graft_entry__.build() where /root/reference exists)"}
+    ref = rh.import_reference()
+    circle = rh.load_targets_reference_semantics(os.path.join(rh.REFERENCE_ROOT, "flight_targets.txt"))
+    v_ref, eps, steps, found = rollout_worker_throughput(lambda a: rh.quiet(ref["FlightSearchEnvEasy"], a, circle), 1, seconds)
+    out = {"workload": "flight_easy 1a15t AM0TM0, single env, reference RolloutWorker.generate_episode + alg=random (common/rollout.py:22-141)",
+           "reference_env": {"value": v_ref, "unit": "env-steps/s", "episodes": eps, "env_steps": steps, "mean_targets_found": found, "cores": 1}}
+    mk = lambda a: cs.SingleEnvAdapter(silence(cs.VecFlightEasyEnv, a, circle, num_envs=1, device=device, seed=7))
+    v_ad, eps, steps, found = rollout_worker_throughput(mk, 1, seconds)
+    out["adapter_e1"] = {"value": v_ad, "unit": "env-steps/s", "episodes": eps, "env_steps": steps, "mean_targets_found": found,
+                         "note": "unmodified reference RolloutWorker on SingleEnvAdapter(VecFlightEasyEnv, num_envs=1): every protocol call is a device round trip"}
+    return out
+
+
 def kernel_name(w, lanes, grouped=False):
-    """The dominant kernel of a workload (csrc/flight.cu, csrc/search.cu)."""
+    """The dominant kernel of a workload (csrc/flight_*.cu, csrc/search.cu)."""
     if w["kind"] == "search":
         return "search_kernel<STEP>"
     if grouped:
@@ -524,10 +663,85 @@ def load_traffic(key):
     return None
 
 
+def config_for(name, world):
+    """The `config` object of the JSON line: a pure function of the workload and the world size, so that both arms
+    (`--impl ours`, `--impl reference`) print the same one."""
+    w = WORKLOADS[name]
+    grouped = bool(w.get("grouped")) and os.environ.get("CS_BENCH_GROUPED", "1") != "0"
+    if w.get("scaling") == "strong":
+        per_gpu, handles = w["total_envs"] // world, 1
+    else:
+        per_gpu, handles = w["envs"] * w["batches"], w["batches"]
+    return {
+        "workload": w["desc"], "envs_per_handle": per_gpu // handles, "handles_per_gpu": handles,
+        "envs_per_launch": per_gpu if (grouped or handles == 1) else per_gpu // handles, "launches_per_step": 1 if grouped else handles,
+        "env_instances_per_gpu": per_gpu, "auto_reset": True,
+        "actions": "uniform-random policy: pre-generated u8 tensors resident in HBM (flight) / drawn in-kernel with Philox (search, shard-invariance runs)",
+        "launch": "the --steps bench steps are captured into one CUDA graph; one step = " +
+                  ("ONE grouped launch that steps every handle (cs_flight_group_step)" if grouped else "one launch per handle"),
+        "timing": "the K-step graph is replayed back to back until the timed region is >= %d ms; every replay is bracketed by CUDA events on the launching stream; "
+                  "the median replay / K is ms_per_step (max over ranks); barrier + synchronize on both sides of the region" % MIN_TIMED_MS,
+        "l2": "working set of all batches exceeds the 126 MB L2; batches are revisited round-robin, no flush",
+        "parallelism": "dp%d (env instances sharded by global id, no data-path collective)" % world,
+    }
+
+
+def reference_arm(args, w, rank):
+    """`--impl reference`: the reference's own CPU implementation of the path -- the UNMODIFIED env classes staged under
+    oracle/_ref (the Python oracle port where that is missing) -- on every host core.  One bench step = a bounded sample:
+    every core runs the reset / get_obs / get_state / step loop on its own env instance for a fixed slice of time."""
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    impl = reference_kind()
+    total = args.steps + args.warmup
+    per_step_seconds = max(0.05, min(8.0, 110.0 / max(1, total)))
+    for _ in range(args.warmup):
+        cpu_env_throughput(w["kind"], w["n"], w["am"], per_step_seconds, cores, impl)
+    vals, total_steps = [], 0
+    for _ in range(args.steps):
+        v, s_ = cpu_env_throughput(w["kind"], w["n"], w["am"], per_step_seconds, cores, impl)
+        vals.append(v); total_steps += s_
+    _pool.close()
+    v = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": "env-steps/s", "value": v, "unit": "env-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * per_step_seconds, "higher_is_better": True,
+        "scaling": WORKLOADS[args.workload].get("scaling", "weak"), "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_for(args.workload, int(os.environ.get("WORLD_SIZE", "1"))),
+        "agent_steps_per_s": v * w["n"],
+        "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": impl,
+                         "sample": "%d env-steps of reset/get_obs/get_state/step under uniform-random actions: %d steps x %.2f s on %d processes, each with its own instance of %s"
+                                   % (total_steps, args.steps, per_step_seconds, cores,
+                                      "the unmodified reference env class (oracle/_ref)" if impl == "reference" else "the Python oracle port (oracle/py_envs.py)"),
+                         "cpu_model": _cpu_model()},
+        "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def extra_entry(cs, torch, name, r, peak, device, with_touched=True):
+    ww = WORKLOADS[name]
+    tch = measure_touched(cs, torch, device) if (ww["kind"] == "flight" and with_touched) else None
+    pu = algorithmic_bytes(ww["kind"], ww["n"], touched_per_step=tch or 0.0) if ww["kind"] != "search" else \
+        algorithmic_bytes("search", 64, m=1000, M=64, R=7)
+    v = r["env_steps_per_step"] / (r["ms_per_step"] / 1000.0)
+    gbs = pu * r["envs_per_launch"] / (1e-6 * r["us_per_launch"]) / 1e9
+    out = {"workload": ww["desc"], "kernel": kernel_name(ww, r["lanes_per_env"], r["grouped"]), "value": v, "unit": "env-steps/s",
+           "agent_steps_per_s": v * ww["n"], "us_per_launch": r["us_per_launch"], "timed_reps": r["timed_reps"], "timed_region_ms": r["timed_region_ms"],
+           "roofline": {"achieved": gbs, "peak": peak, "frac": gbs / peak, "unit": "GB/s", "algorithmic_bytes_per_env_step": pu,
+                        "env_steps_per_launch": r["envs_per_launch"], "map_cells_touched_per_env_step": tch, "traffic": load_traffic(name)}}
+    if "e2e_s_per_step" in r:
+        out["e2e_value"] = r["env_steps_per_step"] / r["e2e_s_per_step"]
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
@@ -540,34 +754,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     if args.impl == "reference":
-        # The reference's own CPU implementation of the path: the Python oracle port on every host core.
-        if rank != 0:
-            return 0
-        t0 = time.perf_counter()
-        per_step_seconds = max(0.5, min(10.0, 60.0 / max(1, args.steps + args.warmup)))
-        for _ in range(min(args.warmup, 3)):
-            cpu_port_throughput(w["kind"], w["n"], w["am"], 0.3, os.cpu_count() or 1)
-        vals, total_steps = [], 0
-        for _ in range(min(args.steps, 20)):
-            v, s = cpu_port_throughput(w["kind"], w["n"], w["am"], per_step_seconds, os.cpu_count() or 1)
-            vals.append(v); total_steps += s
-            if time.perf_counter() - t0 > 150:
-                break
-        v = float(np.mean(vals))
-        line = {
-            "impl": "reference", "metric": "env-steps/s", "value": v, "unit": "env-steps/s", "n_gpus": args.gpus,
-            "steps": len(vals), "warmup": min(args.warmup, 3), "ms_per_step": 1000.0 * per_step_seconds, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": w["desc"], "note": "each step = %.1f s of the Python port of the reference env loop on all host cores" % per_step_seconds},
-            "agent_steps_per_s": v * w["n"],
-            "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": os.cpu_count() or 1, "kind": "port",
-                             "sample": "%d env-steps of reset/get_obs/get_state/step under uniform-random actions" % total_steps,
-                             "cpu_model": _cpu_model()},
-            "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0,
-        }
-        print(json.dumps(line))
-        return 0
+        return reference_arm(args, w, rank)
 
     import torch
     import coopsearch_b200 as cs
@@ -592,6 +779,33 @@ def main():
     stats = dist.allreduce_stats(res["stats"])          # NCCL all-reduce of the episode statistics
     torch.cuda.synchronize(device)
     allreduce_us = 1e6 * (time.perf_counter() - t0)
+
+    # supplementary workloads that run on EVERY rank (max over ranks, like the headline): configs[2] strong-scaled over
+    # the N GPUs with the cross-N shard-invariance statistics, configs[4] at its stated 131072 envs per GPU
+    extra = {}
+    peak, peak_src = load_peaks()
+    if not args.no_extra:
+        for name in ("c3", "c5"):
+            if name == args.workload:
+                continue
+            try:
+                k = min(args.steps, 60 if name != "c5" else 20)
+                r = run_gpu_workload(cs, torch, name, k, 5, device, rank, world, want_e2e=(world == 1), burn_in_s=0.1)
+                r["ms_per_step"] = dist.max_over_ranks(r["ms_per_step"], device=device)
+                r["us_per_launch"] = dist.max_over_ranks(r["us_per_launch"], device=device)
+                st = dist.allreduce_stats(r["stats"])
+                r["env_steps_per_step"] = r["env_steps_per_step"] * world if WORKLOADS[name].get("scaling") != "strong" else WORKLOADS[name]["total_envs"]
+                ent = extra_entry(cs, torch, name, r, peak, device)
+                ent["n_gpus"] = world
+                ent["scaling"] = WORKLOADS[name].get("scaling", "weak")
+                ent["episode_stats_allreduced"] = dict(zip(cs._lib.STAT_NAMES, [float(x) for x in st.tolist()]))
+                if WORKLOADS[name].get("scaling") == "strong":
+                    ent["shard_invariance"] = {
+                        "what": "fresh handles, exactly 400 steps of the in-kernel random policy over the SAME 65536 global env ids, NCCL all-reduced statistics: identical for every N",
+                        "stats": shard_invariance_stats(cs, torch, dist, name, device, rank, world)}
+                extra[name] = ent
+            except Exception as exc:  # supplementary only: never lose the headline line
+                extra[name] = {"error": repr(exc)}
     if rank != 0:
         if world > 1:
             torch.distributed.barrier()
@@ -601,77 +815,65 @@ def main():
     env_steps = res["env_steps_per_step"] * world * args.steps
     value = env_steps / (ms_max / 1000.0)
     e2e_value = res["env_steps_per_step"] * world / e2e_max
-    peak, peak_src = load_peaks()
     touched = None
     if w["kind"] == "flight":
         touched = measure_touched(cs, torch, device)
     per_unit = algorithmic_bytes(w["kind"], w["n"], touched_per_step=touched or 0.0) if w["kind"] != "search" else \
         algorithmic_bytes("search", 64, m=1000, M=64, R=7)
-    bytes_per_launch = per_unit * w["envs"] * (w["batches"] if res["grouped"] else 1)
+    bytes_per_launch = per_unit * res["envs_per_launch"]
     sec_per_launch = (res["ms_total"] / 1000.0) / res["launches"]
     achieved = bytes_per_launch / sec_per_launch / 1e9
+    cfg = config_for(args.workload, world)
     line = {
         "metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": w.get("scaling", "weak"), "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {
-            "workload": w["desc"], "envs_per_handle": w["envs"], "handles_per_gpu": w["batches"],
-            "envs_per_launch": w["envs"] * (w["batches"] if res["grouped"] else 1), "launches_per_step": 1 if res["grouped"] else w["batches"],
-            "env_instances_per_gpu": w["envs"] * w["batches"], "auto_reset": True,
-            "actions": "pre-generated uniform-random u8 tensors resident in HBM" if w["kind"] != "search" else "uniform-random legal policy drawn in-kernel (Philox)",
-            "launch": ("CUDA-graph replay (8 steps per graph) of one grouped launch per step that steps every handle (cs_flight_group_step)" if res["grouped"] else
-                       "CUDA-graph replay of the step launches; the independent batches are forked over %d streams inside the graph" % res["streams"]), "l2": "working set of all batches exceeds the 126 MB L2; batches are revisited round-robin, no flush",
-            "lanes_per_env": res["lanes_per_env"], "parallelism": "dp%d (env instances sharded by global id, no data-path collective)" % world,
-        },
+        "config": cfg,
+        "timed": {"replays_of_the_K_step_graph": res["timed_reps"], "region_ms": res["timed_region_ms"], "median_replay_ms": res["ms_total"],
+                  "min_replay_ms": res["ms_min"], "max_replay_ms": res["ms_max"], "lanes_per_env": res["lanes_per_env"], "streams": res["streams"]},
         "agent_steps_per_s": value * w["n"],
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": res["h2d_bytes_per_step"],
                 "d2h_bytes_per_step": res["d2h_bytes_per_step"], "agent_steps_per_s": e2e_value * w["n"],
-                "steps": res["e2e_steps"],
-                "path": "HostStepper.step() = cs_flight_step_host_many captured in one CUDA graph; per batch: pinned host actions -> H2D -> step kernel -> one D2H of reward/terminated/win/target_find/obs/state into the pinned slab; batches pipelined over 4 streams, all synchronised every step (search: cs_search_step_host per batch)"},
+                "steps": res["e2e_steps"], "blocks": res["e2e_blocks"],
+                "path": "HostStepper.step() = cs_flight_step_host_many captured in one CUDA graph; per batch: pinned host actions -> H2D -> step kernel -> D2H of the step results into the pinned host buffers; batches pipelined over 4 streams, all synchronised every step (search: cs_search_step_host per batch); median block of %d steps, blocks repeated until >= %d ms" % (res["e2e_steps"], MIN_TIMED_MS)},
         "gpu_launches": int(res["kernels"]),
         "gpu_launches_process_total": int(lib.cs_launch_count() - launches0),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": load_traffic(args.workload), "peak_source": peak_src,
                      "kernel": kernel_name(w, res["lanes_per_env"], res["grouped"]),
-                     "algorithmic_bytes_per_env_step": per_unit, "env_steps_per_launch": w["envs"] * (w["batches"] if res["grouped"] else 1),
+                     "algorithmic_bytes_per_env_step": per_unit, "env_steps_per_launch": res["envs_per_launch"],
                      "us_per_launch": 1e6 * sec_per_launch, "map_cells_touched_per_env_step": touched,
-                     "note": "duration = timed region / launches; launches of independent batches overlap when streams > 1"},
+                     "note": "duration = median K-step replay / launches; launches of independent batches overlap when streams > 1"},
         "clocks": clocks,
         "episode_stats_allreduced": dict(zip(cs._lib.STAT_NAMES, [float(x) for x in stats.tolist()])),
         "stats_allreduce_us": allreduce_us,
     }
-    if world == 1 and not args.no_extra:
-        extra = {}
-        for name in ("c2s", "c2w", "c3", "c4", "c5"):
-            if name == args.workload:
-                continue
+    if not args.no_extra:
+        if world == 1:
+            for name in ("c2s", "c2w", "c4"):
+                if name == args.workload:
+                    continue
+                try:
+                    r = run_gpu_workload(cs, torch, name, min(args.steps, 60), 5, device, 0, 1, want_e2e=True, burn_in_s=0.1)
+                    extra[name] = extra_entry(cs, torch, name, r, peak, device)
+                except Exception as exc:
+                    extra[name] = {"error": repr(exc)}
             try:
-                k = 60 if name != "c5" else 30
-                r = run_gpu_workload(cs, torch, name, k, 5, device, 0, 1, want_e2e=True, burn_in_s=0.1)
-                ww = WORKLOADS[name]
-                tch = measure_touched(cs, torch, device) if ww["kind"] == "flight" else None
-                pu = algorithmic_bytes(ww["kind"], ww["n"], touched_per_step=tch or 0.0) if ww["kind"] != "search" else \
-                    algorithmic_bytes("search", 64, m=1000, M=64, R=7)
-                v = r["env_steps_per_step"] / (r["ms_per_step"] / 1000.0)
-                gbs = pu * ww["envs"] * (ww["batches"] if r["grouped"] else 1) / (1e-6 * r["us_per_launch"]) / 1e9
-                extra[name] = {"workload": ww["desc"], "kernel": kernel_name(ww, r["lanes_per_env"], r["grouped"]), "value": v, "unit": "env-steps/s", "agent_steps_per_s": v * ww["n"],
-                               "us_per_launch": r["us_per_launch"], "e2e_value": r["env_steps_per_step"] / r["e2e_s_per_step"],
-                               "roofline": {"achieved": gbs, "peak": peak, "frac": gbs / peak, "unit": "GB/s",
-                                            "algorithmic_bytes_per_env_step": pu, "map_cells_touched_per_env_step": tch,
-                                            "traffic": load_traffic(name)}}
-            except Exception as exc:  # supplementary only: never lose the headline line
-                extra[name] = {"error": repr(exc)}
-        try:
-            extra["c4_obs"] = {"workload": "flight get_obs(): prob_map || features for 16384 envs x 3 agents (656 MB per call)",
-                               "unit": "GB/s", "peak": peak, **measure_obs_full(cs, torch, device, peak)}
-        except Exception as exc:
-            extra["c4_obs"] = {"error": repr(exc)}
-        try:
-            extra["policy"] = measure_policy(cs, torch, device)
-        except Exception as exc:
-            extra["policy"] = {"error": repr(exc)}
+                extra["c4_obs"] = {"workload": "flight get_obs(): prob_map || features for 16384 envs x 3 agents (656 MB per call)",
+                                   "unit": "GB/s", "peak": peak, **measure_obs_full(cs, torch, device, peak)}
+            except Exception as exc:
+                extra["c4_obs"] = {"error": repr(exc)}
+            try:
+                extra["policy"] = measure_policy(cs, torch, device)
+            except Exception as exc:
+                extra["policy"] = {"error": repr(exc)}
+            try:
+                extra["c1"] = measure_c1(cs, torch, device)
+            except Exception as exc:
+                extra["c1"] = {"error": repr(exc)}
+            line["cpu_baseline"] = cpu_baseline(w["kind"], w["n"], w["am"], args.cpu_seconds, 4.0)
+            _pool.close()
         line["extra"] = extra
-        line["cpu_baseline"] = cpu_baseline(w["kind"], w["n"], w["am"], args.cpu_seconds, 4.0)
     print(json.dumps(line))
     if world > 1:
         torch.distributed.barrier()

@@ -1,9 +1,11 @@
 """Harness around the UNMODIFIED reference envs -- TEST INFRASTRUCTURE.
 
-Only usable where ``/root/reference`` exists (the build container).  It is used
-by ``tests/golden/make_golden.py`` to generate the committed golden fixtures and
-by the ``needs_reference`` CPU tests to pin the oracle restatement against the
-real thing.  Nothing here travels to the GPU box and nothing in the product
+Usable where ``/root/reference`` exists (the build container) or where the
+unmodified copies staged by ``oracle/build_ref.py`` under ``oracle/_ref`` exist
+(git-ignored; they travel to the GPU box like the built .so files).  It is used
+by ``tests/golden/make_golden.py`` to generate the committed golden fixtures, by
+the ``needs_reference`` CPU tests to pin the oracle restatement against the real
+thing, and by ``bench.py``'s CPU legs (the reference arm).  Nothing in the product
 package imports it.
 
 What it does:
@@ -25,7 +27,17 @@ import numpy as np
 
 from . import philox
 
-REFERENCE_ROOT = os.environ.get("COOPSEARCH_REFERENCE", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")     # oracle/build_ref.py: unmodified copies
+
+
+def _pick_root():
+    for root in (os.environ.get("COOPSEARCH_REFERENCE", "/root/reference"), _STAGED):
+        if os.path.isfile(os.path.join(root, "env", "flight_env_easy.py")):
+            return root
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _pick_root()
 
 
 def reference_available():
