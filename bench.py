@@ -50,8 +50,9 @@ WORKLOADS = {
     "c3": dict(kind="flight_easy", n=5, am=2, envs=65536, batches=1, scaling="strong", total_envs=65536, policy="kernel",
                desc="flight_easy 5a15t AM2TM0, 65536 envs in total sharded over the N GPUs by global env id (BASELINE.json configs[2]); "
                     "uniform-random policy drawn in-kernel, keyed by the global env id"),
-    "c4": dict(kind="flight", n=3, am=0, envs=16384, batches=1,
-               desc="flight (probability map) 3a15t AM0TM0, 16384 envs per GPU (configs[3])"),
+    "c4": dict(kind="flight", n=3, am=0, envs=16384, batches=1, map_overlap=True,
+               desc="flight (probability map) 3a15t AM0TM0, 16384 envs per GPU (configs[3]); per env-step one step kernel and one "
+                    "belief-map kernel, the map kernel on the handle's own stream (map_overlap: it runs concurrently with the next step kernel)"),
     "c2w": dict(kind="flight_easy", n=3, am=0, envs=1048576, batches=1,
                 desc="flight_easy 3a15t AM0TM0, 1048576 envs in ONE launch (throughput asymptote of the c2 kernel)"),
     "c5": dict(kind="search", n=64, am=0, envs=131072, batches=1,
@@ -355,7 +356,8 @@ def make_envs(cs, w, device, rank, world=1, seed=42, count_touched=False):
                                     seed=seed, env_id_base=base, auto_reset=True, lanes_per_env=lpe)
         elif w["kind"] == "flight":
             e = cs.VecFlightEnv(flight_args("flight", w["n"], w["am"]), TEMPLATE, num_envs=cnt, device=device, seed=seed,
-                                env_id_base=base, auto_reset=True, count_touched=count_touched, lanes_per_env=lpe)
+                                env_id_base=base, auto_reset=True, count_touched=count_touched, lanes_per_env=lpe,
+                                map_overlap=bool(w.get("map_overlap")) and os.environ.get("CS_BENCH_MAP_OVERLAP", "1") != "0")
         else:
             e = cs.VecSearchEnv(search_args(), num_envs=cnt, device=device, seed=seed, env_id_base=base, auto_reset=True)
         envs.append(e)
@@ -417,17 +419,26 @@ def run_gpu_workload(cs, torch, name, steps, warmup, device, rank, world, want_e
         for f in forks:
             side.wait_stream(f)
 
+    def join_maps():
+        """map_overlap handles run their belief-map kernels on their own stream: joined before a capture begins / ends"""
+        for e in envs:
+            if getattr(e, "map_overlap", False):
+                with torch.cuda.stream(side):
+                    e.sync_map()
+
     torch.cuda.synchronize(device)
     lib = cs.load_library()
     with torch.cuda.stream(side):
         k0 = lib.cs_launch_count()
         one_step(0)
         kernels_per_step = int(lib.cs_launch_count() - k0)     # kernels of OUR library one step launches (graph replays repeat them)
+        join_maps()
         torch.cuda.synchronize(device)
         gsteps = torch.cuda.CUDAGraph()                        # exactly `steps` bench steps
         with torch.cuda.graph(gsteps, stream=side):
             for k in range(steps):
                 one_step(k)
+            join_maps()
     torch.cuda.synchronize(device)
 
     # clock burn-in + warm-up: the same work, untimed, so that the sampler sees the GPU under THIS load and clocks have ramped
@@ -444,6 +455,7 @@ def run_gpu_workload(cs, torch, name, steps, warmup, device, rank, world, want_e
             torch.cuda.synchronize(device)
         for k in range(warmup):                                # W warm-up steps (already far exceeded by the burn-in)
             one_step(k)
+        join_maps()
     torch.cuda.synchronize(device)
     reps = int(min(4000, max(1, -(-MIN_TIMED_MS // max(est_ms, 1e-3)))))
     if world > 1:
@@ -643,8 +655,11 @@ def kernel_name(w, lanes, grouped=False):
     if grouped:
         return "flight_tpe_group_kernel<N=%d,K=%d>" % (w["n"], lanes)
     if w["kind"] == "flight":
-        return ("flight_fused_kernel<N=%d,STEP> (step + belief map of an env in one launch, %d lanes per env)" % (w["n"], lanes)) if lanes == 8 else \
-            "flight_kernel<LPE=%s,STEP> + flight_map_generic_kernel" % lanes
+        if lanes == 8:
+            return "flight_fused_kernel<N=%d,STEP> (step + belief map of an env in one launch, 8 lanes per env)" % w["n"]
+        if lanes in (1, 4):
+            return "flight_map_tile_kernel (after flight_tpe_kernel<N=%d,K=%d,STEP,MAP>; two launches per env-step)" % (w["n"], lanes)
+        return "flight_kernel<LPE=%s,STEP> + flight_map_generic_kernel" % lanes
     return ("flight_tpe_kernel<N=%d,K=%d,STEP>" % (w["n"], lanes)) if lanes and lanes <= 4 else "flight_kernel<LPE=%s,STEP>" % lanes
 
 

@@ -30,7 +30,7 @@ class FlightCfg(C.Structure):
         ("target_mode", C.c_int32), ("variant", C.c_int32), ("auto_reset", C.c_int32), ("count_touched", C.c_int32),
         ("lanes_per_env", C.c_int32), ("device", C.c_int32),
         ("velocity", C.c_double), ("detect_prob", C.c_double), ("safe_dist", C.c_double), ("force_dist", C.c_double),
-        ("seed", C.c_uint32), ("env_id_base", C.c_uint32),
+        ("seed", C.c_uint32), ("env_id_base", C.c_uint32), ("map_overlap", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 
@@ -51,6 +51,11 @@ class FlightHostIO(C.Structure):
 
 
 CS_HOST_NO_SYNC = 1
+
+
+class FlightHostViews(C.Structure):      # mirrors cs_flight_host_views
+    _fields_ = [("reward", C.c_void_p), ("target_find", C.c_void_p), ("terminated", C.c_void_p), ("win", C.c_void_p),
+                ("state", C.c_void_p), ("state_stride", C.c_int32), ("h2d_bytes_per_step", C.c_uint64), ("d2h_bytes_per_step", C.c_uint64)]
 
 
 class SearchCfg(C.Structure):
@@ -124,8 +129,14 @@ SIGNATURES = {
     "cs_flight_obs_full": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "cs_flight_map_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "cs_flight_map_import": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cs_flight_map_sync": (C.c_int, [C.c_void_p, C.c_void_p]),
     "cs_flight_step_host": (C.c_int, [C.c_void_p, C.POINTER(FlightHostIO), C.c_void_p]),
     "cs_flight_slab_layout": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "cs_flight_host_compact_begin": (C.c_int, [C.c_void_p, C.POINTER(FlightHostViews)]),
+    "cs_flight_step_host_compact": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "cs_flight_host_expand": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
+    "cs_flight_step_host_compact_many": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int32, C.POINTER(C.c_void_p), C.c_int32, C.c_uint32]),
+    "cs_flight_host_expand_many": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.POINTER(C.c_void_p), C.c_int32, C.c_int32]),
     "cs_flight_step_host_many": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(FlightHostIO), C.c_int32, C.POINTER(C.c_void_p), C.c_int32]),
     "cs_flight_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_void_p]),
     "cs_flight_group_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.POINTER(C.c_void_p)]),

@@ -24,8 +24,10 @@ UNITS = {
     "search": ("search.cu", []),
     "policy": ("policy.cu", []),
     "flight_host": ("flight_host.cu", []),
+    "flight_hostio": ("flight_hostio.cu", []),
     "flight_lpa": ("flight_lpa.cu", []),
     "flight_aux": ("flight_aux.cu", []),
+    "flight_mapk": ("flight_mapk.cu", []),
     "flight_tpe0": ("flight_tpe.cu", ["-DCS_TPE_PART=0"]),
     "flight_tpe1": ("flight_tpe.cu", ["-DCS_TPE_PART=1"]),
     "flight_tpe2": ("flight_tpe.cu", ["-DCS_TPE_PART=2"]),

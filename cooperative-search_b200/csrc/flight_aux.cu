@@ -175,6 +175,39 @@ __global__ void __launch_bounds__(256) flight_live_steps_kernel(const double* __
     if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, (double)acc);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Compact step results for the host-buffer path.  What changes in an env's reference-shaped outputs every step is small:
+// reward / target_find / terminated / win, the n agent rows (x^, y^, cos, sin) and a few find flags; the 2m target
+// coordinates of a state row change only when the env is reset.  One record per env:
+//   { float reward; uint32 found; uint8 target_find, terminated, win, reset; uint32 0 } + n x float4   (16 + 16n bytes)
+// and, for the envs that were reset inside this call (auto-reset), one entry { int32 env; float xy[2m] } in a small
+// side region claimed with an atomic counter.  The host expands this into full rows (flight_host.cu).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) flight_pack_kernel(const FlightParams p, unsigned char* __restrict__ out, int rec_bytes,
+                                                          unsigned char* __restrict__ entries, int ent_bytes, int cap,
+                                                          unsigned int* __restrict__ counter) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= p.E) return;
+    uint4 m0, m1;
+    meta_ld(p, e, &m0, &m1);
+    const uint32_t term = p.terminated[e], reset = (term && p.auto_reset) ? 1u : 0u;
+    uint4* rec = reinterpret_cast<uint4*>(out + (size_t)e * rec_bytes);
+    const uint32_t bytes = (uint32_t)p.target_find[e] | (term << 8) | ((uint32_t)p.win[e] << 16) | (reset << 24);
+    rec[0] = make_uint4(__float_as_uint(p.reward[e]), m0.x, bytes, 0u);
+    const uint4* row = reinterpret_cast<const uint4*>(p.state + (size_t)e * p.state_stride);
+    for (int a = 0; a < p.n; ++a) rec[1 + a] = row[a];
+    if (reset) {
+        const unsigned slot = atomicAdd(counter, 1u);
+        if (slot < (unsigned)cap) {
+            int* ent = reinterpret_cast<int*>(entries + (size_t)slot * ent_bytes);
+            ent[0] = e;
+            const float* tr = p.state + (size_t)e * p.state_stride + 4 * p.n;
+            float* xy = reinterpret_cast<float*>(ent + 1);
+            for (int j = 0; j < p.m; ++j) { xy[2 * j] = tr[3 * j]; xy[2 * j + 1] = tr[3 * j + 1]; }
+        }
+    }
+}
+
 inline int capped_grid(long long items, int per_block, int max_blocks) {
     const long long g = (items + per_block - 1) / per_block;
     return (int)(g < (long long)max_blocks ? (g < 1 ? 1 : g) : max_blocks);
@@ -226,6 +259,16 @@ cudaError_t launch_record_begin(cs_flight* h, const cs_episode_buffers& b, int T
 cudaError_t launch_record(cs_flight* h, const cs_episode_buffers& b, int t, int T, const uint8_t* actions, cudaStream_t st) {
     const FlightParams& p = h->p;
     flight_record_kernel<<<capped_grid((long long)p.E * (4 * p.n + p.state_len + 1), 256, CS_NUM_SMS_B200 * 8), 256, 0, st>>>(p, b, t, T, actions);
+    cs_count_launch(1);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pack(cs_flight* h, cudaStream_t st) {
+    cs_flight_compact* c = h->hc;
+    cudaError_t e = cudaMemsetAsync(c->d_pack + c->off_counter, 0, 16, st);
+    if (e != cudaSuccess) return e;
+    flight_pack_kernel<<<(h->p.E + 127) / 128, 128, 0, st>>>(h->p, c->d_pack, (int)c->rec_bytes, c->d_pack + c->off_entries, (int)c->ent_bytes, c->cap,
+                                                          reinterpret_cast<unsigned int*>(c->d_pack + c->off_counter));
     cs_count_launch(1);
     return cudaGetLastError();
 }

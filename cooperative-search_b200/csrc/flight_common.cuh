@@ -40,8 +40,13 @@ struct FlightParams {
     // belief map, stored as 4x4-cell tiles of 64 bytes: cell (i, j) of env e lives at
     // prob_map[e*map_stride + ((i>>2)*tiles + (j>>2))*16 + (i&3)*4 + (j&3)], tiles = ceil(M/4) per side
     int tiles, map_stride;
-    // fused step+map kernel: per-env shared-memory scratch, offsets / sizes in bytes
+    // tiled map update (fused kernel / flight_map_tile_kernel): per-env shared-memory scratch, offsets / sizes in bytes
     int fm_list, fm_clo, fm_job, fm_jobsz, fm_env;
+    // two-kernel form: belief-map job records the step / reset kernel leaves for flight_map_tile_kernel, one per env:
+    // int2 {jobs (0..2), fill flag} at +0, job slots of fm_jobsz bytes from +16.  Double buffered by the host (the step
+    // kernel of call t+1 may run while the map kernel of call t still reads): `jobs` is the buffer of THIS launch.
+    unsigned char* jobs;
+    int job_stride;
     // generic map kernel: per-warp scratch offsets / size in 8-byte words
     int ms_box, ms_xy, ms_hit, ms_warp;
     int pre_stride;              // doubles per env in `pre`

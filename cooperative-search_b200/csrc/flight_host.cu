@@ -17,14 +17,64 @@ int pick_lpe(const cs_flight_cfg& c) {
     return lpe > 32 ? 32 : lpe;
 }
 
-cudaError_t dispatch(cs_flight* h, int mode, const uint8_t* actions, const uint8_t* mask, uint32_t rflags, cudaStream_t st) {
-    if (!h->tpe) return launch_lpa(h, mode, actions, mask, rflags, st);
+unsigned long long capture_id(cudaStream_t st) {
+    cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
+    unsigned long long id = 0;
+    if (cudaStreamGetCaptureInfo(st, &status, &id) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return status == cudaStreamCaptureStatusActive ? id : 0;
+}
+
+// `st` waits for a map-stream event -- only where that is meaningful: an event recorded in the SAME capture (or, outside
+// captures, a really recorded one).  An event from another context is covered by stream order: cs_flight_map_sync joins
+// the map stream before a capture begins and before it ends.
+cudaError_t wait_map_event(cs_flight* h, int idx, cudaStream_t st) {
+    if (idx < 0 || !h->ev_map[idx].valid || h->ev_map[idx].capture_id != capture_id(st)) return cudaSuccess;
+    return cudaStreamWaitEvent(st, h->ev_map[idx].ev, 0);
+}
+
+cudaError_t launch_step(cs_flight* h, int mode, const uint8_t* actions, const uint8_t* mask, uint32_t rflags, cudaStream_t st) {
     switch ((h->p.n - 1) / 2) {
         case 0: return launch_tpe_part0(h, mode, actions, mask, rflags, st);
         case 1: return launch_tpe_part1(h, mode, actions, mask, rflags, st);
         case 2: return launch_tpe_part2(h, mode, actions, mask, rflags, st);
         default: return launch_tpe_part3(h, mode, actions, mask, rflags, st);
     }
+}
+
+cudaError_t dispatch(cs_flight* h, int mode, const uint8_t* actions, const uint8_t* mask, uint32_t rflags, cudaStream_t st) {
+    if (!h->tpe) return launch_lpa(h, mode, actions, mask, rflags, st);
+    if (!h->tiled) return launch_step(h, mode, actions, mask, rflags, st);
+    // flight variant, two-kernel form: step / reset kernel (leaves one job record per env), then the tiled map kernel.
+    // Job records are double buffered over calls: with map_overlap the map kernel runs on the handle's own stream,
+    // concurrently with the NEXT call's step kernel, which writes the other buffer; before a buffer is rewritten the
+    // map kernel that read it (two calls ago) must be done.
+    const int par = h->job_parity;
+    h->p.jobs = h->d_jobs + (size_t)par * (size_t)h->p.E * (size_t)h->p.job_stride;
+    cudaError_t e = cudaSuccess;
+    if (h->cfg.map_overlap) e = wait_map_event(h, par, st);
+    if (e == cudaSuccess) e = launch_step(h, mode, actions, mask, rflags, st);
+    if (e != cudaSuccess) return e;
+    if (!h->cfg.map_overlap) {
+        e = launch_map_tile(h, st);
+    } else {
+        e = cudaEventRecord(h->ev_step, st);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(h->map_stream, h->ev_step, 0);
+        if (e == cudaSuccess) e = launch_map_tile(h, h->map_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(h->ev_map[par].ev, h->map_stream);
+        if (e == cudaSuccess) {
+            h->ev_map[par].valid = true;
+            h->ev_map[par].capture_id = capture_id(h->map_stream);
+            h->last_map = par;
+        }
+    }
+    h->job_parity = par ^ 1;
+    return e;
+}
+
+// the caller's stream waits for the latest belief-map kernel (no-op unless map_overlap)
+cudaError_t map_join(cs_flight* h, cudaStream_t st) {
+    if (!h->tiled || !h->cfg.map_overlap) return cudaSuccess;
+    return wait_map_event(h, h->last_map, st);
 }
 
 inline int up2(int v) { return (v + 1) & ~1; }
@@ -100,6 +150,17 @@ void build_cell_lut(float qf, std::vector<float>* out) {
         }
 }
 
+}  // namespace
+
+namespace csf {
+cudaError_t flight_dispatch(cs_flight* h, int mode, const uint8_t* actions, const uint8_t* mask, uint32_t rflags, cudaStream_t st) {
+    return dispatch(h, mode, actions, mask, rflags, st);
+}
+cudaError_t flight_map_join(cs_flight* h, cudaStream_t st) { return map_join(h, st); }
+}  // namespace csf
+
+namespace {
+
 // everything cs_flight_create allocates, in one place so that a failure half way frees what exists
 int flight_alloc(cs_flight* h) {
     const cs_flight_cfg* cfg = &h->cfg;
@@ -143,9 +204,20 @@ int flight_alloc(cs_flight* h) {
     if (cfg->variant) {
         CS_CUDA(cudaMalloc(&p.prob_map, E * p.map_stride * sizeof(float)));
         CS_CUDA(cudaMemset(p.prob_map, 0, E * p.map_stride * sizeof(float)));
-        if (!h->fused) {
+        if (!h->fused && !h->tiled) {
             CS_CUDA(cudaMalloc(&p.pre, E * p.pre_stride * sizeof(double)));
             CS_CUDA(cudaMemset(p.pre, 0, E * p.pre_stride * sizeof(double)));
+        }
+        if (h->tiled) {
+            CS_CUDA(cudaMalloc(&h->d_jobs, 2 * E * p.job_stride));
+            CS_CUDA(cudaMemset(h->d_jobs, 0, 2 * E * p.job_stride));
+            p.jobs = h->d_jobs;
+            if (cfg->map_overlap) {
+                CS_CUDA(cudaStreamCreateWithFlags(&h->map_stream, cudaStreamNonBlocking));
+                CS_CUDA(cudaEventCreateWithFlags(&h->ev_step, cudaEventDisableTiming));
+                CS_CUDA(cudaEventCreateWithFlags(&h->ev_map[0].ev, cudaEventDisableTiming));
+                CS_CUDA(cudaEventCreateWithFlags(&h->ev_map[1].ev, cudaEventDisableTiming));
+            }
         }
         std::vector<float> cells;
         build_cell_lut((float)p.q_miss, &cells);
@@ -237,9 +309,12 @@ int cs_flight_create(const cs_flight_cfg* cfg, cs_flight** out) {
     h->lpe = pick_lpe(*cfg);
     // lanes_per_env: 0 = automatic; 1 or 4 = thread-per-env kernel with that many threads per env; larger = lane-per-agent kernel
     h->tpe = n <= kTpeMaxAgents && (cfg->lanes_per_env == 0 || cfg->lanes_per_env == 1 || cfg->lanes_per_env == 4);
-    // the flight variant runs step + belief map in one kernel with 8 lanes per env wherever that kernel applies
-    h->fused = cfg->variant == 1 && h->tpe && M <= 63;
-    if (cfg->variant == 1 && !h->fused) h->tpe = false;          // generic map path: lane-per-agent step kernel + map kernel
+    // the flight variant (map_size <= 63, n_agents <= 8): thread-per-env step kernel + tiled map kernel; lanes_per_env = 8
+    // asks for the fused single-kernel form; everything else takes the lane-per-agent step kernel + generic map kernel
+    h->fused = cfg->variant == 1 && n <= kTpeMaxAgents && M <= 63 && cfg->lanes_per_env == 8;
+    h->tiled = cfg->variant == 1 && h->tpe && M <= 63;
+    if (h->fused) h->tpe = true;
+    if (cfg->variant == 1 && !h->fused && !h->tiled) h->tpe = false;
     // measured on B200 (tools/sweep_step.sh): one thread per env wins from ~32k envs per launch (2.7e9 against 1.7e9
     // env-steps/s at 65536 envs, 5.0e9 against 2.4e9 at 1M); below that a launch cannot fill the GPU with one thread
     // per env and 4 threads per env match the lane-per-agent kernel's latency
@@ -263,6 +338,7 @@ int cs_flight_create(const cs_flight_cfg* cfg, cs_flight** out) {
         p.fm_job = p.fm_clo + ((n * 4 + 15) & ~15);
         p.fm_jobsz = (2 * n * 8 + (1 + m) * 4 + 15) & ~15;
         p.fm_env = p.fm_job + 2 * p.fm_jobsz;
+        p.job_stride = 16 + 2 * p.fm_jobsz;
         p.ms_box = 0;
         p.ms_xy = p.ms_box + 2 * n;
         p.ms_hit = p.ms_xy + 2 * n;
@@ -279,10 +355,12 @@ int cs_flight_create(const cs_flight_cfg* cfg, cs_flight** out) {
     if (h->tpe && h->tpe_k == 1) { p.dyn_rs = (long long)p.E; p.dyn_es = 1; p.tgt_rs = (long long)p.E; p.tgt_es = 1; }
     else { p.dyn_rs = 1; p.dyn_es = p.rec; p.tgt_rs = 1; p.tgt_es = 2 * m; }
     h->seq = 1u;
+    h->last_map = -1;
 
     int rc = CS_OK;
     {
-        const cudaError_t e = lpa_set_smem_limit(h->smem_bytes, cfg->variant ? h->map_smem : 0);
+        cudaError_t e = lpa_set_smem_limit(h->smem_bytes);
+        if (e == cudaSuccess && cfg->variant) e = map_set_smem_limit(h->map_smem);
         if (e != cudaSuccess) { cs_set_error("cudaFuncSetAttribute -> %s", cudaGetErrorString(e)); rc = CS_ERR_CUDA; }
     }
     if (rc == CS_OK) rc = flight_alloc(h);
@@ -301,6 +379,12 @@ void cs_flight_destroy(cs_flight* h) {
     cudaFree(h->p.dyn); cudaFree(h->p.tgt); cudaFree(h->d_slab); cudaFree(h->p.stats); cudaFree(h->d_live);
     cudaFree(h->d_tmpl); cudaFree(h->p.prob_map); cudaFree(h->p.pre); cudaFree(h->d_actions); cudaFree(h->d_lut_meta); cudaFree(h->d_lut);
     cudaFree(h->d_lut_cells);
+    if (h->map_stream) { cudaStreamSynchronize(h->map_stream); cudaStreamDestroy(h->map_stream); }
+    if (h->ev_step) cudaEventDestroy(h->ev_step);
+    if (h->ev_map[0].ev) cudaEventDestroy(h->ev_map[0].ev);
+    if (h->ev_map[1].ev) cudaEventDestroy(h->ev_map[1].ev);
+    cudaFree(h->d_jobs);
+    flight_compact_release(h);
     delete h;
 }
 
@@ -375,24 +459,28 @@ int cs_flight_reset(cs_flight* h, const uint8_t* d_mask, uint32_t flags, void* s
     CS_REQUIRE((flags & CS_RESET_KEEP_TARGETS) || h->p.target_mode == 1 || h->have_tmpl,
                "target_mode 0 needs cs_flight_set_target_template before reset");
     CS_CUDA(dispatch(h, MODE_RESET, nullptr, d_mask, flags, (cudaStream_t)stream));
+    flight_compact_mark_dirty(h);        // the compact host path refreshes its rows in full on the next step
     return CS_OK;
 }
 
 int cs_flight_step(cs_flight* h, const uint8_t* d_actions, void* stream) {
     CS_REQUIRE(h && d_actions, "cs_flight_step: null argument");
     CS_CUDA(dispatch(h, MODE_STEP, d_actions, nullptr, 0u, (cudaStream_t)stream));
+    flight_compact_mark_dirty(h);        // a device-resident step: the compact host path refreshes its rows in full next time
     return CS_OK;
 }
 
 int cs_flight_step_random(cs_flight* h, int32_t k, void* stream) {
     CS_REQUIRE(h && k >= 0, "cs_flight_step_random: bad argument");
     for (int i = 0; i < k; ++i) CS_CUDA(dispatch(h, MODE_STEP, nullptr, nullptr, 0u, (cudaStream_t)stream));
+    flight_compact_mark_dirty(h);
     return CS_OK;
 }
 
 int cs_flight_obs_full(cs_flight* h, float* d_out, void* stream) {
     CS_REQUIRE(h && d_out, "cs_flight_obs_full: null argument");
     CS_REQUIRE(h->p.variant == 1, "cs_flight_obs_full: only the flight (prob map) variant has a map observation");
+    CS_CUDA(map_join(h, (cudaStream_t)stream));
     CS_CUDA(launch_obs_full(h, d_out, (cudaStream_t)stream));
     return CS_OK;
 }
@@ -400,6 +488,7 @@ int cs_flight_obs_full(cs_flight* h, float* d_out, void* stream) {
 int cs_flight_map_export(cs_flight* h, float* d_out, void* stream) {
     CS_REQUIRE(h && d_out, "cs_flight_map_export: null argument");
     CS_REQUIRE(h->p.variant == 1, "cs_flight_map_export: only the flight (prob map) variant has a map");
+    CS_CUDA(map_join(h, (cudaStream_t)stream));
     CS_CUDA(launch_map_export(h, d_out, (cudaStream_t)stream));
     return CS_OK;
 }
@@ -407,7 +496,19 @@ int cs_flight_map_export(cs_flight* h, float* d_out, void* stream) {
 int cs_flight_map_import(cs_flight* h, const float* d_in, void* stream) {
     CS_REQUIRE(h && d_in, "cs_flight_map_import: null argument");
     CS_REQUIRE(h->p.variant == 1, "cs_flight_map_import: only the flight (prob map) variant has a map");
+    CS_CUDA(map_join(h, (cudaStream_t)stream));
     CS_CUDA(launch_map_import(h, d_in, (cudaStream_t)stream));
+    if (h->tiled && h->cfg.map_overlap) {
+        // later map kernels (own stream) must see the imported map: order them after this copy
+        CS_CUDA(cudaEventRecord(h->ev_step, (cudaStream_t)stream));
+        CS_CUDA(cudaStreamWaitEvent(h->map_stream, h->ev_step, 0));
+    }
+    return CS_OK;
+}
+
+int cs_flight_map_sync(cs_flight* h, void* stream) {
+    CS_REQUIRE(h, "cs_flight_map_sync: null handle");
+    CS_CUDA(map_join(h, (cudaStream_t)stream));
     return CS_OK;
 }
 
@@ -426,6 +527,7 @@ int cs_flight_step_host(cs_flight* h, const cs_flight_host_io* io, void* stream)
     CS_CUDA(cudaSetDevice(h->cfg.device));
     CS_CUDA(cudaMemcpyAsync(h->d_actions, io->actions, E * p.n, cudaMemcpyHostToDevice, st));
     CS_CUDA(dispatch(h, MODE_STEP, h->d_actions, nullptr, 0u, st));
+    CS_CUDA(map_join(h, st));             // a host-buffer step is complete when it returns: the belief map too
     if (io->slab) {
         // one copy for everything: reward | target_find | terminated | win | state (cs_flight_slab_layout); the obs
         // rows are the first 4n floats of the state rows and are not sent twice
@@ -512,6 +614,7 @@ int cs_flight_group_step(cs_flight_group* g, const uint8_t* const* d_actions, vo
         default: e = launch_group_part3(g, d_actions, st); break;
     }
     CS_CUDA(e);
+    for (int i = 0; i < g->count; ++i) flight_compact_mark_dirty(g->envs[i]);
     return CS_OK;
 }
 
@@ -551,6 +654,7 @@ int cs_flight_stats(cs_flight* h, double* h_out, void* stream) {
     CS_REQUIRE(h && h_out, "cs_flight_stats: null argument");
     cudaStream_t st = (cudaStream_t)stream;
     CS_CUDA(cudaSetDevice(h->cfg.device));
+    CS_CUDA(map_join(h, st));            // CS_STAT_TOUCHED is accumulated by the map kernel
     // env_steps = lengths of the finished episodes + steps of the episodes still running
     CS_CUDA(cudaMemsetAsync(h->d_live, 0, sizeof(double), st));
     CS_CUDA(launch_live_steps(h, st));

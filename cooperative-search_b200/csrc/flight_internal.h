@@ -10,13 +10,34 @@ constexpr int kTpeMaxAgents = 8;       // thread-per-env kernels are instantiate
 constexpr int kTpeThreads = CS_TPE_THREADS;   // threads per CTA of the thread-per-env kernels
 constexpr int kMaxGroup = 128;         // handles per grouped launch
 
+// Compact host-buffer path (cs_flight_step_host_compact): what the device sends per step and where the host keeps the
+// reference-shaped results it expands them into.
+struct cs_flight_compact {
+    unsigned char* d_pack;       // device: [E records][cap reset entries][counter]
+    unsigned char* h_pack;       // pinned host mirror
+    size_t pack_bytes, rec_bytes, ent_bytes, off_entries, off_counter;
+    int cap;                     // reset entries that fit (envs that were reset inside one call)
+    float* reward; int32_t* target_find; uint8_t* terminated; uint8_t* win;   // host results, library-owned
+    float* state;                // [E][state_stride]
+    uint32_t* shadow_found;      // found mask the host rows currently show
+    bool dirty;                  // the host rows must be refreshed in full (first step, after cs_flight_reset / import)
+};
+
 struct cs_flight {
     cs_flight_cfg cfg;
     csf::FlightParams p;
     int lpe;              // lanes per env of the lane-per-agent kernel
     bool tpe;             // thread-per-env step kernel (n_agents <= kTpeMaxAgents and lanes_per_env in {0, 1, 4})
     int tpe_k;            // threads that share one env's target loop in that kernel (1, 4; 8 in the fused kernel)
-    bool fused;           // flight variant: step + belief map in one kernel (tpe, map_size <= 63)
+    bool fused;           // flight variant: step + belief map in ONE kernel, 8 lanes per env (lanes_per_env = 8, map_size <= 63)
+    bool tiled;           // flight variant: thread-per-env step kernel, then flight_map_tile_kernel (the default, map_size <= 63)
+    // two-kernel form: job records double buffered over calls; with cfg.map_overlap the map kernel runs on map_stream
+    unsigned char* d_jobs;
+    int job_parity;
+    cudaStream_t map_stream;
+    cudaEvent_t ev_step;
+    struct MapEvent { cudaEvent_t ev; unsigned long long capture_id; bool valid; } ev_map[2];
+    int last_map;         // index into ev_map of the latest map launch, -1 = none
     size_t smem_bytes, map_smem;
     int grid, map_grid;
     uint32_t seq;         // generic map path: value of CS_META_SENSE >> 1 that marks "sensed by the latest call" (constant: launches captured in CUDA graphs replay it)
@@ -30,6 +51,7 @@ struct cs_flight {
     double2* d_lut;
     float4* d_lut_cells;
     bool have_tmpl;
+    cs_flight_compact* hc;
 };
 
 struct cs_flight_group {
@@ -53,7 +75,12 @@ int fused_lanes_part0();
 
 // flight_lpa.cu: lane-per-agent step / reset kernel (+ the generic belief-map kernel of the flight variant)
 cudaError_t launch_lpa(cs_flight*, int mode, const uint8_t* actions, const uint8_t* mask, uint32_t rflags, cudaStream_t);
-cudaError_t lpa_set_smem_limit(size_t step_bytes, size_t map_bytes);
+cudaError_t lpa_set_smem_limit(size_t step_bytes);
+
+// flight_mapk.cu: belief-map kernels that run as their own launch
+cudaError_t launch_map_tile(cs_flight*, cudaStream_t);
+cudaError_t launch_map_generic(cs_flight*, cudaStream_t);
+cudaError_t map_set_smem_limit(size_t generic_bytes);
 
 // flight_aux.cu
 cudaError_t launch_obs_full(cs_flight*, float* d_out, cudaStream_t);
@@ -62,5 +89,14 @@ cudaError_t launch_map_import(cs_flight*, const float* d_in, cudaStream_t);
 cudaError_t launch_record_begin(cs_flight*, const cs_episode_buffers&, int T, cudaStream_t);
 cudaError_t launch_record(cs_flight*, const cs_episode_buffers&, int t, int T, const uint8_t* actions, cudaStream_t);
 cudaError_t launch_live_steps(cs_flight*, cudaStream_t);
+cudaError_t launch_pack(cs_flight*, cudaStream_t);
+
+// flight_host.cu
+cudaError_t flight_dispatch(cs_flight*, int mode, const uint8_t* actions, const uint8_t* mask, uint32_t rflags, cudaStream_t);
+cudaError_t flight_map_join(cs_flight*, cudaStream_t);
+
+// flight_hostio.cu
+void flight_compact_release(cs_flight*);
+void flight_compact_mark_dirty(cs_flight*);
 
 }  // namespace csf

@@ -1,8 +1,6 @@
 // Lane-per-agent step / reset kernel of flight_easy / flight (n_agents > 8, or lanes_per_env >= 16) and the launch of
 // the generic belief-map kernel that follows it in the flight variant.  See flight_common.cuh for the file map.
 #include "flight_internal.h"
-#define CS_MAP_GENERIC
-#include "flight_map.cuh"
 
 namespace csf {
 namespace {
@@ -336,8 +334,8 @@ cudaError_t launch_flight(cs_flight* h, int mode, const uint8_t* actions, const 
         else
             flight_kernel<LPE, MODE_RESET, true><<<h->grid, kThreads, h->smem_bytes, st>>>(h->p, actions, mask, rflags, h->seq);
         // the belief maps of the envs the step / reset kernel just sensed (flight_env.py:266)
-        flight_map_generic_kernel<<<h->map_grid, kMapThreads, h->map_smem, st>>>(h->p, h->seq);
-        cs_count_launch(1);
+        const cudaError_t em = launch_map_generic(h, st);
+        if (em != cudaSuccess) return em;
     } else {
         if (mode == MODE_STEP)
             flight_kernel<LPE, MODE_STEP, false><<<h->grid, kThreads, h->smem_bytes, st>>>(h->p, actions, mask, rflags, 0u);
@@ -372,8 +370,8 @@ cudaError_t launch_lpa(cs_flight* h, int mode, const uint8_t* actions, const uin
 
 // Dynamic shared memory limits are per KERNEL, not per handle: they are only ever raised, to the largest request any
 // handle of this process has made (a later, smaller handle must not lower them under an earlier one's launches).
-cudaError_t lpa_set_smem_limit(size_t step_bytes, size_t map_bytes) {
-    static size_t cur_step = 48 * 1024, cur_map = 48 * 1024;
+cudaError_t lpa_set_smem_limit(size_t step_bytes) {
+    static size_t cur_step = 48 * 1024;
     cudaError_t e = cudaSuccess;
     if (step_bytes > cur_step) {
         e = set_smem_attr<1>(step_bytes);
@@ -383,10 +381,6 @@ cudaError_t lpa_set_smem_limit(size_t step_bytes, size_t map_bytes) {
         if (e == cudaSuccess) e = set_smem_attr<16>(step_bytes);
         if (e == cudaSuccess) e = set_smem_attr<32>(step_bytes);
         if (e == cudaSuccess) cur_step = step_bytes;
-    }
-    if (e == cudaSuccess && map_bytes > cur_map) {
-        e = cudaFuncSetAttribute(flight_map_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)map_bytes);
-        if (e == cudaSuccess) cur_map = map_bytes;
     }
     return e;
 }

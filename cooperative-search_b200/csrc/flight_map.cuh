@@ -23,6 +23,10 @@
 #pragma once
 #include "flight_common.cuh"
 
+#ifndef CS_MAP_U
+#define CS_MAP_U 2             // measured on the c4 workload (tools/exp_c4.py): 2 loads in flight per lane at 12 CTAs per SM beat 4 at 10 / 12 / 14
+#endif
+
 namespace csf {
 
 // ---- packed fp32 pairs (sm_100: FADD2 / FMUL2 / FFMA2) ----------------------------------------------------------
@@ -91,7 +95,8 @@ __device__ __forceinline__ void corner_interval_task(const FlightParams& p, int 
     const double A = dx * dx;
     if (!(A < p.R2) || cx < 0 || cx > M) return;                     // past the last corner row of this agent
     // candidate ends in fp32 (ay <= map_size: absolute error ~4e-6, far inside the 1e-3 guard band)
-    const float wf = sqrtf(fmaxf((float)(p.R2 - A), 0.0f));
+    float wf;                                                        // approximate sqrt (2 ulp): far inside the guard band
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(wf) : "f"(fmaxf((float)(p.R2 - A), 0.0f)));
     const float ayf = (float)aya;
     const float yh = ayf + wf, yl = ayf - wf;
     float fh = floorf(yh), cl = ceilf(yl);
@@ -126,7 +131,7 @@ __device__ __forceinline__ void fused_map_phase(const FlightParams& p, int e, in
     static_assert(GL == 4 || GL == 8 || GL == 16, "GL");
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int QP = GL / 4;                                       // tiles the group's lanes cover per float4 slot
-    constexpr int U = 4;                                             // float4 loads in flight per lane
+    constexpr int U = CS_MAP_U;                                      // float4 loads in flight per lane
     const int n = p.n, M = p.M, TC = p.tiles;
     unsigned long long* R = reinterpret_cast<unsigned long long*>(S);
     unsigned short* list = reinterpret_cast<unsigned short*>(S + p.fm_list);
@@ -234,6 +239,49 @@ __device__ __forceinline__ void fused_map_phase(const FlightParams& p, int e, in
 }
 
 // ------------------------------------------------------------------------------------------------
+// Two-kernel form: flight_map_tile_kernel runs after the thread-per-env step / reset kernel (flight_tpe.cu), which
+// left one job record per env in FlightParams::jobs (header {jobs, fill flag}, up to two job slots).  GL = 16 lanes own
+// one env: they copy the record into the env's shared-memory scratch and run fused_map_phase on it.  On its own the
+// map update needs no fp64 state and no Philox: few registers, many resident warps, which is what covers the
+// latency of the scattered 64-byte tile accesses.  With cs_flight_cfg.map_overlap the kernel runs on the handle's own
+// stream, concurrently with the step kernel of the NEXT call (flight_host.cu).
+// ------------------------------------------------------------------------------------------------
+#ifdef CS_MAP_KERNELS           // instantiated by flight_mapk.cu only
+constexpr int kMapThreads = 128;
+#ifndef CS_TILE_LANES
+#define CS_TILE_LANES 16
+#endif
+constexpr int kTileLanes = CS_TILE_LANES;
+#ifndef CS_MAP_MIN_CTAS
+#define CS_MAP_MIN_CTAS 12
+#endif
+
+static __global__ void __launch_bounds__(kMapThreads, CS_MAP_MIN_CTAS) flight_map_tile_kernel(const __grid_constant__ FlightParams p) {
+    constexpr int GL = kTileLanes;
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(16) unsigned char tsm[];
+    const int grp = threadIdx.x / GL, kk = threadIdx.x % GL;
+    const int e_raw = blockIdx.x * (kMapThreads / GL) + grp;
+    const int e = min(e_raw, p.E - 1);
+    const unsigned char* rec = p.jobs + (size_t)e * p.job_stride;
+    const int2 hdr = *reinterpret_cast<const int2*>(rec);
+    const int njobs = e_raw < p.E ? hdr.x : 0;
+    const bool fill = e_raw < p.E && hdr.y != 0;
+    if (!__any_sync(FULL, njobs != 0 || fill)) return;
+    unsigned char* S = tsm + (size_t)grp * p.fm_env;
+    if (fill) {                                                      // reset(init=True): prob_map <- 0.5 (flight_env.py:84-86), tiles incl. padding
+        float4* m4 = reinterpret_cast<float4*>(p.prob_map + (size_t)e * p.map_stride);
+        for (int c = kk; c < p.map_stride / 4; c += GL) m4[c] = make_float4(0.5f, 0.5f, 0.5f, 0.5f);
+    }
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(rec + 16);
+        uint4* dst = reinterpret_cast<uint4*>(S + p.fm_job);
+        for (int c = kk; c < njobs * (p.fm_jobsz / 16); c += GL) dst[c] = src[c];
+    }
+    fused_map_phase<GL>(p, e, kk, S, njobs);                         // its first __syncwarp orders the fill and the copy
+}
+
+// ------------------------------------------------------------------------------------------------
 // Generic form (any map_size, any n_agents): its own kernel after the lane-per-agent step / reset kernel, one warp
 // per env, per-cell corner tests in fp64 like the reference.  The step kernel leaves a job for every env it sensed: a
 // non-zero meta word CS_META_SENSE (cleared again by the next call that does not sense the env), the agent positions
@@ -241,9 +289,6 @@ __device__ __forceinline__ void fused_map_phase(const FlightParams& p, int e, in
 // was sensed twice (flight_env.py:266 runs inside reset() too) and its first job -- positions and hit cells before
 // the reset -- sits in the `pre` side buffer.  Same cell arithmetic as the fused form: bit-identical maps.
 // ------------------------------------------------------------------------------------------------
-#ifdef CS_MAP_GENERIC           // instantiated by flight_lpa.cu only
-constexpr int kMapThreads = 128;
-
 // Loads job `job` of env e into the warp's scratch: agent positions -> xy[2n], hit cells -> hit[]; returns the number
 // of hit cells.  job 0 = the sensing before an in-call auto-reset (side buffer), job 1 = the state record as the step
 // / reset kernel left it.
@@ -348,6 +393,6 @@ static __global__ void __launch_bounds__(kMapThreads) flight_map_generic_kernel(
     }
 }
 
-#endif  // CS_MAP_GENERIC
+#endif  // CS_MAP_KERNELS
 
 }  // namespace csf

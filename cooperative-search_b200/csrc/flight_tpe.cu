@@ -36,9 +36,9 @@ namespace {
 #define CS_TPE_MIN_CTAS 8      // resident CTAs per SM the thread-per-env kernel is compiled for (register budget 65536/(64*N))
 #endif
 
-template <int N, int K, int MODE, bool MAP, int TPB>
+template <int N, int K, int MODE, bool MAP, int TPB, bool FUSED>
 __device__ __forceinline__ int flight_tpe_body(const FlightParams& p, const int block, const uint8_t* __restrict__ actions,
-                                               const uint8_t* __restrict__ mask, uint32_t rflags, unsigned char* scratch) {
+                                               const uint8_t* __restrict__ mask, uint32_t rflags, unsigned char* jobslots) {
     constexpr unsigned FULL = 0xffffffffu;
     __shared__ longlong2 lutm[40];
     static_assert(K == 1 || K == 4 || K == 8, "K");
@@ -81,7 +81,7 @@ __device__ __forceinline__ int flight_tpe_body(const FlightParams& p, const int 
     uint32_t found = m0.x, newf_last = m0.y, outmask = m0.z, time_step = m0.w;
     uint32_t episode = m1.x, flags = m1.y;
     float ep_reward = __uint_as_float(m1.z);
-    int njobs = 0;                              // belief-map jobs stashed in `scratch` (MAP)
+    int njobs = 0;                              // belief-map jobs written to `jobslots` (MAP)
 
     bool done = (flags & CS_FLAG_DONE) != 0;
     bool do_sense = false, emit = false, state_full = false, have_result = false;
@@ -195,7 +195,7 @@ __device__ __forceinline__ int flight_tpe_body(const FlightParams& p, const int 
             }
             // warp-cooperative heavy parts of a reset, one resetting env at a time: its targets (one lane per
             // target, :95-127) and, for reset(init=True), its belief map (flight_env.py:84-86)
-            if (!(rflags & CS_RESET_KEEP_TARGETS) || (MAP && (rflags & CS_RESET_INIT))) {
+            if (!(rflags & CS_RESET_KEEP_TARGETS) || (FUSED && (rflags & CS_RESET_INIT))) {
                 unsigned left = rmask;
                 const int t_first = block * TPB + (tid & ~31);
                 while (left) {
@@ -209,7 +209,7 @@ __device__ __forceinline__ int flight_tpe_body(const FlightParams& p, const int 
                             tgt_st(p, j, es, t);
                         }
                     }
-                    if (MAP && (rflags & CS_RESET_INIT)) {
+                    if (FUSED && (rflags & CS_RESET_INIT)) {     // (the map kernel does this fill in the two-kernel form)
                         float4* map = reinterpret_cast<float4*>(p.prob_map + (size_t)es * p.map_stride);
                         for (int c = lane32; c < p.map_stride / 4; c += 32) map[c] = make_float4(0.5f, 0.5f, 0.5f, 0.5f);
                     }
@@ -298,7 +298,7 @@ __device__ __forceinline__ int flight_tpe_body(const FlightParams& p, const int 
         //      saw and the cells of the targets it found.  An env that is reset inside this call leaves two jobs.
         if (MAP && do_sense) {
             if (kk == 0) {
-                double* jx = reinterpret_cast<double*>(scratch + p.fm_job + njobs * p.fm_jobsz);
+                double* jx = reinterpret_cast<double*>(jobslots + njobs * p.fm_jobsz);
                 int* jh = reinterpret_cast<int*>(jx + 2 * N);
 #pragma unroll
                 for (int a = 0; a < N; ++a) *reinterpret_cast<double2*>(jx + 2 * a) = make_double2(ax[a], ay[a]);
@@ -374,10 +374,23 @@ __device__ __forceinline__ int flight_tpe_body(const FlightParams& p, const int 
     return active ? njobs : 0;
 }
 
-template <int N, int K, int MODE>
+template <int N, int K, int MODE, bool MAP>
 __global__ void __launch_bounds__(kTpeThreads, CS_TPE_MIN_CTAS) flight_tpe_kernel(const __grid_constant__ FlightParams p, const uint8_t* __restrict__ actions,
                                                                  const uint8_t* __restrict__ mask, uint32_t rflags) {
-    flight_tpe_body<N, K, MODE, false, kTpeThreads>(p, (int)blockIdx.x, actions, mask, rflags, nullptr);
+    if (!MAP) {
+        flight_tpe_body<N, K, MODE, false, kTpeThreads, false>(p, (int)blockIdx.x, actions, mask, rflags, nullptr);
+        return;
+    }
+    // flight variant, two-kernel form: this env's belief-map job record for flight_map_tile_kernel, which runs next
+    // (on the same stream, or on the handle's map stream): header {jobs, fill flag} + up to two job slots
+    const int e_raw = (int)((blockIdx.x * kTpeThreads + threadIdx.x) / K);
+    const int e = e_raw < p.E ? e_raw : p.E - 1;
+    unsigned char* rec = p.jobs + (size_t)e * p.job_stride;
+    const int njobs = flight_tpe_body<N, K, MODE, true, kTpeThreads, false>(p, (int)blockIdx.x, actions, mask, rflags, rec + 16);
+    if (e_raw < p.E && threadIdx.x % K == 0) {
+        const int fill = (MODE == MODE_RESET && (rflags & CS_RESET_INIT) && (mask == nullptr || mask[e] != 0)) ? 1 : 0;   // reset(init=True): map <- 0.5 (flight_env.py:84-86)
+        *reinterpret_cast<int2*>(rec) = make_int2(njobs, fill);
+    }
 }
 
 // The flight variant: step / reset and the belief-map update of the same envs in ONE kernel (flight_map.cuh).  8 lanes
@@ -395,7 +408,7 @@ __global__ void __launch_bounds__(kFusedThreads, CS_FUSED_MIN_CTAS) flight_fused
                                                                                        const uint8_t* __restrict__ mask, uint32_t rflags) {
     extern __shared__ __align__(16) unsigned char fsm[];
     unsigned char* S = fsm + (size_t)(threadIdx.x / kFusedLanes) * p.fm_env;
-    const int njobs = flight_tpe_body<N, kFusedLanes, MODE, true, kFusedThreads>(p, (int)blockIdx.x, actions, mask, rflags, S);
+    const int njobs = flight_tpe_body<N, kFusedLanes, MODE, true, kFusedThreads, true>(p, (int)blockIdx.x, actions, mask, rflags, S + p.fm_job);
     const int e = min((int)((blockIdx.x * kFusedThreads + threadIdx.x) / kFusedLanes), p.E - 1);
     fused_map_phase<kFusedLanes>(p, e, (int)(threadIdx.x % kFusedLanes), S, njobs);
 }
@@ -417,7 +430,7 @@ __global__ void __launch_bounds__(kTpeThreads, CS_TPE_MIN_CTAS) flight_tpe_group
     }
     __syncthreads();
     if ((long long)blockIdx.x * kTpeThreads >= (long long)sp.E * K) return;         // handles may differ in num_envs
-    flight_tpe_body<N, K, MODE_STEP, false, kTpeThreads>(sp, (int)blockIdx.x, acts.a[blockIdx.y], nullptr, 0u, nullptr);
+    flight_tpe_body<N, K, MODE_STEP, false, kTpeThreads, false>(sp, (int)blockIdx.x, acts.a[blockIdx.y], nullptr, 0u, nullptr);
 }
 
 
@@ -425,10 +438,17 @@ template <int N, int K>
 cudaError_t launch_tpe_k(cs_flight* h, int mode, const uint8_t* actions, const uint8_t* mask, uint32_t rflags, cudaStream_t st) {
     const long long threads = (long long)h->p.E * K;
     const int grid = (int)((threads + kTpeThreads - 1) / kTpeThreads);
-    if (mode == MODE_STEP)
-        flight_tpe_kernel<N, K, MODE_STEP><<<grid, kTpeThreads, 0, st>>>(h->p, actions, mask, rflags);
-    else
-        flight_tpe_kernel<N, K, MODE_RESET><<<grid, kTpeThreads, 0, st>>>(h->p, actions, mask, rflags);
+    if (h->p.variant) {
+        if (mode == MODE_STEP)
+            flight_tpe_kernel<N, K, MODE_STEP, true><<<grid, kTpeThreads, 0, st>>>(h->p, actions, mask, rflags);
+        else
+            flight_tpe_kernel<N, K, MODE_RESET, true><<<grid, kTpeThreads, 0, st>>>(h->p, actions, mask, rflags);
+    } else {
+        if (mode == MODE_STEP)
+            flight_tpe_kernel<N, K, MODE_STEP, false><<<grid, kTpeThreads, 0, st>>>(h->p, actions, mask, rflags);
+        else
+            flight_tpe_kernel<N, K, MODE_RESET, false><<<grid, kTpeThreads, 0, st>>>(h->p, actions, mask, rflags);
+    }
     cs_count_launch(1);
     return cudaGetLastError();
 }

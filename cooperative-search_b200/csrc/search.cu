@@ -452,6 +452,8 @@ cudaError_t launch_search(cs_search* h, int mode, const uint8_t* actions, const 
 }
 }  // namespace
 
+namespace { int search_init(cs_search* h); }
+
 extern "C" {
 
 int cs_search_create(const cs_search_cfg* cfg, cs_search** out) {
@@ -474,6 +476,22 @@ int cs_search_create(const cs_search_cfg* cfg, cs_search** out) {
     if (!h) { cs_set_error("out of host memory"); return CS_ERR_NOMEM; }
     memset(h, 0, sizeof(*h));
     h->cfg = *cfg;
+    const int rc = search_init(h);
+    if (rc != CS_OK) {            // free whatever exists: a retry with fewer envs must find the memory back
+        cs_search_destroy(h);
+        cudaGetLastError();
+        return rc;
+    }
+    *out = h;
+    return CS_OK;
+}
+
+}  // extern "C"
+
+namespace {
+// everything cs_search_create computes and allocates, in one place so that a failure half way frees what exists
+int search_init(cs_search* h) {
+    const cs_search_cfg* cfg = &h->cfg;
     CS_CUDA(cudaSetDevice(cfg->device));
     SearchParams& p = h->p;
     p.E = cfg->num_envs; p.n = cfg->n_agents; p.m = cfg->target_num; p.M = cfg->map_size; p.R = cfg->view_range;
@@ -486,8 +504,16 @@ int cs_search_create(const cs_search_cfg* cfg, cs_search** out) {
     p.stage_obs = (p.M <= 64 && p.S <= 32 && smem_base_bytes(p) + stage_bytes <= 100 * 1024) ? 1 : 0;
     h->smem_bytes = smem_base_bytes(p) + (p.stage_obs ? stage_bytes : 0);
     CS_REQUIRE(h->smem_bytes <= 200 * 1024, "map too large for the shared-memory bit rows");
-    CS_CUDA(cudaFuncSetAttribute(search_kernel<MODE_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-    CS_CUDA(cudaFuncSetAttribute(search_kernel<MODE_RESET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    {
+        // the limit is per KERNEL, not per handle: only ever raise it (a later, smaller handle must not lower it under
+        // an earlier one's launches)
+        static size_t cur_limit = 48 * 1024;
+        if (h->smem_bytes > cur_limit) {
+            CS_CUDA(cudaFuncSetAttribute(search_kernel<MODE_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+            CS_CUDA(cudaFuncSetAttribute(search_kernel<MODE_RESET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+            cur_limit = h->smem_bytes;
+        }
+    }
     const size_t E = (size_t)p.E, rows = (size_t)p.M * p.W, MM = (size_t)p.M * p.M;
 #define CS_ALLOC0(ptr, bytes)                                   \
     CS_CUDA(cudaMalloc(reinterpret_cast<void**>(&(ptr)), (bytes))); \
@@ -509,9 +535,11 @@ int cs_search_create(const cs_search_cfg* cfg, cs_search** out) {
 #undef CS_ALLOC0
     // episode counter starts at -1 so that the first reset opens episode 0
     CS_CUDA(cudaMemset2D(p.counters + CNT_EPISODE, 4 * sizeof(int32_t), 0xFF, sizeof(int32_t), E));
-    *out = h;
     return CS_OK;
 }
+}  // namespace
+
+extern "C" {
 
 void cs_search_destroy(cs_search* h) {
     if (!h) return;

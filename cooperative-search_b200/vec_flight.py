@@ -65,7 +65,7 @@ class _VecFlightBase:
     ENV_NAME = "flight_easy"
 
     def __init__(self, args, circle_dict=None, num_envs=1, device=None, seed=0, env_id_base=0,
-                 auto_reset=False, lanes_per_env=0, count_touched=False, reset=True):
+                 auto_reset=False, lanes_per_env=0, count_touched=False, reset=True, map_overlap=False):
         if not torch.cuda.is_available():
             raise CoopSearchError("coopsearch_b200 needs a CUDA device (B200); there is no CPU fallback")
         self.lib = _lib.load()
@@ -103,7 +103,9 @@ class _VecFlightBase:
             variant=self.VARIANT, auto_reset=int(self.auto_reset), count_touched=int(count_touched),
             lanes_per_env=int(lanes_per_env), device=self.device.index,
             velocity=self.velocity, detect_prob=self.detect_prob, safe_dist=self.safe_dist,
-            force_dist=self.force_dist, seed=self.seed & 0xFFFFFFFF, env_id_base=self.env_id_base & 0xFFFFFFFF)
+            force_dist=self.force_dist, seed=self.seed & 0xFFFFFFFF, env_id_base=self.env_id_base & 0xFFFFFFFF,
+            map_overlap=int(bool(map_overlap) and self.VARIANT == 1))
+        self.map_overlap = bool(map_overlap) and self.VARIANT == 1
         hp = C.c_void_p()
         with torch.cuda.device(self.device):
             _lib.check(self.lib.cs_flight_create(C.byref(cfg), C.byref(hp)), "cs_flight_create")
@@ -136,9 +138,10 @@ class _VecFlightBase:
         self._stats = _wrap(b.stats, (_lib.CS_NUM_STATS,), "<f8", dev, own)
         self._slab = _wrap(b.slab, (int(b.slab_bytes),), "|u1", dev, own)      # all step outputs (checkpointing)
         # the belief map lives on the device as 4x4-cell tiles (include/coopsearch.h): zero-copy tiled view
-        self.prob_map_tiles = _wrap(b.prob_map, (E, b.map_tiles, b.map_tiles, 4, 4), "<f4", dev, own) if b.prob_map else None
+        self._map_tiles = _wrap(b.prob_map, (E, b.map_tiles, b.map_tiles, 4, 4), "<f4", dev, own) if b.prob_map else None
         self._avail = torch.ones((E, n, self.n_actions), dtype=torch.float32, device=dev)
         self._host = None
+        self._host_c = None
         print('Init Env ' + getattr(args, "env", self.ENV_NAME) + ' {}a{}t(agent mode:{}, target mode:{}) x{} envs on {}'.format(
             self.n_agents, self.target_num, self.agent_mode, self.target_mode, self.num_envs, self.device))
         if reset:
@@ -282,6 +285,21 @@ class _VecFlightBase:
     def stats_tensor(self):
         return self._stats
 
+    def sync_map(self):
+        """map_overlap=True: the current stream waits for the latest belief-map kernel (which runs on the handle's own
+        stream).  The library does this itself wherever it touches the map; call it before reading ``prob_map_tiles``
+        on another stream's schedule, before a CUDA-graph capture of step() calls begins, and before it ends."""
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.cs_flight_map_sync(self._h.ptr, self._stream()), "cs_flight_map_sync")
+
+    @property
+    def prob_map_tiles(self):
+        """Zero-copy view of the belief map in its tiled device layout [E, tiles, tiles, 4, 4]: cell (i, j) of the
+        reference's prob_map is element [e, i // 4, j // 4, i % 4, j % 4] (joined with the map stream first)."""
+        if self._map_tiles is not None and self.map_overlap:
+            self.sync_map()
+        return self._map_tiles
+
     @property
     def prob_map(self):
         """self.prob_map of the reference (flight_env.py:53): [E,M,M] float32, prob_map[e,i,j] with i <-> x -- a fresh
@@ -321,48 +339,90 @@ class _VecFlightBase:
         if self.prob_map_tiles is not None:
             if "prob_map_tiles" in d:
                 self.prob_map_tiles.copy_(d["prob_map_tiles"])
+                if self.map_overlap:          # later map kernels run on the handle's own stream: finish the copy first
+                    torch.cuda.current_stream(self.device).synchronize()
             elif "prob_map" in d:
                 self.prob_map = d["prob_map"]
 
-    def host_buffers(self):
-        """Pinned host staging used by step_host (allocated once): one slab mirroring the device output slab, so
-        a host-buffer step is one H2D copy, one kernel and ONE D2H copy."""
-        if self._host is None:
-            E, n = self.num_envs, self.n_agents
-            lay = (C.c_uint64 * 8)()
-            _lib.check(self.lib.cs_flight_slab_layout(self._h.ptr, lay), "cs_flight_slab_layout")
-            total, o_rew, o_tf, o_term, o_win, o_obs, o_state, pitch = [int(x) for x in lay]
-            slab = torch.empty(total, dtype=torch.uint8).pin_memory()
-            stride = pitch // 4
-            view = lambda off, nbytes, dtype: slab[off:off + nbytes].view(dtype)
-            self._host = {
-                "actions": torch.empty((E, n), dtype=torch.uint8).pin_memory(),
-                "slab": slab,
-                "reward": view(o_rew, 4 * E, torch.float32),
-                "target_find": view(o_tf, 4 * E, torch.int32),
-                "terminated": view(o_term, E, torch.uint8),
-                "win": view(o_win, E, torch.uint8),
-                "state": view(o_state, pitch * E, torch.float32).view(E, stride)[:, :self.state_shape],
-                # get_obs rows are the agent part of the state rows (flight_env_easy.py:192-193): not sent twice
-                "obs": view(o_state, pitch * E, torch.float32).view(E, stride)[:, :4 * n].unflatten(1, (n, 4)),
-            }
-        return self._host
+    def host_buffers(self, compact=True):
+        """Host-side results of step_host (allocated once).
 
-    def step_host(self, actions, want_obs=True, want_state=True, sync=True):
-        """The call a CPU-side rollout makes: HOST actions in, HOST results out (numpy views of pinned
-        buffers).  H2D + kernel + D2H happen inside cs_flight_step_host.  sync=False only enqueues (pipelining
-        several env batches on different streams); synchronise the stream before reading the results."""
-        hb = self.host_buffers()
+        compact=True (default): the library's compact host path -- per step the device sends 16 + 16n bytes per env
+        in one D2H copy and the library rebuilds the reference-shaped rows on the host (cs_flight_host_compact_begin);
+        the returned tensors are views of library-owned host arrays, updated in place by every step_host.
+        compact=False: a pinned mirror of the whole device output slab, fetched with one D2H copy per step."""
+        key = "_host_c" if compact else "_host"
+        if getattr(self, key, None) is None:
+            E, n = self.num_envs, self.n_agents
+            if compact:
+                v = _lib.FlightHostViews()
+                _lib.check(self.lib.cs_flight_host_compact_begin(self._h.ptr, C.byref(v)), "cs_flight_host_compact_begin")
+                stride = int(v.state_stride)
+
+                def arr(ptr, ctype, count, dtype):
+                    a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(count,))
+                    t = torch.from_numpy(a.view(dtype))
+                    t._cs_owner = self._h
+                    return t
+                state = arr(v.state, C.c_float, E * stride, np.float32).view(E, stride)
+                self._host_c = {
+                    "actions": torch.empty((E, n), dtype=torch.uint8).pin_memory(),
+                    "reward": arr(v.reward, C.c_float, E, np.float32),
+                    "target_find": arr(v.target_find, C.c_int32, E, np.int32),
+                    "terminated": arr(v.terminated, C.c_uint8, E, np.uint8),
+                    "win": arr(v.win, C.c_uint8, E, np.uint8),
+                    "state": state[:, :self.state_shape],
+                    # get_obs rows are the agent part of the state rows (flight_env_easy.py:192-193)
+                    "obs": state[:, :4 * n].unflatten(1, (n, 4)),
+                    "d2h_bytes": int(v.d2h_bytes_per_step),
+                }
+            else:
+                lay = (C.c_uint64 * 8)()
+                _lib.check(self.lib.cs_flight_slab_layout(self._h.ptr, lay), "cs_flight_slab_layout")
+                total, o_rew, o_tf, o_term, o_win, o_obs, o_state, pitch = [int(x) for x in lay]
+                slab = torch.empty(total, dtype=torch.uint8).pin_memory()
+                stride = pitch // 4
+                view = lambda off, nbytes, dtype: slab[off:off + nbytes].view(dtype)
+                self._host = {
+                    "actions": torch.empty((E, n), dtype=torch.uint8).pin_memory(),
+                    "slab": slab,
+                    "reward": view(o_rew, 4 * E, torch.float32),
+                    "target_find": view(o_tf, 4 * E, torch.int32),
+                    "terminated": view(o_term, E, torch.uint8),
+                    "win": view(o_win, E, torch.uint8),
+                    "state": view(o_state, pitch * E, torch.float32).view(E, stride)[:, :self.state_shape],
+                    # get_obs rows are the agent part of the state rows (flight_env_easy.py:192-193): not sent twice
+                    "obs": view(o_state, pitch * E, torch.float32).view(E, stride)[:, :4 * n].unflatten(1, (n, 4)),
+                    "d2h_bytes": total,
+                }
+        return getattr(self, key)
+
+    def step_host(self, actions, want_obs=True, want_state=True, sync=True, compact=True):
+        """The call a CPU-side rollout makes: HOST actions in, HOST results out (numpy views of host buffers that the
+        next step_host overwrites).  H2D + kernel(s) + D2H happen inside the library.  sync=False only enqueues
+        (pipelining several env batches on different streams); synchronise the stream -- and, on the compact path, call
+        host_expand() -- before reading the results."""
+        hb = self.host_buffers(compact)
         a = np.asarray(actions, dtype=np.uint8)
         if a.shape != (self.num_envs, self.n_agents):
             raise CoopSearchError('Act num mismatch agent')
         hb["actions"].numpy()[...] = a
-        io = _lib.FlightHostIO(actions=hb["actions"].data_ptr(), slab=hb["slab"].data_ptr(),
-                               flags=0 if sync else _lib.CS_HOST_NO_SYNC)
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.cs_flight_step_host(self._h.ptr, C.byref(io), self._stream()), "cs_flight_step_host")
+            if compact:
+                _lib.check(self.lib.cs_flight_step_host_compact(self._h.ptr, C.c_void_p(hb["actions"].data_ptr()),
+                                                                0 if sync else _lib.CS_HOST_NO_SYNC, self._stream()),
+                           "cs_flight_step_host_compact")
+            else:
+                io = _lib.FlightHostIO(actions=hb["actions"].data_ptr(), slab=hb["slab"].data_ptr(),
+                                       flags=0 if sync else _lib.CS_HOST_NO_SYNC)
+                _lib.check(self.lib.cs_flight_step_host(self._h.ptr, C.byref(io), self._stream()), "cs_flight_step_host")
         return (hb["reward"].numpy(), hb["terminated"].numpy(), hb["win"].numpy(),
                 hb["obs"].numpy() if want_obs else None, hb["state"].numpy() if want_state else None)
+
+    def host_expand(self, sync=True):
+        """Compact path, after step_host(sync=False): wait for the stream (sync=True) and rebuild the host rows."""
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.cs_flight_host_expand(self._h.ptr, self._stream(), 1 if sync else 0), "cs_flight_host_expand")
 
 
 def generate_episodes(env, actions=None, targets=None, generator=None):
@@ -444,58 +504,75 @@ class DeviceStepper:
 
 
 class HostStepper:
-    """Host-buffer steps of many independent env batches (rollout workers) with ONE library call per step
-    (cs_flight_step_host_many): batch i runs on stream i % len(streams); results land in each env's pinned
-    host_buffers().  ``actions`` (optional, at construction): pinned uint8 [E,n] tensors, one per env, that hold
-    the actions of every step; by default each env's own host_buffers()["actions"].
+    """Host-buffer steps of many independent env batches (rollout workers) with ONE library call per step: batch i runs
+    on stream i % len(streams); results land in each env's host_buffers(compact).  ``actions`` (optional, at
+    construction): pinned uint8 [E,n] tensors, one per env, that hold the actions of every step; by default each env's
+    own host_buffers()["actions"].
 
-    graph=True captures the whole step (per batch: H2D copy of the pinned actions, step kernel, D2H copy of the
-    output slab) into one CUDA graph after a first eager step, so that a step costs one graph launch on the host."""
+    compact=True (default): cs_flight_step_host_compact_many -- 16 + 16n bytes per env come back per step and the
+    reference-shaped rows are rebuilt on the host, batch by batch while later batches are still in flight.
+    compact=False: cs_flight_step_host_many -- the whole output slab of every batch comes back.
+    graph=True captures the device side of the step (per batch: H2D copy of the pinned actions, step kernel(s), pack,
+    D2H copy) into one CUDA graph after a first eager step, so that a step costs one graph launch on the host."""
 
-    def __init__(self, envs, streams, actions=None, graph=False):
+    def __init__(self, envs, streams, actions=None, graph=False, compact=True):
         self.envs = list(envs)
         self.lib = self.envs[0].lib
         self.device = self.envs[0].device
         self.streams = list(streams)
+        self.compact = bool(compact)
         n = len(self.envs)
         self._handles = (C.c_void_p * n)(*[e._h.ptr for e in self.envs])
         self._streams = (C.c_void_p * len(self.streams))(*[st.cuda_stream for st in self.streams])
         self._ios = (_lib.FlightHostIO * n)()
+        self._acts = (C.c_void_p * n)()
         self._keep = actions
         for i, e in enumerate(self.envs):
-            hb = e.host_buffers()
-            self._ios[i].actions = (actions[i] if actions is not None else hb["actions"]).data_ptr()
-            self._ios[i].slab = hb["slab"].data_ptr()
+            hb = e.host_buffers(self.compact)
+            self._acts[i] = (actions[i] if actions is not None else hb["actions"]).data_ptr()
+            self._ios[i].actions = self._acts[i]
+            if not self.compact:
+                self._ios[i].slab = hb["slab"].data_ptr()
         self._want_graph = bool(graph)
         self._graph = None
         self._cap = torch.cuda.Stream(device=self.device) if graph else None
 
     def _call(self, flags):
-        for i in range(len(self.envs)):
+        n = len(self.envs)
+        if self.compact:
+            _lib.check(self.lib.cs_flight_step_host_compact_many(self._handles, self._acts, n, self._streams, len(self.streams), flags),
+                       "cs_flight_step_host_compact_many")
+            return
+        for i in range(n):
             self._ios[i].flags = flags
-        _lib.check(self.lib.cs_flight_step_host_many(self._handles, self._ios, len(self.envs), self._streams, len(self.streams)),
+        _lib.check(self.lib.cs_flight_step_host_many(self._handles, self._ios, n, self._streams, len(self.streams)),
                    "cs_flight_step_host_many")
+
+    def _expand(self, sync):
+        if self.compact:
+            _lib.check(self.lib.cs_flight_host_expand_many(self._handles, len(self.envs), self._streams, len(self.streams), 1 if sync else 0),
+                       "cs_flight_host_expand_many")
 
     def step(self):
         """One env-step of every batch; returns when all results are in host memory."""
-        base = 0
         if not self._want_graph:
-            self._call(base)
+            self._call(0)
             return
         if self._graph is None:
-            self._call(base)                     # eager first step (warm-up outside the capture)
+            self._call(0)                        # eager first step (warm-up outside the capture)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=self._cap):
                 for st in self.streams:
                     st.wait_stream(self._cap)
-                self._call(base | _lib.CS_HOST_NO_SYNC)
+                self._call(_lib.CS_HOST_NO_SYNC)
                 for st in self.streams:
                     self._cap.wait_stream(st)
-            self._graph = g
+            self._graph = g                      # (capturing records the launches, it does not run them)
             return
         with torch.cuda.stream(self._cap):
             self._graph.replay()
         self._cap.synchronize()
+        self._expand(sync=False)
 
 
 class VecFlightEasyEnv(_VecFlightBase):

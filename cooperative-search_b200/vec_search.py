@@ -58,6 +58,10 @@ class VecSearchEnv:
             raise CoopSearchError('No circle dictionary')             # :124-125
         if self.target_mode == 3 and not targets_filename:
             raise CoopSearchError('No target file')                   # :139-140
+        if self.target_mode in (2, 3) and auto_reset:
+            # the layouts of modes 2 and 3 are placed from the host at reset(); an in-kernel auto-reset would redraw
+            # uniform targets instead.  Step with auto_reset=False and call reset(mask=terminated).
+            raise CoopSearchError('target_mode 2 / 3 need auto_reset=False (their target layouts are placed by reset())')
         cfg = _lib.SearchCfg(
             struct_size=C.sizeof(_lib.SearchCfg), num_envs=self.num_envs, n_agents=self.n_agents,
             target_num=self.target_num, map_size=self.map_size, view_range=self.view_range,
@@ -86,6 +90,7 @@ class VecSearchEnv:
         self._stats = _wrap(b.stats, (_lib.CS_NUM_STATS,), "<f8", dev, own)
         self._host = None
         self._fixed_cells = None
+        self._reset_calls = 0
         if self.target_mode == 3:
             self._fixed_cells = self._cells_from_file(targets_filename)
         if reset:
@@ -108,11 +113,11 @@ class VecSearchEnv:
 
     def _cells_from_circles(self):
         """target_mode 2 (search_env.py:106-123): host-side sampling from the circle dictionary with a
-        numpy Generator keyed by (seed, env id) -- a reset-time path, not part of the per-step hot path."""
+        numpy Generator keyed by (seed, env id, reset count) -- a reset-time path, not part of the per-step hot path."""
         M, cd = self.map_size, self.circle_dict
         out = np.zeros((self.num_envs, self.target_num, 2), np.int32)
         for e in range(self.num_envs):
-            rng = np.random.default_rng([self.seed, self.env_id_base + e])
+            rng = np.random.default_rng([self.seed, self.env_id_base + e, self._reset_calls])   # a fresh layout every reset (:106-123)
             taken, k = set(), 0
             for i, (cx, cy) in enumerate(cd['circle_center']):
                 r = cd['circle_radius'][i]
@@ -140,6 +145,7 @@ class VecSearchEnv:
             cells = self._fixed_cells
         if cells is None and self.target_mode == 2:
             cells = self._cells_from_circles()
+            self._reset_calls += 1
         if cells is not None:
             c = torch.as_tensor(np.asarray(cells) if not torch.is_tensor(cells) else cells).to(
                 device=self.device, dtype=torch.int32).contiguous()

@@ -100,9 +100,10 @@ typedef struct cs_flight_cfg {
     int32_t auto_reset;     /* 1: a terminated env is reset inside the same step call      */
     int32_t count_touched;  /* 1: accumulate #prob-map cells updated into CS_STAT_TOUCHED  */
     int32_t lanes_per_env;  /* 0 = automatic; 1 or 4 (n_agents <= 8): thread-per-env step kernel with
-                               that many threads per env (the flight variant then runs its fused
-                               step + belief-map kernel, 8 lanes per env); 2, 8, 16, 32:
-                               lane-per-agent kernel (flight variant: + generic map kernel)        */
+                               that many threads per env (flight variant: + the tiled belief-map
+                               kernel); flight variant, 8: step + belief map fused in one kernel;
+                               otherwise 2, 8, 16, 32: lane-per-agent kernel (flight variant: +
+                               generic map kernel)                                                 */
     int32_t device;         /* CUDA device ordinal                                         */
     double velocity;        /* args.agent_velocity                                         */
     double detect_prob;     /* args.detect_prob                                            */
@@ -110,6 +111,13 @@ typedef struct cs_flight_cfg {
     double force_dist;      /* args.force_dist                                             */
     uint32_t seed;          /* Philox key word 0                                           */
     uint32_t env_id_base;   /* global id of local env 0                                    */
+    int32_t map_overlap;    /* flight variant: 1 = the belief-map kernel of a step / reset call runs on
+                               the handle's OWN stream, concurrently with the next call's step kernel
+                               (the step does not read the map).  Every entry point that reads or writes
+                               the map joins that stream first; a caller that touches prob_map directly,
+                               or captures calls into a CUDA graph, calls cs_flight_map_sync (before the
+                               capture begins and before it ends).  0 = everything on the caller's stream */
+    int32_t reserved0;
 } cs_flight_cfg;
 
 typedef struct cs_flight cs_flight;
@@ -182,6 +190,8 @@ int cs_flight_obs_full(cs_flight* env, float* d_out, void* stream);
  * converted from / into the handle's tiled map. */
 int cs_flight_map_export(cs_flight* env, float* d_out, void* stream);
 int cs_flight_map_import(cs_flight* env, const float* d_in, void* stream);
+/* Makes `stream` wait for the latest belief-map kernel of the handle (no-op unless map_overlap). */
+int cs_flight_map_sync(cs_flight* env, void* stream);
 /* Host-buffer step: the call a CPU-side rollout makes.  h_actions [E][n] u8.  Any output pointer
  * may be NULL (not copied).  Blocks until outputs are in host memory. */
 #define CS_HOST_NO_SYNC 1u        /* cs_*_host_io.flags: enqueue only; the caller synchronises the stream */
@@ -201,6 +211,31 @@ int cs_flight_step_host(cs_flight* env, const cs_flight_host_io* io, void* strea
  * streams[i % n_streams]; all streams are synchronised once at the end unless every io carries CS_HOST_NO_SYNC. */
 int cs_flight_step_host_many(cs_flight* const* envs, const cs_flight_host_io* ios, int32_t count, void* const* streams,
                              int32_t n_streams);
+/* Compact host-buffer step (the fast form of cs_flight_step_host).  Per step and env the device sends 16 + 16n bytes
+ * (reward, found mask, target_find, terminated, win and the n agent rows) plus one small entry per env that was reset
+ * inside the call, in ONE D2H copy; the library rebuilds the reference-shaped rows on the host with a few threads
+ * (CS_HOST_THREADS) into arrays it owns: the agent part of a state row (= get_obs, flight_env_easy.py:192-193,218-221)
+ * is overwritten, find flags flip where the found mask changed, target coordinates are rewritten only after a reset.
+ * The views stay valid (and are updated in place) until the handle is destroyed. */
+typedef struct cs_flight_host_views {
+    float* reward;          /* [E]                   step()[0]                                        */
+    int32_t* target_find;   /* [E]                                                                    */
+    uint8_t* terminated;    /* [E]                   step()[1]                                        */
+    uint8_t* win;           /* [E]                   step()[2]                                        */
+    float* state;           /* [E][state_stride]     get_state(); get_obs() = floats 0..4n-1 of a row */
+    int32_t state_stride;   /* floats between rows                                                    */
+    uint64_t h2d_bytes_per_step, d2h_bytes_per_step;
+} cs_flight_host_views;
+int cs_flight_host_compact_begin(cs_flight* env, cs_flight_host_views* out);
+/* h_actions: HOST u8 [E][n] (pinned for full speed).  flags: CS_HOST_NO_SYNC = enqueue only (H2D, step, pack, D2H) --
+ * the caller then calls cs_flight_host_expand, with sync = 1 to wait for `stream` first. */
+int cs_flight_step_host_compact(cs_flight* env, const uint8_t* h_actions, uint32_t flags, void* stream);
+int cs_flight_host_expand(cs_flight* env, void* stream, int32_t sync);
+/* many independent env batches in one call: batch i on streams[i % n_streams]; unless CS_HOST_NO_SYNC, batch by batch
+ * the stream is synchronised and the rows rebuilt (host work of batch i overlaps the transfers of batch i+1) */
+int cs_flight_step_host_compact_many(cs_flight* const* envs, const uint8_t* const* h_actions, int32_t count, void* const* streams,
+                                     int32_t n_streams, uint32_t flags);
+int cs_flight_host_expand_many(cs_flight* const* envs, int32_t count, void* const* streams, int32_t n_streams, int32_t sync);
 /* out8 = { slab bytes, offsets of reward, target_find, terminated, win, obs (unused: = slab bytes), state, state row
  * pitch in bytes }.  The slab does not carry obs separately: obs[e][a][0..3] = state row e, floats 4a..4a+3. */
 int cs_flight_slab_layout(const cs_flight* env, uint64_t* out8);

@@ -161,6 +161,16 @@ def test_search_geometries(n, m, M, R, am, tm):
     assert np.array_equal(cpu(env.freq_map), orc.freq)
 
 
+def test_two_live_search_handles_of_different_size_keep_working():
+    """Dynamic shared-memory limits are per kernel: a second, smaller handle must not break the first (> 48 KB) one."""
+    import coopsearch_b200 as cs
+    big = cs.VecSearchEnv(search_args(64, 1000, 64, 7, 0, 0), num_envs=8, seed=1)
+    small = cs.VecSearchEnv(search_args(2, 5, 10, 2, 0, 0), num_envs=4, seed=1)
+    big.step_random(3); small.step_random(3); big.step_random(3)
+    import torch
+    torch.cuda.synchronize()
+
+
 def test_search_target_modes_2_and_3(tmp_path):
     """target_mode 2 (circle dictionary, main.py:13-15) and 3 (cell file, search_env.py:127-138)."""
     import coopsearch_b200 as cs
@@ -181,6 +191,12 @@ def test_search_target_modes_2_and_3(tmp_path):
     dense = ((tb[:, :, :, None] >> np.arange(32)[None, None, None, :]) & 1).reshape(3, 50, -1)[:, :, :50]
     for e in range(3):
         assert sorted(map(list, np.argwhere(dense[e]))) == sorted(cells)
+    # every reset of a mode-2 env draws a fresh layout (search_env.py:106-123); mode 2 / 3 refuse the in-kernel auto-reset
+    before = cpu(env.target_bits).copy()
+    env.reset()
+    assert not np.array_equal(before, cpu(env.target_bits))
+    with pytest.raises(Exception, match="auto_reset=False"):
+        cs.VecSearchEnv(search_args(3, 15, 50, 7, 0, 2), circle_dict=circle, num_envs=2, auto_reset=True)
     with pytest.raises(Exception, match="No circle dictionary"):
         cs.VecSearchEnv(search_args(3, 15, 50, 7, 0, 2), num_envs=1)
     with pytest.raises(Exception, match="No target file"):

@@ -231,10 +231,12 @@ def test_masked_noop_after_termination_and_partial_reset():
     assert list(cpu(env.meta[:, 4])) == [1, 0, 0, 1, 0, 0, 0, 0]      # episode counters
 
 
+@pytest.mark.parametrize("compact", [True, False])
 @pytest.mark.parametrize("lpe,auto_reset", [(0, True), (0, False), (16, True)])
-def test_host_buffer_step_equals_device_step(lpe, auto_reset):
-    """cs_flight_step_host: the host slab holds exactly what the device buffers hold after every step, also across
-    reset() and device-resident steps in between."""
+def test_host_buffer_step_equals_device_step(lpe, auto_reset, compact):
+    """cs_flight_step_host (whole slab) / cs_flight_step_host_compact (16 + 16n bytes per env, rows rebuilt on the
+    host): the host results are exactly what the device buffers hold after every step, also across reset(), in-call
+    auto-resets and device-resident steps in between."""
     import coopsearch_b200 as cs
     spec = FlightSpec(n_agents=3, time_limit=25)
     args = make_args(dict(spec.__dict__))
@@ -250,16 +252,35 @@ def test_host_buffer_step_equals_device_step(lpe, auto_reset):
         if t == 60:
             a.reset(); b.reset()
         r, term, win = a.step(act)
-        hr, hterm, hwin, hobs, hstate = b.step_host(act)
+        hr, hterm, hwin, hobs, hstate = b.step_host(act, compact=compact)
         where = "step %d" % t
         assert np.array_equal(cpu(r), hr) and np.array_equal(cpu(term), hterm) and np.array_equal(cpu(win), hwin), where
-        assert np.array_equal(cpu(a.target_find), b.host_buffers()["target_find"].numpy()), where
+        assert np.array_equal(cpu(a.target_find), b.host_buffers(compact)["target_find"].numpy()), where
         assert np.array_equal(cpu(a.get_obs()), hobs), where
         assert np.array_equal(cpu(a.get_state()), hstate), where
 
 
+def test_compact_host_step_survives_a_mass_reset():
+    """More envs reset inside one call than the compact path's side region holds (every env hits the time limit at the
+    same step): the rows are refreshed in full and still equal the device rows."""
+    import coopsearch_b200 as cs
+    spec = FlightSpec(n_agents=5, time_limit=6, agent_mode=2)
+    args = make_args(dict(spec.__dict__))
+    E = 2000
+    a = cs.VecFlightEasyEnv(args, TEMPLATE, num_envs=E, seed=3, auto_reset=True)
+    b = cs.VecFlightEasyEnv(args, TEMPLATE, num_envs=E, seed=3, auto_reset=True)
+    rng = np.random.default_rng(0)
+    for t in range(20):
+        act = rng.integers(0, 3, size=(E, 5), dtype=np.uint8)
+        r, term, win = a.step(act)
+        hr, hterm, hwin, hobs, hstate = b.step_host(act)
+        assert np.array_equal(cpu(r), hr) and np.array_equal(cpu(term), hterm), t
+        assert np.array_equal(cpu(a.get_state()), hstate) and np.array_equal(cpu(a.get_obs()), hobs), t
+
+
+@pytest.mark.parametrize("compact", [True, False])
 @pytest.mark.parametrize("graph", [False, True])
-def test_host_stepper_many_batches_one_call(graph):
+def test_host_stepper_many_batches_one_call(graph, compact):
     """cs_flight_step_host_many: several env batches stepped from pinned host actions with one library call (or one
     CUDA-graph launch) equal the same batches stepped one by one on the device."""
     import coopsearch_b200 as cs
@@ -271,7 +292,7 @@ def test_host_stepper_many_batches_one_call(graph):
     streams = [torch.cuda.Stream() for _ in range(2)]
     torch.cuda.synchronize()
     pinned = [torch.empty((E, 3), dtype=torch.uint8).pin_memory() for _ in range(B)]
-    stepper = cs.HostStepper(envs, streams, actions=pinned, graph=graph)
+    stepper = cs.HostStepper(envs, streams, actions=pinned, graph=graph, compact=compact)
     rng = np.random.default_rng(1)
     for t in range(70):
         for b in range(B):
@@ -279,7 +300,7 @@ def test_host_stepper_many_batches_one_call(graph):
         stepper.step()
         for b in range(B):
             r, term, win = ref[b].step(pinned[b].cuda())
-            hb = envs[b].host_buffers()
+            hb = envs[b].host_buffers(compact)
             assert np.array_equal(cpu(r), hb["reward"].numpy()) and np.array_equal(cpu(term), hb["terminated"].numpy())
             assert np.array_equal(cpu(ref[b].get_state()), hb["state"].numpy()), "batch %d step %d" % (b, t)
             assert np.array_equal(cpu(ref[b].get_obs()), hb["obs"].numpy())

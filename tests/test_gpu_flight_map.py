@@ -20,9 +20,9 @@ def assert_map_close(got, want, msg=""):
     np.testing.assert_allclose(got, want32, rtol=MAP_RTOL, atol=MAP_ATOL, err_msg=msg)
 
 
-# lanes 0: the fused step + belief-map kernel (8 lanes per env, tiled sweep); lanes 16: lane-per-agent step kernel
-# followed by the generic per-cell map kernel
-@pytest.mark.parametrize("lanes", [0, 16])
+# lanes 0: thread-per-env step kernel + tiled map kernel (the default); lanes 8: both fused in one kernel (8 lanes per
+# env); lanes 16: lane-per-agent step kernel followed by the generic per-cell map kernel
+@pytest.mark.parametrize("lanes", [0, 8, 16])
 @pytest.mark.parametrize("name", gu.FLIGHT_FIXTURES)
 def test_flight_matches_reference_golden(name, lanes):
     import coopsearch_b200 as cs
@@ -33,7 +33,7 @@ def test_flight_matches_reference_golden(name, lanes):
     n, M = kw["n_agents"], kw["map_size"]
     env = cs.VecFlightEnv(make_args(kw), None, num_envs=E, seed=seed, env_id_base=base, count_touched=touched, reset=False,
                           lanes_per_env=lanes)
-    assert env.lanes_per_env == (8 if lanes == 0 else 16)
+    assert env.lanes_per_env == {0: 4, 8: 8, 16: 16}[lanes]
     env.reset(init=True, targets=g["tgt_xy"])
     assert_map_close(cpu(env.prob_map), g["init_map"], "init map")
     assert np.array_equal(cpu(env.found_mask).astype(np.uint32), g["init_found"])
@@ -64,7 +64,7 @@ def test_flight_matches_reference_golden(name, lanes):
     assert_map_close(cpu(env.prob_map), g["ep2_map"], "second-episode map")
 
 
-@pytest.mark.parametrize("lanes", [0, 16])
+@pytest.mark.parametrize("lanes", [0, 8, 16])
 @pytest.mark.parametrize("n_agents,agent_mode,map_size,view_range", [(3, 0, 50, 7), (5, 1, 30, 5), (2, 3, 64, 9), (4, 2, 17, 3),
                                                                      (5, 0, 16, 7), (3, 2, 62, 6), (8, 1, 63, 7), (1, 0, 5, 2)])
 def test_flight_matches_c_oracle(n_agents, agent_mode, map_size, view_range, lanes):
@@ -97,31 +97,72 @@ def test_flight_matches_c_oracle(n_agents, agent_mode, map_size, view_range, lan
 
 @pytest.mark.parametrize("n_agents,map_size,view_range,time_limit", [(3, 50, 7, 25), (5, 24, 7, 12), (8, 16, 3, 9)])
 def test_map_kernels_and_reset_paths_agree_bitwise(n_agents, map_size, view_range, time_limit):
-    """The fused kernel (corner-row intervals, tile list, packed float4 sweep), the generic kernel (per-cell fp64 corner
-    tests, scalar update) and both ways of ending an episode -- in-call auto-reset (two sensing calls in one launch) and
-    step + reset(mask=terminated) -- must leave bit-identical maps."""
+    """The tiled map kernel and its fused form (corner-row intervals, tile list, packed float4 sweep), the generic kernel
+    (per-cell fp64 corner tests, scalar update), the map kernel on its own stream (map_overlap) and both ways of ending an
+    episode -- in-call auto-reset (two sensing calls in one launch) and step + reset(mask=terminated) -- must leave
+    bit-identical maps."""
     import coopsearch_b200 as cs
     E, T = 512, 60
     spec = FlightSpec(n_agents=n_agents, map_size=map_size, view_range=view_range, time_limit=time_limit, variant="probmap",
                       target_mode=1)
     args = make_args(dict(spec.__dict__))
-    fused_auto = cs.VecFlightEnv(args, None, num_envs=E, seed=4, auto_reset=True)
+    fused_auto = cs.VecFlightEnv(args, None, num_envs=E, seed=4, auto_reset=True, lanes_per_env=8)
+    tiled_auto = cs.VecFlightEnv(args, None, num_envs=E, seed=4, auto_reset=True)
+    tiled_async = cs.VecFlightEnv(args, None, num_envs=E, seed=4, auto_reset=True, map_overlap=True)
     generic_auto = cs.VecFlightEnv(args, None, num_envs=E, seed=4, auto_reset=True, lanes_per_env=16)
-    fused_manual = cs.VecFlightEnv(args, None, num_envs=E, seed=4, auto_reset=False)
-    assert fused_auto.lanes_per_env == 8 and generic_auto.lanes_per_env >= 16
+    fused_manual = cs.VecFlightEnv(args, None, num_envs=E, seed=4, auto_reset=False, lanes_per_env=8)
+    assert fused_auto.lanes_per_env == 8 and generic_auto.lanes_per_env >= 16 and tiled_auto.lanes_per_env in (1, 4)
     actions = torch.from_numpy(np.random.default_rng(8).integers(0, 3, size=(T, E, n_agents), dtype=np.uint8)).cuda()
     resets = 0
     for t in range(T):
         fused_auto.step(actions[t])
+        tiled_auto.step(actions[t])
+        tiled_async.step(actions[t])
         generic_auto.step(actions[t])
         _, term, _ = fused_manual.step(actions[t])
         if bool(term.any()):
             resets += int(term.sum())
             fused_manual.reset(mask=term.clone())
         assert torch.equal(fused_auto.prob_map, generic_auto.prob_map), "fused vs generic, step %d" % t
+        assert torch.equal(fused_auto.prob_map, tiled_auto.prob_map), "fused vs tiled, step %d" % t
+        if t % 7 == 6 or t == T - 1:          # in between, the overlapped map kernels run ahead of / behind the steps
+            assert torch.equal(tiled_auto.prob_map, tiled_async.prob_map), "map on its own stream, step %d" % t
         assert torch.equal(fused_auto.prob_map, fused_manual.prob_map), "auto-reset vs manual reset, step %d" % t
         assert torch.equal(fused_auto.found_mask, fused_manual.found_mask)
     assert resets >= E
+
+
+def test_map_overlap_inside_a_cuda_graph_equals_plain_steps():
+    """map_overlap=True captured into a CUDA graph (step kernels on the capturing stream, map kernels forked onto the
+    handle's stream, joined by sync_map) against plain eager steps: same maps, same state, through auto-resets."""
+    import coopsearch_b200 as cs
+    E, K = 700, 9
+    spec = FlightSpec(n_agents=3, variant="probmap", time_limit=30)
+    args = make_args(dict(spec.__dict__))
+    plain = cs.VecFlightEnv(args, gu.TEMPLATE, num_envs=E, seed=6, auto_reset=True)
+    over = cs.VecFlightEnv(args, gu.TEMPLATE, num_envs=E, seed=6, auto_reset=True, map_overlap=True)
+    acts = torch.from_numpy(np.random.default_rng(1).integers(0, 3, size=(K, E, 3), dtype=np.uint8)).cuda()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        over.step(acts[0]); over.sync_map()                # warm-up outside the capture; joined before it begins
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            for k in range(K):
+                over.step(acts[k])
+            over.sync_map()
+        for _ in range(8):
+            g.replay()
+    torch.cuda.synchronize()
+    plain.step(acts[0])
+    for _ in range(8):
+        for k in range(K):
+            plain.step(acts[k])
+    assert torch.equal(plain.prob_map, over.prob_map)
+    assert torch.equal(plain.get_state(), over.get_state()) and torch.equal(plain._dyn, over._dyn)
+    assert plain.stats() == over.stats()
+    over.step(acts[1]); plain.step(acts[1])                # eager again after the graph
+    assert torch.equal(plain.prob_map, over.prob_map)
 
 
 def test_state_dict_round_trip_restores_outputs_and_map():
@@ -129,8 +170,8 @@ def test_state_dict_round_trip_restores_outputs_and_map():
     of the checkpointed step, and stepping on equals an uninterrupted run."""
     import coopsearch_b200 as cs
     spec = FlightSpec(n_agents=3, variant="probmap", time_limit=40)
-    mk = lambda: cs.VecFlightEnv(make_args(dict(spec.__dict__)), gu.TEMPLATE, num_envs=200, seed=12, auto_reset=True)
-    a, b = mk(), mk()
+    mk = lambda ov: cs.VecFlightEnv(make_args(dict(spec.__dict__)), gu.TEMPLATE, num_envs=200, seed=12, auto_reset=True, map_overlap=ov)
+    a, b = mk(False), mk(True)
     actions = torch.from_numpy(np.random.default_rng(5).integers(0, 3, size=(90, 200, 3), dtype=np.uint8)).cuda()
     for t in range(30):
         a.step(actions[t])
@@ -165,7 +206,7 @@ def test_two_live_handles_of_different_size_keep_working():
     import coopsearch_b200 as cs
     big = FlightSpec(n_agents=8, map_size=63, view_range=7, variant="probmap", target_mode=1)
     small = FlightSpec(n_agents=2, map_size=16, view_range=3, variant="probmap", target_mode=1)
-    for lanes in (0, 32):
+    for lanes in (0, 8, 32):
         e1 = cs.VecFlightEnv(make_args(dict(big.__dict__)), None, num_envs=64, seed=1, lanes_per_env=lanes)
         e2 = cs.VecFlightEnv(make_args(dict(small.__dict__)), None, num_envs=8, seed=1, lanes_per_env=lanes)
         e1.step_random(3); e2.step_random(3); e1.step_random(3)
