@@ -8,6 +8,7 @@ from ._lib import CoopSearchError, load as load_library  # noqa: F401
 from .policy import BatchedRNNAgents  # noqa: F401
 from .vec_flight import VecFlightEasyEnv, VecFlightEnv, HostStepper, DeviceStepper, generate_episodes, load_targets  # noqa: F401
 from .adapter import SingleEnvAdapter  # noqa: F401
+from .replay import DeviceReplayBuffer, collect_replay_stats  # noqa: F401
 from . import dist  # noqa: F401
 
 try:
@@ -15,5 +16,5 @@ try:
 except ImportError:  # pragma: no cover
     pass
 
-__all__ = ["VecFlightEasyEnv", "VecFlightEnv", "VecSearchEnv", "SingleEnvAdapter", "HostStepper", "DeviceStepper", "BatchedRNNAgents", "generate_episodes", "load_targets",
+__all__ = ["VecFlightEasyEnv", "VecFlightEnv", "VecSearchEnv", "SingleEnvAdapter", "HostStepper", "DeviceStepper", "BatchedRNNAgents", "generate_episodes", "load_targets", "DeviceReplayBuffer", "collect_replay_stats",
            "CoopSearchError", "load_library", "dist"]

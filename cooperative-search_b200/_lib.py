@@ -82,7 +82,17 @@ class SearchHostIO(C.Structure):
 
 class PolicyCfg(C.Structure):         # mirrors cs_policy_cfg
     _fields_ = [("struct_size", C.c_uint32), ("device", C.c_int32), ("n_agents", C.c_int32), ("obs_dim", C.c_int32),
-                ("n_actions", C.c_int32), ("hidden_dim", C.c_int32), ("last_action", C.c_int32), ("reuse_network", C.c_int32)]
+                ("n_actions", C.c_int32), ("hidden_dim", C.c_int32), ("last_action", C.c_int32), ("reuse_network", C.c_int32),
+                ("conv_out_dim", C.c_int32)]
+
+
+class PolicyConvCfg(C.Structure):     # mirrors cs_policy_conv_cfg
+    _fields_ = [("struct_size", C.c_uint32)] + [(k, C.c_int32) for k in ("map_size", "dim_1", "kernel_size_1", "stride_1", "dim_2",
+                                                                         "kernel_size_2", "stride_2", "padding_2", "out_dim")]
+
+
+class PolicyConvWeights(C.Structure):  # mirrors cs_policy_conv_weights
+    _fields_ = [(k, C.c_void_p) for k in ("c1_w", "c1_b", "c2_w", "c2_b", "lin_w", "lin_b")]
 
 
 POLICY_WEIGHT_KEYS = ("fc1_w", "fc1_b", "w_ih", "w_hh", "b_ih", "b_hh", "fc2a_w", "fc2a_b", "fc2b_w", "fc2b_b")
@@ -95,7 +105,7 @@ class PolicyWeights(C.Structure):     # mirrors cs_policy_weights
 class PolicyIO(C.Structure):          # mirrors cs_policy_io
     _fields_ = [("rows", C.c_int32), ("evaluate", C.c_int32), ("epsilon", C.c_float), ("seed", C.c_uint32), ("t", C.c_uint32),
                 ("obs", C.c_void_p), ("last_action", C.c_void_p), ("avail", C.c_void_p), ("hidden", C.c_void_p),
-                ("q", C.c_void_p), ("actions", C.c_void_p)]
+                ("q", C.c_void_p), ("actions", C.c_void_p), ("precision", C.c_int32), ("mode", C.c_int32), ("feat", C.c_void_p)]
 
 
 EPISODE_KEYS = ("o", "s", "u", "r", "avail_u", "o_next", "s_next", "avail_u_next", "u_onehot", "padded", "terminated",
@@ -116,6 +126,7 @@ SIGNATURES = {
     "cs_debug_flight_obs_path": (C.c_int, [C.c_void_p, C.c_int32]),
     "cs_debug_heading_lut": (C.c_int, [C.c_int32, C.POINTER(C.c_double), C.c_int32, C.POINTER(C.c_double),
                                        C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
+    "cs_rows_copy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "cs_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint64]),
     "cs_host_free": (C.c_int, [C.c_void_p]),
     "cs_flight_create": (C.c_int, [C.POINTER(FlightCfg), C.POINTER(C.c_void_p)]),
@@ -147,6 +158,8 @@ SIGNATURES = {
     "cs_policy_create": (C.c_int, [C.POINTER(PolicyCfg), C.POINTER(PolicyWeights), C.POINTER(C.c_void_p)]),
     "cs_policy_destroy": (None, [C.c_void_p]),
     "cs_policy_act": (C.c_int, [C.c_void_p, C.POINTER(PolicyIO), C.c_void_p]),
+    "cs_policy_set_conv": (C.c_int, [C.c_void_p, C.POINTER(PolicyConvCfg), C.POINTER(PolicyConvWeights)]),
+    "cs_policy_conv_features": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "cs_search_create": (C.c_int, [C.POINTER(SearchCfg), C.POINTER(C.c_void_p)]),
     "cs_search_destroy": (None, [C.c_void_p]),
     "cs_search_buffers_get": (C.c_int, [C.c_void_p, C.POINTER(SearchBuffers)]),

@@ -20,8 +20,10 @@ namespace {
 class HostPool {
 public:
     static HostPool& get() {
-        static HostPool pool;
-        return pool;
+        // never destroyed: the workers are detached and wait on the condition variable for the life of the process
+        // (destroying a condition variable with waiters blocks at exit)
+        static HostPool* pool = new HostPool();
+        return *pool;
     }
     int size() const { return (int)workers_.size() + 1; }
     void run(const std::function<void(int, int)>& fn) {

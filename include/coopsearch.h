@@ -79,6 +79,11 @@ int cs_debug_heading_lut(int32_t time_limit, const double* h_in, int32_t count, 
 /* measurement hook: how cs_flight_obs_full writes the observation rows (0 = TMA bulk stores, default; 1 = plain stores) */
 int cs_debug_flight_obs_path(struct cs_flight* env, int32_t path);
 
+/* Row gather / scatter on the device: dst row d_dst_idx[i] <- src row d_src_idx[i] for i < count (a NULL index array =
+ * identity), rows of row_bytes bytes.  The data movement of the device replay ring (common/replay_buffer.py:36-79:
+ * store_episode, sample, sample_latest). */
+int cs_rows_copy(void* d_dst, const void* d_src, uint64_t row_bytes, const int64_t* d_dst_idx, const int64_t* d_src_idx, int64_t count,
+                 void* stream);
 /* Pinned host memory for the *_host entry points. */
 int cs_host_alloc(void** out, uint64_t bytes);
 int cs_host_free(void* p);
@@ -338,6 +343,8 @@ typedef struct cs_policy_cfg {
     int32_t hidden_dim;     /* args.rnn_hidden_dim, must be 64                                 */
     int32_t last_action;    /* args.last_action: append the last action one-hot (agent.py:44-45) */
     int32_t reuse_network;  /* args.reuse_network: append the agent id one-hot (agent.py:46-47)  */
+    int32_t conv_out_dim;   /* args.conv_out_dim where args.conv (the `flight` agents, network/base_net.py:10-20),
+                               else 0: that many conv features of the env's map lead the fc1 input   */
 } cs_policy_cfg;
 /* HOST pointers in torch's own layouts (RNN.state_dict(), network/base_net.py:22-28): Linear.weight is (out, in),
  * GRUCell.weight_ih / weight_hh are (3*hidden, hidden) with gate order r | z | n. */
@@ -359,13 +366,37 @@ typedef struct cs_policy_io {          /* DEVICE pointers; row r = env r / n_age
     float* hidden;                     /* [rows][64] in/out  (policy.eval_hidden, init_hidden = zeros)    */
     float* q;                          /* [rows][n_actions] out or NULL                                   */
     uint8_t* actions;                  /* [rows] out; may be the same buffer as last_action               */
+    int32_t precision;                 /* 0 = fp32 on CUDA cores; 1 = bf16 operands on the tcgen05 tensor cores,
+                                          fp32 accumulation and hidden state (input width <= 16)          */
+    int32_t mode;                      /* 0 = masked argmax / epsilon-greedy (agent.py:66-75);
+                                          1 = softmax sampling of alg=reinforce (agent.py:77-97)            */
+    const float* feat;                 /* [rows / n_agents][conv_out_dim] from cs_policy_conv_features, or NULL  */
 } cs_policy_io;
 typedef struct cs_policy cs_policy;
 /* RNN(input_shape, args) + load_state_dict (policy/qmix.py:40-59) */
 int cs_policy_create(const cs_policy_cfg* cfg, const cs_policy_weights* host_weights, cs_policy** out);
 void cs_policy_destroy(cs_policy* policy);
-/* Agents.choose_action for every (env, agent) row at once (agent/agent.py:33-75, alg != random / reinforce) */
+/* Agents.choose_action for every (env, agent) row at once (agent/agent.py:33-97, alg != random) */
 int cs_policy_act(cs_policy* policy, const cs_policy_io* io, void* stream);
+/* Conv front end of the `flight` agents (network/base_net.py:10-20,31-41; args of common/arguments.py:246-265):
+ * Conv2d(1, dim_1, kernel_size_1, stride_1) -> ReLU -> Conv2d(dim_1, dim_2, kernel_size_2, stride_2, padding_2) -> ReLU ->
+ * Linear(dim_2 * conv_size^2, out_dim).  HOST weight pointers in torch's layouts: Conv2d.weight (out, in, kh, kw),
+ * Linear.weight (out, in). */
+typedef struct cs_policy_conv_cfg {
+    uint32_t struct_size;
+    int32_t map_size, dim_1, kernel_size_1, stride_1, dim_2, kernel_size_2, stride_2, padding_2, out_dim;
+} cs_policy_conv_cfg;
+typedef struct cs_policy_conv_weights {
+    const float *c1_w, *c1_b;          /* conv.0 */
+    const float *c2_w, *c2_b;          /* conv.2 */
+    const float *lin_w, *lin_b;        /* linear */
+} cs_policy_conv_weights;
+int cs_policy_set_conv(cs_policy* policy, const cs_policy_conv_cfg* cfg, const cs_policy_conv_weights* host_weights);
+/* The conv features of every env's belief map, read ONCE per env from the flight handle's TILED device map
+ * (cs_flight_buffers.prob_map / map_tiles / map_env_stride) -- the reference replicates the map into every agent's
+ * observation row (flight_env.py:223-230) and convolves it once per agent.  d_feat: device [num_envs][out_dim]. */
+int cs_policy_conv_features(cs_policy* policy, const float* d_map_tiled, int32_t map_tiles, int32_t map_env_stride, int32_t num_envs,
+                            float* d_feat, void* stream);
 
 #ifdef __cplusplus
 }

@@ -288,6 +288,66 @@ def run_policy(model_dir, n_agents, steps=6, rows_envs=5):
     return out
 
 
+def run_policy_conv(model_dir, n_agents, steps=4, rows_envs=4):
+    """The reference's agent network WITH the conv front end (network/base_net.py:10-20,31-41, args of
+    common/arguments.py:246-265) and the `flight` weights it ships, evaluated the way Agents.choose_action does on
+    flight's observation rows: obs = prob_map.ravel() || (x^, y^, cos, sin) per agent (flight_env.py:223-230), then
+    || last action one-hot || agent id one-hot (agent.py:44-47).  The maps mimic belief maps: 0.5 background, decayed
+    patches, a few cells at 1."""
+    import glob
+    import types as _t
+    import torch
+    rh.import_reference()
+    from network.base_net import RNN
+    path = sorted(glob.glob(os.path.join(rh.REFERENCE_ROOT, "model", model_dir, "*_rnn_net_params.pkl")))[0]
+    sd = torch.load(path, map_location="cpu")
+    n_actions, obs_dim, M = 3, 4, 50
+    args = _t.SimpleNamespace(conv=True, rnn_hidden_dim=64, n_actions=n_actions, map_size=M, dim_1=4, kernel_size_1=4, stride_1=2,
+                              dim_2=1, kernel_size_2=3, stride_2=1, padding_2=1, conv_out_dim=16)
+    in_dim = 16 + obs_dim + n_actions + n_agents                       # main.py / agent.py: conv_out_dim + obs_shape + ...
+    net = RNN(in_dim, args)
+    net.load_state_dict(sd)
+    net.eval()
+    rng = np.random.default_rng(13)
+    E = rows_envs
+    maps = np.full((steps, E, M, M), 0.5, np.float32)
+    for t in range(steps):
+        for e in range(E):
+            for _ in range(3):
+                i0, j0 = rng.integers(0, M - 12, size=2)
+                maps[t, e, i0:i0 + 12, j0:j0 + 12] *= rng.uniform(1e-4, 1.0, size=(12, 12)).astype(np.float32)
+            for _ in range(4):
+                maps[t, e, rng.integers(0, M), rng.integers(0, M)] = 1.0
+    sa = rng.uniform(-1, 1, size=(steps, E, n_agents, obs_dim)).astype(np.float32)
+    hidden = torch.zeros(E, n_agents, 64)
+    last = np.zeros((E, n_agents, n_actions), np.float32)
+    qs, hs, acts, feats = [], [], [], []
+    with torch.no_grad():
+        for t in range(steps):
+            q_t = np.zeros((E, n_agents, n_actions), np.float32)
+            a_t = np.zeros((E, n_agents), np.uint8)
+            f_t = np.zeros((E, 16), np.float32)
+            for e in range(E):
+                pm = torch.from_numpy(maps[t, e]).reshape(1, 1, M, M)
+                f_t[e] = net.linear(net.conv(pm).reshape(1, -1))[0].numpy()
+                for a in range(n_agents):
+                    agent_id = np.zeros(n_agents, np.float32); agent_id[a] = 1.0
+                    obs_row = np.concatenate((maps[t, e].ravel(), sa[t, e, a]))                   # flight_env.py:226-229
+                    inputs = np.hstack((obs_row, last[e, a], agent_id))                           # agent.py:44-47
+                    q, h = net(torch.tensor(inputs, dtype=torch.float32).unsqueeze(0), hidden[e, a].unsqueeze(0))
+                    hidden[e, a] = h[0]
+                    q_t[e, a] = q[0].numpy()
+                    act = int(torch.argmax(q))
+                    a_t[e, a] = act
+                    last[e, a] = 0.0; last[e, a, act] = 1.0
+            qs.append(q_t); hs.append(hidden.numpy().copy()); acts.append(a_t); feats.append(f_t)
+    out = {"maps": maps, "obs": sa, "q": np.array(qs), "hidden": np.array(hs), "actions": np.array(acts), "feat": np.array(feats),
+           "meta": np.array([n_agents, obs_dim, n_actions, M], np.int64)}
+    for k, v in sd.items():
+        out["w:" + k] = v.numpy().astype(np.float32)
+    return out
+
+
 def thin(g, keep_every, keys=("obs", "state")):
     """obs/state are derivable from xy/yaw/found; keep every k-th step to bound fixture size."""
     for k in keys:
@@ -317,6 +377,7 @@ def main():
                                                      target_mode=1, map_size=20, view_range=4, time_limit=80,
                                                      second_episode=10, map_steps=(1, 2, 5, 10, 40, 80)), 20),
         "policy_qmix_3a": lambda: run_policy("flight_easy_Seed22322107_qmix_3a15t(AM0TM0)", 3),
+        "policy_conv_qmix_3a": lambda: run_policy_conv("flight_Seed74853802_qmix_3a15t(AM0TM0)", 3),
         "rollout_easy_3a": lambda: run_rollout(3, 0, episodes=4, env_id=950, seed0=77),
         "rollout_easy_5a_am3": lambda: run_rollout(5, 3, episodes=3, env_id=960, seed0=78),
         "search_3a_default": lambda: thin(run_search(3, 15, 50, 7, 0, 0, E=3, T=120, env_id_base=800), 10),
