@@ -4,6 +4,7 @@
 // the rows on the host: the agent part is overwritten, find flags flip where the found mask changed, and the 2m target
 // coordinates are rewritten only for envs that were reset inside the call.  The rebuild is spread over a small pool
 // of host threads.  Results live in library-owned host arrays (cs_flight_host_views), valid until the next step.
+#include <atomic>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -97,7 +98,12 @@ void expand_range(cs_flight* h, int e0, int e1) {
         c->terminated[e] = hd->terminated;
         c->win[e] = hd->win;
         float* row = c->state + (size_t)e * stride;
-        memcpy(row, rec + 16, (size_t)16 * n);                       // agent part = get_obs rows (flight_env_easy.py:192-193)
+        {                                                            // agent part = get_obs rows (flight_env_easy.py:192-193)
+            typedef float v4 __attribute__((vector_size(16), aligned(4)));
+            const v4* src = reinterpret_cast<const v4*>(rec + 16);
+            v4* dst = reinterpret_cast<v4*>(row);
+            for (int a = 0; a < n; ++a) dst[a] = src[a];
+        }
         if (!hd->reset) {
             uint32_t diff = hd->found ^ c->shadow_found[e];
             while (diff) {                                           // find flags that changed (:206-209)
@@ -193,14 +199,16 @@ int cs_flight_host_compact_begin(cs_flight* h, cs_flight_host_views* out) {
     return CS_OK;
 }
 
-int cs_flight_host_expand(cs_flight* h, void* stream, int32_t sync) {
-    CS_REQUIRE(h && h->hc, "cs_flight_host_expand: call cs_flight_host_compact_begin first");
+namespace {
+// first part of an expansion: wait for the transfer, refresh the rows in full where needed; returns the number of reset
+// entries to apply afterwards (0 after a full refresh) through *entries
+int expand_prepare(cs_flight* h, cudaStream_t st, int sync, unsigned* entries) {
     cs_flight_compact* c = h->hc;
     const FlightParams& p = h->p;
-    cudaStream_t st = (cudaStream_t)stream;
     if (sync) CS_CUDA(cudaStreamSynchronize(st));
     const unsigned count = *reinterpret_cast<const unsigned*>(c->h_pack + c->off_counter);
     const bool overflow = count > (unsigned)c->cap;
+    *entries = overflow ? 0u : count;
     if (c->dirty || overflow) {
         // full refresh: the device holds the complete rows (first step, after a reset / import, or more envs were reset
         // inside one call than the side region holds)
@@ -211,14 +219,15 @@ int cs_flight_host_expand(cs_flight* h, void* stream, int32_t sync) {
             c->shadow_found[e] = reinterpret_cast<const PackHdr*>(c->h_pack + (size_t)e * c->rec_bytes)->found;
         c->dirty = false;
     }
-    const int E = p.E;
-    HostPool::get().run([&](int t, int T) {
-        const int chunk = (E + T - 1) / T;
-        const int e0 = t * chunk, e1 = e0 + chunk < E ? e0 + chunk : E;
-        if (e0 < e1) expand_range(h, e0, e1);
-    });
-    if (!overflow) apply_reset_entries(h, count);
     return CS_OK;
+}
+}  // namespace
+
+int cs_flight_host_expand(cs_flight* h, void* stream, int32_t sync) {
+    CS_REQUIRE(h && h->hc, "cs_flight_host_expand: call cs_flight_host_compact_begin first");
+    cs_flight* one[1] = {h};
+    void* st[1] = {stream};
+    return cs_flight_host_expand_many(one, 1, st, 1, sync);
 }
 
 int cs_flight_step_host_compact(cs_flight* h, const uint8_t* h_actions, uint32_t flags, void* stream) {
@@ -247,19 +256,38 @@ int cs_flight_step_host_compact_many(cs_flight* const* envs, const uint8_t* cons
         if (rc != CS_OK) return rc;
     }
     if (flags & CS_HOST_NO_SYNC) return CS_OK;
-    for (int i = 0; i < count; ++i) {
-        const int rc = cs_flight_host_expand(envs[i], streams[i % n_streams], 1);
-        if (rc != CS_OK) return rc;
-    }
-    return CS_OK;
+    return cs_flight_host_expand_many(envs, count, streams, n_streams, 1);
 }
 
+// All batches share ONE fork-join of the host pool: the work items are (batch, env range) pairs of ~4096 envs, handed out
+// through an atomic counter (a fork-join per batch costs more than rebuilding a few thousand rows).
 int cs_flight_host_expand_many(cs_flight* const* envs, int32_t count, void* const* streams, int32_t n_streams, int32_t sync) {
     CS_REQUIRE(envs && streams && count >= 0 && n_streams >= 1, "cs_flight_host_expand_many: bad argument");
+    std::vector<unsigned> entries((size_t)count, 0u);
+    std::vector<int> first((size_t)count + 1, 0);
+    constexpr int kChunk = 4096;
     for (int i = 0; i < count; ++i) {
-        const int rc = cs_flight_host_expand(envs[i], streams[i % n_streams], sync);
+        CS_REQUIRE(envs[i] && envs[i]->hc, "cs_flight_host_expand_many: call cs_flight_host_compact_begin first (batch %d)", i);
+        const int rc = expand_prepare(envs[i], (cudaStream_t)streams[i % n_streams], sync, &entries[(size_t)i]);
         if (rc != CS_OK) return rc;
+        first[(size_t)i + 1] = first[(size_t)i] + (envs[i]->p.E + kChunk - 1) / kChunk;
     }
+    const int items = first[(size_t)count];
+    std::atomic<int> next{0};
+    auto work = [&](int, int) {
+        for (;;) {
+            const int it = next.fetch_add(1, std::memory_order_relaxed);
+            if (it >= items) break;
+            int b = 0;
+            while (first[(size_t)b + 1] <= it) ++b;
+            const int e0 = (it - first[(size_t)b]) * kChunk;
+            const int e1 = e0 + kChunk < envs[b]->p.E ? e0 + kChunk : envs[b]->p.E;
+            expand_range(envs[b], e0, e1);
+        }
+    };
+    if (items <= 2) work(0, 1);
+    else HostPool::get().run(work);
+    for (int i = 0; i < count; ++i) apply_reset_entries(envs[i], entries[(size_t)i]);
     return CS_OK;
 }
 
