@@ -569,13 +569,25 @@ int cs_flight_group_create(cs_flight* const* envs, int32_t count, cs_flight_grou
     cs_flight_group* g = new (std::nothrow) cs_flight_group();
     if (!g) { cs_set_error("out of host memory"); return CS_ERR_NOMEM; }
     memset(g, 0, sizeof(*g));
-    std::vector<FlightParams> table((size_t)count);
+    // the configuration shared by the group: handle 0's parameter block with the per-handle fields blanked
+    auto shared_part = [](const FlightParams& src) {
+        FlightParams c = src;
+        c.E = 0; c.env_id_base = 0; c.seed = 0; c.dyn_rs = c.dyn_es = c.tgt_rs = c.tgt_es = 0;
+        c.dyn = nullptr; c.tgt = nullptr; c.obs = nullptr; c.state = nullptr; c.reward = nullptr; c.terminated = nullptr; c.win = nullptr;
+        c.target_find = nullptr; c.stats = nullptr; c.tmpl = nullptr; c.pre = nullptr; c.prob_map = nullptr; c.jobs = nullptr; c.lut_cells = nullptr;
+        c.lut_meta = nullptr; c.lut = nullptr;       // per-handle copies of the same table (same time_limit)
+        return c;
+    };
     for (int i = 0; i < count; ++i) {
         cs_flight* h = envs[i];
-        const bool ok = h && h->tpe && h->p.variant == 0 && (i == 0 || (h->p.n == g->n && h->tpe_k == g->k && h->cfg.device == g->device));
+        bool ok = h && h->tpe && h->p.variant == 0 && (i == 0 || (h->p.n == g->n && h->tpe_k == g->k && h->cfg.device == g->device));
+        if (ok && i > 0) {
+            const FlightParams a = shared_part(envs[0]->p), b = shared_part(h->p);
+            ok = memcmp(&a, &b, sizeof(FlightParams)) == 0;
+        }
         if (!ok) {
             delete g;
-            cs_set_error("cs_flight_group_create: handle %d is not a flight_easy handle with n_agents <= %d, or differs from handle 0 in n_agents / threads per env / device", i, kTpeMaxAgents);
+            cs_set_error("cs_flight_group_create: handle %d is not a flight_easy handle with n_agents <= %d, or differs from handle 0 in its configuration (everything but num_envs, env_id_base and seed must be equal) / threads per env / device", i, kTpeMaxAgents);
             return CS_ERR_INVALID;
         }
         if (i == 0) { g->n = h->p.n; g->k = h->tpe_k; g->device = h->cfg.device; }
@@ -583,22 +595,18 @@ int cs_flight_group_create(cs_flight* const* envs, int32_t count, cs_flight_grou
         const int gx = (int)((threads + kTpeThreads - 1) / kTpeThreads);
         if (gx > g->grid_x) g->grid_x = gx;
         g->envs[i] = h;
-        table[(size_t)i] = h->p;
+        GroupEntry& t = g->table.h[i];
+        const FlightParams& p = h->p;
+        t.E = p.E; t.env_id_base = p.env_id_base; t.seed = p.seed; t.dyn_rs = p.dyn_rs; t.dyn_es = p.dyn_es; t.tgt_rs = p.tgt_rs; t.tgt_es = p.tgt_es;
+        t.dyn = p.dyn; t.tgt = p.tgt; t.obs = p.obs; t.state = p.state; t.reward = p.reward; t.terminated = p.terminated; t.win = p.win;
+        t.target_find = p.target_find; t.stats = p.stats; t.tmpl = p.tmpl;
     }
     g->count = count;
-    cudaError_t e = cudaSetDevice(g->device);
-    if (e == cudaSuccess) e = cudaMalloc(&g->d_table, (size_t)count * sizeof(FlightParams));
-    if (e == cudaSuccess) e = cudaMemcpy(g->d_table, table.data(), (size_t)count * sizeof(FlightParams), cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) { cudaFree(g->d_table); delete g; }
-    CS_CUDA(e);
     *out = g;
     return CS_OK;
 }
 
 void cs_flight_group_destroy(cs_flight_group* g) {
-    if (!g) return;
-    cudaSetDevice(g->device);
-    cudaFree(g->d_table);
     delete g;
 }
 

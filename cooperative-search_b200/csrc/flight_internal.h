@@ -54,10 +54,20 @@ struct cs_flight {
     cs_flight_compact* hc;
 };
 
+// what differs between the handles of a grouped launch (everything else of FlightParams must be equal)
+struct GroupEntry {
+    int E;
+    uint32_t env_id_base, seed, pad;
+    long long dyn_rs, dyn_es, tgt_rs, tgt_es;
+    double* dyn; double* tgt; float* obs; float* state; float* reward; uint8_t* terminated; uint8_t* win; int32_t* target_find;
+    double* stats; const double* tmpl;
+};
+struct GroupTable { GroupEntry h[kMaxGroup]; };
+
 struct cs_flight_group {
     int count, n, k, grid_x, device;
     cs_flight* envs[kMaxGroup];
-    csf::FlightParams* d_table;
+    GroupTable table;
 };
 
 namespace csf {

@@ -419,17 +419,29 @@ __global__ void __launch_bounds__(kFusedThreads, CS_FUSED_MIN_CTAS) flight_fused
 // grouped, the same batches fill the GPU like one large handle.  flight_easy variant only.
 struct GroupActions { const uint8_t* a[kMaxGroup]; };
 
+// Everything arrives through the kernel parameter space (constant bank): the configuration the group's handles share
+// (`common`), what differs per handle (GroupTable: sizes, global ids, buffers) and the action pointers -- a CTA assembles
+// its handle's parameter block in shared memory without a global-memory round trip before its first state load.
 template <int N, int K>
-__global__ void __launch_bounds__(kTpeThreads, CS_TPE_MIN_CTAS) flight_tpe_group_kernel(const FlightParams* __restrict__ table,
+__global__ void __launch_bounds__(kTpeThreads, CS_TPE_MIN_CTAS) flight_tpe_group_kernel(const __grid_constant__ FlightParams common,
+                                                                                       const __grid_constant__ GroupTable tab,
                                                                                        const __grid_constant__ GroupActions acts) {
     __shared__ FlightParams sp;
+    const GroupEntry& g = tab.h[blockIdx.y];
+    if ((long long)blockIdx.x * kTpeThreads >= (long long)g.E * K) return;          // handles may differ in num_envs
     {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(table + blockIdx.y);
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&common);
         uint32_t* dst = reinterpret_cast<uint32_t*>(&sp);
         for (int i = threadIdx.x; i < (int)(sizeof(FlightParams) / 4); i += kTpeThreads) dst[i] = src[i];
     }
     __syncthreads();
-    if ((long long)blockIdx.x * kTpeThreads >= (long long)sp.E * K) return;         // handles may differ in num_envs
+    if (threadIdx.x == 0) {
+        sp.E = g.E; sp.env_id_base = g.env_id_base; sp.seed = g.seed;
+        sp.dyn_rs = g.dyn_rs; sp.dyn_es = g.dyn_es; sp.tgt_rs = g.tgt_rs; sp.tgt_es = g.tgt_es;
+        sp.dyn = g.dyn; sp.tgt = g.tgt; sp.obs = g.obs; sp.state = g.state; sp.reward = g.reward; sp.terminated = g.terminated;
+        sp.win = g.win; sp.target_find = g.target_find; sp.stats = g.stats; sp.tmpl = g.tmpl;
+    }
+    __syncthreads();
     flight_tpe_body<N, K, MODE_STEP, false, kTpeThreads, false>(sp, (int)blockIdx.x, acts.a[blockIdx.y], nullptr, 0u, nullptr);
 }
 
@@ -478,8 +490,8 @@ cudaError_t launch_tpe_n(cs_flight* h, int mode, const uint8_t* actions, const u
 template <int N>
 cudaError_t launch_group_n(const cs_flight_group* g, const GroupActions& acts, cudaStream_t st) {
     const dim3 grid((unsigned)g->grid_x, (unsigned)g->count);
-    if (g->k == 1) flight_tpe_group_kernel<N, 1><<<grid, kTpeThreads, 0, st>>>(g->d_table, acts);
-    else flight_tpe_group_kernel<N, 4><<<grid, kTpeThreads, 0, st>>>(g->d_table, acts);
+    if (g->k == 1) flight_tpe_group_kernel<N, 1><<<grid, kTpeThreads, 0, st>>>(g->envs[0]->p, g->table, acts);
+    else flight_tpe_group_kernel<N, 4><<<grid, kTpeThreads, 0, st>>>(g->envs[0]->p, g->table, acts);
     cs_count_launch(1);
     return cudaGetLastError();
 }

@@ -77,14 +77,22 @@ __device__ __forceinline__ void tc_wait(uint32_t bar, uint32_t parity) {
     }
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
-// 8 consecutive fp32 columns of this thread's TMEM lane (= its row of the accumulator)
-__device__ __forceinline__ void tc_ld8(uint32_t taddr, float* v) {
-    uint32_t r[8];
+// 8 / 16 consecutive fp32 columns of this thread's TMEM lane (= its row of the accumulator).  The loads are asynchronous:
+// several are issued back to back and tc_ld_wait() orders them before the registers are read.
+__device__ __forceinline__ void tc_ld8_issue(uint32_t taddr, float* v) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld16_issue(uint32_t taddr, float* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]),
+                   "=f"(v[8]), "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]) : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// ties 8 loaded registers to a point after tc_ld_wait(): an empty volatile asm that "rewrites" them, so that no consumer can be
+// scheduled ahead of the wait (volatile asm statements keep their order)
+__device__ __forceinline__ void tc_ld_tie8(float* v) {
+    asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]));
 }
 __device__ __forceinline__ float tc_tanh(float x) {
     float y;
@@ -157,13 +165,18 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const __grid_c
                 for (int i = 0; i < 8; ++i) x[i] = policy_input(p, r, la, 8 * c + i);
                 *reinterpret_cast<uint4*>(myA0 + c * kALbo) = tc_pack8(x);
             }
+        }
+        // the row's hidden state: read once (fp32, 16 loads in flight), kept in registers for the GRU blend, bf16 copy -> A operand
+        float hreg[64];
+        {
             const float4* hp = reinterpret_cast<const float4*>(p.hidden + (size_t)r * 64);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const float4 h0 = hp[2 * c], h1 = hp[2 * c + 1];
-                const float v[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-                *reinterpret_cast<uint4*>(myAH + c * kALbo) = tc_pack8(v);
+            for (int c = 0; c < 16; ++c) {
+                const float4 h4 = hp[c];
+                hreg[4 * c] = h4.x; hreg[4 * c + 1] = h4.y; hreg[4 * c + 2] = h4.z; hreg[4 * c + 3] = h4.w;
             }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(myAH + c * kALbo) = tc_pack8(hreg + 8 * c);
         }
         tc_operands_ready();
         // ---- fc1
@@ -174,12 +187,16 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const __grid_c
         }
         tc_wait(bar, phase); phase ^= 1u;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            float v[8];
-            tc_ld8(trow + 8 * c, v);
+        for (int c = 0; c < 2; ++c) {
+            float v[32];
+            tc_ld16_issue(trow + 32 * c, v);
+            tc_ld16_issue(trow + 32 * c + 16, v + 16);
+            tc_ld_wait();
+            tc_ld_tie8(v); tc_ld_tie8(v + 8); tc_ld_tie8(v + 16); tc_ld_tie8(v + 24);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i] + b1[8 * c + i], 0.f);
-            *reinterpret_cast<uint4*>(myAX + c * kALbo) = tc_pack8(v);
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + b1[32 * c + i], 0.f);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(myAX + (4 * c + q) * kALbo) = tc_pack8(v + 8 * q);
         }
         tc_operands_ready();
         // ---- GRU gates: r | z accumulate x1 W_i^T + h W_h^T in columns 0..127; n keeps its two halves apart
@@ -193,30 +210,29 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const __grid_c
         }
         tc_wait(bar, phase); phase ^= 1u;
         {
-            const float4* hp = reinterpret_cast<const float4*>(p.hidden + (size_t)r * 64);
             float4* ho = reinterpret_cast<float4*>(p.hidden + (size_t)r * 64);
-#pragma unroll 2
+#pragma unroll
             for (int c = 0; c < 8; ++c) {
-                float gr[8], gz[8], gi[8], gh[8], hn[8];
-                tc_ld8(trow + 8 * c, gr);
-                tc_ld8(trow + 64 + 8 * c, gz);
-                tc_ld8(trow + 128 + 8 * c, gi);
-                tc_ld8(trow + 192 + 8 * c, gh);
-                const float4 h0 = hp[2 * c], h1 = hp[2 * c + 1];
-                const float ho_[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+                float gr[8], gz[8], gi[8], gh[8];
+                tc_ld8_issue(trow + 8 * c, gr);
+                tc_ld8_issue(trow + 64 + 8 * c, gz);
+                tc_ld8_issue(trow + 128 + 8 * c, gi);
+                tc_ld8_issue(trow + 192 + 8 * c, gh);
+                tc_ld_wait();
+                tc_ld_tie8(gr); tc_ld_tie8(gz); tc_ld_tie8(gi); tc_ld_tie8(gh);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int j = 8 * c + i;
                     const float rg = tc_sigmoid(gr[i] + b_rz[j]);
                     const float zg = tc_sigmoid(gz[i] + b_rz[64 + j]);
                     const float ng = tc_tanh(gi[i] + b_in[j] + rg * (gh[i] + b_hn[j]));
-                    hn[i] = (1.f - zg) * ng + zg * ho_[i];
+                    hreg[j] = (1.f - zg) * ng + zg * hreg[j];
                 }
                 if (live) {
-                    ho[2 * c] = make_float4(hn[0], hn[1], hn[2], hn[3]);
-                    ho[2 * c + 1] = make_float4(hn[4], hn[5], hn[6], hn[7]);
+                    ho[2 * c] = make_float4(hreg[8 * c], hreg[8 * c + 1], hreg[8 * c + 2], hreg[8 * c + 3]);
+                    ho[2 * c + 1] = make_float4(hreg[8 * c + 4], hreg[8 * c + 5], hreg[8 * c + 6], hreg[8 * c + 7]);
                 }
-                *reinterpret_cast<uint4*>(myAH + c * kALbo) = tc_pack8(hn);
+                *reinterpret_cast<uint4*>(myAH + c * kALbo) = tc_pack8(hreg + 8 * c);
             }
         }
         tc_operands_ready();
@@ -228,12 +244,16 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const __grid_c
         }
         tc_wait(bar, phase); phase ^= 1u;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            float v[8];
-            tc_ld8(trow + 8 * c, v);
+        for (int c = 0; c < 2; ++c) {
+            float v[32];
+            tc_ld16_issue(trow + 32 * c, v);
+            tc_ld16_issue(trow + 32 * c + 16, v + 16);
+            tc_ld_wait();
+            tc_ld_tie8(v); tc_ld_tie8(v + 8); tc_ld_tie8(v + 16); tc_ld_tie8(v + 24);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i] + b2a[8 * c + i], 0.f);
-            *reinterpret_cast<uint4*>(myAX + c * kALbo) = tc_pack8(v);
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + b2a[32 * c + i], 0.f);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(myAX + (4 * c + q) * kALbo) = tc_pack8(v + 8 * q);
         }
         tc_operands_ready();
         // ---- fc2.2 -> action values
@@ -245,7 +265,9 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const __grid_c
         tc_wait(bar, phase); phase ^= 1u;
         {
             float qv[8];
-            tc_ld8(trow + 64, qv);
+            tc_ld8_issue(trow + 64, qv);
+            tc_ld_wait();
+            tc_ld_tie8(qv);
 #pragma unroll
             for (int a = 0; a < 8; ++a) qv[a] += b2b[a];
             if (live) policy_choose_action(p, r, qv);
