@@ -36,9 +36,13 @@ CS_HD cs_u4 cs_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
     return o;
 }
 
+// Key word 1 of a stream: the stream tag, with the episode's bits 16..31 above it -- the counter word holds
+// (episode & 0xFFFF) << 16 | t, so together every episode of an env has its own streams (no repeat after 65536 episodes).
+CS_HD uint32_t cs_stream_key(uint32_t stream, uint32_t episode) { return stream | ((episode >> 16) << 8); }
+
 // Words serving agents 4*blk..4*blk+3 for target j at sensing call t of (env, episode).
 CS_HD cs_u4 cs_detect_words(uint32_t seed, uint32_t env_id, uint32_t episode, uint32_t t, uint32_t blk, uint32_t j) {
-    return cs_philox4x32_10(env_id, ((episode & 0xFFFFu) << 16) | (t & 0xFFFFu), blk, j, seed, CS_STREAM_DETECT);
+    return cs_philox4x32_10(env_id, ((episode & 0xFFFFu) << 16) | (t & 0xFFFFu), blk, j, seed, cs_stream_key(CS_STREAM_DETECT, episode));
 }
 
 CS_HD uint32_t cs_word(const cs_u4& w, int k) { return k == 0 ? w.x : (k == 1 ? w.y : (k == 2 ? w.z : w.w)); }

@@ -234,7 +234,7 @@ __device__ __forceinline__ bool wall_reg(const FlightParams& p, double& x, doubl
 
 // Reset-time target placement (env/flight_env_easy.py:95-127) from the keyed stream; cold, out of line.
 static __device__ __noinline__ double2 draw_target(const FlightParams& p, uint32_t env_id, uint32_t episode, int j) {
-    const cs_u4 w = cs_philox4x32_10(env_id, (episode & 0xFFFFu) << 16, (uint32_t)j, 0u, p.seed, CS_STREAM_TARGET);
+    const cs_u4 w = cs_philox4x32_10(env_id, (episode & 0xFFFFu) << 16, (uint32_t)j, 0u, p.seed, cs_stream_key(CS_STREAM_TARGET, episode));
     const double u1 = cs_u53(w.x, w.y), u2 = cs_u53(w.z, w.w);
     double x, y;
     if (p.target_mode == 0) {

@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(kThreads, 8) flight_kernel(const __grid_consta
             if (actions == nullptr) {
                 // one Philox block serves 4 agents; action = word % 3 (np.random.randint(0, 3), agent.py:36)
                 const cs_u4 w = cs_philox4x32_10(env_id, ((episode & 0xFFFFu) << 16) | ((time_step + 1u) & 0xFFFFu),
-                                                 (uint32_t)(lane >> 2), 0u, p.seed, CS_STREAM_POLICY);
+                                                 (uint32_t)(lane >> 2), 0u, p.seed, cs_stream_key(CS_STREAM_POLICY, episode));
                 act = (int)(cs_word(w, lane & 3) % 3u);
             }
             double h = yaw + ((act == 1) ? p.turn : ((act == 2) ? -p.turn : 0.0));   // dyaw = [0, pi/18, -pi/18] (:259-262)

@@ -103,7 +103,7 @@ __device__ __forceinline__ int flight_tpe_body(const FlightParams& p, const int 
                     // one Philox block serves 4 agents; action = word % 3 (np.random.randint(0, 3), agent.py:36)
                     if ((a & 3) == 0)
                         pw = cs_philox4x32_10(env_id, ((episode & 0xFFFFu) << 16) | ((time_step + 1u) & 0xFFFFu),
-                                              (uint32_t)(a >> 2), 0u, p.seed, CS_STREAM_POLICY);
+                                              (uint32_t)(a >> 2), 0u, p.seed, cs_stream_key(CS_STREAM_POLICY, episode));
                     act = (int)(cs_word(pw, a & 3) % 3u);
                 }
                 double h = yaw[a] + ((act == 1) ? p.turn : ((act == 2) ? -p.turn : 0.0));   // dyaw = [0, pi/18, -pi/18] (:259-262)

@@ -110,7 +110,7 @@ __device__ void search_reset(const SearchParams& p, const SearchSmem& s, int e, 
         for (int batch = 0; batch < (1 << 14); ++batch) {
             const int base = s.scal[SC_NEXTK];
             const cs_u4 w = cs_philox4x32_10(env_id, ((uint32_t)episode & 0xFFFFu) << 16, (uint32_t)(base + tid), 0u, p.seed,
-                                             CS_STREAM_SEARCH);
+                                             cs_stream_key(CS_STREAM_SEARCH, (uint32_t)episode));
             s.cand[2 * tid] = (int)(w.x % (uint32_t)M);
             s.cand[2 * tid + 1] = (int)(w.y % (uint32_t)M);
             __syncthreads();
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(kThreads) search_kernel(const SearchParams p, 
                     act = actions[(size_t)e * n + a];
                 } else {
                     const cs_u4 w = cs_philox4x32_10(env_id, (((uint32_t)cnt[CNT_EPISODE] & 0xFFFFu) << 16) | ((uint32_t)t1 & 0xFFFFu),
-                                                     (uint32_t)(a >> 2), 0u, p.seed, CS_STREAM_POLICY);
+                                                     (uint32_t)(a >> 2), 0u, p.seed, cs_stream_key(CS_STREAM_POLICY, (uint32_t)cnt[CNT_EPISODE]));
                     const int av0 = x > 0, av1 = y > 0, av2 = x < M - 1, av3 = y < M - 1;
                     int pick = (int)(cs_word(w, a & 3) % (uint32_t)(av0 + av1 + av2 + av3));
                     act = 0;

@@ -36,7 +36,7 @@ def lib():
     global _lib
     if _lib is None:
         _lib = C.CDLL(build())
-        for name in ("of_flight_reset", "of_flight_step", "of_flight_obs_state", "os_reset", "os_step", "os_views", "of_philox"):
+        for name in ("of_flight_reset", "of_flight_step", "of_flight_obs_state", "os_reset", "os_step", "os_views", "of_philox", "of_set_square"):
             getattr(_lib, name).restype = None
     return _lib
 
@@ -47,6 +47,12 @@ def _p(a):
 
 _threads = 1
 _pool = None
+
+
+def set_square(mode):
+    """How the flight oracle squares coordinate differences: "pow" (default) = libm pow(v, 2.0), what Python's ** does in
+    the reference; "mul" = v * v, what the CUDA kernels do (the two differ in the last bit for ~0.08 % of arguments)."""
+    lib().of_set_square(C.c_int({"pow": 0, "mul": 1}[mode]))
 
 
 def set_threads(k):

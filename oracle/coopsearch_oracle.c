@@ -39,6 +39,8 @@
 #define STREAM_TARGET 2u
 #define STREAM_POLICY 3u
 #define STREAM_SEARCH 4u
+/* key word 1 of a stream: the tag with the episode's bits 16..31 above it (csrc/cs_philox.cuh: cs_stream_key) */
+#define STREAM_KEY(stream, episode) ((stream) | ((((uint32_t)(episode)) >> 16) << 8))
 
 typedef struct of_spec {
     int32_t n, m, M, R, T, agent_mode, target_mode, variant, auto_reset;
@@ -71,7 +73,13 @@ static int64_t threshold(double d) {
     return (int64_t)floor(d * 4294967296.0);
 }
 
-static double sq(double v) { return pow(v, 2.0); }   /* Python float ** 2 */
+/* Python float ** 2 is libm pow(v, 2.0) (built with -fno-builtin-pow so that gcc does not fold it into v * v): glibc's pow is
+ * not correctly rounded, and pow(v, 2.0) differs from v * v in the last bit for ~0.08 % of arguments.
+ * The CUDA kernels square by multiplication; of_set_square(1) makes this oracle do the same, for the tests that demand
+ * bit-identical float64 positions from the GPU.  Default 0 = the reference's arithmetic. */
+static int g_square_mul = 0;
+void of_set_square(int mul) { g_square_mul = mul; }
+static double sq(double v) { return g_square_mul ? v * v : pow(v, 2.0); }
 
 /* ---------------------------------------------------------------- belief map (flight_env.py:275-303) */
 static int64_t belief_update(const of_spec* s, const double* xy, const double* tgt, uint32_t newf, double* map) {
@@ -138,7 +146,7 @@ static int sense(const of_spec* s, uint32_t env_id, uint32_t t, const double* xy
             if (sq(tgt[2 * j] - x) + sq(tgt[2 * j + 1] - y) <= R2) {
                 uint32_t w[4];
                 philox(env_id, ((episode & 0xFFFFu) << 16) | (t & 0xFFFFu), (uint32_t)(i >> 2), (uint32_t)j, s->seed,
-                       STREAM_DETECT, w);
+                       STREAM_KEY(STREAM_DETECT, episode), w);
                 if (!((found >> j) & 1u) && (int64_t)w[i & 3] <= thr) {
                     found |= 1u << j;
                     newf |= 1u << j;
@@ -200,7 +208,7 @@ static void place(const of_spec* s, uint32_t env_id, const double* tmpl, int kee
     if (!keep_targets)
         for (int j = 0; j < m; ++j) {
             uint32_t w[4];
-            philox(env_id, (episode & 0xFFFFu) << 16, (uint32_t)j, 0u, s->seed, STREAM_TARGET, w);
+            philox(env_id, (episode & 0xFFFFu) << 16, (uint32_t)j, 0u, s->seed, STREAM_KEY(STREAM_TARGET, episode), w);
             const double u1 = u53(w[0], w[1]), u2 = u53(w[2], w[3]);
             double x, y;
             if (s->target_mode == 0) {
@@ -260,7 +268,7 @@ void of_flight_step(const of_spec* s, int E, uint32_t base, const double* tmpl, 
                 for (int a = 0; a < s->n; ++a) {
                     uint32_t w[4];
                     philox(base + e, ((mt[META_EPISODE] & 0xFFFFu) << 16) | ((mt[META_TIME] + 1u) & 0xFFFFu), (uint32_t)(a >> 2),
-                           0u, s->seed, STREAM_POLICY, w);
+                           0u, s->seed, STREAM_KEY(STREAM_POLICY, mt[META_EPISODE]), w);
                     buf[a] = (uint8_t)(w[a & 3] % 3u);
                 }
             const uint32_t outbits = move(s, pxy, pyaw, act);
@@ -340,7 +348,7 @@ static void search_place_targets(const os_spec* s, uint32_t env_id, uint32_t epi
     uint32_t k = 0;
     while (got < s->m) {
         uint32_t w[4];
-        philox(env_id, (episode & 0xFFFFu) << 16, k++, 0u, s->seed, STREAM_SEARCH, w);
+        philox(env_id, (episode & 0xFFFFu) << 16, k++, 0u, s->seed, STREAM_KEY(STREAM_SEARCH, episode), w);
         const int x = (int)(w[0] % (uint32_t)M), y = (int)(w[1] % (uint32_t)M);
         if (tmap[x * M + y]) continue;
         if (s->target_mode == 1 && !(x <= lo || x >= hi || y <= lo || y >= hi)) continue;
@@ -386,7 +394,7 @@ void os_step(const os_spec* s, int E, uint32_t base, const uint8_t* actions, int
                 /* uniform over the AVAILABLE moves (agent.py:34-36 picks among avail actions) */
                 uint32_t w[4];
                 philox(base + e, (((uint32_t)ct[3] & 0xFFFFu) << 16) | ((uint32_t)ct[1] & 0xFFFFu), (uint32_t)(i >> 2), 0u, s->seed,
-                       STREAM_POLICY, w);
+                       STREAM_KEY(STREAM_POLICY, ct[3]), w);
                 const int av[4] = {p[2 * i] > 0, p[2 * i + 1] > 0, p[2 * i] < M - 1, p[2 * i + 1] < M - 1};
                 const int na = av[0] + av[1] + av[2] + av[3];
                 int pick = (int)(w[i & 3] % (uint32_t)na);

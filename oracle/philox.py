@@ -56,6 +56,11 @@ def philox4x32_np(c0, c1, c2, c3, k0, k1, rounds=10):
     return c0, c1, c2, c3
 
 
+def stream_key(stream, episode):
+    """Key word 1 of a stream: the stream tag with the episode's bits 16..31 above it (csrc/cs_philox.cuh: cs_stream_key)."""
+    return (stream | (((episode & MASK) >> 16) << 8)) & MASK
+
+
 def detect_counter(env_id, episode, t, i, j):
     """Counter layout shared with the CUDA kernels (csrc/philox.cuh: cs_detect_words).
     One Philox block serves agents 4*(i>>2) .. 4*(i>>2)+3 for target j."""
@@ -66,7 +71,7 @@ def detect_draw(seed, env_id, episode, t, i, j):
     """uint32 detection draw for pair (agent i, target j) of `env_id` at `_update_obs` call `t`.
     t = 0 is the call made inside reset(); step k (1-based) uses t = k."""
     c = detect_counter(env_id, episode, t, i, j)
-    return philox4x32(c[0], c[1], c[2], c[3], seed, STREAM_DETECT)[i & 3]
+    return philox4x32(c[0], c[1], c[2], c[3], seed, stream_key(STREAM_DETECT, episode))[i & 3]
 
 
 def detect_threshold(detect_prob):

@@ -61,7 +61,7 @@ def keyed_target_layout(spec, template, seed, env_id, episode):
     M = spec.map_size
     out = []
     for j in range(spec.target_num):
-        w = philox.philox4x32(env_id, (episode & 0xFFFF) << 16, j, 0, seed, philox.STREAM_TARGET)
+        w = philox.philox4x32(env_id, (episode & 0xFFFF) << 16, j, 0, seed, philox.stream_key(philox.STREAM_TARGET, episode))
         u1, u2 = philox.u53(w[0], w[1]), philox.u53(w[2], w[3])
         if spec.target_mode == 0:
             a = M / 10
@@ -335,7 +335,7 @@ def keyed_search_cells(spec, seed, env_id, episode):
     lo, hi = M // 4, 3 * M // 4
     cells, taken, k = [], set(), 0
     while len(cells) < spec.target_num:
-        w = philox.philox4x32(env_id, (episode & 0xFFFF) << 16, k, 0, seed, philox.STREAM_SEARCH)
+        w = philox.philox4x32(env_id, (episode & 0xFFFF) << 16, k, 0, seed, philox.stream_key(philox.STREAM_SEARCH, episode))
         k += 1
         x, y = w[0] % M, w[1] % M
         if (x, y) in taken:

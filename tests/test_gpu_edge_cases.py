@@ -69,13 +69,36 @@ def test_extreme_agent_and_target_counts(n, m):
     run_against_oracle(spec, 24, 80, template_for(m))
 
 
-def test_crowded_agents_repulsion_and_walls():
+def test_crowded_agents_repulsion_and_walls(oracle_squares_by_multiplication):
     """16 agents on a 10x10 map: the sequential repulsion path and the wall reflection fire on every step."""
     spec = FlightSpec(n_agents=16, target_num=8, map_size=10, view_range=2, agent_mode=1, target_mode=1, time_limit=150)
     run_against_oracle(spec, 40, 150, None)
 
 
-def test_coincident_agents_guard():
+def test_episode_counter_beyond_16_bits():
+    """Episodes 65536 + k use their own Philox streams (cs_stream_key): device and oracle agree there too, and the
+    draws differ from episode k's."""
+    import coopsearch_b200 as cs
+    spec = FlightSpec(n_agents=3, time_limit=40)
+    E = 64
+    env = cs.VecFlightEasyEnv(make_args(dict(spec.__dict__)), gu.TEMPLATE, num_envs=E, seed=3, auto_reset=True)
+    low = cs.VecFlightEasyEnv(make_args(dict(spec.__dict__)), gu.TEMPLATE, num_envs=E, seed=3, auto_reset=True)
+    orc = c_oracle.FlightBatch(spec, gu.TEMPLATE, 3, 0, E, auto_reset=True)
+    env._meta_word(4).fill_(65536 + 2)                # the next reset opens episode 65539
+    low._meta_word(4).fill_(2)
+    orc.meta[:, 4] = 65536 + 2
+    env.reset(); low.reset(); orc.reset()
+    assert np.array_equal(cpu(env.tgt_xy), orc.tgt) or np.allclose(cpu(env.tgt_xy), orc.tgt, rtol=0, atol=1e-9)
+    assert not torch.equal(env.tgt_xy, low.tgt_xy)
+    acts = np.random.default_rng(0).integers(0, 3, size=(90, E, 3), dtype=np.uint8)
+    for t in range(90):
+        r, term, _ = env.step(acts[t])
+        orr, ot, _ = orc.step(acts[t])
+        assert np.array_equal(cpu(env.found_mask).astype(np.uint32), orc.found), t
+        assert np.array_equal(cpu(r), orr.astype(np.float32)) and np.array_equal(cpu(term), ot), t
+
+
+def test_coincident_agents_guard(oracle_squares_by_multiplication):
     """Agents at exactly the same point exert no force on each other (flight_env_easy.py:298)."""
     import coopsearch_b200 as cs
     spec = FlightSpec(n_agents=4, agent_mode=0, time_limit=30)

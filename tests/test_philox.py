@@ -47,3 +47,14 @@ def test_uniformity_smoke():
     r = philox.philox4x32_np(np.arange(200000), 1, 0, 0, 42, philox.STREAM_DETECT)[0]
     frac = float(np.mean(r <= philox.detect_threshold(0.9)))
     assert abs(frac - 0.9) < 0.004
+
+
+def test_streams_do_not_repeat_after_65536_episodes():
+    """The counter word holds episode & 0xFFFF; the episode's upper bits go into the stream key (cs_stream_key), so
+    episode e and e + 65536 of an env draw from different streams."""
+    from oracle import philox
+    a = [philox.detect_draw(7, 123, 5, t, 1, 2) for t in range(1, 9)]
+    b = [philox.detect_draw(7, 123, 5 + 65536, t, 1, 2) for t in range(1, 9)]
+    c = [philox.detect_draw(7, 123, 5, t, 1, 2) for t in range(1, 9)]
+    assert a == c and a != b
+    assert philox.stream_key(philox.STREAM_DETECT, 5) == philox.STREAM_DETECT          # unchanged below 65536 episodes
