@@ -138,48 +138,6 @@ __device__ __forceinline__ void meta_st(const FlightParams& p, int e, uint4 m0, 
     *meta_at(p, 3, e) = make_uint2(m1.z, m1.w);
 }
 
-// The same accessors with the layout known at compile time (thread-per-env kernel: structure of arrays with one thread
-// per env, record per env with 4 threads per env): no stride arithmetic, 16-byte accesses in the record layout.
-template <bool SOA>
-struct Lay {
-    static __device__ __forceinline__ double2 xy_ld(const FlightParams& p, int a, int e) {
-        if (SOA) { const double* q = p.dyn + (size_t)(2 * a) * p.E + e; return make_double2(q[0], q[p.E]); }
-        return *reinterpret_cast<const double2*>(p.dyn + (size_t)e * p.rec + 2 * a);
-    }
-    static __device__ __forceinline__ void xy_st(const FlightParams& p, int a, int e, double x, double y) {
-        if (SOA) { double* q = p.dyn + (size_t)(2 * a) * p.E + e; q[0] = x; q[p.E] = y; return; }
-        *reinterpret_cast<double2*>(p.dyn + (size_t)e * p.rec + 2 * a) = make_double2(x, y);
-    }
-    static __device__ __forceinline__ double* yaw_at(const FlightParams& p, int a, int e) {
-        return SOA ? p.dyn + (size_t)(p.yaw_off + a) * p.E + e : p.dyn + (size_t)e * p.rec + p.yaw_off + a;
-    }
-    static __device__ __forceinline__ double2 tgt_ld(const FlightParams& p, int j, int e) {
-        if (SOA) { const double* t = p.tgt + (size_t)(2 * j) * p.E + e; return make_double2(t[0], t[p.E]); }
-        return *reinterpret_cast<const double2*>(p.tgt + ((size_t)e * p.m + j) * 2);
-    }
-    static __device__ __forceinline__ void meta_ld(const FlightParams& p, int e, uint4* m0, uint4* m1) {
-        if (SOA) {
-            const uint2* q = reinterpret_cast<const uint2*>(p.dyn + (size_t)p.meta_off * p.E + e);
-            const uint2 a = q[0], b = q[p.E], c = q[2 * (size_t)p.E], d = q[3 * (size_t)p.E];
-            *m0 = make_uint4(a.x, a.y, b.x, b.y);
-            *m1 = make_uint4(c.x, c.y, d.x, d.y);
-            return;
-        }
-        const uint4* mp = reinterpret_cast<const uint4*>(p.dyn + (size_t)e * p.rec + p.meta_off);
-        *m0 = mp[0]; *m1 = mp[1];
-    }
-    static __device__ __forceinline__ void meta_st(const FlightParams& p, int e, uint4 m0, uint4 m1) {
-        if (SOA) {
-            uint2* q = reinterpret_cast<uint2*>(p.dyn + (size_t)p.meta_off * p.E + e);
-            q[0] = make_uint2(m0.x, m0.y); q[p.E] = make_uint2(m0.z, m0.w);
-            q[2 * (size_t)p.E] = make_uint2(m1.x, m1.y); q[3 * (size_t)p.E] = make_uint2(m1.z, m1.w);
-            return;
-        }
-        uint4* mp = reinterpret_cast<uint4*>(p.dyn + (size_t)e * p.rec + p.meta_off);
-        mp[0] = m0; mp[1] = m1;
-    }
-};
-
 // ------------------------------------------------------------------------------------------------
 // cos/sin of a heading.
 //
@@ -193,27 +151,24 @@ struct Lay {
 // the pair up (one 16-byte load) -- bit-identical to the reference and cheaper than evaluating sincos().
 // Off-lattice headings (user-injected state) fall back to CUDA's sincos (<= 2 ulp).
 // ------------------------------------------------------------------------------------------------
-static __device__ __noinline__ void offlattice_sincos(double h, double* sn, double* c) { sincos(h, sn, c); }
+// (returns by value: results handed back through pointers would live in local memory for every lookup)
+static __device__ __noinline__ double2 offlattice_sincos(double h) {
+    double sn, c;
+    sincos(h, &sn, &c);
+    return make_double2(sn, c);
+}
 
-__device__ __forceinline__ void heading_sincos(const FlightParams& p, const longlong2* lutm, double h, double* sn, double* c) {
+// (sin, cos) of heading h
+__device__ __forceinline__ double2 heading_sincos(const FlightParams& p, const longlong2* lutm, double h) {
     const int k = __double2int_rn(h * p.inv_turn);
-    if (k == 0 && fabs(h) < 7.450580596923828e-09) {   // |h| < 2^-27: libm returns sin = h, cos = 1
-        *sn = h;
-        *c = 1.0;
-        return;
-    }
+    if (k == 0 && fabs(h) < 7.450580596923828e-09) return make_double2(h, 1.0);   // |h| < 2^-27: libm returns sin = h, cos = 1
     if (k >= 1 && k <= 36) {
-        const longlong2 mt = lutm[k];                      // cluster index staged in shared memory by the warp
+        const longlong2 mt = lutm[k];                      // cluster index staged in shared memory by the CTA
         const long long off = __double_as_longlong(h) - mt.x;
         const long long half = mt.y >> 32;
-        if (off >= -half && off <= half) {
-            const double2 v = __ldg(p.lut + ((mt.y & 0xffffffffLL) + half + off));
-            *sn = v.x;
-            *c = v.y;
-            return;
-        }
+        if (off >= -half && off <= half) return __ldg(p.lut + ((mt.y & 0xffffffffLL) + half + off));
     }
-    offlattice_sincos(h, sn, c);
+    return offlattice_sincos(h);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -233,12 +188,12 @@ __device__ __forceinline__ bool wall_reg(const FlightParams& p, double& x, doubl
 }
 
 // Reset-time target placement (env/flight_env_easy.py:95-127) from the keyed stream; cold, out of line.
-static __device__ __noinline__ double2 draw_target(const FlightParams& p, uint32_t env_id, uint32_t episode, int j) {
-    const cs_u4 w = cs_philox4x32_10(env_id, (episode & 0xFFFFu) << 16, (uint32_t)j, 0u, p.seed, cs_stream_key(CS_STREAM_TARGET, episode));
+static __device__ __noinline__ double2 draw_target(const FlightParams& p, const double* tmpl, uint32_t seed, uint32_t env_id, uint32_t episode, int j) {
+    const cs_u4 w = cs_philox4x32_10(env_id, (episode & 0xFFFFu) << 16, (uint32_t)j, 0u, seed, cs_stream_key(CS_STREAM_TARGET, episode));
     const double u1 = cs_u53(w.x, w.y), u2 = cs_u53(w.z, w.w);
     double x, y;
     if (p.target_mode == 0) {
-        const double* row = p.tmpl + 5 * j;
+        const double* row = tmpl + 5 * j;
         x = row[0];
         y = row[1];
         if (row[4] != 0.0) {                      // deter == 'f' (:106-110)

@@ -594,6 +594,9 @@ int cs_flight_group_create(cs_flight* const* envs, int32_t count, cs_flight_grou
         const long long threads = (long long)h->p.E * h->tpe_k;
         const int gx = (int)((threads + kTpeThreads - 1) / kTpeThreads);
         if (gx > g->grid_x) g->grid_x = gx;
+        if (h->p.E > g->max_E) g->max_E = h->p.E;
+        if (i == 0) g->all_even = true;
+        if (h->p.E % 2) g->all_even = false;
         g->envs[i] = h;
         GroupEntry& t = g->table.h[i];
         const FlightParams& p = h->p;

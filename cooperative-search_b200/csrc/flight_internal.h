@@ -63,9 +63,12 @@ struct GroupEntry {
     double* stats; const double* tmpl;
 };
 struct GroupTable { GroupEntry h[kMaxGroup]; };
+struct GroupActions { const uint8_t* a[kMaxGroup]; };
 
 struct cs_flight_group {
     int count, n, k, grid_x, device;
+    int max_E;            // the largest handle's num_envs
+    bool all_even;        // every handle has an even num_envs (what the streaming step kernel needs)
     cs_flight* envs[kMaxGroup];
     GroupTable table;
 };

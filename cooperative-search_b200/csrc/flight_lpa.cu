@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(kThreads, 8) flight_kernel(const __grid_consta
             double h = yaw + ((act == 1) ? p.turn : ((act == 2) ? -p.turn : 0.0));   // dyaw = [0, pi/18, -pi/18] (:259-262)
             if (h > p.two_pi) h -= p.two_pi;                                          // strict tests (:263-266)
             else if (h < 0.0) h += p.two_pi;
-            heading_sincos(p, lutm, h, &s_h, &c_h);
+            { const double2 sc = heading_sincos(p, lutm, h); s_h = sc.x; c_h = sc.y; }
             yaw = h;
         }
         // Can any repulsion term be non-zero this step?  If every pair of OLD positions is farther apart than
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(kThreads, 8) flight_kernel(const __grid_consta
                 found = 0; outmask = 0; time_step = 0; flags = 0; ep_reward = 0.f; done = false;
                 if (!(rflags & CS_RESET_KEEP_TARGETS)) {
                     if (is_tgt) {
-                        const double2 t = draw_target(p, env_id, episode, lane);
+                        const double2 t = draw_target(p, p.tmpl, p.seed, env_id, episode, lane);
                         tx = t.x; ty = t.y;
                     }
                     tgt_dirty = true;

@@ -149,13 +149,38 @@ def test_thread_per_env_kernel_equals_lane_per_agent_kernel(n_agents, agent_mode
     target, lanes_per_env > 0) are the same arithmetic in a different arrangement: every buffer must agree bit for
     bit, through episode ends, in-call auto-resets and device-drawn targets, under device actions and the in-kernel
     random policy."""
+    compare_step_kernels(n_agents, agent_mode, target_mode, map_size, time_limit, variant, 1000, 0)
+
+
+@pytest.mark.parametrize("n_agents,agent_mode,target_mode,time_limit,E",
+                         [(3, 0, 0, 40, 1000), (3, 0, 0, 12, 2), (5, 2, 1, 30, 130), (8, 3, 1, 25, 4222), (1, 1, 0, 20, 258), (4, 0, 0, 15, 640)])
+def test_streaming_step_kernel_equals_lane_per_agent_kernel(monkeypatch, n_agents, agent_mode, target_mode, time_limit, E):
+    """flight_stream_kernel (opt-in with CS_STREAM=1: persistent CTAs, state tiles staged in shared memory by cp.async.bulk;
+    lanes_per_env = 1 and an even num_envs) against flight_kernel, bit for bit: partial tiles, one and many tiles per CTA,
+    auto-resets whose redrawn targets are read back from the tile, device actions and the in-kernel random policy."""
+    monkeypatch.setenv("CS_STREAM", "1")
+    compare_step_kernels(n_agents, agent_mode, target_mode, 50, time_limit, "easy", E, 1)
+
+
+@pytest.mark.parametrize("groups,slots,grid", [(2, 3, 3), (6, 7, 1), (1, 2, 2), (5, 10, 2), (6, 10, 148)])
+def test_streaming_step_kernel_ring_reuse(monkeypatch, groups, slots, grid):
+    """The same comparison with few CTAs and a short ring, so that every ring slot is refilled many times and the warp
+    groups of a CTA run far apart (the tuning variables are read at every launch)."""
+    monkeypatch.setenv("CS_STREAM", "1")
+    monkeypatch.setenv("CS_STREAM_GROUPS", str(groups))
+    monkeypatch.setenv("CS_STREAM_SLOTS", str(slots))
+    monkeypatch.setenv("CS_STREAM_GRID", str(grid))
+    compare_step_kernels(3, 0, 0, 50, 12, "easy", 4222 if grid < 148 else 40000, 1)
+
+
+def compare_step_kernels(n_agents, agent_mode, target_mode, map_size, time_limit, variant, E, lanes):
     import coopsearch_b200 as cs
-    E, T = 1000, 3 * time_limit + 7
+    T = 3 * time_limit + 7
     spec = FlightSpec(n_agents=n_agents, agent_mode=agent_mode, target_mode=target_mode, map_size=map_size,
                       view_range=min(7, map_size // 3), time_limit=time_limit, variant=variant)
     args = make_args(dict(spec.__dict__))
     cls = cs.VecFlightEasyEnv if variant == "easy" else cs.VecFlightEnv
-    tpe = cls(args, TEMPLATE, num_envs=E, seed=11, env_id_base=77, auto_reset=True)
+    tpe = cls(args, TEMPLATE, num_envs=E, seed=11, env_id_base=77, auto_reset=True, lanes_per_env=lanes)
     lpa = cls(args, TEMPLATE, num_envs=E, seed=11, env_id_base=77, auto_reset=True, lanes_per_env=16 if n_agents <= 16 else 32)
     assert tpe.lanes_per_env <= 8 and lpa.lanes_per_env >= 16
     actions = torch.from_numpy(np.random.default_rng(2).integers(0, 3, size=(T, E, n_agents), dtype=np.uint8)).cuda()
@@ -306,13 +331,15 @@ def test_host_stepper_many_batches_one_call(graph, compact):
             assert np.array_equal(cpu(ref[b].get_obs()), hb["obs"].numpy())
 
 
-@pytest.mark.parametrize("lpe,sizes", [(1, [700, 4096, 33]), (4, [256, 256, 256, 1000]), (0, [512, 512])])
-def test_grouped_device_step_equals_separate_steps(lpe, sizes):
+@pytest.mark.parametrize("lpe,sizes", [(1, [700, 4096, 33]), (1, [700, 4096, 34, 2, 128]), (-1, [700, 4096, 34, 2, 128]), (4, [256, 256, 256, 1000]), (0, [512, 512])])
+def test_grouped_device_step_equals_separate_steps(monkeypatch, lpe, sizes):
     """cs_flight_group_step: env batches of different sizes stepped in ONE launch end up bit-identical to the same
     batches stepped one by one (state, targets, outputs, statistics), through episode ends and in-call auto-resets."""
     import coopsearch_b200 as cs
     spec = FlightSpec(n_agents=3, time_limit=20)
     args = make_args(dict(spec.__dict__))
+    stream_group = lpe == -1           # the grouped launch through the streaming kernel, the separate steps through flight_tpe_kernel
+    lpe = 1 if stream_group else lpe
     mk = lambda: [cs.VecFlightEasyEnv(args, TEMPLATE, num_envs=E, seed=9, env_id_base=1000 * b, auto_reset=True, lanes_per_env=lpe)
                   for b, E in enumerate(sizes)]
     ref, envs = mk(), mk()
@@ -320,7 +347,10 @@ def test_grouped_device_step_equals_separate_steps(lpe, sizes):
     gen = torch.Generator(device="cuda").manual_seed(3)
     for t in range(50):
         acts = [torch.randint(0, 3, (E, 3), dtype=torch.uint8, device="cuda", generator=gen) for E in sizes]
+        if stream_group:
+            monkeypatch.setenv("CS_STREAM", "1")
         stepper.step(acts)
+        monkeypatch.delenv("CS_STREAM", raising=False)
         for a, e, r in zip(acts, envs, ref):
             rr, rt, rw = r.step(a)
             assert torch.equal(rr, e._reward) and torch.equal(rt, e._terminated) and torch.equal(rw, e._win), "step %d" % t
