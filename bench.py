@@ -521,17 +521,27 @@ def run_gpu_workload(cs, torch, name, steps, warmup, device, rank, world, want_e
                        h2d_bytes_per_step=sum(e.host_buffers()["actions"].numel() for e in envs),
                        d2h_bytes_per_step=sum(sum(v.numel() * v.element_size() for kname, v in e.host_buffers().items() if kname != "actions") for e in envs))
         else:
-            # this step's actions are in PINNED host memory (two alternating sets); one library call steps every batch:
-            # independent env batches are pipelined over a few streams, the call returns when every batch's results are in
-            # host memory.  Two forms of the same call are timed, the faster one is the e2e figure: "compact" (16 + 16n
-            # bytes per env over PCIe, reference-shaped rows rebuilt by host threads) and "slab" (the whole output slab).
+            # this step's actions are in PINNED host memory (two alternating sets); one library call steps every batch and
+            # returns when every batch's results are in host memory.  Two forms of the same call are timed, the faster
+            # one is the e2e figure: "compact" (pooled buffers: 16 + 16n bytes per env over PCIe -- the 16-byte records in
+            # one flat copy, the agent rows written in place into the reference-shaped host rows by one strided copy; host
+            # threads update result arrays and find flags) and "slab" (the whole output slab of every batch, batches
+            # pipelined over a few streams).
             host_actions = [[rng.integers(0, A, size=(e.num_envs, n), dtype=np.uint8) for e in envs] for _ in range(2)]
             pinned = [[torch.from_numpy(a).pin_memory() for a in host_actions[k]] for k in range(2)]
+            pooled_actions = [torch.from_numpy(np.concatenate(host_actions[k], axis=0)).pin_memory() for k in range(2)]
             use_graph = os.environ.get("CS_BENCH_E2E_GRAPH", "1") != "0"
             forms = {}
-            for form in ("compact", "slab"):
-                steppers = [cs.HostStepper(envs, streams, actions=pinned[k], graph=use_graph, compact=(form == "compact")) for k in range(2)]
-                dt, nblocks = time_blocks(lambda k: steppers[k % 2].step())
+            # slab first: the compact form's pooled buffers stay attached to the envs afterwards
+            for form in ("slab", "compact"):
+                if form == "compact":
+                    stepper = cs.HostStepper(envs, streams, graph=False, compact=True)      # six enqueues per step: no graph needed
+                    if stepper._pool is None:
+                        raise RuntimeError("the env batches of workload %s did not pool" % name)
+                    dt, nblocks = time_blocks(lambda k: stepper.step(actions=pooled_actions[k % 2]))
+                else:
+                    steppers = [cs.HostStepper(envs, streams, actions=pinned[k], graph=use_graph, compact=False) for k in range(2)]
+                    dt, nblocks = time_blocks(lambda k: steppers[k % 2].step())
                 forms[form] = dict(s_per_step=dt, blocks=nblocks, d2h=sum(int(e.host_buffers(form == "compact")["d2h_bytes"]) for e in envs))
             best = min(forms, key=lambda f: forms[f]["s_per_step"])
             out.update(e2e_s_per_step=forms[best]["s_per_step"], e2e_steps=e2e_steps, e2e_blocks=forms[best]["blocks"], e2e_form=best,
@@ -880,7 +890,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": res["h2d_bytes_per_step"],
                 "d2h_bytes_per_step": res["d2h_bytes_per_step"], "agent_steps_per_s": e2e_value * w["n"],
                 "steps": res["e2e_steps"], "blocks": res["e2e_blocks"], "form": res.get("e2e_form"), "forms": res.get("e2e_forms"),
-                "path": "HostStepper.step(): one library call for all batches, its device side captured in one CUDA graph; per batch: pinned host actions -> H2D -> step kernel -> [compact: pack kernel ->] D2H into pinned host memory; batches pipelined over 4 streams, all synchronised every step; compact form: reference-shaped rows rebuilt on the host by the library's thread pool inside the timed region (search: cs_search_step_host per batch); median block of %d steps, blocks repeated until >= %d ms" % (res["e2e_steps"], MIN_TIMED_MS)},
+                "path": "HostStepper.step(): one library call for all batches, its device side captured in one CUDA graph.  compact form (cs_flight_host_pool_step): pinned host actions of all batches -> ONE H2D copy -> one (grouped) step launch -> one pack launch -> two D2H copies into pinned host memory (16-byte records; the agent rows of all envs written in place into the reference-shaped state rows by a strided copy) -> host threads update reward / terminated / win / target_find and the find flags, rewrite target coordinates of reset envs -- all inside the timed region, synchronised every step.  slab form (cs_flight_step_host_many): per batch H2D -> step kernel -> D2H of the whole output slab, batches pipelined over 4 streams (search: cs_search_step_host per batch); median block of %d steps, blocks repeated until >= %d ms" % (res["e2e_steps"], MIN_TIMED_MS)},
         "gpu_launches": int(res["kernels"]),
         "gpu_launches_process_total": int(lib.cs_launch_count() - launches0),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

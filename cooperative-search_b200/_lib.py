@@ -148,6 +148,11 @@ SIGNATURES = {
     "cs_flight_host_expand": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
     "cs_flight_step_host_compact_many": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int32, C.POINTER(C.c_void_p), C.c_int32, C.c_uint32]),
     "cs_flight_host_expand_many": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.POINTER(C.c_void_p), C.c_int32, C.c_int32]),
+    "cs_flight_host_pool_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.POINTER(C.c_void_p)]),
+    "cs_flight_host_pool_destroy": (None, [C.c_void_p]),
+    "cs_flight_host_pool_views": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(FlightHostViews), C.POINTER(C.c_void_p)]),
+    "cs_flight_host_pool_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "cs_flight_host_pool_expand": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
     "cs_flight_step_host_many": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(FlightHostIO), C.c_int32, C.POINTER(C.c_void_p), C.c_int32]),
     "cs_flight_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_void_p]),
     "cs_flight_group_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.POINTER(C.c_void_p)]),

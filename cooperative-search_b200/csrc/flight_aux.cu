@@ -179,9 +179,10 @@ __global__ void __launch_bounds__(256) flight_live_steps_kernel(const double* __
 // Compact step results for the host-buffer path.  What changes in an env's reference-shaped outputs every step is small:
 // reward / target_find / terminated / win, the n agent rows (x^, y^, cos, sin) and a few find flags; the 2m target
 // coordinates of a state row change only when the env is reset.  One record per env:
-//   { float reward; uint32 found; uint8 target_find, terminated, win, reset; uint32 0 } + n x float4   (16 + 16n bytes)
+//   { float reward; uint32 found; uint8 target_find, terminated, win, reset; uint32 0 }   (16 bytes; with rec_bytes > 16
+//   followed by the n agent rows -- the host path has the copy engine scatter those straight from `obs`, flight_hostio.cu)
 // and, for the envs that were reset inside this call (auto-reset), one entry { int32 env; float xy[2m] } in a small
-// side region claimed with an atomic counter.  The host expands this into full rows (flight_host.cu).
+// side region claimed with an atomic counter.  The host expands this into full rows (flight_hostio.cu).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) flight_pack_kernel(const FlightParams p, unsigned char* __restrict__ out, int rec_bytes,
                                                           unsigned char* __restrict__ entries, int ent_bytes, int cap,
@@ -194,8 +195,10 @@ __global__ void __launch_bounds__(128) flight_pack_kernel(const FlightParams p, 
     uint4* rec = reinterpret_cast<uint4*>(out + (size_t)e * rec_bytes);
     const uint32_t bytes = (uint32_t)p.target_find[e] | (term << 8) | ((uint32_t)p.win[e] << 16) | (reset << 24);
     rec[0] = make_uint4(__float_as_uint(p.reward[e]), m0.x, bytes, 0u);
-    const uint4* row = reinterpret_cast<const uint4*>(p.state + (size_t)e * p.state_stride);
-    for (int a = 0; a < p.n; ++a) rec[1 + a] = row[a];
+    if (rec_bytes > 16) {
+        const uint4* row = reinterpret_cast<const uint4*>(p.state + (size_t)e * p.state_stride);
+        for (int a = 0; a < p.n; ++a) rec[1 + a] = row[a];
+    }
     if (reset) {
         const unsigned slot = atomicAdd(counter, 1u);
         if (slot < (unsigned)cap) {
@@ -204,6 +207,41 @@ __global__ void __launch_bounds__(128) flight_pack_kernel(const FlightParams p, 
             const float* tr = p.state + (size_t)e * p.state_stride + 4 * p.n;
             float* xy = reinterpret_cast<float*>(ent + 1);
             for (int j = 0; j < p.m; ++j) { xy[2 * j] = tr[3 * j]; xy[2 * j + 1] = tr[3 * j + 1]; }
+        }
+    }
+}
+
+// The same for all batches of a host pool in ONE launch (blockIdx.y = batch), as dense arrays at the batch's env offset:
+// reward / target_find / terminated / win / found mask land in the pool's result block exactly as the host reads them
+// (its views are the pinned mirror of that block), the agent rows in one contiguous array for the strided copy; reset
+// entries carry the pooled env index.
+struct PoolOut { float* reward; int32_t* target_find; uint8_t* terminated; uint8_t* win; uint32_t* found; uint4* agent; };
+
+__global__ void __launch_bounds__(128) flight_pack_pool_kernel(const __grid_constant__ FlightParams common, const __grid_constant__ GroupTable tab,
+                                                               const __grid_constant__ PoolGeom geo, const PoolOut out,
+                                                               unsigned char* __restrict__ entries, int ent_bytes, int cap,
+                                                               unsigned int* __restrict__ counter) {
+    const GroupEntry& g = tab.h[blockIdx.y];
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= g.E) return;
+    const int ge = geo.first[blockIdx.y] + e;
+    const uint32_t term = g.terminated[e];
+    out.reward[ge] = g.reward[e];
+    out.target_find[ge] = g.target_find[e];
+    out.terminated[ge] = (uint8_t)term;
+    out.win[ge] = g.win[e];
+    out.found[ge] = reinterpret_cast<const uint2*>(g.dyn + (size_t)common.meta_off * g.dyn_rs + (size_t)e * g.dyn_es)->x;
+    const uint4* orow = reinterpret_cast<const uint4*>(g.obs) + (size_t)e * common.n;
+    uint4* arow = out.agent + (size_t)ge * common.n;
+    for (int a = 0; a < common.n; ++a) arow[a] = orow[a];
+    if (term && common.auto_reset) {
+        const unsigned slot = atomicAdd(counter, 1u);
+        if (slot < (unsigned)cap) {
+            int* ent = reinterpret_cast<int*>(entries + (size_t)slot * ent_bytes);
+            ent[0] = ge;
+            const float* tr = g.state + (size_t)e * common.state_stride + 4 * common.n;
+            float* xy = reinterpret_cast<float*>(ent + 1);
+            for (int j = 0; j < common.m; ++j) { xy[2 * j] = tr[3 * j]; xy[2 * j + 1] = tr[3 * j + 1]; }
         }
     }
 }
@@ -269,6 +307,26 @@ cudaError_t launch_pack(cs_flight* h, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     flight_pack_kernel<<<(h->p.E + 127) / 128, 128, 0, st>>>(h->p, c->d_pack, (int)c->rec_bytes, c->d_pack + c->off_entries, (int)c->ent_bytes, c->cap,
                                                           reinterpret_cast<unsigned int*>(c->d_pack + c->off_counter));
+    cs_count_launch(1);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pack_pool(cs_flight_host_pool* pl, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(pl->d_rec + pl->off_counter, 0, 16, st);
+    if (e != cudaSuccess) return e;
+    int max_E = 0;
+    for (int i = 0; i < pl->count; ++i) max_E = pl->envs[i]->p.E > max_E ? pl->envs[i]->p.E : max_E;
+    const dim3 grid((unsigned)((max_E + 127) / 128), (unsigned)pl->count);
+    PoolOut out;
+    out.reward = reinterpret_cast<float*>(pl->d_rec);
+    out.target_find = reinterpret_cast<int32_t*>(pl->d_rec + pl->off_tf);
+    out.terminated = pl->d_rec + pl->off_term;
+    out.win = pl->d_rec + pl->off_win;
+    out.found = reinterpret_cast<uint32_t*>(pl->d_rec + pl->off_found);
+    out.agent = reinterpret_cast<uint4*>(pl->d_agent);
+    flight_pack_pool_kernel<<<grid, 128, 0, st>>>(pl->envs[0]->p, pl->table, pl->geo, out,
+                                                  pl->d_rec + pl->off_entries, (int)pl->ent_bytes, pl->cap,
+                                                  reinterpret_cast<unsigned int*>(pl->d_rec + pl->off_counter));
     cs_count_launch(1);
     return cudaGetLastError();
 }

@@ -1,9 +1,14 @@
 // Compact host-buffer path of the flight envs: the call a CPU-side rollout makes every step
 // (reward, terminated, info = env.step(actions); env.get_obs(); env.get_state(), common/rollout.py:45-63) moves
-// 16 + 16n bytes per env over PCIe instead of the full reference-shaped state row (4(4n + 3m) + 10 bytes) and rebuilds
-// the rows on the host: the agent part is overwritten, find flags flip where the found mask changed, and the 2m target
-// coordinates are rewritten only for envs that were reset inside the call.  The rebuild is spread over a small pool
-// of host threads.  Results live in library-owned host arrays (cs_flight_host_views), valid until the next step.
+// 16 + 16n bytes per env over PCIe instead of the full reference-shaped state row (4(4n + 3m) + 10 bytes) and keeps the
+// reference-shaped rows up to date in (pinned) host memory:
+//   * the agent part of every row (= the get_obs rows, 16n bytes) is written IN PLACE by the copy engine: one strided
+//     device-to-host copy (cudaMemcpy2DAsync, rows state_stride floats apart) -- measured on B200 / PCIe 5: 262144 rows of
+//     48 bytes in 0.45 ms, where host threads need ~2 ms for the same scatter (one cache miss per row);
+//   * a 16-byte record per env {reward, found mask, target_find, terminated, win, reset} comes back in one flat copy; host
+//     threads spread it over the result arrays and flip the find flags whose bit changed;
+//   * the 2m target coordinates are rewritten only for envs that were reset inside the call (a small side list).
+// Results live in library-owned host arrays (cs_flight_host_views), valid until the next step.
 #include <atomic>
 #include <condition_variable>
 #include <functional>
@@ -27,6 +32,7 @@ public:
         return *pool;
     }
     int size() const { return (int)workers_.size() + 1; }
+    // fn(thread index, thread count) on every worker; workers with index >= the count the caller wants simply return
     void run(const std::function<void(int, int)>& fn) {
         const int T = size();
         if (T == 1) { fn(0, 1); return; }
@@ -86,9 +92,7 @@ struct PackHdr { float reward; uint32_t found; uint8_t target_find, terminated, 
 static_assert(sizeof(PackHdr) == 16, "PackHdr");
 
 // rebuilds the host rows of envs [e0, e1) from the packed records
-void expand_range(cs_flight* h, int e0, int e1) {
-    cs_flight_compact* c = h->hc;
-    const FlightParams& p = h->p;
+void expand_range(const FlightParams& p, cs_flight_compact* c, int e0, int e1) {
     const int n = p.n, m = p.m, stride = p.state_stride;
     for (int e = e0; e < e1; ++e) {
         const unsigned char* rec = c->h_pack + (size_t)e * c->rec_bytes;
@@ -97,15 +101,9 @@ void expand_range(cs_flight* h, int e0, int e1) {
         c->target_find[e] = hd->target_find;
         c->terminated[e] = hd->terminated;
         c->win[e] = hd->win;
-        float* row = c->state + (size_t)e * stride;
-        {                                                            // agent part = get_obs rows (flight_env_easy.py:192-193)
-            typedef float v4 __attribute__((vector_size(16), aligned(4)));
-            const v4* src = reinterpret_cast<const v4*>(rec + 16);
-            v4* dst = reinterpret_cast<v4*>(row);
-            for (int a = 0; a < n; ++a) dst[a] = src[a];
-        }
         if (!hd->reset) {
             uint32_t diff = hd->found ^ c->shadow_found[e];
+            float* row = c->state + (size_t)e * stride;                // (the agent part arrives by DMA)
             while (diff) {                                           // find flags that changed (:206-209)
                 const int j = __builtin_ctz(diff);
                 diff &= diff - 1;
@@ -138,9 +136,15 @@ void apply_reset_entries(cs_flight* h, unsigned count) {
 
 void free_compact(cs_flight_compact* c) {
     if (!c) return;
+    if (c->pooled) {                                // the pool owns the arrays; it must not touch this env any more
+        if (c->pool) c->pool->envs[c->pool_index] = nullptr;
+        delete c;
+        return;
+    }
     cudaFree(c->d_pack);
     cudaFreeHost(c->h_pack);
-    free(c->reward); free(c->target_find); free(c->terminated); free(c->win); free(c->state); free(c->shadow_found);
+    cudaFreeHost(c->state);
+    free(c->reward); free(c->target_find); free(c->terminated); free(c->win); free(c->shadow_found);
     delete c;
 }
 
@@ -166,7 +170,7 @@ int cs_flight_host_compact_begin(cs_flight* h, cs_flight_host_views* out) {
         if (!c) { cs_set_error("out of host memory"); return CS_ERR_NOMEM; }
         memset(c, 0, sizeof(*c));
         const size_t E = (size_t)p.E;
-        c->rec_bytes = 16 + 16 * (size_t)p.n;
+        c->rec_bytes = 16;
         c->ent_bytes = (4 + 8 * (size_t)p.m + 15) & ~(size_t)15;
         c->cap = (int)(E / 16 > 64 ? E / 16 : (E < 64 ? E : 64));
         c->off_entries = (E * c->rec_bytes + 255) & ~(size_t)255;
@@ -178,11 +182,12 @@ int cs_flight_host_compact_begin(cs_flight* h, cs_flight_host_views* out) {
         if (e == cudaSuccess) e = cudaMalloc(&c->d_pack, c->pack_bytes);
         if (e == cudaSuccess) e = cudaMemset(c->d_pack, 0, c->pack_bytes);
         if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&c->h_pack), c->pack_bytes, cudaHostAllocDefault);
+        if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&c->state), E * p.state_stride * sizeof(float), cudaHostAllocDefault);   // DMA target
+        if (e == cudaSuccess) memset(c->state, 0, E * p.state_stride * sizeof(float));
         c->reward = (float*)calloc(E, sizeof(float));
         c->target_find = (int32_t*)calloc(E, sizeof(int32_t));
         c->terminated = (uint8_t*)calloc(E, 1);
         c->win = (uint8_t*)calloc(E, 1);
-        c->state = (float*)calloc(E * p.state_stride, sizeof(float));
         c->shadow_found = (uint32_t*)calloc(E, sizeof(uint32_t));
         if (e != cudaSuccess || !c->reward || !c->target_find || !c->terminated || !c->win || !c->state || !c->shadow_found) {
             flight_compact_release(h);
@@ -195,7 +200,7 @@ int cs_flight_host_compact_begin(cs_flight* h, cs_flight_host_views* out) {
     out->reward = c->reward; out->target_find = c->target_find; out->terminated = c->terminated; out->win = c->win;
     out->state = c->state; out->state_stride = p.state_stride;
     out->h2d_bytes_per_step = (uint64_t)p.E * p.n;
-    out->d2h_bytes_per_step = c->pack_bytes;
+    out->d2h_bytes_per_step = (c->pooled ? (uint64_t)p.E * c->rec_bytes : c->pack_bytes) + (uint64_t)p.E * 16 * p.n;
     return CS_OK;
 }
 
@@ -232,6 +237,7 @@ int cs_flight_host_expand(cs_flight* h, void* stream, int32_t sync) {
 
 int cs_flight_step_host_compact(cs_flight* h, const uint8_t* h_actions, uint32_t flags, void* stream) {
     CS_REQUIRE(h && h_actions && h->hc, "cs_flight_step_host_compact: bad argument (cs_flight_host_compact_begin first)");
+    CS_REQUIRE(!h->hc->pooled, "cs_flight_step_host_compact: the env belongs to a host pool -- step it with cs_flight_host_pool_step");
     cs_flight_compact* c = h->hc;
     const FlightParams& p = h->p;
     cudaStream_t st = (cudaStream_t)stream;
@@ -241,6 +247,9 @@ int cs_flight_step_host_compact(cs_flight* h, const uint8_t* h_actions, uint32_t
     CS_CUDA(flight_map_join(h, st));      // a host-buffer step is complete when it returns: the belief map too
     CS_CUDA(launch_pack(h, st));
     CS_CUDA(cudaMemcpyAsync(c->h_pack, c->d_pack, c->pack_bytes, cudaMemcpyDeviceToHost, st));
+    // the agent part of every host row, in place: E pieces of 16n bytes, state_stride floats apart
+    CS_CUDA(cudaMemcpy2DAsync(c->state, (size_t)p.state_stride * sizeof(float), p.obs, 16 * (size_t)p.n, 16 * (size_t)p.n, (size_t)p.E,
+                              cudaMemcpyDeviceToHost, st));
     CS_CUDA(cudaGetLastError());
     if (!(flags & CS_HOST_NO_SYNC)) return cs_flight_host_expand(h, stream, 1);
     return CS_OK;
@@ -282,12 +291,259 @@ int cs_flight_host_expand_many(cs_flight* const* envs, int32_t count, void* cons
             while (first[(size_t)b + 1] <= it) ++b;
             const int e0 = (it - first[(size_t)b]) * kChunk;
             const int e1 = e0 + kChunk < envs[b]->p.E ? e0 + kChunk : envs[b]->p.E;
-            expand_range(envs[b], e0, e1);
+            expand_range(envs[b]->p, envs[b]->hc, e0, e1);
         }
     };
     if (items <= 2) work(0, 1);
     else HostPool::get().run(work);
     for (int i = 0; i < count; ++i) apply_reset_entries(envs[i], entries[(size_t)i]);
+    return CS_OK;
+}
+
+}  // extern "C"
+
+// ---- pooled host buffers: every batch's arrays are segments of single allocations ------------------------------------
+namespace {
+
+void pool_free(cs_flight_host_pool* pl) {
+    if (!pl) return;
+    for (int i = 0; i < pl->count; ++i)
+        if (pl->envs[i] && pl->envs[i]->hc && pl->envs[i]->hc->pooled) flight_compact_release(pl->envs[i]);
+    if (pl->group) cs_flight_group_destroy(pl->group);
+    cudaFreeHost(pl->h_actions); cudaFree(pl->d_actions); cudaFree(pl->d_rec); cudaFreeHost(pl->h_rec); cudaFree(pl->d_agent);
+    cudaFreeHost(pl->h_state);
+    if (pl->ev_rec) cudaEventDestroy(pl->ev_rec);
+    free(pl->shadow_found);
+    delete pl;
+}
+
+inline const uint32_t* pool_found(const cs_flight_host_pool* pl) { return reinterpret_cast<const uint32_t*>(pl->h_rec + pl->off_found); }
+
+// rows of the envs that were reset inside the call: the new episode's targets (flight_env_easy.py:201-211)
+void pool_apply_entries(cs_flight_host_pool* pl, unsigned count) {
+    const FlightParams& p = pl->envs[0]->p;
+    const int n = p.n, m = p.m;
+    const uint32_t* found_all = pool_found(pl);
+    for (unsigned k = 0; k < count; ++k) {
+        const int* ent = reinterpret_cast<const int*>(pl->h_rec + pl->off_entries + (size_t)k * pl->ent_bytes);
+        const int ge = ent[0];
+        const float* xy = reinterpret_cast<const float*>(ent + 1);
+        const uint32_t found = found_all[ge];
+        float* tr = pl->h_state + (size_t)ge * p.state_stride + 4 * n;
+        for (int j = 0; j < m; ++j) {
+            tr[3 * j] = xy[2 * j];
+            tr[3 * j + 1] = xy[2 * j + 1];
+            tr[3 * j + 2] = ((found >> j) & 1u) ? 1.0f : 0.0f;
+        }
+        pl->shadow_found[ge] = found;
+    }
+}
+
+// find flags whose bit changed, envs [e0, e1) (:206-209)
+void pool_scan_found(cs_flight_host_pool* pl, int e0, int e1) {
+    const FlightParams& p = pl->envs[0]->p;
+    const uint32_t* found = pool_found(pl);
+    uint32_t* shadow = pl->shadow_found;
+    const int n = p.n, stride = p.state_stride;
+    int e = e0;
+    while (e < e1) {
+        const int blk = e + 16 <= e1 ? 16 : e1 - e;
+        if (memcmp(found + e, shadow + e, (size_t)blk * 4) != 0) {
+            for (int k = e; k < e + blk; ++k) {
+                uint32_t diff = found[k] ^ shadow[k];
+                if (!diff) continue;
+                float* row = pl->h_state + (size_t)k * stride;
+                while (diff) {
+                    const int j = __builtin_ctz(diff);
+                    diff &= diff - 1;
+                    row[4 * n + 3 * j + 2] = ((found[k] >> j) & 1u) ? 1.0f : 0.0f;
+                }
+                shadow[k] = found[k];
+            }
+        }
+        e += blk;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int cs_flight_host_pool_create(cs_flight* const* envs, int32_t count, cs_flight_host_pool** out) {
+    CS_REQUIRE(envs && out && count >= 1 && count <= kMaxGroup, "cs_flight_host_pool_create: count must be in 1..%d", kMaxGroup);
+    for (int i = 0; i < count; ++i) {
+        CS_REQUIRE(envs[i] && !envs[i]->hc, "cs_flight_host_pool_create: batch %d is null or already has compact host buffers", i);
+        const FlightParams &a = envs[0]->p, &b = envs[i]->p;
+        CS_REQUIRE(a.n == b.n && a.m == b.m && a.state_stride == b.state_stride && a.auto_reset == b.auto_reset && a.meta_off == b.meta_off &&
+                   envs[0]->cfg.device == envs[i]->cfg.device, "cs_flight_host_pool_create: batch %d differs from batch 0 in n_agents / target_num / auto_reset / device", i);
+    }
+    cs_flight_host_pool* pl = new (std::nothrow) cs_flight_host_pool();
+    if (!pl) { cs_set_error("out of host memory"); return CS_ERR_NOMEM; }
+    memset(pl, 0, sizeof(*pl));
+    pl->count = count;
+    pl->device = envs[0]->cfg.device;
+    const FlightParams& p0 = envs[0]->p;
+    for (int i = 0; i < count; ++i) {
+        pl->envs[i] = envs[i];
+        pl->geo.first[i + 1] = pl->geo.first[i] + envs[i]->p.E;
+        const FlightParams& p = envs[i]->p;
+        GroupEntry& t = pl->table.h[i];
+        t.E = p.E; t.env_id_base = p.env_id_base; t.seed = p.seed; t.dyn_rs = p.dyn_rs; t.dyn_es = p.dyn_es; t.tgt_rs = p.tgt_rs; t.tgt_es = p.tgt_es;
+        t.dyn = p.dyn; t.tgt = p.tgt; t.obs = p.obs; t.state = p.state; t.reward = p.reward; t.terminated = p.terminated; t.win = p.win;
+        t.target_find = p.target_find; t.stats = p.stats; t.tmpl = p.tmpl;
+    }
+    pl->total = pl->geo.first[count];
+    const size_t T = (size_t)pl->total, n = (size_t)p0.n;
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    pl->ent_bytes = (4 + 8 * (size_t)p0.m + 15) & ~(size_t)15;
+    pl->cap = (int)(T / 16 > 64 ? T / 16 : (T < 64 ? T : 64));
+    // a step copies the result arrays, the counter and the first cap_fast reset entries; the rest of the list only when it
+    // is used (many envs reset inside one call)
+    pl->cap_fast = (int)(T / 48 > 64 ? T / 48 : 64);
+    if (pl->cap_fast > pl->cap) pl->cap_fast = pl->cap;
+    pl->off_tf = al(T * 4);
+    pl->off_term = pl->off_tf + al(T * 4);
+    pl->off_win = pl->off_term + al(T);
+    pl->off_found = pl->off_win + al(T);
+    pl->off_counter = pl->off_found + al(T * 4);
+    pl->off_entries = pl->off_counter + 256;
+    pl->fast_bytes = pl->off_entries + (size_t)pl->cap_fast * pl->ent_bytes;
+    pl->rec_block_bytes = pl->off_entries + (size_t)pl->cap * pl->ent_bytes;
+    cudaError_t e = cudaSetDevice(pl->device);
+    if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&pl->h_actions), T * n, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaMalloc(&pl->d_actions, T * n);
+    if (e == cudaSuccess) e = cudaMalloc(&pl->d_rec, pl->rec_block_bytes);
+    if (e == cudaSuccess) e = cudaMemset(pl->d_rec, 0, pl->rec_block_bytes);
+    if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&pl->h_rec), pl->rec_block_bytes, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaMalloc(&pl->d_agent, T * 16 * n);
+    if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&pl->h_state), T * p0.state_stride * sizeof(float), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_rec, cudaEventDisableTiming | cudaEventBlockingSync);
+    pl->shadow_found = (uint32_t*)calloc(T, sizeof(uint32_t));
+    bool ok = e == cudaSuccess && pl->shadow_found;
+    if (ok) {
+        memset(pl->h_actions, 0, T * n);
+        memset(pl->h_rec, 0, pl->rec_block_bytes);
+        memset(pl->h_state, 0, T * p0.state_stride * sizeof(float));
+        for (int i = 0; i < count && ok; ++i) {
+            cs_flight_compact* c = new (std::nothrow) cs_flight_compact();
+            if (!c) { ok = false; break; }
+            memset(c, 0, sizeof(*c));
+            const size_t f = (size_t)pl->geo.first[i];
+            c->pooled = true; c->dirty = true; c->rec_bytes = 14;
+            c->pool = pl; c->pool_index = i;
+            c->reward = reinterpret_cast<float*>(pl->h_rec) + f;
+            c->target_find = reinterpret_cast<int32_t*>(pl->h_rec + pl->off_tf) + f;
+            c->terminated = pl->h_rec + pl->off_term + f;
+            c->win = pl->h_rec + pl->off_win + f;
+            c->state = pl->h_state + f * p0.state_stride; c->shadow_found = pl->shadow_found + f;
+            envs[i]->hc = c;
+            pl->act_ptrs[i] = pl->d_actions + f * n;
+        }
+    }
+    if (!ok) {
+        pool_free(pl);
+        if (e != cudaSuccess) CS_CUDA(e);
+        cs_set_error("out of host memory");
+        return CS_ERR_NOMEM;
+    }
+    // one grouped step launch when the handles allow it (flight_easy, thread-per-env kernel, same configuration)
+    if (cs_flight_group_create(envs, count, &pl->group) != CS_OK) pl->group = nullptr;
+    *out = pl;
+    return CS_OK;
+}
+
+void cs_flight_host_pool_destroy(cs_flight_host_pool* pl) {
+    if (!pl) return;
+    cudaSetDevice(pl->device);
+    pool_free(pl);
+}
+
+int cs_flight_host_pool_views(cs_flight_host_pool* pl, int32_t i, cs_flight_host_views* out, uint8_t** h_actions) {
+    CS_REQUIRE(pl && out && i >= 0 && i < pl->count && pl->envs[i], "cs_flight_host_pool_views: bad argument");
+    if (h_actions) *h_actions = pl->h_actions + (size_t)pl->geo.first[i] * pl->envs[i]->p.n;
+    return cs_flight_host_compact_begin(pl->envs[i], out);
+}
+
+int cs_flight_host_pool_expand(cs_flight_host_pool* pl, void* stream, int32_t sync) {
+    CS_REQUIRE(pl, "cs_flight_host_pool_expand: null pool");
+    for (int i = 0; i < pl->count; ++i) CS_REQUIRE(pl->envs[i], "cs_flight_host_pool_expand: batch %d was destroyed", i);
+    cudaStream_t st = (cudaStream_t)stream;
+    const FlightParams& p0 = pl->envs[0]->p;
+    bool any_dirty = false;
+    for (int i = 0; i < pl->count; ++i) any_dirty |= pl->envs[i]->hc->dirty;
+    // sync = 1: the host work below only needs the result block -- it runs while the copy engine still scatters the agent
+    // rows (different bytes of the same host rows; DMA writes are coherent with the cores' caches), and the stream is
+    // joined at the end.  A full refresh needs everything first.
+    if (sync) {
+        if (any_dirty) CS_CUDA(cudaStreamSynchronize(st));
+        else CS_CUDA(cudaEventSynchronize(pl->ev_rec));
+    }
+    const unsigned count = *reinterpret_cast<const unsigned*>(pl->h_rec + pl->off_counter);
+    const bool overflow = count > (unsigned)pl->cap;
+    if (!overflow && count > (unsigned)pl->cap_fast) {          // the tail of the reset list (rare)
+        CS_CUDA(cudaSetDevice(pl->device));
+        CS_CUDA(cudaStreamSynchronize(st));
+        CS_CUDA(cudaMemcpy(pl->h_rec + pl->fast_bytes, pl->d_rec + pl->fast_bytes, (size_t)(count - pl->cap_fast) * pl->ent_bytes, cudaMemcpyDeviceToHost));
+    }
+    bool refreshed = false;
+    if (any_dirty || overflow) {
+        if (sync && !any_dirty) CS_CUDA(cudaStreamSynchronize(st));
+        for (int i = 0; i < pl->count; ++i) {
+            cs_flight* h = pl->envs[i];
+            if (!h->hc->dirty && !overflow) continue;
+            // full refresh of this batch's rows (first step, after a reset / import, or more resets than the side list holds)
+            if (!refreshed) CS_CUDA(cudaSetDevice(pl->device));
+            CS_CUDA(cudaMemcpyAsync(h->hc->state, h->p.state, (size_t)h->p.E * p0.state_stride * sizeof(float), cudaMemcpyDeviceToHost, st));
+            refreshed = true;
+        }
+    }
+    if (refreshed) {
+        CS_CUDA(cudaStreamSynchronize(st));
+        const uint32_t* found = pool_found(pl);
+        for (int i = 0; i < pl->count; ++i) {
+            cs_flight_compact* c = pl->envs[i]->hc;
+            if (!c->dirty && !overflow) continue;
+            memcpy(c->shadow_found, found + pl->geo.first[i], (size_t)pl->envs[i]->p.E * 4);
+            c->dirty = false;
+        }
+    }
+    if (!overflow) pool_apply_entries(pl, count);
+    // few threads on purpose: a D2H copy into lines that sit in many cores' caches runs at a fraction of its speed
+    // (measured: the 4 MB result block in 95 us after one thread read it, 530 us after sixteen did)
+    constexpr int kScanThreads = 2;
+    const int chunk = (pl->total + kScanThreads - 1) / kScanThreads;
+    if (pl->total < 65536 || HostPool::get().size() < kScanThreads) pool_scan_found(pl, 0, pl->total);
+    else HostPool::get().run([&](int idx, int) { if (idx < kScanThreads) pool_scan_found(pl, idx * chunk, (idx + 1) * chunk < pl->total ? (idx + 1) * chunk : pl->total); });
+    if (sync) CS_CUDA(cudaStreamSynchronize(st));               // the agent rows are in place
+    return CS_OK;
+}
+
+int cs_flight_host_pool_step(cs_flight_host_pool* pl, const uint8_t* h_actions, uint32_t flags, void* stream) {
+    CS_REQUIRE(pl, "cs_flight_host_pool_step: null pool");
+    for (int i = 0; i < pl->count; ++i) CS_REQUIRE(pl->envs[i], "cs_flight_host_pool_step: batch %d was destroyed", i);
+    cudaStream_t st = (cudaStream_t)stream;
+    const FlightParams& p0 = pl->envs[0]->p;
+    const size_t T = (size_t)pl->total, n = (size_t)p0.n;
+    CS_CUDA(cudaSetDevice(pl->device));
+    CS_CUDA(cudaMemcpyAsync(pl->d_actions, h_actions ? h_actions : pl->h_actions, T * n, cudaMemcpyHostToDevice, st));
+    if (pl->group) {
+        bool was_dirty[kMaxGroup];
+        for (int i = 0; i < pl->count; ++i) was_dirty[i] = pl->envs[i]->hc->dirty;
+        const int rc = cs_flight_group_step(pl->group, pl->act_ptrs, stream);      // (marks the host rows stale; this step refreshes them)
+        for (int i = 0; i < pl->count; ++i) pl->envs[i]->hc->dirty = was_dirty[i];
+        if (rc != CS_OK) return rc;
+    } else {
+        for (int i = 0; i < pl->count; ++i) {
+            CS_CUDA(flight_dispatch(pl->envs[i], MODE_STEP, pl->act_ptrs[i], nullptr, 0u, st));
+            CS_CUDA(flight_map_join(pl->envs[i], st));
+        }
+    }
+    CS_CUDA(launch_pack_pool(pl, st));
+    CS_CUDA(cudaMemcpyAsync(pl->h_rec, pl->d_rec, pl->fast_bytes, cudaMemcpyDeviceToHost, st));
+    CS_CUDA(cudaEventRecord(pl->ev_rec, st));
+    // the agent part of every host row, in place: `total` pieces of 16n bytes, state_stride floats apart
+    CS_CUDA(cudaMemcpy2DAsync(pl->h_state, (size_t)p0.state_stride * sizeof(float), pl->d_agent, 16 * n, 16 * n, T, cudaMemcpyDeviceToHost, st));
+    if (!(flags & CS_HOST_NO_SYNC)) return cs_flight_host_pool_expand(pl, stream, 1);
     return CS_OK;
 }
 

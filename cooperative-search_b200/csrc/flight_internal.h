@@ -21,6 +21,9 @@ struct cs_flight_compact {
     float* state;                // [E][state_stride]
     uint32_t* shadow_found;      // found mask the host rows currently show
     bool dirty;                  // the host rows must be refreshed in full (first step, after cs_flight_reset / import)
+    bool pooled;                 // the arrays are segments of a cs_flight_host_pool's (which owns them)
+    struct cs_flight_host_pool* pool;   // that pool, and this env's batch index in it
+    int pool_index;
 };
 
 struct cs_flight {
@@ -73,6 +76,30 @@ struct cs_flight_group {
     GroupTable table;
 };
 
+// Host-buffer steps of many env batches with pooled buffers (cs_flight_host_pool_*, flight_hostio.cu): the batches' host
+// rows, records, agent rows and actions are segments of single allocations, so that a step of ALL batches is one H2D
+// copy, one grouped step launch, one grouped pack launch and two D2H copies.
+struct PoolGeom { int first[kMaxGroup + 1]; };       // env offset of every batch in the pooled arrays
+struct cs_flight_host_pool {
+    int count, device, total;
+    cs_flight* envs[kMaxGroup];
+    PoolGeom geo;
+    cs_flight_group* group;      // grouped step launch when the handles allow it (flight_easy, thread-per-env), else null
+    GroupTable table;            // per-batch buffers for the grouped pack kernel
+    const uint8_t* act_ptrs[kMaxGroup];
+    uint8_t* h_actions; uint8_t* d_actions;          // [total][n] (pinned / device)
+    // result block (device / pinned mirror): reward f32[total] | target_find i32[total] | terminated u8[total] |
+    // win u8[total] | found mask u32[total] | counter | reset entries.  The host views of the first four ARE the mirror.
+    unsigned char* d_rec; unsigned char* h_rec;
+    size_t rec_block_bytes, off_tf, off_term, off_win, off_found, off_entries, off_counter, ent_bytes;
+    size_t fast_bytes;           // what every step copies: records, counter and the first cap_fast entries
+    int cap, cap_fast;
+    cudaEvent_t ev_rec;          // the record block has arrived (the strided copy of the agent rows is still running)
+    float* d_agent;              // device [total][4n]
+    float* h_state;              // pinned [total][state_stride]
+    uint32_t* shadow_found;      // found mask the host rows currently show
+};
+
 namespace csf {
 
 // flight_tpe.cu, one translation unit per pair of n_agents (part P: 2P+1, 2P+2)
@@ -103,6 +130,7 @@ cudaError_t launch_record_begin(cs_flight*, const cs_episode_buffers&, int T, cu
 cudaError_t launch_record(cs_flight*, const cs_episode_buffers&, int t, int T, const uint8_t* actions, cudaStream_t);
 cudaError_t launch_live_steps(cs_flight*, cudaStream_t);
 cudaError_t launch_pack(cs_flight*, cudaStream_t);
+cudaError_t launch_pack_pool(cs_flight_host_pool*, cudaStream_t);
 
 // flight_host.cu
 cudaError_t flight_dispatch(cs_flight*, int mode, const uint8_t* actions, const uint8_t* mask, uint32_t rflags, cudaStream_t);

@@ -347,8 +347,9 @@ class _VecFlightBase:
     def host_buffers(self, compact=True):
         """Host-side results of step_host (allocated once).
 
-        compact=True (default): the library's compact host path -- per step the device sends 16 + 16n bytes per env
-        in one D2H copy and the library rebuilds the reference-shaped rows on the host (cs_flight_host_compact_begin);
+        compact=True (default): the library's compact host path -- per step the device sends 16 + 16n bytes per env (a
+        16-byte record, and the agent rows scattered in place by the copy engine) and the library keeps the
+        reference-shaped rows up to date on the host (cs_flight_host_compact_begin);
         the returned tensors are views of library-owned host arrays, updated in place by every step_host.
         compact=False: a pinned mirror of the whole device output slab, fetched with one D2H copy per step."""
         key = "_host_c" if compact else "_host"
@@ -357,25 +358,7 @@ class _VecFlightBase:
             if compact:
                 v = _lib.FlightHostViews()
                 _lib.check(self.lib.cs_flight_host_compact_begin(self._h.ptr, C.byref(v)), "cs_flight_host_compact_begin")
-                stride = int(v.state_stride)
-
-                def arr(ptr, ctype, count, dtype):
-                    a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(count,))
-                    t = torch.from_numpy(a.view(dtype))
-                    t._cs_owner = self._h
-                    return t
-                state = arr(v.state, C.c_float, E * stride, np.float32).view(E, stride)
-                self._host_c = {
-                    "actions": torch.empty((E, n), dtype=torch.uint8).pin_memory(),
-                    "reward": arr(v.reward, C.c_float, E, np.float32),
-                    "target_find": arr(v.target_find, C.c_int32, E, np.int32),
-                    "terminated": arr(v.terminated, C.c_uint8, E, np.uint8),
-                    "win": arr(v.win, C.c_uint8, E, np.uint8),
-                    "state": state[:, :self.state_shape],
-                    # get_obs rows are the agent part of the state rows (flight_env_easy.py:192-193)
-                    "obs": state[:, :4 * n].unflatten(1, (n, 4)),
-                    "d2h_bytes": int(v.d2h_bytes_per_step),
-                }
+                self._host_c = self._compact_views(v, torch.empty((E, n), dtype=torch.uint8).pin_memory(), self._h)
             else:
                 lay = (C.c_uint64 * 8)()
                 _lib.check(self.lib.cs_flight_slab_layout(self._h.ptr, lay), "cs_flight_slab_layout")
@@ -396,6 +379,28 @@ class _VecFlightBase:
                     "d2h_bytes": total,
                 }
         return getattr(self, key)
+
+    def _compact_views(self, v, actions, owner):
+        """Tensor views of the library-owned host arrays described by a cs_flight_host_views."""
+        E, n, stride = self.num_envs, self.n_agents, int(v.state_stride)
+
+        def arr(ptr, ctype, count, dtype):
+            a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(count,))
+            t = torch.from_numpy(a.view(dtype))
+            t._cs_owner = owner
+            return t
+        state = arr(v.state, C.c_float, E * stride, np.float32).view(E, stride)
+        return {
+            "actions": actions,
+            "reward": arr(v.reward, C.c_float, E, np.float32),
+            "target_find": arr(v.target_find, C.c_int32, E, np.int32),
+            "terminated": arr(v.terminated, C.c_uint8, E, np.uint8),
+            "win": arr(v.win, C.c_uint8, E, np.uint8),
+            "state": state[:, :self.state_shape],
+            # get_obs rows are the agent part of the state rows (flight_env_easy.py:192-193)
+            "obs": state[:, :4 * n].unflatten(1, (n, 4)),
+            "d2h_bytes": int(v.d2h_bytes_per_step),
+        }
 
     def step_host(self, actions, want_obs=True, want_state=True, sync=True, compact=True):
         """The call a CPU-side rollout makes: HOST actions in, HOST results out (numpy views of host buffers that the
@@ -503,19 +508,39 @@ class DeviceStepper:
             pass
 
 
+class _Pool:
+    """Owner of a cs_flight_host_pool: freed with the last reference (the stepper, or a view of the pooled arrays).  The
+    library detaches envs that are destroyed first."""
+
+    def __init__(self, lib, ptr):
+        self.lib, self.ptr = lib, ptr
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self.lib.cs_flight_host_pool_destroy(C.c_void_p(self.ptr))
+        except Exception:  # pragma: no cover
+            pass
+        self.ptr = None
+
+
 class HostStepper:
-    """Host-buffer steps of many independent env batches (rollout workers) with ONE library call per step: batch i runs
-    on stream i % len(streams); results land in each env's host_buffers(compact).  ``actions`` (optional, at
-    construction): pinned uint8 [E,n] tensors, one per env, that hold the actions of every step; by default each env's
-    own host_buffers()["actions"].
+    """Host-buffer steps of many independent env batches (rollout workers) with ONE library call per step; results land
+    in each env's host_buffers(compact).
 
-    compact=True (default): cs_flight_step_host_compact_many -- 16 + 16n bytes per env come back per step and the
-    reference-shaped rows are rebuilt on the host, batch by batch while later batches are still in flight.
+    compact=True (default), pooled (the default whenever the envs have no compact host buffers yet): the batches share
+    pooled buffers (cs_flight_host_pool_*): one H2D copy of all actions, one grouped step launch, one pack launch, one
+    flat D2H copy of the 16-byte records and one strided D2H copy that writes every agent row in place into the
+    reference-shaped host rows; host threads then update result arrays and find flags.  ``self.actions`` is the pinned
+    uint8 [sum E, n] action buffer of all batches (each env's host_buffers()["actions"] is its segment); step(actions=t)
+    takes the actions from another pinned tensor of that shape instead.
+    compact=True, not pooled: cs_flight_step_host_compact_many, batch i on stream i % len(streams).
     compact=False: cs_flight_step_host_many -- the whole output slab of every batch comes back.
-    graph=True captures the device side of the step (per batch: H2D copy of the pinned actions, step kernel(s), pack,
-    D2H copy) into one CUDA graph after a first eager step, so that a step costs one graph launch on the host."""
+    ``actions`` (optional, at construction; not pooled): pinned uint8 [E,n] tensors, one per env, that hold the actions
+    of every step.  graph=True captures the device side of the step into one CUDA graph after a first eager step, so
+    that a step costs one graph launch on the host."""
 
-    def __init__(self, envs, streams, actions=None, graph=False, compact=True):
+    def __init__(self, envs, streams, actions=None, graph=False, compact=True, pooled=None):
         self.envs = list(envs)
         self.lib = self.envs[0].lib
         self.device = self.envs[0].device
@@ -524,6 +549,13 @@ class HostStepper:
         n = len(self.envs)
         self._handles = (C.c_void_p * n)(*[e._h.ptr for e in self.envs])
         self._streams = (C.c_void_p * len(self.streams))(*[st.cuda_stream for st in self.streams])
+        self._pool = None
+        self.actions = None
+        can_pool = self.compact and actions is None and all(getattr(e, "_host_c", None) is None for e in self.envs)
+        if pooled and not can_pool:
+            raise CoopSearchError("HostStepper(pooled=True) needs compact=True, no per-env action tensors and envs without compact host buffers")
+        if can_pool and pooled is not False:
+            self._make_pool()
         self._ios = (_lib.FlightHostIO * n)()
         self._acts = (C.c_void_p * n)()
         self._keep = actions
@@ -535,10 +567,39 @@ class HostStepper:
                 self._ios[i].slab = hb["slab"].data_ptr()
         self._want_graph = bool(graph)
         self._graph = None
+        self._graph_actions = None
         self._cap = torch.cuda.Stream(device=self.device) if graph else None
 
-    def _call(self, flags):
+    def _make_pool(self):
+        hp = C.c_void_p()
+        with torch.cuda.device(self.device):
+            rc = self.lib.cs_flight_host_pool_create(self._handles, len(self.envs), C.byref(hp))
+        if rc != 0:
+            return                       # batches that do not pool keep their own buffers
+        self._pool = _Pool(self.lib, hp.value)
+        total = sum(e.num_envs for e in self.envs)
+        n_agents = self.envs[0].n_agents
+        first = None
+        for i, e in enumerate(self.envs):
+            v, ap = _lib.FlightHostViews(), C.c_void_p()
+            _lib.check(self.lib.cs_flight_host_pool_views(hp, i, C.byref(v), C.byref(ap)), "cs_flight_host_pool_views")
+            if i == 0:
+                first = ap.value
+            a = np.ctypeslib.as_array(C.cast(ap, C.POINTER(C.c_uint8)), shape=(e.num_envs * n_agents,))
+            act = torch.from_numpy(a).view(e.num_envs, n_agents)
+            act._cs_owner = self._pool
+            e._host_c = e._compact_views(v, act, self._pool)
+        a = np.ctypeslib.as_array(C.cast(C.c_void_p(first), C.POINTER(C.c_uint8)), shape=(total * n_agents,))
+        self.actions = torch.from_numpy(a).view(total, n_agents)
+        self.actions._cs_owner = self._pool
+
+    def _call(self, flags, actions=None):
         n = len(self.envs)
+        if self._pool is not None:
+            ptr = C.c_void_p(actions.data_ptr()) if actions is not None else None
+            st = torch.cuda.current_stream(self.device).cuda_stream if self._want_graph else self.streams[0].cuda_stream
+            _lib.check(self.lib.cs_flight_host_pool_step(C.c_void_p(self._pool.ptr), ptr, flags, C.c_void_p(st)), "cs_flight_host_pool_step")
+            return
         if self.compact:
             _lib.check(self.lib.cs_flight_step_host_compact_many(self._handles, self._acts, n, self._streams, len(self.streams), flags),
                        "cs_flight_step_host_compact_many")
@@ -549,28 +610,42 @@ class HostStepper:
                    "cs_flight_step_host_many")
 
     def _expand(self, sync):
-        if self.compact:
+        if self._pool is not None:
+            st = self._cap.cuda_stream if self._want_graph else self.streams[0].cuda_stream
+            _lib.check(self.lib.cs_flight_host_pool_expand(C.c_void_p(self._pool.ptr), C.c_void_p(st), 1 if sync else 0), "cs_flight_host_pool_expand")
+        elif self.compact:
             _lib.check(self.lib.cs_flight_host_expand_many(self._handles, len(self.envs), self._streams, len(self.streams), 1 if sync else 0),
                        "cs_flight_host_expand_many")
 
-    def step(self):
-        """One env-step of every batch; returns when all results are in host memory."""
+    def step(self, actions=None):
+        """One env-step of every batch; returns when all results are in host memory.  actions (pooled only): a pinned
+        uint8 [sum E, n] tensor to take this step's actions from instead of ``self.actions``."""
+        if actions is not None and self._pool is None:
+            raise CoopSearchError("HostStepper.step(actions=...) needs the pooled form")
         if not self._want_graph:
-            self._call(0)
+            with torch.cuda.device(self.device):
+                self._call(0, actions)
             return
-        if self._graph is None:
-            self._call(0)                        # eager first step (warm-up outside the capture)
+        key = None if actions is None else actions.data_ptr()
+        if self._graph is None or key not in self._graph:
+            if self._graph is None:
+                self._graph = {}
+                self._cap.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(self._cap):
+                    self._call(0, actions)               # eager first step (warm-up outside the capture)
+                return
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=self._cap):
                 for st in self.streams:
                     st.wait_stream(self._cap)
-                self._call(_lib.CS_HOST_NO_SYNC)
+                self._call(_lib.CS_HOST_NO_SYNC, actions)
                 for st in self.streams:
                     self._cap.wait_stream(st)
-            self._graph = g                      # (capturing records the launches, it does not run them)
-            return
+            self._graph[key] = g                 # (capturing records the launches, it does not run them; one graph per action buffer)
+            self._keep_actions = getattr(self, "_keep_actions", []) + [actions]
+        self._cap.wait_stream(torch.cuda.current_stream(self.device))       # e.g. a reset issued on the caller's stream
         with torch.cuda.stream(self._cap):
-            self._graph.replay()
+            self._graph[key].replay()
         self._cap.synchronize()
         self._expand(sync=False)
 

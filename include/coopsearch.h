@@ -216,11 +216,12 @@ int cs_flight_step_host(cs_flight* env, const cs_flight_host_io* io, void* strea
  * streams[i % n_streams]; all streams are synchronised once at the end unless every io carries CS_HOST_NO_SYNC. */
 int cs_flight_step_host_many(cs_flight* const* envs, const cs_flight_host_io* ios, int32_t count, void* const* streams,
                              int32_t n_streams);
-/* Compact host-buffer step (the fast form of cs_flight_step_host).  Per step and env the device sends 16 + 16n bytes
- * (reward, found mask, target_find, terminated, win and the n agent rows) plus one small entry per env that was reset
- * inside the call, in ONE D2H copy; the library rebuilds the reference-shaped rows on the host with a few threads
- * (CS_HOST_THREADS) into arrays it owns: the agent part of a state row (= get_obs, flight_env_easy.py:192-193,218-221)
- * is overwritten, find flags flip where the found mask changed, target coordinates are rewritten only after a reset.
+/* Compact host-buffer step (the fast form of cs_flight_step_host).  Per step and env the device sends 16 + 16n bytes:
+ * a 16-byte record (reward, found mask, target_find, terminated, win, reset flag; one flat D2H copy, plus one small entry
+ * per env that was reset inside the call) and the n agent rows, which the copy engine writes IN PLACE into the agent
+ * part of the library's reference-shaped host rows (= get_obs, flight_env_easy.py:192-193,218-221) with one strided D2H
+ * copy.  A few host threads (CS_HOST_THREADS) spread the records over the result arrays, flip the find flags whose bit
+ * changed and rewrite target coordinates after a reset.  `state` is pinned host memory.
  * The views stay valid (and are updated in place) until the handle is destroyed. */
 typedef struct cs_flight_host_views {
     float* reward;          /* [E]                   step()[0]                                        */
@@ -241,6 +242,23 @@ int cs_flight_host_expand(cs_flight* env, void* stream, int32_t sync);
 int cs_flight_step_host_compact_many(cs_flight* const* envs, const uint8_t* const* h_actions, int32_t count, void* const* streams,
                                      int32_t n_streams, uint32_t flags);
 int cs_flight_host_expand_many(cs_flight* const* envs, int32_t count, void* const* streams, int32_t n_streams, int32_t sync);
+/* Pooled form of the compact host-buffer step for many env batches (rollout workers) of one GPU: the batches' host rows,
+ * records, agent rows and actions are segments of single allocations, so that ONE call steps every batch with one H2D copy
+ * of all actions, one grouped step launch (cs_flight_group_step; per-batch launches when the handles do not group), one
+ * pack launch and two D2H copies -- a flat copy of the dense result arrays (reward, target_find, terminated, win, found
+ * masks: 14 bytes per env; the host views of the first four ARE that pinned block) and the strided copy that writes all
+ * agent rows in place.  Host work per step: the find flags whose bit changed and the rows of envs that were reset.  Batches must agree in n_agents, target_num, auto_reset and device and must not have compact host buffers yet;
+ * afterwards cs_flight_host_compact_begin(env) returns the env's segment of the pooled arrays.  Destroy the pool before
+ * its envs. */
+typedef struct cs_flight_host_pool cs_flight_host_pool;
+int cs_flight_host_pool_create(cs_flight* const* envs, int32_t count, cs_flight_host_pool** out);
+void cs_flight_host_pool_destroy(cs_flight_host_pool* pool);
+/* batch i's views (as cs_flight_host_compact_begin) and its segment of the pool's pinned action buffer [E_i][n] */
+int cs_flight_host_pool_views(cs_flight_host_pool* pool, int32_t i, cs_flight_host_views* out, uint8_t** h_actions);
+/* h_actions: HOST u8 [sum of num_envs][n], batch after batch (pinned for full speed), or NULL = the pool's own buffer.
+ * flags: CS_HOST_NO_SYNC = enqueue only; then cs_flight_host_pool_expand (sync = 1 waits for `stream` first). */
+int cs_flight_host_pool_step(cs_flight_host_pool* pool, const uint8_t* h_actions, uint32_t flags, void* stream);
+int cs_flight_host_pool_expand(cs_flight_host_pool* pool, void* stream, int32_t sync);
 /* out8 = { slab bytes, offsets of reward, target_find, terminated, win, obs (unused: = slab bytes), state, state row
  * pitch in bytes }.  The slab does not carry obs separately: obs[e][a][0..3] = state row e, floats 4a..4a+3. */
 int cs_flight_slab_layout(const cs_flight* env, uint64_t* out8);

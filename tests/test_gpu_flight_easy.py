@@ -331,6 +331,51 @@ def test_host_stepper_many_batches_one_call(graph, compact):
             assert np.array_equal(cpu(ref[b].get_obs()), hb["obs"].numpy())
 
 
+@pytest.mark.parametrize("variant,graph,sizes,lpe", [("easy", False, [200, 200, 200], 0), ("easy", True, [700, 64, 4096], 1),
+                                                      ("easy", True, [256, 256], 4), ("probmap", False, [96, 160], 0), ("probmap", True, [64, 64, 64], 0)])
+def test_pooled_host_stepper_equals_device_steps(variant, graph, sizes, lpe):
+    """cs_flight_host_pool_*: all batches stepped from ONE pinned action buffer with one H2D copy, one (grouped) step, one
+    pack launch, the flat record copy and the strided copy that writes the agent rows in place -- host rows, rewards and
+    flags equal the same batches stepped on the device, through auto-resets, a manual reset in between, an external action
+    buffer, and (flight variant) the per-batch launch fallback."""
+    import coopsearch_b200 as cs
+    spec = FlightSpec(n_agents=3, time_limit=25, variant=variant)
+    args = make_args(dict(spec.__dict__))
+    cls = cs.VecFlightEasyEnv if variant == "easy" else cs.VecFlightEnv
+    mk = lambda: [cls(args, TEMPLATE, num_envs=E, seed=6, env_id_base=10000 * b, auto_reset=True, lanes_per_env=lpe) for b, E in enumerate(sizes)]
+    ref, envs = mk(), mk()
+    streams = [torch.cuda.Stream() for _ in range(2)]
+    torch.cuda.synchronize()
+    stepper = cs.HostStepper(envs, streams, graph=graph, compact=True)
+    assert stepper._pool is not None and stepper.actions.shape == (sum(sizes), 3)
+    other = torch.empty_like(stepper.actions).pin_memory()
+    first = np.concatenate([[0], np.cumsum(sizes)])
+    rng = np.random.default_rng(1)
+    for t in range(80):
+        buf = other if t % 3 == 2 else stepper.actions
+        buf.numpy()[...] = rng.integers(0, 3, size=buf.shape, dtype=np.uint8)
+        if t == 40:                                    # a reset from outside: the host rows are refreshed in full
+            for e, r in zip(envs, ref):
+                e.reset(); r.reset()
+        stepper.step(actions=other) if t % 3 == 2 else stepper.step()
+        for b in range(len(sizes)):
+            act = buf[first[b]:first[b + 1]]
+            if t % 3 != 2:
+                assert np.array_equal(envs[b].host_buffers()["actions"].numpy(), act.numpy())      # each env's segment of the pooled buffer
+            r, term, win = ref[b].step(act.cuda())
+            hb = envs[b].host_buffers()
+            where = "batch %d step %d" % (b, t)
+            assert np.array_equal(cpu(r), hb["reward"].numpy()) and np.array_equal(cpu(term), hb["terminated"].numpy()), where
+            assert np.array_equal(cpu(win), hb["win"].numpy()) and np.array_equal(cpu(ref[b].target_find), hb["target_find"].numpy()), where
+            assert np.array_equal(cpu(ref[b].get_state()), hb["state"].numpy()), where
+            assert np.array_equal(cpu(ref[b].get_obs(full=False) if variant != "easy" else ref[b].get_obs()), hb["obs"].numpy()), where
+    if variant != "easy":
+        assert torch.equal(ref[0].prob_map, envs[0].prob_map)
+    with pytest.raises(cs.CoopSearchError):
+        envs[0].step_host(np.zeros((sizes[0], 3), np.uint8))          # a pooled env is stepped through its pool
+    del stepper, envs                                                  # pool and envs go away in either order
+
+
 @pytest.mark.parametrize("lpe,sizes", [(1, [700, 4096, 33]), (1, [700, 4096, 34, 2, 128]), (-1, [700, 4096, 34, 2, 128]), (4, [256, 256, 256, 1000]), (0, [512, 512])])
 def test_grouped_device_step_equals_separate_steps(monkeypatch, lpe, sizes):
     """cs_flight_group_step: env batches of different sizes stepped in ONE launch end up bit-identical to the same
