@@ -5,7 +5,9 @@
 //   GRU   [128 x 64] x W_ih^T and [128 x 64] x W_hh^T   -> gates r | z | n    -> h'     (network/base_net.py:43, torch GRUCell)
 //   fc2.0 [128 x 64] x [64 -> 64]                       -> +b, ReLU           -> f
 //   fc2.2 [128 x 64] x [64 -> A (padded to 16)]         -> +b                 -> q
-// One CTA of 128 threads owns a tile; thread t owns row t.  Operands are bf16 in shared memory in the canonical
+// One CTA of 256 threads owns a tile; threads t and t + 128 share row t -- each takes half of the columns of every
+// epilogue (a warp reads the TMEM lanes 32 * (warp % 4) ..., so warps w and w + 4 see the same rows), which halves the
+// dependent chain per tile and doubles the warps per SM that cover it (measured: 2.4e9 -> see DESIGN.md rows/s).  Operands are bf16 in shared memory in the canonical
 // K-major, no-swizzle UMMA layout -- 16-byte chunks of 8 consecutive k, element (row, k) at
 // chunk(k/8) * LBO + row * 16 + (k % 8) * 2 -- so that a thread writes its row's next operand with plain 16-byte
 // stores; the weights (torch's (out, in) layout is already K-major) are packed into the same form by the host and
@@ -20,7 +22,7 @@
 
 namespace cspol {
 
-constexpr int kTcThreads = 128;
+constexpr int kTcThreads = 256;                    // two threads per row
 constexpr int kTcRows = 128;                       // rows per tile = UMMA M
 constexpr int kTcK1 = 32;                          // fc1 input width, padded
 constexpr int kTcNq = 16;                          // action-value width, padded (UMMA N is a multiple of 16)
@@ -119,6 +121,7 @@ template <class P>
 __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const __grid_constant__ P p) {
     extern __shared__ __align__(128) unsigned char sm[];
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int row = tid & (kTcRows - 1), half = tid >> 7;             // this thread's row of the tile and its half of the columns
     const uint32_t sbase = tc_smem_u32(sm);
     const uint32_t bar = sbase + kOffBar;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + kOffBar + 8);
@@ -143,15 +146,15 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const __grid_c
     tc_operands_ready();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);       // this warp's 32 TMEM lanes
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);  // this warp's 32 TMEM lanes
     uint32_t phase = 0;
 
-    unsigned char* myA0 = sm + kOffA0 + tid * 16;
-    unsigned char* myAX = sm + kOffAX + tid * 16;
-    unsigned char* myAH = sm + kOffAH + tid * 16;
+    unsigned char* myA0 = sm + kOffA0 + row * 16;
+    unsigned char* myAX = sm + kOffAX + row * 16;
+    unsigned char* myAH = sm + kOffAH + row * 16;
 
     for (int tile = blockIdx.x; tile * kTcRows < p.rows; tile += gridDim.x) {
-        const int r_raw = tile * kTcRows + tid;
+        const int r_raw = tile * kTcRows + row;
         const bool live = r_raw < p.rows;
         const int r = live ? r_raw : p.rows - 1;
         // ---- inputs: [conv features of the env's map ||] obs || last-action one-hot || agent-id one-hot
@@ -159,24 +162,26 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const __grid_c
         {
             const int la = (p.use_last && p.last_action) ? (int)p.last_action[r] : 255;
 #pragma unroll
-            for (int c = 0; c < kTcK1 / 8; ++c) {
+            for (int cc = 0; cc < kTcK1 / 16; ++cc) {
+                const int c = (kTcK1 / 16) * half + cc;
                 float x[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) x[i] = policy_input(p, r, la, 8 * c + i);
                 *reinterpret_cast<uint4*>(myA0 + c * kALbo) = tc_pack8(x);
             }
         }
-        // the row's hidden state: read once (fp32, 16 loads in flight), kept in registers for the GRU blend, bf16 copy -> A operand
-        float hreg[64];
+        // this thread's half of the row's hidden state (units 32 * half ...): read once (fp32, 8 loads in flight), kept in
+        // registers for the GRU blend, bf16 copy -> A operand
+        float hreg[32];
         {
-            const float4* hp = reinterpret_cast<const float4*>(p.hidden + (size_t)r * 64);
+            const float4* hp = reinterpret_cast<const float4*>(p.hidden + (size_t)r * 64 + 32 * half);
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
+            for (int c = 0; c < 8; ++c) {
                 const float4 h4 = hp[c];
                 hreg[4 * c] = h4.x; hreg[4 * c + 1] = h4.y; hreg[4 * c + 2] = h4.z; hreg[4 * c + 3] = h4.w;
             }
 #pragma unroll
-            for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(myAH + c * kALbo) = tc_pack8(hreg + 8 * c);
+            for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(myAH + (4 * half + c) * kALbo) = tc_pack8(hreg + 8 * c);
         }
         tc_operands_ready();
         // ---- fc1
@@ -186,8 +191,8 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const __grid_c
             tc_commit(bar);
         }
         tc_wait(bar, phase); phase ^= 1u;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        {
+            const int c = half;                                        // 32 of the 64 columns each
             float v[32];
             tc_ld16_issue(trow + 32 * c, v);
             tc_ld16_issue(trow + 32 * c + 16, v + 16);
@@ -210,9 +215,10 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const __grid_c
         }
         tc_wait(bar, phase); phase ^= 1u;
         {
-            float4* ho = reinterpret_cast<float4*>(p.hidden + (size_t)r * 64);
+            float4* ho = reinterpret_cast<float4*>(p.hidden + (size_t)r * 64 + 32 * half);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
+            for (int cc = 0; cc < 4; ++cc) {
+                const int c = 4 * half + cc;                           // hidden units 8c .. 8c+7
                 float gr[8], gz[8], gi[8], gh[8];
                 tc_ld8_issue(trow + 8 * c, gr);
                 tc_ld8_issue(trow + 64 + 8 * c, gz);
@@ -222,17 +228,17 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const __grid_c
                 tc_ld_tie8(gr); tc_ld_tie8(gz); tc_ld_tie8(gi); tc_ld_tie8(gh);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const int j = 8 * c + i;
+                    const int j = 8 * c + i, jl = 8 * cc + i;
                     const float rg = tc_sigmoid(gr[i] + b_rz[j]);
                     const float zg = tc_sigmoid(gz[i] + b_rz[64 + j]);
                     const float ng = tc_tanh(gi[i] + b_in[j] + rg * (gh[i] + b_hn[j]));
-                    hreg[j] = (1.f - zg) * ng + zg * hreg[j];
+                    hreg[jl] = (1.f - zg) * ng + zg * hreg[jl];
                 }
                 if (live) {
-                    ho[2 * c] = make_float4(hreg[8 * c], hreg[8 * c + 1], hreg[8 * c + 2], hreg[8 * c + 3]);
-                    ho[2 * c + 1] = make_float4(hreg[8 * c + 4], hreg[8 * c + 5], hreg[8 * c + 6], hreg[8 * c + 7]);
+                    ho[2 * cc] = make_float4(hreg[8 * cc], hreg[8 * cc + 1], hreg[8 * cc + 2], hreg[8 * cc + 3]);
+                    ho[2 * cc + 1] = make_float4(hreg[8 * cc + 4], hreg[8 * cc + 5], hreg[8 * cc + 6], hreg[8 * cc + 7]);
                 }
-                *reinterpret_cast<uint4*>(myAH + c * kALbo) = tc_pack8(hreg + 8 * c);
+                *reinterpret_cast<uint4*>(myAH + c * kALbo) = tc_pack8(hreg + 8 * cc);
             }
         }
         tc_operands_ready();
@@ -243,8 +249,8 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const __grid_c
             tc_commit(bar);
         }
         tc_wait(bar, phase); phase ^= 1u;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        {
+            const int c = half;                                        // 32 of the 64 columns each
             float v[32];
             tc_ld16_issue(trow + 32 * c, v);
             tc_ld16_issue(trow + 32 * c + 16, v + 16);
@@ -263,7 +269,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const __grid_c
             tc_commit(bar);
         }
         tc_wait(bar, phase); phase ^= 1u;
-        {
+        if (half == 0) {                                               // (warp-uniform: warps 0..3)
             float qv[8];
             tc_ld8_issue(trow + 64, qv);
             tc_ld_wait();

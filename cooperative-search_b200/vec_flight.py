@@ -202,7 +202,12 @@ class _VecFlightBase:
         if torch.is_tensor(actions):
             a = actions.to(device=self.device, dtype=torch.uint8)
         else:
-            a = torch.as_tensor(np.asarray(actions, dtype=np.uint8), device=self.device)
+            h = np.asarray(actions)
+            if h.size and (h.min() < 0 or h.max() >= self.n_actions):
+                # the reference indexes dyaw[act] (flight_env_easy.py:259-262): IndexError.  Host actions are checked here;
+                # device tensors are not (that would cost a synchronisation): the kernels treat a byte > 2 as "no turn"
+                raise IndexError('list index out of range')
+            a = torch.as_tensor(h.astype(np.uint8), device=self.device)
         if a.dim() == 1 and self.num_envs == 1:
             a = a.unsqueeze(0)
         if a.dim() != 2 or a.shape[0] != self.num_envs or a.shape[1] != self.n_agents:

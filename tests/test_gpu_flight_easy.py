@@ -415,6 +415,8 @@ def test_reference_error_behaviour():
         env.step(np.zeros((4, 2), np.uint8))
     with pytest.raises(Exception, match="Agent id out of range"):
         env.get_avail_agent_actions(3)
+    with pytest.raises(IndexError):                                   # dyaw[act] with act = 3 (flight_env_easy.py:259-262)
+        env.step(np.full((4, 3), 3))
     assert env.get_avail_agent_actions(2).shape == (4, 3) and bool((env.get_avail_actions() == 1).all())
     bad = make_args(dict(spec.__dict__)); bad.agent_mode = 7
     with pytest.raises(Exception, match="No such agent mode"):
