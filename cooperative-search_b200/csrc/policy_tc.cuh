@@ -182,6 +182,12 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const __grid_c
             }
 #pragma unroll
             for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(myAH + (4 * half + c) * kALbo) = tc_pack8(hreg + 8 * c);
+            // the same half row of this CTA's NEXT tile: pull it into L2 now (the loads above are the longest stall of a tile)
+            const long long rn = (long long)(tile + (int)gridDim.x) * kTcRows + row;
+            if (rn < p.rows) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.hidden + (size_t)rn * 64 + 32 * half));
+                if (half == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.obs + (size_t)rn * p.obs_dim));
+            }
         }
         tc_operands_ready();
         // ---- fc1

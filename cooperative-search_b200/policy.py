@@ -1,4 +1,4 @@
-"""Batched agents: the reference's RNN agent network (network/base_net.py:5-47, without the conv front end) and the
+"""Batched agents: the reference's RNN agent network (network/base_net.py:5-47, with the optional conv front end of the flight agents) and the
 action choice of Agents.choose_action (agent/agent.py:33-97) for every (env, agent) row of a vectorised env at once,
 in one kernel launch (csrc/policy.cu, csrc/policy_tc.cuh).  The reference evaluates one (1, in) row per agent per step.
 
