@@ -417,7 +417,7 @@ int cs_flight_host_pool_create(cs_flight* const* envs, int32_t count, cs_flight_
     if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&pl->h_rec), pl->rec_block_bytes, cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaMalloc(&pl->d_agent, T * 16 * n);
     if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&pl->h_state), T * p0.state_stride * sizeof(float), cudaHostAllocDefault);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_rec, cudaEventDisableTiming | cudaEventBlockingSync);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_rec, cudaEventDisableTiming);
     pl->shadow_found = (uint32_t*)calloc(T, sizeof(uint32_t));
     bool ok = e == cudaSuccess && pl->shadow_found;
     if (ok) {
