@@ -114,6 +114,36 @@ struct GlobalView {
             if (kk == K - 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(tb + m * 16 - 1));
         }
     }
+    __device__ __forceinline__ void targets_ready() const {}
+};
+
+// Structure-of-arrays state with the env's 2m target rows STAGED in shared memory: every thread copies its own column
+// with 8-byte cp.async (LDGSTS) at kernel entry -- all 2m loads of a warp in flight at once, no registers held, one HBM
+// round trip that overlaps the state loads and the agent phase -- and reads it back before the sensing loop.  (The L1
+// prefetch of GlobalView does not do that job: with and without it the kernel takes the same time, and the sensing loop
+// pays a round trip per block of targets.)
+template <int TE>
+struct StagedView : GlobalView<true> {
+    struct Ctx { double* col; };                 // this thread's column of the CTA's staging area: row r at col[r * TE]
+    double* col;
+    __device__ __forceinline__ StagedView(const FlightParams& p_, const GroupEntry& g_, int e_, Ctx c) : GlobalView<true>(p_, g_, e_, GlobalView<true>::Ctx{}), col(c.col) {}
+    __device__ __forceinline__ double2 tgt_ld(int j) const { return make_double2(col[(2 * j) * TE], col[(2 * j + 1) * TE]); }
+    __device__ __forceinline__ void tgt_publish(int j, int es, int src, double2 v) const {
+        double* t = this->g.tgt + (size_t)(2 * j) * this->g.E + es;
+        t[0] = v.x; t[this->g.E] = v.y;
+        double* w = col - (int)(threadIdx.x & 31) + src + (2 * j) * TE;                // the owner reads it back from its column
+        w[0] = v.x; w[TE] = v.y;
+    }
+    template <int K>
+    __device__ __forceinline__ void prefetch_targets(int) const {
+        const double* tp = this->g.tgt + this->e;
+        const size_t E = (size_t)this->g.E;
+        uint32_t d = smem_u32(col);
+        for (int r = 0; r < 2 * this->p.m; ++r, d += TE * 8, tp += E)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(tp) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    __device__ __forceinline__ void targets_ready() const { asm volatile("cp.async.wait_all;" ::: "memory"); }
 };
 
 template <int N, int TE>
@@ -148,6 +178,7 @@ struct TileView {
     }
     template <int K>
     __device__ __forceinline__ void prefetch_targets(int) const {}
+    __device__ __forceinline__ void targets_ready() const {}
 };
 
 __device__ __forceinline__ GroupEntry entry_of(const FlightParams& p) {
@@ -282,6 +313,7 @@ __device__ __forceinline__ int flight_tpe_body(const FlightParams& p, const Grou
         }
     }
 
+    L.targets_ready();                                  // (staged targets: every lane's own column has landed)
     for (int pass = 0; pass < 2; ++pass) {
         if (pass == 1) {
             const bool do_reset = active && ((MODE == MODE_RESET) ? (mask == nullptr || mask[e] != 0) : (p.auto_reset && done));
@@ -491,10 +523,18 @@ __global__ void __launch_bounds__(kTpeThreads, CS_TPE_MIN_CTAS) flight_tpe_kerne
                                                                  const uint8_t* __restrict__ mask, uint32_t rflags) {
     __shared__ longlong2 lutm[40];
     if (MODE == MODE_STEP) stage_lut_meta(p, lutm);
-    using V = GlobalView<K == 1>;                                       // one thread per env <-> structure of arrays (cs_flight_create)
     const GroupEntry g = entry_of(p);
     const int t0 = (int)blockIdx.x * kTpeThreads + (int)threadIdx.x;
     const int e_raw = t0 / K, t_first = t0 & ~31;
+    if (K == 1 && MODE == MODE_STEP && !MAP) {                          // one thread per env: targets staged in shared memory
+        extern __shared__ __align__(16) double tstage[];
+        using S = StagedView<kTpeThreads>;
+        typename S::Ctx ctx;
+        ctx.col = tstage + threadIdx.x;
+        flight_tpe_body<N, K, MODE, false, false, S>(p, g, ctx, lutm, e_raw, t_first, actions, 0u, mask, rflags, nullptr);
+        return;
+    }
+    using V = GlobalView<K == 1>;                                       // one thread per env <-> structure of arrays (cs_flight_create)
     if (!MAP) {
         flight_tpe_body<N, K, MODE, false, false, V>(p, g, typename V::Ctx{}, lutm, e_raw, t_first, actions, 0u, mask, rflags, nullptr);
         return;
@@ -549,8 +589,16 @@ __global__ void __launch_bounds__(kTpeThreads, CS_TPE_MIN_CTAS) flight_tpe_group
     const GroupEntry& g = tab.h[blockIdx.y];
     if ((long long)blockIdx.x * kTpeThreads >= (long long)g.E * K) return;          // handles may differ in num_envs
     stage_lut_meta(common, lutm);
-    using V = GlobalView<K == 1>;
     const int t0 = (int)blockIdx.x * kTpeThreads + (int)threadIdx.x;
+    if (K == 1) {
+        extern __shared__ __align__(16) double tstage[];
+        using S = StagedView<kTpeThreads>;
+        typename S::Ctx ctx;
+        ctx.col = tstage + threadIdx.x;
+        flight_tpe_body<N, K, MODE_STEP, false, false, S>(common, g, ctx, lutm, t0, t0 & ~31, acts.a[blockIdx.y], 0u, nullptr, 0u, nullptr);
+        return;
+    }
+    using V = GlobalView<false>;
     flight_tpe_body<N, K, MODE_STEP, false, false, V>(common, g, typename V::Ctx{}, lutm, t0 / K, t0 & ~31, acts.a[blockIdx.y], 0u, nullptr, 0u, nullptr);
 }
 
@@ -763,6 +811,9 @@ inline bool stream_enabled() {
     return v && atoi(v) == 1;
 }
 
+// shared-memory staging area of the targets in the one-thread-per-env step kernels: 2m rows of kTpeThreads doubles
+inline size_t tstage_bytes(int m) { return (size_t)2 * m * kTpeThreads * sizeof(double); }
+
 template <int N, int K>
 cudaError_t launch_tpe_k(cs_flight* h, int mode, const uint8_t* actions, const uint8_t* mask, uint32_t rflags, cudaStream_t st) {
     if (K == 1 && mode == MODE_STEP && !h->p.variant && h->p.E % 2 == 0 && stream_enabled()) {
@@ -785,7 +836,7 @@ cudaError_t launch_tpe_k(cs_flight* h, int mode, const uint8_t* actions, const u
             flight_tpe_kernel<N, K, MODE_RESET, true><<<grid, kTpeThreads, 0, st>>>(h->p, actions, mask, rflags);
     } else {
         if (mode == MODE_STEP)
-            flight_tpe_kernel<N, K, MODE_STEP, false><<<grid, kTpeThreads, 0, st>>>(h->p, actions, mask, rflags);
+            flight_tpe_kernel<N, K, MODE_STEP, false><<<grid, kTpeThreads, K == 1 ? tstage_bytes(h->p.m) : 0, st>>>(h->p, actions, mask, rflags);
         else
             flight_tpe_kernel<N, K, MODE_RESET, false><<<grid, kTpeThreads, 0, st>>>(h->p, actions, mask, rflags);
     }
@@ -823,7 +874,7 @@ cudaError_t launch_group_n(const cs_flight_group* g, const GroupActions& acts, c
                                            reinterpret_cast<const GroupActionsT<kMaxGroup>&>(acts), g->count, g->max_E, st);
     }
     const dim3 grid((unsigned)g->grid_x, (unsigned)g->count);
-    if (g->k == 1) flight_tpe_group_kernel<N, 1><<<grid, kTpeThreads, 0, st>>>(g->envs[0]->p, g->table, acts);
+    if (g->k == 1) flight_tpe_group_kernel<N, 1><<<grid, kTpeThreads, tstage_bytes(g->envs[0]->p.m), st>>>(g->envs[0]->p, g->table, acts);
     else flight_tpe_group_kernel<N, 4><<<grid, kTpeThreads, 0, st>>>(g->envs[0]->p, g->table, acts);
     cs_count_launch(1);
     return cudaGetLastError();
