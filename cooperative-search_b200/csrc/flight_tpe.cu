@@ -35,6 +35,11 @@ namespace {
 #ifndef CS_TPE_MIN_CTAS
 #define CS_TPE_MIN_CTAS 8      // resident CTAs per SM the thread-per-env kernel is compiled for (register budget 65536/(64*N))
 #endif
+// One thread per env with the targets staged in shared memory (StagedView): up to three agents fit 10 CTAs per SM (102
+// registers) without spills when the sensing loop takes one target at a time -- measured on B200 (tools/sweep_stream.sh):
+// 1M envs 5.5e9 -> 6.2e9 env-steps/s, the grouped c2 launch 4.79e9 -> 4.83e9; with five agents the same setting spills
+// (65536 envs: 3.15e9 -> 2.78e9), so larger teams keep 8 CTAs and blocks of CS_TPE_TU targets.
+constexpr int tpe_min_ctas(int N, int K, int mode) { return (K == 1 && mode == 0 && N <= 3) ? 10 : CS_TPE_MIN_CTAS; }
 
 // Where a thread finds its env's state.  GlobalView: straight from HBM, layout known at compile time (structure of arrays with
 // one thread per env, record per env otherwise).  TileView (flight_stream_kernel): the loads come from the shared-memory tile
@@ -55,7 +60,7 @@ __device__ __forceinline__ void st_s(uint2* q, uint2 v) { *q = v; }
 
 template <bool SOA>
 struct GlobalView {
-    static constexpr bool kTile = false;
+    static constexpr bool kTile = false, kStaged = false;
     struct Ctx {};
     const FlightParams& p; const GroupEntry& g; int e;
     __device__ __forceinline__ GlobalView(const FlightParams& p_, const GroupEntry& g_, int e_, Ctx) : p(p_), g(g_), e(e_) {}
@@ -124,6 +129,7 @@ struct GlobalView {
 // pays a round trip per block of targets.)
 template <int TE>
 struct StagedView : GlobalView<true> {
+    static constexpr bool kStaged = true;
     struct Ctx { double* col; };                 // this thread's column of the CTA's staging area: row r at col[r * TE]
     double* col;
     __device__ __forceinline__ StagedView(const FlightParams& p_, const GroupEntry& g_, int e_, Ctx c) : GlobalView<true>(p_, g_, e_, GlobalView<true>::Ctx{}), col(c.col) {}
@@ -148,7 +154,7 @@ struct StagedView : GlobalView<true> {
 
 template <int N, int TE>
 struct TileView {
-    static constexpr bool kTile = true;
+    static constexpr bool kTile = true, kStaged = false;
     struct Ctx { double* mine; };                 // this thread's column of the tile
     const FlightParams& p; const GroupEntry& g; int e; double* mine;
     static constexpr int kMetaRow = 3 * N, kTgtRow = 3 * N + 4;
@@ -370,7 +376,7 @@ __device__ __forceinline__ int flight_tpe_body(const FlightParams& p, const Grou
         if (do_sense) {
             // the env's K threads share the targets; TU of a thread's targets are loaded together so that their
             // latency is paid once per block, not once per target
-            constexpr int TU = (K >= 8) ? 2 : CS_TPE_TU;
+            constexpr int TU = (K >= 8) ? 2 : ((V::kStaged && N <= 3) ? 1 : CS_TPE_TU);
             for (int j0 = kk; j0 < m; j0 += K * TU) {
                 double2 t[TU];
 #pragma unroll
@@ -519,7 +525,7 @@ __device__ __forceinline__ int flight_tpe_body(const FlightParams& p, const Grou
 }
 
 template <int N, int K, int MODE, bool MAP>
-__global__ void __launch_bounds__(kTpeThreads, CS_TPE_MIN_CTAS) flight_tpe_kernel(const __grid_constant__ FlightParams p, const uint8_t* __restrict__ actions,
+__global__ void __launch_bounds__(kTpeThreads, tpe_min_ctas(N, K, MAP ? 1 : MODE)) flight_tpe_kernel(const __grid_constant__ FlightParams p, const uint8_t* __restrict__ actions,
                                                                  const uint8_t* __restrict__ mask, uint32_t rflags) {
     __shared__ longlong2 lutm[40];
     if (MODE == MODE_STEP) stage_lut_meta(p, lutm);
@@ -582,7 +588,7 @@ __global__ void __launch_bounds__(kFusedThreads, CS_FUSED_MIN_CTAS) flight_fused
 // arrives through the kernel parameter space (constant bank): the configuration the group's handles share (`common`), what
 // differs per handle (GroupTable: sizes, global ids, buffers) and the action pointers.  flight_easy variant only.
 template <int N, int K>
-__global__ void __launch_bounds__(kTpeThreads, CS_TPE_MIN_CTAS) flight_tpe_group_kernel(const __grid_constant__ FlightParams common,
+__global__ void __launch_bounds__(kTpeThreads, tpe_min_ctas(N, K, 0)) flight_tpe_group_kernel(const __grid_constant__ FlightParams common,
                                                                                        const __grid_constant__ GroupTable tab,
                                                                                        const __grid_constant__ GroupActions acts) {
     __shared__ longlong2 lutm[40];
