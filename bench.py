@@ -595,6 +595,64 @@ def measure_obs_full(cs, torch, device, peak):
     return out
 
 
+def measure_spread(cs, torch, device, peak, E=1048576, n=3, m=3, K=20):
+    """simple_spread (env/simple_spread.py): env-steps/s of the batched step on E envs, K steps per CUDA
+    graph replayed until >= 60 ms, auto-reset, pre-generated device actions; and the unmodified reference class on one core."""
+    from oracle.refharness import make_args as ref_args
+    args = ref_args("simple_spread", n_agents=n, target_num=m, map_size=50)
+    env = silence(cs.VecSimpleSpreadEnv, args, num_envs=E, device=device, seed=42, auto_reset=True)
+    gen = torch.Generator(device=device).manual_seed(3)
+    acts = [torch.randint(0, 5, (E, n), generator=gen, device=device, dtype=torch.uint8) for _ in range(4)]
+    side = torch.cuda.Stream(device=device)
+    with torch.cuda.stream(side):
+        for k in range(5):
+            env.step(acts[k % 4])
+        torch.cuda.synchronize(device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            for k in range(K):
+                env.step(acts[k % 4])
+        torch.cuda.synchronize(device)
+        for _ in range(3):
+            g.replay()
+        torch.cuda.synchronize(device)
+        times, t_region = [], time.perf_counter()
+        while True:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); g.replay(); e1.record()
+            torch.cuda.synchronize(device)
+            times.append(e0.elapsed_time(e1))
+            if (time.perf_counter() - t_region) * 1000.0 >= MIN_TIMED_MS and len(times) >= 3:
+                break
+    us = 1000.0 * sorted(times)[len(times) // 2] / K
+    obs_dim = 2 + 2 * (n - 1) + 4 * m
+    # read: coordinates 16(n+m), meta 16, episode reward 8, actions n; write: agent coordinates 16n, obs 4*n*obs_dim,
+    # state 8(n+m), occupied m, reward 4+8, terminated 1, meta 16, episode reward 8
+    per_env = (16 * (n + m) + 24 + n) + (16 * n + 4 * n * obs_dim + 8 * (n + m) + m + 13 + 24)
+    out = {"workload": "simple_spread %da%dt map 50, %d envs in one launch, auto-reset" % (n, m, E), "kernel": "spread_kernel<STEP> (one warp per env)",
+           "value": E / (us * 1e-6), "unit": "env-steps/s", "agent_steps_per_s": n * E / (us * 1e-6), "us_per_launch": us,
+           "roofline": {"bound": "hbm", "achieved": per_env * E / (us * 1e-6) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": per_env * E / (us * 1e-6) / 1e9 / peak, "algorithmic_bytes_per_env_step": per_env, "traffic": load_traffic("spread")}}
+    try:                                                   # the unmodified reference class, one core, bounded sample
+        from oracle import refharness as rh
+        ref = rh.import_reference()["SimpleSpreadEnv"]
+        renv = rh.quiet(ref, args)
+        renv.reset()
+        rng = np.random.default_rng(1)
+        t0, steps = time.perf_counter(), 0
+        while time.perf_counter() - t0 < 2.0:
+            for _ in range(100):
+                renv.step([int(a) for a in rng.integers(0, 5, size=n)]); renv.get_obs(); renv.get_state()
+            steps += 100
+            if steps % 1000 == 0:
+                renv.reset()
+        out["reference_one_core"] = {"value": steps / (time.perf_counter() - t0), "unit": "env-steps/s",
+                                     "sample": "2 s of step/get_obs/get_state on the unmodified reference class (oracle/_ref)"}
+    except Exception as exc:                               # the staged reference is absent: no CPU figure
+        out["reference_one_core"] = {"error": repr(exc)}
+    return out
+
+
 def measure_policy(cs, torch, device, n=3, iters=30):
     """Batched agent network + action choice (csrc/policy.cu, policy_tc.cuh) on random-init weights of the
     reference's architecture (in 10 -> 64 -> GRU 64 -> 64 -> 3): rows/s of one choose_actions launch for the tensor-core
@@ -922,6 +980,10 @@ def main():
                 extra["policy"] = measure_policy(cs, torch, device)
             except Exception as exc:
                 extra["policy"] = {"error": repr(exc)}
+            try:
+                extra["spread"] = measure_spread(cs, torch, device, peak)
+            except Exception as exc:
+                extra["spread"] = {"error": repr(exc)}
             try:
                 extra["c1"] = measure_c1(cs, torch, device)
             except Exception as exc:

@@ -1,7 +1,7 @@
 """coopsearch_b200 -- B200-native batched env-step hot path of WZN1ng/Cooperative-Search.
 
 Public surface (mirrors the reference's env protocol):
-    VecFlightEasyEnv, VecFlightEnv, VecSearchEnv, SingleEnvAdapter, load_targets
+    VecFlightEasyEnv, VecFlightEnv, VecSearchEnv, VecSimpleSpreadEnv, SingleEnvAdapter, load_targets
     dist.shard_range / dist.allreduce_stats for the one-process-per-GPU launch
 """
 from ._lib import CoopSearchError, load as load_library  # noqa: F401
@@ -9,6 +9,7 @@ from .policy import BatchedRNNAgents  # noqa: F401
 from .vec_flight import VecFlightEasyEnv, VecFlightEnv, HostStepper, DeviceStepper, generate_episodes, load_targets  # noqa: F401
 from .adapter import SingleEnvAdapter  # noqa: F401
 from .replay import DeviceReplayBuffer, collect_replay_stats  # noqa: F401
+from .vec_spread import VecSimpleSpreadEnv  # noqa: F401
 from . import dist  # noqa: F401
 
 try:
@@ -16,5 +17,5 @@ try:
 except ImportError:  # pragma: no cover
     pass
 
-__all__ = ["VecFlightEasyEnv", "VecFlightEnv", "VecSearchEnv", "SingleEnvAdapter", "HostStepper", "DeviceStepper", "BatchedRNNAgents", "generate_episodes", "load_targets", "DeviceReplayBuffer", "collect_replay_stats",
+__all__ = ["VecFlightEasyEnv", "VecFlightEnv", "VecSearchEnv", "VecSimpleSpreadEnv", "SingleEnvAdapter", "HostStepper", "DeviceStepper", "BatchedRNNAgents", "generate_episodes", "load_targets", "DeviceReplayBuffer", "collect_replay_stats",
            "CoopSearchError", "load_library", "dist"]

@@ -75,6 +75,17 @@ class SearchBuffers(C.Structure):
     ]
 
 
+class SpreadCfg(C.Structure):          # mirrors cs_spread_cfg
+    _fields_ = [("struct_size", C.c_uint32), ("num_envs", C.c_int32), ("n_agents", C.c_int32), ("target_num", C.c_int32),
+                ("map_size", C.c_int32), ("time_limit", C.c_int32), ("auto_reset", C.c_int32), ("device", C.c_int32),
+                ("seed", C.c_uint32), ("env_id_base", C.c_uint32)]
+
+
+class SpreadBuffers(C.Structure):      # mirrors cs_spread_buffers
+    _fields_ = [(k, C.c_void_p) for k in ("pos", "meta", "obs", "state", "reward", "reward64", "terminated", "occupied", "stats",
+                                          "episode_reward")] + [("obs_dim", C.c_int32), ("state_dim", C.c_int32)]
+
+
 class SearchHostIO(C.Structure):
     _fields_ = [("actions", C.c_void_p), ("reward", C.c_void_p), ("terminated", C.c_void_p), ("obs", C.c_void_p),
                 ("state", C.c_void_p), ("avail", C.c_void_p)]
@@ -148,6 +159,15 @@ SIGNATURES = {
     "cs_flight_host_expand": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
     "cs_flight_step_host_compact_many": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int32, C.POINTER(C.c_void_p), C.c_int32, C.c_uint32]),
     "cs_flight_host_expand_many": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.POINTER(C.c_void_p), C.c_int32, C.c_int32]),
+    "cs_spread_create": (C.c_int, [C.POINTER(SpreadCfg), C.POINTER(C.c_void_p)]),
+    "cs_spread_destroy": (None, [C.c_void_p]),
+    "cs_spread_env_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
+    "cs_spread_buffers_get": (C.c_int, [C.c_void_p, C.POINTER(SpreadBuffers)]),
+    "cs_spread_reset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "cs_spread_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cs_spread_step_random": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "cs_spread_step_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cs_spread_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_void_p]),
     "cs_flight_host_pool_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.POINTER(C.c_void_p)]),
     "cs_flight_host_pool_destroy": (None, [C.c_void_p]),
     "cs_flight_host_pool_views": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(FlightHostViews), C.POINTER(C.c_void_p)]),

@@ -23,6 +23,7 @@ UNITS = {
     "runtime": ("runtime.cu", []),
     "search": ("search.cu", []),
     "policy": ("policy.cu", []),
+    "spread": ("spread.cu", []),
     "flight_host": ("flight_host.cu", []),
     "flight_hostio": ("flight_hostio.cu", []),
     "flight_lpa": ("flight_lpa.cu", []),

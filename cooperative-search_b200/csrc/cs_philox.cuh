@@ -14,6 +14,7 @@
 #define CS_STREAM_TARGET 2u
 #define CS_STREAM_POLICY 3u
 #define CS_STREAM_SEARCH 4u
+#define CS_STREAM_SPREAD 5u
 
 struct cs_u4 { uint32_t x, y, z, w; };
 

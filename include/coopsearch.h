@@ -350,6 +350,47 @@ int cs_search_step_host(cs_search* env, const cs_search_host_io* io, void* strea
 int cs_search_stats(cs_search* env, double* h_out, void* stream);
 
 /* ===================================================================================
+ * simple_spread  (env/simple_spread.py; SURVEY 8f "next" row 4)
+ * =================================================================================== */
+typedef struct cs_spread_cfg {
+    uint32_t struct_size;
+    int32_t num_envs;
+    int32_t n_agents;       /* simple_spread.py:23 */
+    int32_t target_num;     /* :21 */
+    int32_t map_size;       /* :20 */
+    int32_t time_limit;     /* :25 -- the reference hard-codes 100 */
+    int32_t auto_reset;     /* 1: an env that terminates is reset inside the same call (the step still reports it) */
+    int32_t device;
+    uint32_t seed, env_id_base;   /* reset placement is keyed by (seed, global env id, episode): shard invariant */
+} cs_spread_cfg;
+typedef struct cs_spread cs_spread;
+typedef struct cs_spread_buffers {
+    double* pos;            /* [E][n + m][2]  agents, then targets (float64 like the reference's Python floats)    */
+    int32_t* meta;          /* [E][4]         time_step, episode, done, 0                                          */
+    float* obs;             /* [E][n][obs_dim]   get_obs()   (:78-101,112-114), obs_dim = 2 + 2(n-1) + 4m          */
+    float* state;           /* [E][state_dim]    get_state() (:116-128), state_dim = 2n + 2m                       */
+    float* reward;          /* [E]            step()[0] (:141-167)                                                 */
+    double* reward64;       /* [E]            the same in float64                                                  */
+    uint8_t* terminated;    /* [E]            step()[1] (:176-178)                                                 */
+    uint8_t* occupied;      /* [E][m]         (:96-110)                                                            */
+    double* stats;          /* [CS_NUM_STATS] episodes, reward sum, episode length sum                             */
+    double* episode_reward; /* [E]            total_reward of the running episode (:175)                           */
+    int32_t obs_dim, state_dim;
+} cs_spread_buffers;
+int cs_spread_create(const cs_spread_cfg* cfg, cs_spread** out);                  /* SimpleSpreadEnv.__init__ (:16-39) */
+void cs_spread_destroy(cs_spread* env);
+int cs_spread_env_info(const cs_spread* env, int32_t* out4);                      /* get_env_info (:41-46) */
+int cs_spread_buffers_get(cs_spread* env, cs_spread_buffers* out);
+/* reset (:48-70) of the envs with d_mask[e] != 0 (NULL = all).  CS_RESET_KEEP_TARGETS keeps every coordinate currently in
+ * `pos` (a layout the caller injected), CS_RESET_KEEP_EPISODE does not advance the episode counter. */
+int cs_spread_reset(cs_spread* env, const uint8_t* d_mask, uint32_t flags, void* stream);
+int cs_spread_step(cs_spread* env, const uint8_t* d_actions, void* stream);       /* step (:169-180); actions u8 [E][n] in 0..4 */
+int cs_spread_step_random(cs_spread* env, int32_t k, void* stream);               /* k steps, actions drawn in the kernel */
+/* HOST buffers: H2D of the actions, the step, D2H of whatever is non-NULL; synchronises the stream */
+int cs_spread_step_host(cs_spread* env, const uint8_t* h_actions, float* h_reward, uint8_t* h_terminated, float* h_obs, float* h_state, void* stream);
+int cs_spread_stats(cs_spread* env, double* h_out, void* stream);
+
+/* ===================================================================================
  * batched agent network + action selection  (network/base_net.py, agent/agent.py; SURVEY 8f "next" row 1)
  * =================================================================================== */
 typedef struct cs_policy_cfg {

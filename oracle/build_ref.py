@@ -16,7 +16,7 @@ REF_SRC = os.environ.get("COOPSEARCH_REFERENCE", "/root/reference")
 REF_DST = os.path.join(HERE, "_ref")
 # the env-step path and its caller (common/rollout.py + the Agents facade it needs for alg=random)
 FILES = [
-    "env/flight_env_easy.py", "env/flight_env.py", "env/search_env.py",
+    "env/flight_env_easy.py", "env/flight_env.py", "env/search_env.py", "env/simple_spread.py",
     "common/rollout.py", "common/arguments.py", "common/replay_buffer.py",
     "agent/agent.py",
     "policy/qmix.py", "policy/vdn.py", "policy/dop.py", "policy/reinforce.py", "policy/trandition.py",

@@ -23,6 +23,7 @@ STREAM_DETECT = 1     # detection uniforms
 STREAM_TARGET = 2     # on-device target randomisation at reset
 STREAM_POLICY = 3     # in-kernel uniform-random policy (step_k)
 STREAM_SEARCH = 4     # search_env on-device target placement
+STREAM_SPREAD = 5     # simple_spread on-device reset placement
 
 
 def philox4x32(c0, c1, c2, c3, k0, k1, rounds=10):

@@ -499,3 +499,193 @@ class SearchOracle:
         self._windows()
         self._planes()
         return rew, terminated, ""
+
+
+# =============================================================================
+#  simple_spread  (env/simple_spread.py)
+# =============================================================================
+@dataclass
+class SpreadSpec:
+    n_agents: int = 3
+    target_num: int = 3
+    map_size: int = 50
+    time_limit: int = 100          # hard-coded in the reference (simple_spread.py:25)
+    agent_radius: int = 6          # (:24)
+
+    @property
+    def n_actions(self):
+        return 5                   # (:26)
+
+    @property
+    def state_shape(self):
+        return self.n_agents * 2 + self.target_num * 2                                   # (:27)
+
+    @property
+    def obs_shape(self):
+        return 2 + (self.n_agents - 1) * 2 + self.target_num * 4                         # (:28)
+
+
+def keyed_spread_layout(spec, seed, env_id, episode):
+    """Device-side reset placement (reference: map_size * np.random.rand() twice per entity, targets first, then agents,
+    simple_spread.py:57-68).  Entity k (targets 0..m-1, then agents) takes one Philox block: x = M * u53(w0, w1),
+    y = M * u53(w2, w3)."""
+    M = spec.map_size
+    out = []
+    for k in range(spec.target_num + spec.n_agents):
+        w = philox.philox4x32(env_id, (episode & 0xFFFF) << 16, k, 0, seed, philox.stream_key(philox.STREAM_SPREAD, episode))
+        out.append([M * philox.u53(w[0], w[1]), M * philox.u53(w[2], w[3])])
+    return out[:spec.target_num], out[spec.target_num:]
+
+
+class SimpleSpreadOracle:
+    """Scalar restatement of SimpleSpreadEnv in the reference's operation order (Python floats, `**2`, np.sqrt)."""
+    DPOS = [[0, 0], [1, 0], [0, 1], [-1, 0], [0, -1]]                                     # (:135)
+
+    def __init__(self, spec, seed=0, env_id=0):
+        self.spec, self.seed, self.env_id = spec, seed, env_id
+        self.episode = -1
+        self.time_step = 0
+        self.total_reward = 0.0
+        self.tgt, self.agents, self.occupied = [], [], []
+
+    def reset(self, targets=None, agents=None):
+        """(:48-70); targets / agents inject a layout (e.g. the reference's own MT19937 draws)."""
+        self.episode += 1
+        self.time_step = 0
+        self.total_reward = 0.0
+        if targets is None or agents is None:
+            kt, ka = keyed_spread_layout(self.spec, self.seed, self.env_id, self.episode)
+            targets = kt if targets is None else targets
+            agents = ka if agents is None else agents
+        self.tgt = [[float(p[0]), float(p[1])] for p in targets]
+        self.agents = [[float(p[0]), float(p[1])] for p in agents]
+        self._update_occupied()
+
+    def _update_occupied(self):
+        """(:96-110)"""
+        self.occupied = []
+        for t in self.tgt:
+            occ = 0
+            for a in self.agents:
+                dis = 0
+                for k in range(2):
+                    dis += (t[k] - a[k]) ** 2
+                if np.sqrt(dis) < self.spec.agent_radius:
+                    occ = 1
+                    break
+            self.occupied.append(occ)
+
+    def get_obs(self):
+        """(:78-101,112-114): own position, targets relative, other agents relative, then targets absolute."""
+        h = 0.5 * self.spec.map_size
+        obs = []
+        for i, a in enumerate(self.agents):
+            row = [a[0] - h, a[1] - h]
+            for t in self.tgt:
+                row += [t[0] - a[0], t[1] - a[1]]
+            for j, o in enumerate(self.agents):
+                if i != j:
+                    row += [o[0] - a[0], o[1] - a[1]]
+            obs.append(row)
+        for t in self.tgt:
+            for row in obs:
+                row += [t[0] - h, t[1] - h]
+        return np.array(obs)
+
+    def get_state(self):
+        """(:116-128)"""
+        h = 0.5 * self.spec.map_size
+        s = []
+        for a in self.agents:
+            s += [a[0] - h, a[1] - h]
+        for t in self.tgt:
+            s += [t[0] - h, t[1] - h]
+        return np.array(s)
+
+    def reward(self):
+        """(:141-153): minus the distance from every target to its nearest agent, summed in target order."""
+        r = 0
+        for t in self.tgt:
+            dis = []
+            for a in self.agents:
+                d = 0
+                for k in range(2):
+                    d += (a[k] - t[k]) ** 2
+                dis.append(np.sqrt(d))
+            r -= min(dis)
+        return r
+
+    def step(self, act_list):
+        """(:130-139,169-180)"""
+        if len(act_list) != self.spec.n_agents:
+            raise Exception('Act num mismatch agent')
+        M = self.spec.map_size
+        for i, a in enumerate(self.agents):
+            for k in range(2):
+                a[k] += self.DPOS[act_list[i]][k]
+                a[k] = min(max(0, a[k]), M)
+        self._update_occupied()
+        r = self.reward()
+        self.total_reward += r
+        self.time_step += 1
+        return r, self.time_step >= self.spec.time_limit, False
+
+
+class SpreadBatch:
+    """numpy-vectorised form of SimpleSpreadOracle for the configuration-size GPU tests (squares by multiplication; the
+    reference's `**2` is libm pow, which differs in the last bit for ~0.08 % of arguments -- only the float64 reward can see
+    it, by one ulp)."""
+
+    def __init__(self, spec, seed, env_id_base, E, auto_reset=False):
+        self.spec, self.seed, self.base, self.E, self.auto_reset = spec, seed, env_id_base, E, auto_reset
+        self.tgt = np.zeros((E, spec.target_num, 2))
+        self.agents = np.zeros((E, spec.n_agents, 2))
+        self.time_step = np.zeros(E, np.int32)
+        self.episode = np.full(E, -1, np.int64)
+        self.done = np.zeros(E, bool)
+
+    def reset(self, mask=None):
+        sel = np.ones(self.E, bool) if mask is None else np.asarray(mask, bool)
+        for e in np.nonzero(sel)[0]:
+            self.episode[e] += 1
+            t, a = keyed_spread_layout(self.spec, self.seed, self.base + int(e), int(self.episode[e]))
+            self.tgt[e], self.agents[e] = np.array(t), np.array(a)
+        self.time_step[sel] = 0
+        self.done[sel] = False
+
+    def obs_state(self):
+        sp, h = self.spec, 0.5 * self.spec.map_size
+        n, m, E = sp.n_agents, sp.target_num, self.E
+        obs = np.zeros((E, n, sp.obs_shape))
+        obs[:, :, 0:2] = self.agents - h
+        rel_t = self.tgt[:, None, :, :] - self.agents[:, :, None, :]                      # [E,n,m,2]
+        obs[:, :, 2:2 + 2 * m] = rel_t.reshape(E, n, 2 * m)
+        for i in range(n):
+            others = [j for j in range(n) if j != i]
+            rel_a = self.agents[:, others, :] - self.agents[:, i:i + 1, :]
+            obs[:, i, 2 + 2 * m:2 + 2 * m + 2 * (n - 1)] = rel_a.reshape(E, 2 * (n - 1))
+        obs[:, :, 2 + 2 * m + 2 * (n - 1):] = np.broadcast_to((self.tgt - h).reshape(E, 1, 2 * m), (E, n, 2 * m))
+        state = np.concatenate([(self.agents - h).reshape(E, 2 * n), (self.tgt - h).reshape(E, 2 * m)], axis=1)
+        return obs, state
+
+    def step(self, actions):
+        sp = self.spec
+        dpos = np.array(SimpleSpreadOracle.DPOS, np.float64)
+        live = ~self.done
+        act = np.asarray(actions)
+        moved = np.minimum(np.maximum(0.0, self.agents + dpos[act]), float(sp.map_size))
+        self.agents[live] = moved[live]
+        d = self.agents[:, None, :, :] - self.tgt[:, :, None, :]                          # [E,m,n,2]
+        dist = np.sqrt(d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1])
+        mins = dist.min(axis=2)                                                           # [E,m]
+        r = np.zeros(self.E)
+        for j in range(sp.target_num):                                                    # the reference's summation order
+            r = r - mins[:, j]
+        r[~live] = 0.0
+        self.time_step[live] += 1
+        term = self.time_step >= sp.time_limit
+        term[~live] = True
+        self.done = term.copy()
+        if self.auto_reset:
+            self.reset(mask=term & live)
+        return r, term

@@ -81,7 +81,7 @@ _ref_modules = {}
 
 
 def import_reference():
-    """Returns dict with the three reference env classes."""
+    """Returns dict with the reference env classes."""
     if _ref_modules:
         return _ref_modules
     if not reference_available():
@@ -93,8 +93,12 @@ def import_reference():
         from env.flight_env_easy import FlightSearchEnvEasy
         from env.flight_env import FlightSearchEnv
         from env.search_env import SearchEnv
+        try:
+            from env.simple_spread import SimpleSpreadEnv
+        except ImportError:          # an oracle/_ref staged before simple_spread was added
+            SimpleSpreadEnv = None
     _ref_modules.update(FlightSearchEnvEasy=FlightSearchEnvEasy, FlightSearchEnv=FlightSearchEnv,
-                        SearchEnv=SearchEnv)
+                        SearchEnv=SearchEnv, SimpleSpreadEnv=SimpleSpreadEnv)
     return _ref_modules
 
 

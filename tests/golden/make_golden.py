@@ -348,6 +348,42 @@ def run_policy_conv(model_dir, n_agents, steps=4, rows_envs=4):
     return out
 
 
+def run_spread(n_agents, target_num, map_size, E, T, env_id_base):
+    """SimpleSpreadEnv (env/simple_spread.py): reset() draws the layout from the seeded MT19937 stream, then T steps under
+    uniform-random actions.  Everything is stored in float64 as the reference returns it."""
+    ref = rh.import_reference()
+    cls = ref["SimpleSpreadEnv"]
+    args = rh.make_args("simple_spread", n_agents=n_agents, target_num=target_num, map_size=map_size)
+    obs_shape = 2 + (n_agents - 1) * 2 + target_num * 4
+    rng = np.random.default_rng(4321)
+    g = dict(tgt=np.zeros((E, target_num, 2)), agents0=np.zeros((E, n_agents, 2)),
+             init_obs=np.zeros((E, n_agents, obs_shape)), init_state=np.zeros((E, 2 * n_agents + 2 * target_num)),
+             actions=np.zeros((T, E, n_agents), np.uint8), reward=np.zeros((T, E)), terminated=np.zeros((T, E), np.uint8),
+             obs=np.zeros((T, E, n_agents, obs_shape)), state=np.zeros((T, E, 2 * n_agents + 2 * target_num)),
+             agents=np.zeros((T, E, n_agents, 2)), occupied=np.zeros((T, E, target_num), np.uint8))
+    for e in range(E):
+        np.random.seed(20_000 + env_id_base + e)
+        env = rh.quiet(cls, args)
+        env.reset()
+        g["tgt"][e] = np.array([t.pos for t in env.target_list])
+        g["agents0"][e] = np.array([a.pos for a in env.agent_list])
+        g["init_obs"][e] = env.get_obs()
+        g["init_state"][e] = env.get_state()
+        for t in range(T):
+            act = rng.integers(0, 5, size=n_agents).astype(np.uint8)
+            g["actions"][t, e] = act
+            r, term, _ = env.step([int(a) for a in act])
+            g["reward"][t, e] = r
+            g["terminated"][t, e] = int(term)
+            g["obs"][t, e] = env.get_obs()
+            g["state"][t, e] = env.get_state()
+            g["agents"][t, e] = np.array([a.pos for a in env.agent_list])
+            g["occupied"][t, e] = np.array(env.occupied, np.uint8)
+    g["meta"] = np.array([n_agents, target_num, map_size, env_id_base], np.int64)
+    g["info"] = np.array([env.get_env_info()[k] for k in ("n_actions", "state_shape", "obs_shape", "episode_limit")], np.int64)
+    return g
+
+
 def thin(g, keep_every, keys=("obs", "state")):
     """obs/state are derivable from xy/yaw/found; keep every k-th step to bound fixture size."""
     for k in keys:
@@ -384,6 +420,8 @@ def main():
         "search_4a_am1_tm1": lambda: thin(run_search(4, 10, 20, 4, 1, 1, E=3, T=80, env_id_base=850), 10),
         "search_5a_am2": lambda: thin(run_search(5, 12, 24, 3, 2, 0, E=2, T=80, env_id_base=870), 10),
         "search_64a_1000t": lambda: thin(run_search(64, 1000, 64, 7, 0, 0, E=1, T=30, env_id_base=900), 10),
+        "spread_3a3t": lambda: run_spread(3, 3, 50, E=4, T=100, env_id_base=1000),
+        "spread_5a7t_small": lambda: run_spread(5, 7, 12, E=3, T=100, env_id_base=1100),
     }
     only = sys.argv[1:]
     for name, job in jobs.items():
