@@ -19,7 +19,3 @@ with open("gpurun_out/profiles_r02/r02_bench_launches.csv", "w") as fh:
 PY
 rm -f $P/r02_bench_launches_raw.csv
 cat $P/r02_bench_launches.csv
-name=policy_tc
-ncu --set full --clock-control none --import-source on -k regex:policy_tc_kernel -s 12 -c 1 -f -o /tmp/prof_$name python tools/prof_policy.py > /dev/null 2>&1
-{ echo "# ncu --set full --clock-control none --import-source on -k regex:policy_tc_kernel -s 12 -c 1 python tools/prof_policy.py  (786432 rows)"; python tools/ncu_summary.py /tmp/prof_$name.ncu-rep; echo "# top source lines by stall samples"; python tools/ncu_lines.py /tmp/prof_$name.ncu-rep 25; echo "# top SASS instructions by stall samples"; python tools/ncu_sass.py /tmp/prof_$name.ncu-rep 16; } > $P/r02_${name}_ncu_full.txt 2>&1
-head -20 $P/r02_${name}_ncu_full.txt
