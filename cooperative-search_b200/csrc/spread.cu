@@ -52,10 +52,10 @@ __device__ __forceinline__ void place(const SpreadParams& p, double* xy, int e, 
     }
 }
 
-// element q of the env's observation block (agent i = q / obs_dim, slot s = q % obs_dim), simple_spread.py:82-101
-__device__ __forceinline__ float obs_element(const SpreadParams& p, const double* xy, int q) {
+// slot s of agent i's observation row (element i * obs_dim + s of the env's observation block), simple_spread.py:82-101
+__device__ __forceinline__ float obs_element(const SpreadParams& p, const double* xy, int i, int s) {
     const int n = p.n, m = p.m;
-    const int i = q / p.obs_dim, s = q - i * p.obs_dim, k = s & 1;
+    const int k = s & 1;
     const double own = xy[2 * i + k];
     if (s < 2) return (float)(own - p.half_M);                                     // own position
     if (s < 2 + 2 * m) return (float)(xy[2 * (n + ((s - 2) >> 1)) + k] - own);       // targets, relative
@@ -156,7 +156,12 @@ __global__ void __launch_bounds__(kThreads) spread_kernel(const SpreadParams p, 
     if (emit && active) {
         for (int c = lane; c < (do_reset ? 2 * ne : 2 * n); c += G) gp[c] = xy[c];   // targets only move at a reset
         float* ob = p.obs + (size_t)e * n * p.obs_dim;
-        for (int q = lane; q < n * p.obs_dim; q += G) ob[q] = obs_element(p, xy, q);
+        int oi = lane / p.obs_dim, os = lane - oi * p.obs_dim;                        // (agent, slot) of element q, kept incrementally
+        for (int q = lane; q < n * p.obs_dim; q += G) {
+            ob[q] = obs_element(p, xy, oi, os);
+            os += G;
+            while (os >= p.obs_dim) { os -= p.obs_dim; ++oi; }
+        }
         float* st = p.state + (size_t)e * p.state_dim;
         for (int q = lane; q < 2 * ne; q += G) st[q] = (float)(xy[q] - p.half_M);    // agents, then targets (:116-128)
         if (lane == 0) {

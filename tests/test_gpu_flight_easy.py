@@ -376,6 +376,33 @@ def test_pooled_host_stepper_equals_device_steps(variant, graph, sizes, lpe):
     del stepper, envs                                                  # pool and envs go away in either order
 
 
+def test_pooled_host_stepper_reset_list_tail_and_overflow():
+    """The pooled step copies the first num_envs/48 reset entries with the results; 150 envs that end in one call take the
+    separate tail copy, ~3900 envs that end in one call overflow the list (num_envs/16) and force a full refresh of the host rows."""
+    import coopsearch_b200 as cs
+    spec = FlightSpec(n_agents=3, time_limit=10)
+    args = make_args(dict(spec.__dict__))
+    E = 4096
+    mk = lambda: cs.VecFlightEasyEnv(args, TEMPLATE, num_envs=E, seed=2, auto_reset=True)
+    env, ref = mk(), mk()
+    stepper = cs.HostStepper([env], [torch.cuda.Stream()])
+    assert stepper._pool is not None
+    rng = np.random.default_rng(3)
+    mask = (np.arange(E) >= 150).astype(np.uint8)
+    resets_seen = []
+    for t in range(26):
+        if t == 4:                                   # envs >= 150 start over: the first 150 end 6 calls later, on their own
+            env.reset(mask=mask); ref.reset(mask=mask)
+        stepper.actions.numpy()[...] = rng.integers(0, 3, size=(E, 3), dtype=np.uint8)
+        stepper.step()
+        r, term, win = ref.step(stepper.actions.cuda())
+        hb = env.host_buffers()
+        resets_seen.append(int(cpu(term).sum()))
+        assert np.array_equal(cpu(r), hb["reward"].numpy()) and np.array_equal(cpu(term), hb["terminated"].numpy()), t
+        assert np.array_equal(cpu(ref.get_state()), hb["state"].numpy()), t
+    assert any(85 < c <= 256 for c in resets_seen) and any(c > 256 for c in resets_seen), resets_seen
+
+
 @pytest.mark.parametrize("lpe,sizes", [(1, [700, 4096, 33]), (1, [700, 4096, 34, 2, 128]), (-1, [700, 4096, 34, 2, 128]), (4, [256, 256, 256, 1000]), (0, [512, 512])])
 def test_grouped_device_step_equals_separate_steps(monkeypatch, lpe, sizes):
     """cs_flight_group_step: env batches of different sizes stepped in ONE launch end up bit-identical to the same
