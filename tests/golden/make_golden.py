@@ -384,6 +384,20 @@ def run_spread(n_agents, target_num, map_size, E, T, env_id_base):
     return g
 
 
+def compact_anchor(g):
+    """A wide run reduced to what a device test needs: the inputs (targets, actions), every discrete per-step output, the
+    final float64 positions / headings and a float32 observation / state checkpoint every 50 steps."""
+    keep = {k: g[k] for k in ("tgt_xy", "init_xy", "init_yaw", "init_found", "actions", "found", "terminated", "win", "time_step", "out",
+                              "n_steps", "meta", "fmeta")}
+    keep["reward"] = g["reward"].astype(np.float32)
+    keep["final_xy"], keep["final_yaw"] = g["xy"][-1], g["yaw"][-1]
+    keep["chk_steps"] = np.arange(49, g["obs"].shape[0], 50, dtype=np.int32)
+    keep["chk_obs"] = g["obs"][49::50].astype(np.float32)
+    keep["chk_state"] = g["state"][49::50].astype(np.float32)
+    keep["chk_xy"] = g["xy"][49::50]
+    return keep
+
+
 def thin(g, keep_every, keys=("obs", "state")):
     """obs/state are derivable from xy/yaw/found; keep every k-th step to bound fixture size."""
     for k in keys:
@@ -420,6 +434,9 @@ def main():
         "search_4a_am1_tm1": lambda: thin(run_search(4, 10, 20, 4, 1, 1, E=3, T=80, env_id_base=850), 10),
         "search_5a_am2": lambda: thin(run_search(5, 12, 24, 3, 2, 0, E=2, T=80, env_id_base=870), 10),
         "search_64a_1000t": lambda: thin(run_search(64, 1000, 64, 7, 0, 0, E=1, T=30, env_id_base=900), 10),
+        # wide anchors for the device tests: hundreds of reference trajectories, compacted
+        "anchor_easy_3a_384": lambda: compact_anchor(run_flight("FlightSearchEnvEasy", 3, 0, E=384, T=200, env_id_base=40_000)),
+        "anchor_easy_5a_am2_192": lambda: compact_anchor(run_flight("FlightSearchEnvEasy", 5, 2, E=192, T=200, env_id_base=41_000)),
         "spread_3a3t": lambda: run_spread(3, 3, 50, E=4, T=100, env_id_base=1000),
         "spread_5a7t_small": lambda: run_spread(5, 7, 12, E=3, T=100, env_id_base=1100),
     }
