@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const __grid_c
         const bool live = r_raw < p.rows;
         const int r = live ? r_raw : p.rows - 1;
         // ---- inputs: [conv features of the env's map ||] obs || last-action one-hot || agent-id one-hot
-        //      (network/base_net.py:31-41, agent/agent.py:38-50), and the hidden state
+        //      (network/base_net.py:31-41, agent/agent.py:38-50)
         {
             const int la = (p.use_last && p.last_action) ? (int)p.last_action[r] : 255;
 #pragma unroll
@@ -170,8 +170,15 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const __grid_c
                 *reinterpret_cast<uint4*>(myA0 + c * kALbo) = tc_pack8(x);
             }
         }
-        // this thread's half of the row's hidden state (units 32 * half ...): read once (fp32, 8 loads in flight), kept in
-        // registers for the GRU blend, bf16 copy -> A operand
+        tc_operands_ready();
+        // ---- fc1
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            tc_gemm(tmem + 0, sbase + kOffA0, sbase + kOffW1, 64, 0, 64, kTcK1 / 16, false);
+            tc_commit(bar);
+        }
+        // ... and while the tensor core works on fc1: this thread's half of the row's hidden state (units 32 * half ...), read
+        // once (fp32, 8 loads in flight), kept in registers for the GRU blend, bf16 copy -> A operand of the GRU GEMMs
         float hreg[32];
         {
             const float4* hp = reinterpret_cast<const float4*>(p.hidden + (size_t)r * 64 + 32 * half);
@@ -182,19 +189,12 @@ __global__ void __launch_bounds__(kTcThreads, 2) policy_tc_kernel(const __grid_c
             }
 #pragma unroll
             for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(myAH + (4 * half + c) * kALbo) = tc_pack8(hreg + 8 * c);
-            // the same half row of this CTA's NEXT tile: pull it into L2 now (the loads above are the longest stall of a tile)
+            // the same half row of this CTA's NEXT tile: pull it into L2 now
             const long long rn = (long long)(tile + (int)gridDim.x) * kTcRows + row;
             if (rn < p.rows) {
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(p.hidden + (size_t)rn * 64 + 32 * half));
                 if (half == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.obs + (size_t)rn * p.obs_dim));
             }
-        }
-        tc_operands_ready();
-        // ---- fc1
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            tc_gemm(tmem + 0, sbase + kOffA0, sbase + kOffW1, 64, 0, 64, kTcK1 / 16, false);
-            tc_commit(bar);
         }
         tc_wait(bar, phase); phase ^= 1u;
         {
