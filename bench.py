@@ -873,7 +873,7 @@ def main():
     from coopsearch_b200 import dist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl ours needs a CUDA device: the product has no CPU path")
-    rank, local, world = dist.init_from_env("nccl" if world > 1 else None)
+    rank, local, world = dist.init_from_env("nccl" if world > 1 else None, bind_cpus=True)
     device = torch.device("cuda", local if world > 1 else 0)
     torch.cuda.set_device(device)
     lib = cs.load_library()
