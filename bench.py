@@ -598,8 +598,8 @@ def measure_obs_full(cs, torch, device, peak):
 def measure_spread(cs, torch, device, peak, E=1048576, n=3, m=3, K=20):
     """simple_spread (env/simple_spread.py): env-steps/s of the batched step on E envs, K steps per CUDA
     graph replayed until >= 60 ms, auto-reset, pre-generated device actions; and the unmodified reference class on one core."""
-    from oracle.refharness import make_args as ref_args
-    args = ref_args("simple_spread", n_agents=n, target_num=m, map_size=50)
+    import types
+    args = types.SimpleNamespace(env="simple_spread", n_agents=n, target_num=m, map_size=50)
     env = silence(cs.VecSimpleSpreadEnv, args, num_envs=E, device=device, seed=42, auto_reset=True)
     gen = torch.Generator(device=device).manual_seed(3)
     acts = [torch.randint(0, 5, (E, n), generator=gen, device=device, dtype=torch.uint8) for _ in range(4)]
