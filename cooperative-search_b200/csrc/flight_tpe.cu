@@ -145,6 +145,7 @@ struct StagedView : GlobalView<true> {
         const double* tp = this->g.tgt + this->e;
         const size_t E = (size_t)this->g.E;
         uint32_t d = smem_u32(col);
+#pragma unroll 6
         for (int r = 0; r < 2 * this->p.m; ++r, d += TE * 8, tp += E)
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(tp) : "memory");
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -377,6 +378,7 @@ __device__ __forceinline__ int flight_tpe_body(const FlightParams& p, const Grou
             // the env's K threads share the targets; TU of a thread's targets are loaded together so that their
             // latency is paid once per block, not once per target
             constexpr int TU = (K >= 8) ? 2 : ((V::kStaged && N <= 3) ? 1 : CS_TPE_TU);
+            uint32_t need = 0;                          // targets in view of some agent and not found yet
             for (int j0 = kk; j0 < m; j0 += K * TU) {
                 double2 t[TU];
 #pragma unroll
@@ -394,19 +396,31 @@ __device__ __forceinline__ int flight_tpe_body(const FlightParams& p, const Grou
                         const double dx = t[u].x - ax[a], dy = t[u].y - ay[a];
                         if (dx * dx + dy * dy <= p.R2) amask |= 1u << a;               // '<=' (:237)
                     }
-                    if (amask && !((found >> j) & 1u)) {                               // draw is irrelevant once found (:239)
-                        bool got = false;
-#pragma unroll
-                        for (int blk = 0; 4 * blk < N; ++blk) {
-                            const uint32_t bits = (amask >> (4 * blk)) & 0xFu;
-                            if (!bits || got) continue;
-                            const cs_u4 w = cs_detect_words(g.seed, env_id, episode, t_key, (uint32_t)blk, (uint32_t)j);
-                            got = ((bits & 1u) && (long long)w.x <= p.thr) || ((bits & 2u) && (long long)w.y <= p.thr) ||
-                                  ((bits & 4u) && (long long)w.z <= p.thr) || ((bits & 8u) && (long long)w.w <= p.thr);
-                        }
-                        if (got) newf |= 1u << j;
-                    }
+                    if (amask && !((found >> j) & 1u)) need |= 1u << j;                // draw is irrelevant once found (:239)
                 }
+            }
+            // The detection draws, in a second loop over the targets that need one.  Inside the loop above the warp would
+            // run the Philox rounds in every iteration where ANY of its 32 envs has the target in view (about half of the
+            // iterations); here it runs them max-over-lanes(number of needed targets) times -- two or three.
+            for (uint32_t left = need; left; left &= left - 1u) {
+                const int j = __ffs(left) - 1;
+                const double2 tj = L.tgt_ld(j);
+                uint32_t amask = 0;
+#pragma unroll
+                for (int a = 0; a < N; ++a) {
+                    const double dx = tj.x - ax[a], dy = tj.y - ay[a];
+                    if (dx * dx + dy * dy <= p.R2) amask |= 1u << a;
+                }
+                bool got = false;
+#pragma unroll
+                for (int blk = 0; 4 * blk < N; ++blk) {
+                    const uint32_t bits = (amask >> (4 * blk)) & 0xFu;
+                    if (!bits || got) continue;
+                    const cs_u4 w = cs_detect_words(g.seed, env_id, episode, t_key, (uint32_t)blk, (uint32_t)j);
+                    got = ((bits & 1u) && (long long)w.x <= p.thr) || ((bits & 2u) && (long long)w.y <= p.thr) ||
+                          ((bits & 4u) && (long long)w.z <= p.thr) || ((bits & 8u) && (long long)w.w <= p.thr);
+                }
+                if (got) newf |= 1u << j;
             }
         }
 #pragma unroll
