@@ -39,7 +39,10 @@ namespace {
 // registers) without spills when the sensing loop takes one target at a time -- measured on B200 (tools/sweep_stream.sh):
 // 1M envs 5.5e9 -> 6.2e9 env-steps/s, the grouped c2 launch 4.79e9 -> 4.83e9; with five agents the same setting spills
 // (65536 envs: 3.15e9 -> 2.78e9), so larger teams keep 8 CTAs and blocks of CS_TPE_TU targets.
-constexpr int tpe_min_ctas(int N, int K, int mode) { return (K == 1 && mode == 0 && N <= 3) ? 10 : CS_TPE_MIN_CTAS; }
+#ifndef CS_TPE_SMALL_CTAS
+#define CS_TPE_SMALL_CTAS 10
+#endif
+constexpr int tpe_min_ctas(int N, int K, int mode) { return (K == 1 && mode == 0 && N <= 3) ? CS_TPE_SMALL_CTAS : CS_TPE_MIN_CTAS; }
 
 // Where a thread finds its env's state.  GlobalView: straight from HBM, layout known at compile time (structure of arrays with
 // one thread per env, record per env otherwise).  TileView (flight_stream_kernel): the loads come from the shared-memory tile
