@@ -36,6 +36,7 @@ public:
     void run(const std::function<void(int, int)>& fn) {
         const int T = size();
         if (T == 1) { fn(0, 1); return; }
+        std::lock_guard<std::mutex> one_at_a_time(run_m_);           // callers on several host threads take turns
         {
             std::lock_guard<std::mutex> lk(m_);
             fn_ = &fn;
@@ -81,7 +82,7 @@ private:
         }
     }
     std::vector<std::thread> workers_;
-    std::mutex m_;
+    std::mutex m_, run_m_;
     std::condition_variable cv_, done_;
     const std::function<void(int, int)>* fn_ = nullptr;
     unsigned long long gen_ = 0;
