@@ -153,7 +153,9 @@ struct StagedView : GlobalView<true> {
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(tp) : "memory");
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    __device__ __forceinline__ void targets_ready() const { asm volatile("cp.async.wait_all;" ::: "memory"); }
+    // every lane's own copies have landed; the warp barrier orders them before tgt_publish writes of OTHER lanes into this
+    // lane's column (auto-reset, later in the kernel)
+    __device__ __forceinline__ void targets_ready() const { asm volatile("cp.async.wait_all;" ::: "memory"); __syncwarp(); }
 };
 
 template <int N, int TE>
