@@ -163,7 +163,14 @@ __device__ __forceinline__ double2 heading_sincos(const FlightParams& p, const l
     const int k = __double2int_rn(h * p.inv_turn);
     if (k == 0 && fabs(h) < 7.450580596923828e-09) return make_double2(h, 1.0);   // |h| < 2^-27: libm returns sin = h, cos = 1
     if (k >= 1 && k <= 36) {
+#ifdef CS_LUTM_STAGED
         const longlong2 mt = lutm[k];                      // cluster index staged in shared memory by the CTA
+#else
+        // the 37-entry cluster index straight from L1 (every warp of the SM reads the same 592 bytes).  Staging it in shared
+        // memory per CTA costs 37 loads and a block barrier before the first state load: measured +2..3 % on the grouped
+        // c2 launch and on c3 without it, -1 % on the 1M-env launch.
+        const longlong2 mt = __ldg(p.lut_meta + k);
+#endif
         const long long off = __double_as_longlong(h) - mt.x;
         const long long half = mt.y >> 32;
         if (off >= -half && off <= half) return __ldg(p.lut + ((mt.y & 0xffffffffLL) + half + off));

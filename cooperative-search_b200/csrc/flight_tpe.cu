@@ -204,8 +204,10 @@ __device__ __forceinline__ GroupEntry entry_of(const FlightParams& p) {
 
 // heading-table index: 37 entries staged in shared memory once per CTA
 __device__ __forceinline__ void stage_lut_meta(const FlightParams& p, longlong2* lutm) {
+#ifdef CS_LUTM_STAGED
     if (threadIdx.x < 37) lutm[threadIdx.x] = __ldg(p.lut_meta + threadIdx.x);
     __syncthreads();
+#endif
 }
 
 // e_raw: the env of this thread (>= g.E: none); t_first: e_raw * K + kk of lane 0 of this warp; pre_act: for a TileView the
