@@ -173,6 +173,13 @@ def test_streaming_step_kernel_ring_reuse(monkeypatch, groups, slots, grid):
     compare_step_kernels(3, 0, 0, 50, 12, "easy", 4222 if grid < 148 else 40000, 1)
 
 
+@pytest.mark.parametrize("variant,n_agents", [("probmap", 3), ("easy", 5), ("probmap", 6)])
+def test_one_thread_per_env_forms_equal_lane_per_agent_kernel(variant, n_agents):
+    """lanes_per_env = 1 (what handles of >= 32768 envs get by default): structure-of-arrays state, staged targets for
+    flight_easy, the job records for the tiled map kernel for the flight variant -- against flight_kernel, bit for bit."""
+    compare_step_kernels(n_agents, 0, 0, 50, 30, variant, 1001 if variant == "easy" else 600, 1)
+
+
 def compare_step_kernels(n_agents, agent_mode, target_mode, map_size, time_limit, variant, E, lanes):
     import coopsearch_b200 as cs
     T = 3 * time_limit + 7
