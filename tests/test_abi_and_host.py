@@ -32,9 +32,10 @@ def test_struct_sizes_match_the_header():
     src = r'''
     #include <stdio.h>
     #include "coopsearch.h"
-    int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(cs_flight_cfg), sizeof(cs_flight_buffers),
+    int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(cs_flight_cfg), sizeof(cs_flight_buffers),
         sizeof(cs_flight_host_io), sizeof(cs_search_cfg), sizeof(cs_search_buffers), sizeof(cs_search_host_io),
-        sizeof(cs_episode_buffers), sizeof(cs_policy_cfg), sizeof(cs_policy_weights), sizeof(cs_policy_io)); return 0; }
+        sizeof(cs_episode_buffers), sizeof(cs_policy_cfg), sizeof(cs_policy_weights), sizeof(cs_policy_io),
+        sizeof(cs_spread_cfg), sizeof(cs_spread_buffers), sizeof(cs_flight_host_views)); return 0; }
     '''
     exe = "/tmp/cs_sizes_%d" % os.getpid()
     subprocess.run(["gcc", "-x", "c", "-I", os.path.join(ROOT, "include"), "-o", exe, "-"], input=src.encode(), check=True)
@@ -42,7 +43,7 @@ def test_struct_sizes_match_the_header():
     os.remove(exe)
     want = [C.sizeof(t) for t in (_lib.FlightCfg, _lib.FlightBuffers, _lib.FlightHostIO, _lib.SearchCfg,
                                   _lib.SearchBuffers, _lib.SearchHostIO, _lib.EpisodeBuffers, _lib.PolicyCfg,
-                                  _lib.PolicyWeights, _lib.PolicyIO)]
+                                  _lib.PolicyWeights, _lib.PolicyIO, _lib.SpreadCfg, _lib.SpreadBuffers, _lib.FlightHostViews)]
     assert got == want
 
 
